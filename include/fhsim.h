@@ -1,0 +1,153 @@
+/* fhsim.h -- C-ABI of libfhsim.so: the B200 (sm_100a) complex128 statevector engine.
+ *
+ * This is the drop-in boundary for the hot path of
+ * chuntse0514/Quantum-Simulation-of-Fermi-Hubbard-model.  The reference has no FFI of its own: the
+ * seam is PennyLane's device/QNode API as its drivers use it.  Each entry point cites the reference
+ * call it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - state = complex128[2^n] (interleaved re,im), wire/qubit q <-> bit (n-1-q) of the flat index
+ *     (wire 0 = MSB; reference linalg/exact_diagonalization.py:23, PennyLane qml.state()).
+ *   - Pauli string = (x, z): i^k X^x Z^z with k = popcount(x&z) (every Y = iXZ),
+ *     (P psi)[i] = i^k (-1)^popcount((i^x)&z) psi[i^x].
+ *   - all functions return 0 on success, a negative FH_E* code otherwise; fh_last_error() gives the
+ *     thread-local message.  No C++ exception crosses the boundary.
+ *   - host arrays are borrowed for the duration of the call; outputs are caller-allocated.
+ *   - every call is ordered on the stream given to fh_ctx_create; calls that return host scalars
+ *     synchronise that stream.  Handles are not thread-safe.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with FH_ECUDA.
+ */
+#ifndef FHSIM_H
+#define FHSIM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FH_OK 0
+#define FH_EINVAL (-1)   /* bad argument                      -> ValueError   */
+#define FH_ECUDA (-2)    /* CUDA runtime error / no device     -> RuntimeError */
+#define FH_ENOMEM (-3)   /* host or device allocation failed   -> MemoryError  */
+#define FH_ESTATE (-4)   /* object used in the wrong state     -> RuntimeError */
+
+typedef struct fh_ctx fh_ctx;         /* device + stream + scratch                                 */
+typedef struct fh_state fh_state;     /* complex128[2^n] on the device                             */
+typedef struct fh_table fh_table;     /* observable: packed Pauli table grouped by x-mask           */
+typedef struct fh_pool fh_pool;       /* screening pool: generators in pair form                    */
+typedef struct fh_program fh_program; /* compiled circuit (ordered ops, parameters, fused tiles)   */
+
+int fh_version(void);
+const char *fh_last_error(void);
+
+/* ---- context ------------------------------------------------------------------------------
+ * replaces qml.device('default.qubit.torch' | 'lightning.gpu', wires=n)  (models/adapt_vqe.py:299-304).
+ * stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or NULL for a private one. */
+int fh_ctx_create(int device, void *stream, fh_ctx **out);
+int fh_ctx_destroy(fh_ctx *ctx);
+int fh_ctx_sync(fh_ctx *ctx);
+int fh_ctx_info(fh_ctx *ctx, int *sm_count, size_t *free_bytes, size_t *total_bytes);
+/* write `bytes` of scratch (>= L2 size) so the next kernel starts with a cold L2 (benchmark hygiene) */
+int fh_ctx_flush_l2(fh_ctx *ctx, size_t bytes);
+
+/* ---- state --------------------------------------------------------------------------------
+ * replaces the PennyLane state tensor and qml.state() (models/adapt_vqe.py:358-359, 404-407). */
+int fh_state_create(fh_ctx *ctx, int n_qubits, fh_state **out);
+/* borrow caller-owned device memory (e.g. a torch complex128 tensor's data_ptr()) */
+int fh_state_wrap(fh_ctx *ctx, int n_qubits, void *device_ptr, fh_state **out);
+int fh_state_destroy(fh_state *st);
+int fh_state_set_basis(fh_state *st, uint64_t index);                  /* |index>, qml.PauliX prep (adapt_vqe.py:328-329) */
+int fh_state_copy(fh_state *dst, const fh_state *src);
+int fh_state_to_host(const fh_state *st, double *out_re_im);           /* 2*2^n doubles */
+int fh_state_from_host(fh_state *st, const double *in_re_im);
+int fh_state_device_ptr(const fh_state *st, void **ptr);
+int fh_state_inner(const fh_state *a, const fh_state *b, double *re, double *im);   /* <a|b>, fidelity (adapt_vqe.py:408) */
+int fh_state_norm2(const fh_state *st, double *out);
+
+/* ---- K1: rotations, immediate mode ----------------------------------------------------------
+ * pair op: for every index i with (i & fixmask) == fixval, j = i ^ x, s = (-1)^popcount(i & zeta):
+ *     psi[i] <- m00 psi[i] + s m01 psi[j];   psi[j] <- s m10 psi[i] + m11 psi[j]
+ * m = {re00,im00, re01,im01, re10,im10, re11,im11}.  fixmask must contain the top bit of x and fixval
+ * must have it clear.  Covers exp(-i theta P/2) (models/utils.py:58-83), the fused 8-string
+ * fermionic double-excitation rotation (models/adapt_vqe.py:87-98 on a pool generator),
+ * qml.SingleExcitation / PauliX / CNOT / RX / RY (adapt_vqe.py:329,353; vqe_hea.py:47-52). */
+int fh_apply_pair(fh_state *st, uint64_t x, uint64_t fixmask, uint64_t fixval, uint64_t zeta, const double m[8]);
+/* diagonal op: psi[i] <- exp(-i sum_m angle[m] (-1)^popcount(i & z[m])) psi[i]   (qml.RZ, Z-string rotations) */
+int fh_apply_diag(fh_state *st, int n_terms, const uint64_t *z, const double *angle);
+/* sequence of single-string rotations  prod_m exp(-i half_angle[m] P_m), applied in order m = 0..M-1
+ * (the literal Trotterize_generator loop, models/adapt_vqe.py:91-98, one launch per string) */
+int fh_apply_pauli_rot_batch(fh_state *st, int m, const uint64_t *x, const uint64_t *z, const double *half_angles);
+
+/* ---- K2: observables ------------------------------------------------------------------------
+ * replaces QubitOperator_to_qmlHamiltonian + qml.expval(qml.Hamiltonian) (models/utils.py:30-56,
+ * adapt_vqe.py:357,361).  Terms are given in table order; coeff is the coefficient of the Hermitian
+ * string.  The table may be re-uploaded at any time (iQCC dressing, iqcc_hubbard.py:184-189). */
+int fh_table_upload(fh_ctx *ctx, int n_qubits, int n_terms, const uint64_t *x, const uint64_t *z,
+                    const double *coeff_re, const double *coeff_im, fh_table **out);
+int fh_table_free(fh_table *tab);
+int fh_table_info(const fh_table *tab, int *n_terms, int *n_groups);
+/* out <- H in (out may be NULL: expectation only); *e = <in|H|in>.  in and out must differ. */
+int fh_apply_table(const fh_table *tab, const fh_state *in, fh_state *out, double *e_re, double *e_im);
+
+/* ---- K3: pool screening ---------------------------------------------------------------------
+ * replaces ADAPT.select_operator's append-and-backprop (models/adapt_vqe.py:297-310):
+ *   g[o] = sum over entries e with out_index[e]==o of
+ *          2 Im sum_{i in pattern e} ( conj(lam_i) s B psi_j + conj(lam_j) s conj(B) psi_i ),  j = i^x
+ * which equals 2 Im <lambda| G_o |psi> for a generator whose x-mask groups are the entries. */
+int fh_pool_upload(fh_ctx *ctx, int n_qubits, int n_entries, const uint64_t *x, const uint64_t *fixmask,
+                   const uint64_t *fixval, const uint64_t *zeta, const double *b_re, const double *b_im,
+                   const int32_t *out_index, int n_out, fh_pool **out);
+int fh_pool_free(fh_pool *pool);
+/* gradients of outputs [first, first+count) -> out[count]   (pool sharding across GPUs uses first/count) */
+int fh_pool_gradients(const fh_pool *pool, const fh_state *psi, const fh_state *lambda, int first, int count, double *out);
+
+/* ---- compiled circuits ----------------------------------------------------------------------
+ * replaces the QNode tape built by ADAPT.circuit / HVA.circuit / IQCC.get_circuit / VQE.circuit
+ * (models/adapt_vqe.py:325-361, hva.py:273-303, iqcc_hubbard.py:59-80, vqe_hea.py:43-57).
+ * Ops are appended in circuit order.  kind 0: fixed matrix m[8]; kind 1: rotation
+ * exp(-i (scale*theta[param]) Ghat) with (Ghat psi)[i] = s bhat psi[j], (Ghat psi)[j] = s conj(bhat) psi[i]. */
+int fh_program_create(fh_ctx *ctx, int n_qubits, int n_params, fh_program **out);
+int fh_program_destroy(fh_program *prog);
+int fh_program_add_pair(fh_program *prog, uint64_t x, uint64_t fixmask, uint64_t fixval, uint64_t zeta,
+                        int kind, int param, double scale, double bhat_re, double bhat_im, const double m[8]);
+/* diagonal op; param < 0: fixed angles coef[m]; else angle[m] = theta[param] * coef[m] */
+int fh_program_add_diag(fh_program *prog, int n_terms, const uint64_t *z, const double *coef, int param);
+/* ops added between begin/end are fused into ONE shared-memory tile kernel over the given bit positions
+ * (ascending; every pair op inside must have its x-mask within those bits) */
+int fh_program_begin_tile(fh_program *prog, int n_bits, const int32_t *bits);
+int fh_program_end_tile(fh_program *prog);
+int fh_program_finalize(fh_program *prog);
+int fh_program_info(const fh_program *prog, int *n_ops, int *n_launches);
+/* apply ops [first, first+count) to st (dagger != 0: the inverse, in reverse order) */
+int fh_program_run(fh_program *prog, fh_state *st, const double *thetas, int n_thetas, int first, int count, int dagger);
+
+/* One full evaluation (the body of one optimiser step / one screening), captured as a CUDA graph:
+ *   psi = ops |basis_index>;  expvals[t] = <psi|tables[t]|psi>  (tables[0] is the cost Hamiltonian);
+ *   if grads != NULL: grads[p] = d expvals[0] / d theta[p] by the adjoint sweep
+ *     (replaces loss.backward() through the QNode, models/adapt_vqe.py:416-418, hva.py:324-326);
+ *   if pool != NULL: pool_out[k] = 2 Im <lambda_s| G_k |psi_s> with psi_s the state after ops[0:pool_pos)
+ *     and lambda_s the back-propagated H psi  (replaces select_operator, adapt_vqe.py:297-310);
+ *   if n_overlaps > 0: overlaps[2v], [2v+1] = <targets[v]|psi>  (fidelity, adapt_vqe.py:404-408);
+ *   if state_out != NULL it receives psi. */
+int fh_program_evaluate(fh_program *prog, uint64_t basis_index, const double *thetas, int n_thetas,
+                        int n_tables, fh_table *const *tables, double *expvals,
+                        double *grads,
+                        const fh_pool *pool, int pool_pos, int pool_first, int pool_count, double *pool_out,
+                        int n_overlaps, fh_state *const *targets, double *overlaps,
+                        fh_state *state_out);
+
+/* ---- K4: Lanczos ground states --------------------------------------------------------------
+ * replaces linalg/exact_diagonalization.py:34-51, 181-229 (scipy eigsh, which='SA') and
+ * openfermion.get_ground_state (models/iqcc_hubbard.py:57).  Matrix-free on fh_apply_table.
+ * n_up/n_dn >= 0 restrict to the (N_up, N_dn) sector (even wires = up); -1 = full space.
+ * Finds the k lowest eigenpairs (degenerate levels resolved by deflation); evals[k];
+ * evecs (may be NULL) receives k device states. */
+int fh_lanczos(const fh_table *tab, int n_up, int n_dn, int k, double tol, int max_iter, uint64_t seed,
+               double *evals, fh_state *const *evecs, int *iterations);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FHSIM_H */

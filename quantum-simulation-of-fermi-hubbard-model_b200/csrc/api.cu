@@ -1,0 +1,567 @@
+// C-ABI of libfhsim.so: context, states, observables (K2), pool screening (K3), immediate-mode ops (K1).
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <new>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void fh_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *fh_last_error(void) { return g_err; }
+extern "C" int fh_version(void) { return 100; }
+
+static inline int popcnt(u64 v) { return __builtin_popcountll(v); }
+
+// ----------------------------------------------------------------------------------------------
+// context
+// ----------------------------------------------------------------------------------------------
+extern "C" int fh_ctx_create(int device, void *stream, fh_ctx **out) {
+    FH_REQUIRE(out != nullptr, "fh_ctx_create: out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        fh_set_error("fh_ctx_create: no CUDA device available (%s); libfhsim has no CPU fallback",
+                     e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return FH_ECUDA;
+    }
+    FH_REQUIRE(device >= 0 && device < count, "fh_ctx_create: device %d out of range (have %d)", device, count);
+    FH_CUDA(cudaSetDevice(device));
+    fh_ctx *ctx = new (std::nothrow) fh_ctx();
+    if (!ctx) return FH_ENOMEM;
+    ctx->device = device;
+    if (stream) {
+        ctx->stream = reinterpret_cast<cudaStream_t>(stream);
+    } else {
+        FH_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    cudaDeviceProp prop;
+    FH_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    FH_CUDA(cudaMalloc(&ctx->d_partials, sizeof(double) * 2 * FH_MAX_PARTIALS));
+    FH_CUDA(cudaMalloc(&ctx->d_result, sizeof(double) * 64));
+    FH_CUDA(cudaMallocHost(&ctx->h_result, sizeof(double) * 64));
+    *out = ctx;
+    return FH_OK;
+}
+
+extern "C" int fh_ctx_destroy(fh_ctx *ctx) {
+    if (!ctx) return FH_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_partials);
+    cudaFree(ctx->d_result);
+    cudaFreeHost(ctx->h_result);
+    if (ctx->d_flush) cudaFree(ctx->d_flush);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return FH_OK;
+}
+
+extern "C" int fh_ctx_sync(fh_ctx *ctx) {
+    FH_REQUIRE(ctx, "fh_ctx_sync: ctx is NULL");
+    FH_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FH_OK;
+}
+
+extern "C" int fh_ctx_info(fh_ctx *ctx, int *sm_count, size_t *free_bytes, size_t *total_bytes) {
+    FH_REQUIRE(ctx, "fh_ctx_info: ctx is NULL");
+    FH_CUDA(cudaSetDevice(ctx->device));
+    if (sm_count) *sm_count = ctx->sm_count;
+    size_t f = 0, t = 0;
+    FH_CUDA(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return FH_OK;
+}
+
+extern "C" int fh_ctx_flush_l2(fh_ctx *ctx, size_t bytes) {
+    FH_REQUIRE(ctx, "fh_ctx_flush_l2: ctx is NULL");
+    FH_CUDA(cudaSetDevice(ctx->device));
+    bytes = (bytes + 31) & ~(size_t)31;
+    if (bytes > ctx->flush_bytes) {
+        if (ctx->d_flush) cudaFree(ctx->d_flush);
+        ctx->d_flush = nullptr;
+        ctx->flush_bytes = 0;
+        FH_CUDA(cudaMalloc(&ctx->d_flush, bytes));
+        ctx->flush_bytes = bytes;
+    }
+    launch_flush(ctx->stream, ctx->d_flush, bytes);
+    FH_CUDA(cudaGetLastError());
+    return FH_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// states
+// ----------------------------------------------------------------------------------------------
+extern "C" int fh_state_create(fh_ctx *ctx, int n_qubits, fh_state **out) {
+    FH_REQUIRE(ctx && out, "fh_state_create: NULL argument");
+    FH_REQUIRE(n_qubits >= 1 && n_qubits <= 33, "fh_state_create: n_qubits=%d outside [1, 33]", n_qubits);
+    FH_CUDA(cudaSetDevice(ctx->device));
+    fh_state *st = new (std::nothrow) fh_state();
+    if (!st) return FH_ENOMEM;
+    st->ctx = ctx;
+    st->n = n_qubits;
+    st->dim = 1ull << n_qubits;
+    st->owned = true;
+    cudaError_t e = cudaMalloc(&st->d, st->dim * sizeof(double2));
+    if (e != cudaSuccess) {
+        delete st;
+        fh_set_error("fh_state_create: cudaMalloc of %llu bytes failed: %s", st->dim * 16ull, cudaGetErrorString(e));
+        cudaGetLastError();
+        return FH_ENOMEM;
+    }
+    launch_set_basis(ctx->stream, st->d, st->dim, 0);
+    *out = st;
+    return FH_OK;
+}
+
+extern "C" int fh_state_wrap(fh_ctx *ctx, int n_qubits, void *device_ptr, fh_state **out) {
+    FH_REQUIRE(ctx && out && device_ptr, "fh_state_wrap: NULL argument");
+    FH_REQUIRE(n_qubits >= 1 && n_qubits <= 33, "fh_state_wrap: n_qubits=%d outside [1, 33]", n_qubits);
+    FH_REQUIRE((reinterpret_cast<uintptr_t>(device_ptr) & 15) == 0, "fh_state_wrap: pointer must be 16-byte aligned");
+    fh_state *st = new (std::nothrow) fh_state();
+    if (!st) return FH_ENOMEM;
+    st->ctx = ctx;
+    st->n = n_qubits;
+    st->dim = 1ull << n_qubits;
+    st->owned = false;
+    st->d = reinterpret_cast<double2 *>(device_ptr);
+    *out = st;
+    return FH_OK;
+}
+
+extern "C" int fh_state_destroy(fh_state *st) {
+    if (!st) return FH_OK;
+    if (st->owned) {
+        cudaSetDevice(st->ctx->device);
+        cudaStreamSynchronize(st->ctx->stream);
+        cudaFree(st->d);
+    }
+    delete st;
+    return FH_OK;
+}
+
+extern "C" int fh_state_set_basis(fh_state *st, uint64_t index) {
+    FH_REQUIRE(st, "fh_state_set_basis: state is NULL");
+    FH_REQUIRE(index < st->dim, "fh_state_set_basis: index %llu >= 2^%d", (u64)index, st->n);
+    launch_set_basis(st->ctx->stream, st->d, st->dim, index);
+    FH_CUDA(cudaGetLastError());
+    return FH_OK;
+}
+
+extern "C" int fh_state_copy(fh_state *dst, const fh_state *src) {
+    FH_REQUIRE(dst && src, "fh_state_copy: NULL argument");
+    FH_REQUIRE(dst->n == src->n, "fh_state_copy: qubit counts differ (%d vs %d)", dst->n, src->n);
+    FH_CUDA(cudaMemcpyAsync(dst->d, src->d, src->dim * sizeof(double2), cudaMemcpyDeviceToDevice, dst->ctx->stream));
+    return FH_OK;
+}
+
+extern "C" int fh_state_to_host(const fh_state *st, double *out) {
+    FH_REQUIRE(st && out, "fh_state_to_host: NULL argument");
+    FH_CUDA(cudaMemcpyAsync(out, st->d, st->dim * sizeof(double2), cudaMemcpyDeviceToHost, st->ctx->stream));
+    FH_CUDA(cudaStreamSynchronize(st->ctx->stream));
+    return FH_OK;
+}
+
+extern "C" int fh_state_from_host(fh_state *st, const double *in) {
+    FH_REQUIRE(st && in, "fh_state_from_host: NULL argument");
+    FH_CUDA(cudaMemcpyAsync(st->d, in, st->dim * sizeof(double2), cudaMemcpyHostToDevice, st->ctx->stream));
+    FH_CUDA(cudaStreamSynchronize(st->ctx->stream));
+    return FH_OK;
+}
+
+extern "C" int fh_state_device_ptr(const fh_state *st, void **ptr) {
+    FH_REQUIRE(st && ptr, "fh_state_device_ptr: NULL argument");
+    *ptr = st->d;
+    return FH_OK;
+}
+
+extern "C" int fh_state_inner(const fh_state *a, const fh_state *b, double *re, double *im) {
+    FH_REQUIRE(a && b && re && im, "fh_state_inner: NULL argument");
+    FH_REQUIRE(a->n == b->n, "fh_state_inner: qubit counts differ");
+    fh_ctx *ctx = a->ctx;
+    launch_inner(ctx->stream, ctx->sm_count, a->d, b->d, a->dim, ctx->d_partials, ctx->d_result);
+    FH_CUDA(cudaGetLastError());
+    FH_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FH_CUDA(cudaStreamSynchronize(ctx->stream));
+    *re = ctx->h_result[0];
+    *im = ctx->h_result[1];
+    return FH_OK;
+}
+
+extern "C" int fh_state_norm2(const fh_state *st, double *out) {
+    double im = 0.0;
+    return fh_state_inner(st, st, out, &im);
+}
+
+// ----------------------------------------------------------------------------------------------
+// pair / diag descriptors from user masks
+// ----------------------------------------------------------------------------------------------
+int fh_fill_pair(PairOp *op, int n, u64 x, u64 fixmask, u64 fixval, u64 zeta, const double m[8]) {
+    const u64 full = n >= 64 ? ~0ull : ((1ull << n) - 1ull);
+    FH_REQUIRE(x != 0 && (x & ~full) == 0, "pair op: x-mask 0x%llx invalid for %d qubits", x, n);
+    FH_REQUIRE((fixmask & ~full) == 0 && (zeta & ~full) == 0, "pair op: mask outside %d qubits", n);
+    const u64 top = 1ull << (63 - __builtin_clzll(x));
+    FH_REQUIRE(fixmask & top, "pair op: fixmask must contain the top bit of x");
+    FH_REQUIRE((fixval & ~fixmask) == 0, "pair op: fixval has bits outside fixmask");
+    FH_REQUIRE((fixval & top) == 0, "pair op: fixval must have the top bit of x clear");
+    FH_REQUIRE(popcnt(fixmask) <= FH_MAX_FIX, "pair op: more than %d fixed bits", FH_MAX_FIX);
+    memset(op, 0, sizeof(*op));
+    op->x = x;
+    op->fixmask = fixmask;
+    op->fixval = fixval;
+    op->zeta = zeta;
+    if (m) memcpy(op->m, m, sizeof(double) * 8);
+    op->param = -1;
+    int k = 0;
+    for (int b = 0; b < n; ++b)
+        if (fixmask >> b & 1) op->pos[k++] = (unsigned char)b;
+    op->npos = (unsigned char)k;
+    return FH_OK;
+}
+
+extern "C" int fh_apply_pair(fh_state *st, uint64_t x, uint64_t fixmask, uint64_t fixval, uint64_t zeta,
+                             const double m[8]) {
+    FH_REQUIRE(st && m, "fh_apply_pair: NULL argument");
+    PairOp op;
+    FH_TRY(fh_fill_pair(&op, st->n, x, fixmask, fixval, zeta, m));
+    fh_ctx *ctx = st->ctx;
+    PairOp *d_op = nullptr;
+    FH_CUDA(cudaMallocAsync(&d_op, sizeof(PairOp), ctx->stream));
+    FH_CUDA(cudaMemcpyAsync(d_op, &op, sizeof(PairOp), cudaMemcpyHostToDevice, ctx->stream));
+    launch_pair(ctx->stream, ctx->sm_count, st->d, d_op, st->n, op.npos, 0);
+    FH_CUDA(cudaGetLastError());
+    FH_CUDA(cudaFreeAsync(d_op, ctx->stream));
+    FH_CUDA(cudaStreamSynchronize(ctx->stream));   // `op` is a pageable stack source
+    return FH_OK;
+}
+
+extern "C" int fh_apply_diag(fh_state *st, int n_terms, const uint64_t *z, const double *angle) {
+    FH_REQUIRE(st && (n_terms == 0 || (z && angle)), "fh_apply_diag: NULL argument");
+    FH_REQUIRE(n_terms >= 0, "fh_apply_diag: negative term count");
+    if (n_terms == 0) return FH_OK;
+    std::vector<DiagTerm> terms(n_terms);
+    for (int m = 0; m < n_terms; ++m) {
+        terms[m].z = z[m];
+        terms[m].angle = angle[m];
+        terms[m].c = cos(angle[m]);
+        terms[m].s = sin(angle[m]);
+        terms[m].coef = 0.0;
+    }
+    fh_ctx *ctx = st->ctx;
+    DiagTerm *d = nullptr;
+    FH_CUDA(cudaMallocAsync(&d, sizeof(DiagTerm) * n_terms, ctx->stream));
+    FH_CUDA(cudaMemcpyAsync(d, terms.data(), sizeof(DiagTerm) * n_terms, cudaMemcpyHostToDevice, ctx->stream));
+    launch_diag(ctx->stream, ctx->sm_count, st->d, d, n_terms, st->n, 0);
+    FH_CUDA(cudaGetLastError());
+    FH_CUDA(cudaFreeAsync(d, ctx->stream));
+    FH_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FH_OK;
+}
+
+extern "C" int fh_apply_pauli_rot_batch(fh_state *st, int m, const uint64_t *x, const uint64_t *z,
+                                        const double *half_angles) {
+    FH_REQUIRE(st && (m == 0 || (x && z && half_angles)), "fh_apply_pauli_rot_batch: NULL argument");
+    FH_REQUIRE(m >= 0, "fh_apply_pauli_rot_batch: negative count");
+    if (m == 0) return FH_OK;
+    fh_ctx *ctx = st->ctx;
+    // descriptors for every string up front, one upload, then one launch per string (in order)
+    std::vector<PairOp> pairs;
+    std::vector<DiagTerm> diags;
+    std::vector<int> order;   // >=0: pair index; <0: ~diag index
+    for (int t = 0; t < m; ++t) {
+        const double a = half_angles[t], c = cos(a), s = sin(a);
+        if (x[t] == 0) {
+            if (z[t] == 0) continue;   // identity string: global phase, dropped (reference adapt_vqe.py:92-93)
+            DiagTerm d;
+            d.z = z[t];
+            d.angle = a;
+            d.c = c;
+            d.s = s;
+            d.coef = 0.0;
+            order.push_back(~(int)diags.size());
+            diags.push_back(d);
+            continue;
+        }
+        // w(i) = B (-1)^popcount(i&z),  B = i^k (-1)^popcount(x&z),  k = popcount(x&z)
+        const int k = popcnt(x[t] & z[t]);
+        static const double ipow[4][2] = {{1, 0}, {0, 1}, {-1, 0}, {0, -1}};
+        double br = ipow[k & 3][0], bi = ipow[k & 3][1];
+        if (k & 1) { br = -br; bi = -bi; }
+        // exp(-i a P): m00 = m11 = c, m01 = -i s B, m10 = -i s conj(B)
+        const double mm[8] = {c, 0, s * bi, -s * br, -s * bi, -s * br, c, 0};
+        const u64 top = 1ull << (63 - __builtin_clzll(x[t]));
+        PairOp op;
+        FH_TRY(fh_fill_pair(&op, st->n, x[t], top, 0, z[t], mm));
+        order.push_back((int)pairs.size());
+        pairs.push_back(op);
+    }
+    PairOp *d_pairs = nullptr;
+    DiagTerm *d_diags = nullptr;
+    if (!pairs.empty()) {
+        FH_CUDA(cudaMallocAsync(&d_pairs, sizeof(PairOp) * pairs.size(), ctx->stream));
+        FH_CUDA(cudaMemcpyAsync(d_pairs, pairs.data(), sizeof(PairOp) * pairs.size(), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (!diags.empty()) {
+        FH_CUDA(cudaMallocAsync(&d_diags, sizeof(DiagTerm) * diags.size(), ctx->stream));
+        FH_CUDA(cudaMemcpyAsync(d_diags, diags.data(), sizeof(DiagTerm) * diags.size(), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    for (int o : order) {
+        if (o >= 0)
+            launch_pair(ctx->stream, ctx->sm_count, st->d, d_pairs + o, st->n, 1, 0);
+        else
+            launch_diag(ctx->stream, ctx->sm_count, st->d, d_diags + (~o), 1, st->n, 0);
+    }
+    FH_CUDA(cudaGetLastError());
+    if (d_pairs) FH_CUDA(cudaFreeAsync(d_pairs, ctx->stream));
+    if (d_diags) FH_CUDA(cudaFreeAsync(d_diags, ctx->stream));
+    FH_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FH_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// observables
+// ----------------------------------------------------------------------------------------------
+extern "C" int fh_table_upload(fh_ctx *ctx, int n_qubits, int n_terms, const uint64_t *x, const uint64_t *z,
+                               const double *coeff_re, const double *coeff_im, fh_table **out) {
+    FH_REQUIRE(ctx && out, "fh_table_upload: NULL argument");
+    FH_REQUIRE(n_terms >= 0 && (n_terms == 0 || (x && z && coeff_re)), "fh_table_upload: NULL term arrays");
+    FH_REQUIRE(n_qubits >= 1 && n_qubits <= 33, "fh_table_upload: n_qubits=%d outside [1, 33]", n_qubits);
+    const u64 full = (1ull << n_qubits) - 1ull;
+    fh_table *tab = new (std::nothrow) fh_table();
+    if (!tab) return FH_ENOMEM;
+    tab->ctx = ctx;
+    tab->n = n_qubits;
+    tab->n_terms = n_terms;
+    tab->all_real = true;
+    tab->d_groups = nullptr;
+    tab->d_terms = nullptr;
+    // group by x-mask in first-seen order; term order inside a group = table order
+    std::map<u64, int> group_of;
+    std::vector<std::vector<TabTerm>> buckets;
+    std::vector<u64> group_x;
+    for (int t = 0; t < n_terms; ++t) {
+        if ((x[t] | z[t]) & ~full) {
+            delete tab;
+            fh_set_error("fh_table_upload: term %d has bits outside %d qubits", t, n_qubits);
+            return FH_EINVAL;
+        }
+        auto it = group_of.find(x[t]);
+        int g;
+        if (it == group_of.end()) {
+            g = (int)buckets.size();
+            group_of[x[t]] = g;
+            buckets.emplace_back();
+            group_x.push_back(x[t]);
+        } else {
+            g = it->second;
+        }
+        const int k = popcnt(x[t] & z[t]) & 3;
+        const double cr = coeff_re[t], ci = coeff_im ? coeff_im[t] : 0.0;
+        TabTerm tt;
+        tt.z = z[t];
+        switch (k) {   // (cr + i ci) * i^k
+            case 0: tt.dr = cr;  tt.di = ci;  break;
+            case 1: tt.dr = -ci; tt.di = cr;  break;
+            case 2: tt.dr = -cr; tt.di = -ci; break;
+            default: tt.dr = ci; tt.di = -cr; break;
+        }
+        if (tt.di != 0.0) tab->all_real = false;
+        buckets[g].push_back(tt);
+    }
+    for (size_t g = 0; g < buckets.size(); ++g) {
+        TabGroup grp;
+        grp.x = group_x[g];
+        grp.first = (int)tab->terms.size();
+        grp.count = (int)buckets[g].size();
+        tab->groups.push_back(grp);
+        tab->terms.insert(tab->terms.end(), buckets[g].begin(), buckets[g].end());
+    }
+    tab->n_groups = (int)tab->groups.size();
+    FH_CUDA(cudaSetDevice(ctx->device));
+    if (tab->n_groups) {
+        FH_CUDA(cudaMalloc(&tab->d_groups, sizeof(TabGroup) * tab->groups.size()));
+        FH_CUDA(cudaMalloc(&tab->d_terms, sizeof(TabTerm) * tab->terms.size()));
+        FH_CUDA(cudaMemcpyAsync(tab->d_groups, tab->groups.data(), sizeof(TabGroup) * tab->groups.size(),
+                                cudaMemcpyHostToDevice, ctx->stream));
+        FH_CUDA(cudaMemcpyAsync(tab->d_terms, tab->terms.data(), sizeof(TabTerm) * tab->terms.size(),
+                                cudaMemcpyHostToDevice, ctx->stream));
+        FH_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    *out = tab;
+    return FH_OK;
+}
+
+extern "C" int fh_table_free(fh_table *tab) {
+    if (!tab) return FH_OK;
+    cudaSetDevice(tab->ctx->device);
+    cudaStreamSynchronize(tab->ctx->stream);
+    cudaFree(tab->d_groups);
+    cudaFree(tab->d_terms);
+    delete tab;
+    return FH_OK;
+}
+
+extern "C" int fh_table_info(const fh_table *tab, int *n_terms, int *n_groups) {
+    FH_REQUIRE(tab, "fh_table_info: table is NULL");
+    if (n_terms) *n_terms = tab->n_terms;
+    if (n_groups) *n_groups = tab->n_groups;
+    return FH_OK;
+}
+
+// enqueue K2 without synchronising; result lands in ctx->d_result[slot*2 .. slot*2+1]
+int fh_enqueue_apply_table(const fh_table *tab, const double2 *in, double2 *out, int result_slot) {
+    fh_ctx *ctx = tab->ctx;
+    launch_apply_table(ctx->stream, ctx->sm_count, tab->d_groups, tab->n_groups, tab->d_terms, (int)tab->terms.size(),
+                       tab->all_real, in, out, tab->n, ctx->d_partials, ctx->d_result + 2 * result_slot);
+    FH_CUDA(cudaGetLastError());
+    return FH_OK;
+}
+
+extern "C" int fh_apply_table(const fh_table *tab, const fh_state *in, fh_state *out, double *e_re, double *e_im) {
+    FH_REQUIRE(tab && in, "fh_apply_table: NULL argument");
+    FH_REQUIRE(in->n == tab->n, "fh_apply_table: table is for %d qubits, state has %d", tab->n, in->n);
+    FH_REQUIRE(!out || out->n == in->n, "fh_apply_table: output qubit count differs");
+    FH_REQUIRE(!out || out->d != in->d, "fh_apply_table: in and out must be different buffers");
+    fh_ctx *ctx = tab->ctx;
+    FH_TRY(fh_enqueue_apply_table(tab, in->d, out ? out->d : nullptr, 0));
+    FH_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FH_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (e_re) *e_re = ctx->h_result[0];
+    if (e_im) *e_im = ctx->h_result[1];
+    return FH_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// pool
+// ----------------------------------------------------------------------------------------------
+extern "C" int fh_pool_upload(fh_ctx *ctx, int n_qubits, int n_entries, const uint64_t *x, const uint64_t *fixmask,
+                              const uint64_t *fixval, const uint64_t *zeta, const double *b_re, const double *b_im,
+                              const int32_t *out_index, int n_out, fh_pool **out) {
+    FH_REQUIRE(ctx && out, "fh_pool_upload: NULL argument");
+    FH_REQUIRE(n_entries >= 0 && n_out >= 0, "fh_pool_upload: negative size");
+    FH_REQUIRE(n_entries == 0 || (x && fixmask && fixval && zeta && b_re && b_im && out_index),
+               "fh_pool_upload: NULL entry arrays");
+    fh_pool *pool = new (std::nothrow) fh_pool();
+    if (!pool) return FH_ENOMEM;
+    pool->ctx = ctx;
+    pool->n = n_qubits;
+    pool->n_entries = n_entries;
+    pool->n_out = n_out;
+    pool->d_entries = nullptr;
+    pool->d_out_first = nullptr;
+    pool->d_partials = nullptr;
+    pool->d_out = nullptr;
+    pool->h_out = nullptr;
+    int min_fix = 64;
+    int prev_out = 0;
+    pool->out_first.assign(n_out + 1, 0);
+    for (int e = 0; e < n_entries; ++e) {
+        PairOp tmp;
+        int rc = fh_fill_pair(&tmp, n_qubits, x[e], fixmask[e], fixval[e], zeta[e], nullptr);
+        if (rc == FH_OK && (out_index[e] < prev_out || out_index[e] >= n_out)) {
+            fh_set_error("fh_pool_upload: out_index must be non-decreasing and < n_out (entry %d)", e);
+            rc = FH_EINVAL;
+        }
+        if (rc != FH_OK) {
+            delete pool;
+            return rc;
+        }
+        prev_out = out_index[e];
+        PoolEntry pe;
+        memset(&pe, 0, sizeof(pe));
+        pe.x = tmp.x;
+        pe.fixmask = tmp.fixmask;
+        pe.fixval = tmp.fixval;
+        pe.zeta = tmp.zeta;
+        pe.br = b_re[e];
+        pe.bi = b_im[e];
+        pe.out = out_index[e];
+        pe.npos = tmp.npos;
+        memcpy(pe.pos, tmp.pos, FH_MAX_FIX);
+        pool->entries.push_back(pe);
+        pool->out_first[out_index[e] + 1] = e + 1;
+        if (tmp.npos < min_fix) min_fix = tmp.npos;
+    }
+    for (int o = 1; o <= n_out; ++o)
+        if (pool->out_first[o] < pool->out_first[o - 1]) pool->out_first[o] = pool->out_first[o - 1];
+    if (n_entries == 0) min_fix = 1;
+    const u64 max_pairs = 1ull << (n_qubits - min_fix);
+    u64 chunks = (max_pairs + 128 * 8 - 1) / (128 * 8);
+    if (chunks < 1) chunks = 1;
+    if (chunks > 1024) chunks = 1024;
+    pool->chunks = (int)chunks;
+    FH_CUDA(cudaSetDevice(ctx->device));
+    if (n_entries) {
+        FH_CUDA(cudaMalloc(&pool->d_entries, sizeof(PoolEntry) * n_entries));
+        FH_CUDA(cudaMemcpyAsync(pool->d_entries, pool->entries.data(), sizeof(PoolEntry) * n_entries,
+                                cudaMemcpyHostToDevice, ctx->stream));
+        FH_CUDA(cudaMalloc(&pool->d_partials, sizeof(double) * (size_t)n_entries * pool->chunks));
+    }
+    FH_CUDA(cudaMalloc(&pool->d_out_first, sizeof(int) * (n_out + 1)));
+    FH_CUDA(cudaMemcpyAsync(pool->d_out_first, pool->out_first.data(), sizeof(int) * (n_out + 1), cudaMemcpyHostToDevice,
+                            ctx->stream));
+    FH_CUDA(cudaMalloc(&pool->d_out, sizeof(double) * (n_out > 0 ? n_out : 1)));
+    FH_CUDA(cudaMallocHost(&pool->h_out, sizeof(double) * (n_out > 0 ? n_out : 1)));
+    FH_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = pool;
+    return FH_OK;
+}
+
+extern "C" int fh_pool_free(fh_pool *pool) {
+    if (!pool) return FH_OK;
+    cudaSetDevice(pool->ctx->device);
+    cudaStreamSynchronize(pool->ctx->stream);
+    cudaFree(pool->d_entries);
+    cudaFree(pool->d_out_first);
+    cudaFree(pool->d_partials);
+    cudaFree(pool->d_out);
+    cudaFreeHost(pool->h_out);
+    delete pool;
+    return FH_OK;
+}
+
+// enqueue K3 for outputs [first, first+count) without synchronising; results in pool->d_out[first..]
+int fh_enqueue_pool(const fh_pool *pool, const double2 *psi, const double2 *lam, int first, int count) {
+    fh_ctx *ctx = pool->ctx;
+    const int e0 = pool->out_first[first], e1 = pool->out_first[first + count];
+    launch_pool(ctx->stream, pool->d_entries, e0, e1 - e0, pool->chunks, pool->n, psi, lam, pool->d_partials);
+    launch_pool_finalize(ctx->stream, pool->d_partials, pool->d_out_first, pool->chunks, first, count, pool->d_out);
+    FH_CUDA(cudaGetLastError());
+    return FH_OK;
+}
+
+extern "C" int fh_pool_gradients(const fh_pool *pool, const fh_state *psi, const fh_state *lambda, int first, int count,
+                                 double *out) {
+    FH_REQUIRE(pool && psi && lambda && out, "fh_pool_gradients: NULL argument");
+    FH_REQUIRE(psi->n == pool->n && lambda->n == pool->n, "fh_pool_gradients: qubit count mismatch");
+    FH_REQUIRE(first >= 0 && count >= 0 && first + count <= pool->n_out, "fh_pool_gradients: range [%d, %d) outside pool of %d",
+               first, first + count, pool->n_out);
+    if (count == 0) return FH_OK;
+    fh_ctx *ctx = pool->ctx;
+    FH_TRY(fh_enqueue_pool(pool, psi->d, lambda->d, first, count));
+    FH_CUDA(cudaMemcpyAsync(pool->h_out, pool->d_out + first, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    FH_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(out, pool->h_out, sizeof(double) * count);
+    return FH_OK;
+}
+
+int fh_alloc_check(void *p, const char *what) {
+    if (!p) {
+        fh_set_error("allocation failed: %s", what);
+        return FH_ENOMEM;
+    }
+    return FH_OK;
+}

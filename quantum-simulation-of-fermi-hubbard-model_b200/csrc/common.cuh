@@ -1,0 +1,192 @@
+// Shared types for libfhsim (sm_100a).  Host structs mirror the device descriptors 1:1.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/fhsim.h"
+
+typedef unsigned long long u64;
+
+// ----------------------------------------------------------------------------------------------
+// error plumbing: thread-local message, no exceptions across the ABI
+// ----------------------------------------------------------------------------------------------
+void fh_set_error(const char *fmt, ...);
+
+#define FH_CUDA(call)                                                                           \
+    do {                                                                                        \
+        cudaError_t _e = (call);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            fh_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return FH_ECUDA;                                                                    \
+        }                                                                                       \
+    } while (0)
+
+#define FH_REQUIRE(cond, ...)              \
+    do {                                   \
+        if (!(cond)) {                     \
+            fh_set_error(__VA_ARGS__);     \
+            return FH_EINVAL;              \
+        }                                  \
+    } while (0)
+
+#define FH_TRY(call)                \
+    do {                            \
+        int _rc = (call);           \
+        if (_rc != FH_OK) return _rc; \
+    } while (0)
+
+// ----------------------------------------------------------------------------------------------
+// device descriptors (plain data, uploaded verbatim)
+// ----------------------------------------------------------------------------------------------
+#define FH_MAX_FIX 16      // max bits in a pair op's fixmask
+#define FH_MAX_TILE_BITS 13
+
+// 2x2 op on index pairs (i, i^x) selected by (i & fixmask) == fixval, sign s = parity(i & zeta).
+struct __align__(16) PairOp {
+    u64 x, fixmask, fixval, zeta;       // 32
+    double m[8];                        // m00 m01 m10 m11 (re,im)  64
+    double bhat[2];                     // normalised generator element (rotation ops)  16
+    double gscale;                      // d(angle)/d(theta); 0 for fixed ops  8
+    int param;                          // parameter index or -1
+    int kind;                           // 0 fixed, 1 rotation
+    unsigned char npos;                 // popcount(fixmask)
+    unsigned char pos[FH_MAX_FIX];      // ascending bit positions of fixmask
+    unsigned char pad[7];
+};
+
+struct DiagTerm {
+    u64 z;
+    double angle;    // current angle (theta*coef or fixed)
+    double c, s;     // cos(angle), sin(angle)
+    double coef;     // d(angle)/d(theta) (0 for fixed)
+};
+
+struct DiagOp {
+    int first, count;   // range in the DiagTerm array
+    int param;
+    int pad;
+};
+
+// one entry of a fused tile kernel's op list
+struct TileSub {
+    int type;        // 1 pair, 2 diag
+    int index;       // index into PairOp / DiagOp arrays
+    int lpivot;      // local (tile) position of the top x bit (pair)
+    unsigned int xlocal;   // x in tile-local coordinates (pair)
+};
+
+struct TileOp {
+    int nbits;                          // T
+    int first_sub, nsub;
+    int pad;
+    unsigned char bits[16];             // ascending global bit positions of the tile
+};
+
+struct TabGroup {
+    u64 x;
+    int first, count;
+};
+
+struct TabTerm {
+    u64 z;
+    double dr, di;    // coefficient * i^k  (weight of psi[i^x] is sum_m d_m (-1)^popcount((i^x)&z_m))
+};
+
+struct PoolEntry {
+    u64 x, fixmask, fixval, zeta;
+    double br, bi;
+    int out;
+    unsigned char npos;
+    unsigned char pos[FH_MAX_FIX];
+    unsigned char pad[3];
+};
+
+// ----------------------------------------------------------------------------------------------
+// host objects behind the opaque handles
+// ----------------------------------------------------------------------------------------------
+struct fh_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    // scratch for reductions
+    double *d_partials = nullptr;     // 2 * FH_MAX_PARTIALS doubles
+    unsigned int *d_counter = nullptr;
+    double *d_result = nullptr;       // small device result buffer (64 doubles)
+    double *h_result = nullptr;       // pinned mirror
+    void *d_flush = nullptr;
+    size_t flush_bytes = 0;
+};
+
+#define FH_MAX_PARTIALS 4096
+
+struct fh_state {
+    fh_ctx *ctx;
+    int n;
+    u64 dim;
+    double2 *d;
+    bool owned;
+};
+
+struct fh_table {
+    fh_ctx *ctx;
+    int n;
+    int n_terms, n_groups;
+    bool all_real;
+    TabGroup *d_groups;
+    TabTerm *d_terms;
+    std::vector<TabGroup> groups;
+    std::vector<TabTerm> terms;
+};
+
+struct fh_pool {
+    fh_ctx *ctx;
+    int n;
+    int n_entries, n_out;
+    int chunks;                 // blocks per entry
+    PoolEntry *d_entries;
+    int *d_out_first;           // [n_out+1] entry ranges per output (entries sorted by out)
+    double *d_partials;         // [n_entries * chunks]
+    double *d_out;              // [n_out]
+    double *h_out;              // pinned [n_out]
+    std::vector<PoolEntry> entries;
+    std::vector<int> out_first;
+};
+
+// ----------------------------------------------------------------------------------------------
+// kernel launch wrappers (kernels.cu)
+// ----------------------------------------------------------------------------------------------
+void launch_pair(cudaStream_t s, int sm, double2 *psi, const PairOp *d_op, int n, int nfix, int dagger);
+// adjoint step: grad partial of Ghat at (psi, lam), then apply op^dagger to both
+void launch_pair_adjoint(cudaStream_t s, int sm, double2 *psi, double2 *lam, const PairOp *d_op, int n, int nfix,
+                         double *d_partials, int max_blocks, int *blocks_used);
+void launch_diag(cudaStream_t s, int sm, double2 *psi, const DiagTerm *d_terms, int nterms, int n, int dagger);
+void launch_diag_adjoint(cudaStream_t s, int sm, double2 *psi, double2 *lam, const DiagTerm *d_terms, int nterms, int n,
+                         double *d_partials, int max_blocks, int *blocks_used);
+void launch_tile(cudaStream_t s, double2 *psi, const TileOp *d_tile, const TileSub *d_subs, const PairOp *d_pairs,
+                 const DiagOp *d_diags, const DiagTerm *d_terms, int n, int nbits, int dagger, double2 *psi2);
+void launch_apply_table(cudaStream_t s, int sm, const TabGroup *g, int ngroups, const TabTerm *t, int nterms,
+                        bool all_real, const double2 *in, double2 *out, int n, double *d_partials, double *d_result);
+void launch_pool(cudaStream_t s, const PoolEntry *entries, int first_entry, int n_entries, int chunks, int n,
+                 const double2 *psi, const double2 *lam, double *d_partials);
+void launch_pool_finalize(cudaStream_t s, const double *d_partials, const int *d_out_first, int chunks, int first_out,
+                          int count, double *d_out);
+void launch_inner(cudaStream_t s, int sm, const double2 *a, const double2 *b, u64 dim, double *d_partials,
+                  double *d_result);
+void launch_sum_segments(cudaStream_t s, const double *d_partials, const int *d_first, int nseg, double *d_out);
+void launch_sum_strided(cudaStream_t s, const double *d_partials, int stride, int nseg, double *d_out);
+void launch_set_basis(cudaStream_t s, double2 *psi, u64 dim, u64 index);
+void launch_flush(cudaStream_t s, void *buf, size_t bytes);
+// Lanczos helpers
+void launch_axpby(cudaStream_t s, int sm, double2 *y, double a, const double2 *x, double b, u64 dim);          // y = a*x + b*y
+void launch_lanczos_update(cudaStream_t s, int sm, double2 *w, const double2 *v, const double2 *vprev, double alpha,
+                           double beta, u64 dim);                                                           // w -= alpha v + beta vprev
+void launch_scale(cudaStream_t s, int sm, double2 *y, double a, u64 dim);
+void launch_sector_random(cudaStream_t s, int sm, double2 *v, int n, int n_up, int n_dn, u64 seed);
+void launch_caxpy(cudaStream_t s, int sm, double2 *y, double ar, double ai, const double2 *x, u64 dim);      // y += (ar + i ai) x
+
+int fh_alloc_check(void *p, const char *what);

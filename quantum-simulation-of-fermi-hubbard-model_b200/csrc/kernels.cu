@@ -1,0 +1,672 @@
+// Hand-written sm_100a kernels of the complex128 statevector hot path.
+//
+// Everything here is HBM/L2-bandwidth work on 16-byte amplitudes: one complex128 == one 128-bit
+// LDG/STG (double2), warps walk consecutive indices so every request is a full 32-byte sector and,
+// whenever the fixed bits of an op are not the lowest ones, full 128-byte lines.  No tensor cores:
+// nothing on this path is a dense contraction.
+//
+//   k_pair / k_pair_adjoint   K1: 2x2 rotations on index pairs (Pauli / fermionic / Givens / CNOT)
+//   k_diag / k_diag_adjoint   K1: diagonal phase ops (RZ, Z-string rotations)
+//   k_tile                    K1: run of ops fused in a shared-memory tile of 2^T amplitudes
+//   k_apply_table             K2: out = H in fused with <in|H|in>
+//   k_pool / k_pool_finalize  K3: batched pool gradients 2 Im <lambda|G_k|psi>
+//   k_inner, k_axpby, ...     K4: Lanczos vector kernels
+#include "common.cuh"
+
+#define FULL 0xffffffffu
+
+// ----------------------------------------------------------------------------------------------
+// small device helpers
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 cscale(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
+// Im(conj(a) * b)
+__device__ __forceinline__ double im_conj_mul(double2 a, double2 b) { return a.x * b.y - a.y * b.x; }
+
+// insert a zero bit at each (ascending) position: maps a dense counter onto indices whose fixed bits are 0
+__device__ __forceinline__ u64 deposit_zeros(u64 v, const unsigned char *pos, int npos) {
+    for (int k = 0; k < npos; ++k) {
+        const unsigned p = pos[k];
+        const u64 low = v & ((1ull << p) - 1ull);
+        v = ((v >> p) << (p + 1)) | low;
+    }
+    return v;
+}
+
+__device__ __forceinline__ double sign_of(u64 masked) { return (__popcll(masked) & 1) ? -1.0 : 1.0; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// deterministic block sum (fixed tree); result valid in thread 0
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double *sh /* NT/32 doubles */) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (w == 0) {
+        r = (lane < NT / 32) ? sh[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    __syncthreads();
+    return r;
+}
+
+__device__ __forceinline__ void load_pair_op(PairOp *dst, const PairOp *src) {
+    const int words = sizeof(PairOp) / 8;
+    for (int t = threadIdx.x; t < words; t += blockDim.x)
+        reinterpret_cast<u64 *>(dst)[t] = __ldg(reinterpret_cast<const u64 *>(src) + t);
+    __syncthreads();
+}
+
+struct Mat2 {
+    double2 m00, m01, m10, m11;
+};
+
+__device__ __forceinline__ Mat2 op_matrix(const PairOp &op, int dagger) {
+    Mat2 M;
+    M.m00 = make_double2(op.m[0], op.m[1]);
+    M.m01 = make_double2(op.m[2], op.m[3]);
+    M.m10 = make_double2(op.m[4], op.m[5]);
+    M.m11 = make_double2(op.m[6], op.m[7]);
+    if (dagger) {
+        const double2 t01 = cconj(M.m10), t10 = cconj(M.m01);
+        M.m00 = cconj(M.m00);
+        M.m11 = cconj(M.m11);
+        M.m01 = t01;
+        M.m10 = t10;
+    }
+    return M;
+}
+
+__device__ __forceinline__ void rot2(const Mat2 &M, double sgn, double2 &a, double2 &b) {
+    const double2 sb = cscale(b, sgn), sa = cscale(a, sgn);
+    const double2 ra = cadd(cmul(M.m00, a), cmul(M.m01, sb));
+    const double2 rb = cadd(cmul(M.m10, sa), cmul(M.m11, b));
+    a = ra;
+    b = rb;
+}
+
+// ----------------------------------------------------------------------------------------------
+// K1: pair op on the whole state
+// ----------------------------------------------------------------------------------------------
+template <int UNROLL>
+__global__ void __launch_bounds__(128) k_pair(double2 *__restrict__ psi, const PairOp *__restrict__ opp, u64 npairs,
+                                              int dagger) {
+    __shared__ PairOp op;
+    load_pair_op(&op, opp);
+    const Mat2 M = op_matrix(op, dagger);
+    const u64 x = op.x, fixval = op.fixval, zeta = op.zeta;
+    const int npos = op.npos;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 base = (u64)blockIdx.x * blockDim.x + threadIdx.x; base < npairs; base += stride * UNROLL) {
+        u64 ii[UNROLL];
+        double2 a[UNROLL], b[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const u64 idx = base + (u64)u * stride;
+            if (idx < npairs) {
+                ii[u] = deposit_zeros(idx, op.pos, npos) | fixval;
+                a[u] = psi[ii[u]];
+                b[u] = psi[ii[u] ^ x];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const u64 idx = base + (u64)u * stride;
+            if (idx < npairs) {
+                rot2(M, sign_of(ii[u] & zeta), a[u], b[u]);
+                psi[ii[u]] = a[u];
+                psi[ii[u] ^ x] = b[u];
+            }
+        }
+    }
+}
+
+// adjoint step of a rotation op U = exp(-i a Ghat): partial of Im<lam|Ghat|psi> at the current
+// (post-op) states, then psi <- U^dagger psi, lam <- U^dagger lam.  One partial per block.
+__global__ void __launch_bounds__(128) k_pair_adjoint(double2 *__restrict__ psi, double2 *__restrict__ lam,
+                                                      const PairOp *__restrict__ opp, u64 npairs,
+                                                      double *__restrict__ partials) {
+    __shared__ PairOp op;
+    __shared__ double red[4];
+    load_pair_op(&op, opp);
+    const Mat2 M = op_matrix(op, 1);
+    const double2 bh = make_double2(op.bhat[0], op.bhat[1]);
+    const u64 x = op.x, fixval = op.fixval, zeta = op.zeta;
+    const int npos = op.npos;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < npairs; idx += stride) {
+        const u64 i = deposit_zeros(idx, op.pos, npos) | fixval, j = i ^ x;
+        double2 a = psi[i], b = psi[j], la = lam[i], lb = lam[j];
+        const double sgn = sign_of(i & zeta);
+        const double2 gi = cscale(cmul(bh, b), sgn);           // (Ghat psi)_i
+        const double2 gj = cscale(cmul(cconj(bh), a), sgn);    // (Ghat psi)_j
+        acc += im_conj_mul(la, gi) + im_conj_mul(lb, gj);
+        rot2(M, sgn, a, b);
+        rot2(M, sgn, la, lb);
+        psi[i] = a;
+        psi[j] = b;
+        lam[i] = la;
+        lam[j] = lb;
+    }
+    const double r = block_sum<128>(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = r;
+}
+
+// ----------------------------------------------------------------------------------------------
+// K1: diagonal op on the whole state
+// ----------------------------------------------------------------------------------------------
+#define DIAG_SMEM_TERMS 512
+
+__device__ __forceinline__ double2 diag_phase(const DiagTerm *t, int nterms, u64 i, int dagger) {
+    double2 ph;
+    if (nterms <= 4) {
+        ph = make_double2(1.0, 0.0);
+        for (int m = 0; m < nterms; ++m) {
+            const double sg = sign_of(i & t[m].z);
+            ph = cmul(ph, make_double2(t[m].c, -sg * t[m].s));
+        }
+    } else {
+        double tot = 0.0;
+        for (int m = 0; m < nterms; ++m) tot += sign_of(i & t[m].z) * t[m].angle;
+        double s, c;
+        sincos(tot, &s, &c);
+        ph = make_double2(c, -s);
+    }
+    if (dagger) ph.y = -ph.y;
+    return ph;
+}
+
+__global__ void __launch_bounds__(256) k_diag(double2 *__restrict__ psi, const DiagTerm *__restrict__ terms, int nterms,
+                                              u64 dim, int dagger) {
+    __shared__ DiagTerm st[DIAG_SMEM_TERMS];
+    for (int t = threadIdx.x; t < nterms; t += blockDim.x) st[t] = terms[t];
+    __syncthreads();
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += stride) {
+        const double2 ph = diag_phase(st, nterms, i, dagger);
+        psi[i] = cmul(ph, psi[i]);
+    }
+}
+
+// adjoint step of exp(-i theta D), D(i) = sum coef_m sgn_m: partial of Im<lam|D|psi>, then undo on both
+__global__ void __launch_bounds__(256) k_diag_adjoint(double2 *__restrict__ psi, double2 *__restrict__ lam,
+                                                      const DiagTerm *__restrict__ terms, int nterms, u64 dim,
+                                                      double *__restrict__ partials) {
+    __shared__ DiagTerm st[DIAG_SMEM_TERMS];
+    __shared__ double red[8];
+    for (int t = threadIdx.x; t < nterms; t += blockDim.x) st[t] = terms[t];
+    __syncthreads();
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += stride) {
+        double d = 0.0;
+        for (int m = 0; m < nterms; ++m) d += sign_of(i & st[m].z) * st[m].coef;
+        const double2 a = psi[i], l = lam[i];
+        acc += d * im_conj_mul(l, a);
+        const double2 ph = diag_phase(st, nterms, i, 1);
+        psi[i] = cmul(ph, a);
+        lam[i] = cmul(ph, l);
+    }
+    const double r = block_sum<256>(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = r;
+}
+
+// ----------------------------------------------------------------------------------------------
+// K1: fused run of ops inside a shared-memory tile
+// ----------------------------------------------------------------------------------------------
+// A tile = all 2^T amplitudes that differ only in the T tile bits.  Each CTA stages one tile in shared
+// memory (plus the global index of every slot), applies the whole run of ops to it with one
+// __syncthreads per op, and writes it back: one global read + one write for the whole run.
+__global__ void __launch_bounds__(256) k_tile(double2 *__restrict__ psi, const TileOp *__restrict__ tilep,
+                                              const TileSub *__restrict__ subs, const PairOp *__restrict__ pairs,
+                                              const DiagOp *__restrict__ diags, const DiagTerm *__restrict__ terms,
+                                              int n, int dagger) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ TileOp tile;
+    if (threadIdx.x < sizeof(TileOp) / 4)
+        reinterpret_cast<unsigned int *>(&tile)[threadIdx.x] = reinterpret_cast<const unsigned int *>(tilep)[threadIdx.x];
+    __syncthreads();
+    const int T = tile.nbits;
+    const unsigned L = 1u << T;
+    double2 *buf = reinterpret_cast<double2 *>(smem_raw);
+    unsigned int *gidx = reinterpret_cast<unsigned int *>(buf + L);
+    const u64 ntiles = 1ull << (n - T);
+    for (u64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const u64 base = deposit_zeros(t, tile.bits, T);
+        for (unsigned l = threadIdx.x; l < L; l += blockDim.x) {
+            u64 g = base;
+            for (int b = 0; b < T; ++b) g |= (u64)((l >> b) & 1u) << tile.bits[b];
+            gidx[l] = (unsigned int)g;
+            buf[l] = psi[g];
+        }
+        __syncthreads();
+        for (int sidx = 0; sidx < tile.nsub; ++sidx) {
+            const TileSub sub = subs[tile.first_sub + (dagger ? tile.nsub - 1 - sidx : sidx)];
+            if (sub.type == 1) {
+                const PairOp *op = pairs + sub.index;
+                const Mat2 M = op_matrix(*op, dagger);
+                const u64 fixmask = op->fixmask, fixval = op->fixval, zeta = op->zeta;
+                const unsigned lowmask = (1u << sub.lpivot) - 1u;
+                for (unsigned k = threadIdx.x; k < (L >> 1); k += blockDim.x) {
+                    const unsigned il = ((k >> sub.lpivot) << (sub.lpivot + 1)) | (k & lowmask);
+                    const u64 gi = gidx[il];
+                    if ((gi & fixmask) == fixval) {
+                        const unsigned jl = il ^ sub.xlocal;
+                        double2 a = buf[il], b = buf[jl];
+                        rot2(M, sign_of(gi & zeta), a, b);
+                        buf[il] = a;
+                        buf[jl] = b;
+                    }
+                }
+            } else {
+                const DiagOp d = diags[sub.index];
+                const DiagTerm *dt = terms + d.first;
+                for (unsigned l = threadIdx.x; l < L; l += blockDim.x) {
+                    const double2 ph = diag_phase(dt, d.count, (u64)gidx[l], dagger);
+                    buf[l] = cmul(ph, buf[l]);
+                }
+            }
+            __syncthreads();
+        }
+        for (unsigned l = threadIdx.x; l < L; l += blockDim.x) psi[gidx[l]] = buf[l];
+        __syncthreads();
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K2: out = H in, e = <in|H|in>
+// ----------------------------------------------------------------------------------------------
+// One thread owns output index i and walks the x-mask groups: weight of in[i^x_g] is
+// w_g = sum_m d_m (-1)^popcount((i^x_g) & z_m) (pure integer work on chip), so the memory traffic is
+// one gather per group plus one store -- independent of the term count.
+template <bool REAL, bool WRITE>
+__global__ void __launch_bounds__(256) k_apply_table(const TabGroup *__restrict__ groups, int ngroups,
+                                                     const TabTerm *__restrict__ terms, int nterms, int use_smem,
+                                                     const double2 *__restrict__ in, double2 *__restrict__ out, u64 dim,
+                                                     double *__restrict__ partials) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[8];
+    const TabGroup *G = groups;
+    const TabTerm *Tm = terms;
+    if (use_smem) {
+        TabGroup *sg = reinterpret_cast<TabGroup *>(smem_raw);
+        TabTerm *stm = reinterpret_cast<TabTerm *>(sg + ngroups);
+        for (int t = threadIdx.x; t < ngroups; t += blockDim.x) sg[t] = groups[t];
+        for (int t = threadIdx.x; t < nterms; t += blockDim.x) stm[t] = terms[t];
+        __syncthreads();
+        G = sg;
+        Tm = stm;
+    }
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    double er = 0.0, ei = 0.0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += stride) {
+        double2 acc = make_double2(0.0, 0.0);
+        for (int g = 0; g < ngroups; ++g) {
+            const TabGroup grp = G[g];
+            const u64 j = i ^ grp.x;
+            double wr = 0.0, wi = 0.0;
+            for (int m = grp.first; m < grp.first + grp.count; ++m) {
+                const TabTerm tt = Tm[m];
+                const double sg = sign_of(j & tt.z);
+                wr += sg * tt.dr;
+                if (!REAL) wi += sg * tt.di;
+            }
+            if (REAL) {
+                if (wr != 0.0) {
+                    const double2 v = in[j];
+                    acc.x += wr * v.x;
+                    acc.y += wr * v.y;
+                }
+            } else {
+                if (wr != 0.0 || wi != 0.0) acc = cadd(acc, cmul(make_double2(wr, wi), in[j]));
+            }
+        }
+        const double2 self = in[i];
+        er += self.x * acc.x + self.y * acc.y;     // conj(self) * acc
+        ei += self.x * acc.y - self.y * acc.x;
+        if (WRITE) out[i] = acc;
+    }
+    const double sr = block_sum<256>(er, red);
+    const double si = block_sum<256>(ei, red);
+    if (threadIdx.x == 0) {
+        partials[2 * blockIdx.x] = sr;
+        partials[2 * blockIdx.x + 1] = si;
+    }
+}
+
+// sum `count` (re,im) partial pairs in a fixed order -> result[0..1]; single block
+__global__ void __launch_bounds__(256) k_finalize_pairs(const double *__restrict__ partials, int count,
+                                                        double *__restrict__ result) {
+    __shared__ double red[8];
+    double r = 0.0, im = 0.0;
+    for (int t = threadIdx.x; t < count; t += blockDim.x) {
+        r += partials[2 * t];
+        im += partials[2 * t + 1];
+    }
+    const double sr = block_sum<256>(r, red);
+    const double si = block_sum<256>(im, red);
+    if (threadIdx.x == 0) {
+        result[0] = sr;
+        result[1] = si;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K3: pool gradients
+// ----------------------------------------------------------------------------------------------
+// grid = (chunks, entries).  Only the 2^(n-|fixmask|) connected index pairs of an entry are enumerated
+// (bit-deposit of the free bits around the fixed pattern), never all 2^n.
+__global__ void __launch_bounds__(128) k_pool(const PoolEntry *__restrict__ entries, int first_entry, int n,
+                                              const double2 *__restrict__ psi, const double2 *__restrict__ lam,
+                                              double *__restrict__ partials) {
+    __shared__ PoolEntry e;
+    __shared__ double red[4];
+    {
+        const int words = sizeof(PoolEntry) / 8;
+        const u64 *src = reinterpret_cast<const u64 *>(entries + first_entry + blockIdx.y);
+        for (int t = threadIdx.x; t < words; t += blockDim.x) reinterpret_cast<u64 *>(&e)[t] = __ldg(src + t);
+        __syncthreads();
+    }
+    const u64 npairs = 1ull << (n - e.npos);
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const double2 B = make_double2(e.br, e.bi);
+    const double2 Bc = make_double2(e.br, -e.bi);
+    double acc = 0.0;
+    u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    // two pairs in flight per iteration
+    for (; idx + stride < npairs; idx += 2 * stride) {
+        const u64 i0 = deposit_zeros(idx, e.pos, e.npos) | e.fixval, j0 = i0 ^ e.x;
+        const u64 i1 = deposit_zeros(idx + stride, e.pos, e.npos) | e.fixval, j1 = i1 ^ e.x;
+        const double2 a0 = psi[i0], b0 = psi[j0], la0 = lam[i0], lb0 = lam[j0];
+        const double2 a1 = psi[i1], b1 = psi[j1], la1 = lam[i1], lb1 = lam[j1];
+        acc += sign_of(i0 & e.zeta) * (im_conj_mul(la0, cmul(B, b0)) + im_conj_mul(lb0, cmul(Bc, a0)));
+        acc += sign_of(i1 & e.zeta) * (im_conj_mul(la1, cmul(B, b1)) + im_conj_mul(lb1, cmul(Bc, a1)));
+    }
+    for (; idx < npairs; idx += stride) {
+        const u64 i0 = deposit_zeros(idx, e.pos, e.npos) | e.fixval, j0 = i0 ^ e.x;
+        const double2 a0 = psi[i0], b0 = psi[j0], la0 = lam[i0], lb0 = lam[j0];
+        acc += sign_of(i0 & e.zeta) * (im_conj_mul(la0, cmul(B, b0)) + im_conj_mul(lb0, cmul(Bc, a0)));
+    }
+    const double r = block_sum<128>(acc, red);
+    if (threadIdx.x == 0) partials[(size_t)(first_entry + blockIdx.y) * gridDim.x + blockIdx.x] = 2.0 * r;
+}
+
+// one warp per output: fixed-order sum over its entries' chunk partials
+__global__ void __launch_bounds__(32) k_pool_finalize(const double *__restrict__ partials,
+                                                      const int *__restrict__ out_first, int chunks, int first_out,
+                                                      double *__restrict__ out) {
+    const int o = first_out + blockIdx.x;
+    const int lo = out_first[o] * chunks, hi = out_first[o + 1] * chunks;
+    double acc = 0.0;
+    for (int t = lo + threadIdx.x; t < hi; t += 32) acc += partials[t];
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) out[o] = acc;
+}
+
+// generic segmented sum: out[s] = sum partials[first[s] .. first[s+1])
+__global__ void __launch_bounds__(32) k_sum_segments(const double *__restrict__ partials, const int *__restrict__ first,
+                                                     double *__restrict__ out) {
+    const int s = blockIdx.x;
+    double acc = 0.0;
+    for (int t = first[s] + threadIdx.x; t < first[s + 1]; t += 32) acc += partials[t];
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) out[s] = acc;
+}
+
+// ----------------------------------------------------------------------------------------------
+// K4 / misc vector kernels
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_inner(const double2 *__restrict__ a, const double2 *__restrict__ b, u64 dim,
+                                               double *__restrict__ partials) {
+    __shared__ double red[8];
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    double r = 0.0, im = 0.0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += stride) {
+        const double2 x = a[i], y = b[i];
+        r += x.x * y.x + x.y * y.y;
+        im += x.x * y.y - x.y * y.x;
+    }
+    const double sr = block_sum<256>(r, red);
+    const double si = block_sum<256>(im, red);
+    if (threadIdx.x == 0) {
+        partials[2 * blockIdx.x] = sr;
+        partials[2 * blockIdx.x + 1] = si;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_set_basis(double2 *psi, u64 dim, u64 index) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += stride)
+        psi[i] = make_double2(i == index ? 1.0 : 0.0, 0.0);
+}
+
+__global__ void __launch_bounds__(256) k_flush(double4 *buf, size_t count) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        buf[i] = make_double4(0.0, 0.0, 0.0, 0.0);
+}
+
+__global__ void __launch_bounds__(256) k_axpby(double2 *__restrict__ y, double a, const double2 *__restrict__ x,
+                                               double b, u64 dim) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += stride) {
+        const double2 xv = x[i], yv = y[i];
+        y[i] = make_double2(a * xv.x + b * yv.x, a * xv.y + b * yv.y);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_caxpy(double2 *__restrict__ y, double ar, double ai,
+                                               const double2 *__restrict__ x, u64 dim) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const double2 a = make_double2(ar, ai);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += stride) y[i] = cadd(y[i], cmul(a, x[i]));
+}
+
+__global__ void __launch_bounds__(256) k_lanczos_update(double2 *__restrict__ w, const double2 *__restrict__ v,
+                                                        const double2 *__restrict__ vprev, double alpha, double beta,
+                                                        u64 dim) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += stride) {
+        const double2 wv = w[i], a = v[i], b = vprev[i];
+        w[i] = make_double2(wv.x - alpha * a.x - beta * b.x, wv.y - alpha * a.y - beta * b.y);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_scale(double2 *__restrict__ y, double a, u64 dim) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += stride) y[i] = cscale(y[i], a);
+}
+
+__device__ __forceinline__ u64 mix64(u64 z) {
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+// Gaussian start vector supported on the (n_up, n_dn) sector (even wires = up); n_up < 0: full space
+__global__ void __launch_bounds__(256) k_sector_random(double2 *v, int n, int n_up, int n_dn, u64 seed) {
+    const u64 dim = 1ull << n;
+    u64 upmask = 0;
+    for (int q = 0; q < n; q += 2) upmask |= 1ull << (n - 1 - q);
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += stride) {
+        double val = 0.0;
+        const bool in_sector = n_up < 0 || (__popcll(i & upmask) == n_up && __popcll(i & ~upmask) == n_dn);
+        if (in_sector) {
+            const u64 h1 = mix64(i * 2 + seed * 0x100000001b3ull), h2 = mix64(h1 + 1);
+            const double u1 = ((h1 >> 11) + 1.0) * (1.0 / 9007199254740993.0);
+            const double u2 = (h2 >> 11) * (1.0 / 9007199254740992.0);
+            val = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+        }
+        v[i] = make_double2(val, 0.0);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// launch wrappers
+// ----------------------------------------------------------------------------------------------
+static inline int grid_for(u64 work_items, int threads, int per_thread, int sm, int max_blocks) {
+    u64 blocks = (work_items + (u64)threads * per_thread - 1) / ((u64)threads * per_thread);
+    if (blocks < 1) blocks = 1;
+    if (blocks > (u64)max_blocks) blocks = max_blocks;
+    (void)sm;
+    return (int)blocks;
+}
+
+void launch_pair(cudaStream_t s, int sm, double2 *psi, const PairOp *d_op, int n, int nfix, int dagger) {
+    const u64 npairs = 1ull << (n - nfix);
+    if (npairs >= (u64)sm * 128 * 16) {
+        const int grid = grid_for(npairs, 128, 4, sm, sm * 32);
+        k_pair<4><<<grid, 128, 0, s>>>(psi, d_op, npairs, dagger);
+    } else {
+        const int grid = grid_for(npairs, 128, 1, sm, sm * 32);
+        k_pair<1><<<grid, 128, 0, s>>>(psi, d_op, npairs, dagger);
+    }
+}
+
+void launch_pair_adjoint(cudaStream_t s, int sm, double2 *psi, double2 *lam, const PairOp *d_op, int n, int nfix,
+                         double *d_partials, int max_blocks, int *blocks_used) {
+    const u64 npairs = 1ull << (n - nfix);
+    int grid = grid_for(npairs, 128, npairs >= (u64)sm * 128 * 8 ? 2 : 1, sm, max_blocks);
+    k_pair_adjoint<<<grid, 128, 0, s>>>(psi, lam, d_op, npairs, d_partials);
+    *blocks_used = grid;
+}
+
+void launch_diag(cudaStream_t s, int sm, double2 *psi, const DiagTerm *d_terms, int nterms, int n, int dagger) {
+    const u64 dim = 1ull << n;
+    for (int off = 0; off < nterms; off += DIAG_SMEM_TERMS) {
+        const int cnt = nterms - off < DIAG_SMEM_TERMS ? nterms - off : DIAG_SMEM_TERMS;
+        const int grid = grid_for(dim, 256, dim >= (u64)sm * 256 * 8 ? 2 : 1, sm, sm * 16);
+        k_diag<<<grid, 256, 0, s>>>(psi, d_terms + off, cnt, dim, dagger);
+    }
+}
+
+void launch_diag_adjoint(cudaStream_t s, int sm, double2 *psi, double2 *lam, const DiagTerm *d_terms, int nterms, int n,
+                         double *d_partials, int max_blocks, int *blocks_used) {
+    const u64 dim = 1ull << n;
+    int grid = grid_for(dim, 256, 1, sm, max_blocks);
+    k_diag_adjoint<<<grid, 256, 0, s>>>(psi, lam, d_terms, nterms, dim, d_partials);
+    *blocks_used = grid;
+}
+
+static bool g_tile_attr_set = false;
+
+void launch_tile(cudaStream_t s, double2 *psi, const TileOp *d_tile, const TileSub *d_subs, const PairOp *d_pairs,
+                 const DiagOp *d_diags, const DiagTerm *d_terms, int n, int nbits, int dagger, double2 *psi2) {
+    const size_t smem = ((size_t)1 << nbits) * (sizeof(double2) + sizeof(unsigned int));
+    if (!g_tile_attr_set) {
+        cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        g_tile_attr_set = true;
+    }
+    u64 ntiles = 1ull << (n - nbits);
+    const int grid = (int)(ntiles > 148ull * 16 ? 148ull * 16 : ntiles);
+    k_tile<<<grid, 256, smem, s>>>(psi, d_tile, d_subs, d_pairs, d_diags, d_terms, n, dagger);
+    if (psi2) k_tile<<<grid, 256, smem, s>>>(psi2, d_tile, d_subs, d_pairs, d_diags, d_terms, n, dagger);
+}
+
+void launch_apply_table(cudaStream_t s, int sm, const TabGroup *g, int ngroups, const TabTerm *t, int nterms,
+                        bool all_real, const double2 *in, double2 *out, int n, double *d_partials, double *d_result);
+
+void launch_apply_table(cudaStream_t s, int sm, const TabGroup *g, int ngroups, const TabTerm *t, int nterms,
+                        bool all_real, const double2 *in, double2 *out, int n, double *d_partials, double *d_result) {
+    const u64 dim = 1ull << n;
+    const size_t need = (size_t)ngroups * sizeof(TabGroup) + (size_t)nterms * sizeof(TabTerm);
+    const int use_smem = need <= 40 * 1024;
+    const size_t smem = use_smem ? need : 0;
+    int grid = grid_for(dim, 256, 1, sm, FH_MAX_PARTIALS);
+    if (grid > sm * 8 && dim > (u64)sm * 8 * 256) grid = sm * 8;
+#define LAUNCH_TAB(R, W) \
+    k_apply_table<R, W><<<grid, 256, smem, s>>>(g, ngroups, t, nterms, use_smem, in, out, dim, d_partials)
+    if (all_real) {
+        if (out) LAUNCH_TAB(true, true); else LAUNCH_TAB(true, false);
+    } else {
+        if (out) LAUNCH_TAB(false, true); else LAUNCH_TAB(false, false);
+    }
+#undef LAUNCH_TAB
+    k_finalize_pairs<<<1, 256, 0, s>>>(d_partials, grid, d_result);
+}
+
+void launch_pool(cudaStream_t s, const PoolEntry *entries, int first_entry, int n_entries, int chunks, int n,
+                 const double2 *psi, const double2 *lam, double *d_partials) {
+    if (n_entries <= 0) return;
+    // gridDim.y is limited to 65535
+    for (int off = 0; off < n_entries; off += 32768) {
+        const int cnt = n_entries - off < 32768 ? n_entries - off : 32768;
+        dim3 grid(chunks, cnt);
+        k_pool<<<grid, 128, 0, s>>>(entries, first_entry + off, n, psi, lam, d_partials);
+    }
+}
+
+void launch_pool_finalize(cudaStream_t s, const double *d_partials, const int *d_out_first, int chunks, int first_out,
+                          int count, double *d_out) {
+    if (count <= 0) return;
+    k_pool_finalize<<<count, 32, 0, s>>>(d_partials, d_out_first, chunks, first_out, d_out);
+}
+
+void launch_inner(cudaStream_t s, int sm, const double2 *a, const double2 *b, u64 dim, double *d_partials,
+                  double *d_result) {
+    int grid = grid_for(dim, 256, 4, sm, sm * 8);
+    k_inner<<<grid, 256, 0, s>>>(a, b, dim, d_partials);
+    k_finalize_pairs<<<1, 256, 0, s>>>(d_partials, grid, d_result);
+}
+
+void launch_sum_segments(cudaStream_t s, const double *d_partials, const int *d_first, int nseg, double *d_out) {
+    if (nseg <= 0) return;
+    k_sum_segments<<<nseg, 32, 0, s>>>(d_partials, d_first, d_out);
+}
+
+// out[s] = sum_{t < stride} partials[s*stride + t]   (fixed order; unused slots are pre-zeroed)
+__global__ void __launch_bounds__(32) k_sum_strided(const double *__restrict__ partials, int stride,
+                                                    double *__restrict__ out) {
+    const double *seg = partials + (size_t)blockIdx.x * stride;
+    double acc = 0.0;
+    for (int t = threadIdx.x; t < stride; t += 32) acc += seg[t];
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) out[blockIdx.x] = acc;
+}
+
+void launch_sum_strided(cudaStream_t s, const double *d_partials, int stride, int nseg, double *d_out) {
+    if (nseg <= 0) return;
+    k_sum_strided<<<nseg, 32, 0, s>>>(d_partials, stride, d_out);
+}
+
+void launch_set_basis(cudaStream_t s, double2 *psi, u64 dim, u64 index) {
+    int grid = (int)((dim + 255) / 256 > 148 * 16 ? 148 * 16 : (dim + 255) / 256);
+    k_set_basis<<<grid, 256, 0, s>>>(psi, dim, index);
+}
+
+void launch_flush(cudaStream_t s, void *buf, size_t bytes) {
+    k_flush<<<148 * 8, 256, 0, s>>>(reinterpret_cast<double4 *>(buf), bytes / sizeof(double4));
+}
+
+static inline int vec_grid(u64 dim, int sm) { return grid_for(dim, 256, 2, sm, sm * 16); }
+
+void launch_axpby(cudaStream_t s, int sm, double2 *y, double a, const double2 *x, double b, u64 dim) {
+    k_axpby<<<vec_grid(dim, sm), 256, 0, s>>>(y, a, x, b, dim);
+}
+void launch_caxpy(cudaStream_t s, int sm, double2 *y, double ar, double ai, const double2 *x, u64 dim) {
+    k_caxpy<<<vec_grid(dim, sm), 256, 0, s>>>(y, ar, ai, x, dim);
+}
+void launch_lanczos_update(cudaStream_t s, int sm, double2 *w, const double2 *v, const double2 *vprev, double alpha,
+                           double beta, u64 dim) {
+    k_lanczos_update<<<vec_grid(dim, sm), 256, 0, s>>>(w, v, vprev, alpha, beta, dim);
+}
+void launch_scale(cudaStream_t s, int sm, double2 *y, double a, u64 dim) {
+    k_scale<<<vec_grid(dim, sm), 256, 0, s>>>(y, a, dim);
+}
+void launch_sector_random(cudaStream_t s, int sm, double2 *v, int n, int n_up, int n_dn, u64 seed) {
+    k_sector_random<<<vec_grid(1ull << n, sm), 256, 0, s>>>(v, n, n_up, n_dn, seed);
+}

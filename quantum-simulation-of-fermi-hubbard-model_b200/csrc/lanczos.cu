@@ -1,0 +1,297 @@
+// K4: matrix-free Lanczos on the fused H|v> kernel (fh_apply_table) -- the replacement for
+// scipy.sparse.linalg.eigsh(which='SA') in the reference's linalg/exact_diagonalization.py:34-51,
+// 181-229 and for openfermion.get_ground_state (models/iqcc_hubbard.py:57).
+//
+// Full re-orthogonalisation against the Krylov basis (one batched multi-dot + one multi-axpy launch per
+// iteration), deflation against already converged eigenvectors (resolves the 4-fold degenerate 3x3
+// ground level), restart from the current Ritz vector when the basis buffer is full.  The start
+// vector lives in the (N_up, N_dn) sector; H maps the sector to itself exactly because each x-mask
+// group's weight is summed before it multiplies an amplitude (+t/2 - t/2 = 0 exactly).
+#include <math.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+#define FULL 0xffffffffu
+#define MD_CHUNKS 32
+
+__device__ __forceinline__ double lz_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// partials[(r*MD_CHUNKS + c)*2 + {0,1}] = chunk c of <V_r | w>
+__global__ void __launch_bounds__(256) k_multi_dot(const double2 *__restrict__ V, u64 dim, const double2 *__restrict__ w,
+                                                   double *__restrict__ partials) {
+    __shared__ double red[16];
+    const double2 *v = V + (size_t)blockIdx.y * dim;
+    const u64 per = (dim + MD_CHUNKS - 1) / MD_CHUNKS;
+    const u64 lo = (u64)blockIdx.x * per;
+    const u64 hi = lo + per < dim ? lo + per : dim;
+    double re = 0.0, im = 0.0;
+    for (u64 i = lo + threadIdx.x; i < hi; i += 256) {
+        const double2 a = v[i], b = w[i];
+        re += a.x * b.x + a.y * b.y;
+        im += a.x * b.y - a.y * b.x;
+    }
+    re = lz_warp_sum(re);
+    im = lz_warp_sum(im);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+        red[2 * wid] = re;
+        red[2 * wid + 1] = im;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sr = 0.0, si = 0.0;
+        for (int k = 0; k < 8; ++k) {
+            sr += red[2 * k];
+            si += red[2 * k + 1];
+        }
+        partials[((size_t)blockIdx.y * MD_CHUNKS + blockIdx.x) * 2] = sr;
+        partials[((size_t)blockIdx.y * MD_CHUNKS + blockIdx.x) * 2 + 1] = si;
+    }
+}
+
+__global__ void __launch_bounds__(32) k_multi_dot_finalize(const double *__restrict__ partials, double *__restrict__ coef) {
+    const double *p = partials + (size_t)blockIdx.x * MD_CHUNKS * 2;
+    double re = threadIdx.x < MD_CHUNKS ? p[2 * threadIdx.x] : 0.0;
+    double im = threadIdx.x < MD_CHUNKS ? p[2 * threadIdx.x + 1] : 0.0;
+    re = lz_warp_sum(re);
+    im = lz_warp_sum(im);
+    if (threadIdx.x == 0) {
+        coef[2 * blockIdx.x] = re;
+        coef[2 * blockIdx.x + 1] = im;
+    }
+}
+
+// w[i] += sign * sum_r coef[r] * V_r[i]
+__global__ void __launch_bounds__(256) k_multi_axpy(double2 *__restrict__ w, const double2 *__restrict__ V, u64 dim,
+                                                    const double *__restrict__ coef, int nvec, double sign) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += stride) {
+        double re = 0.0, im = 0.0;
+        for (int r = 0; r < nvec; ++r) {
+            const double cr = __ldg(coef + 2 * r), ci = __ldg(coef + 2 * r + 1);
+            const double2 v = V[(size_t)r * dim + i];
+            re += cr * v.x - ci * v.y;
+            im += cr * v.y + ci * v.x;
+        }
+        double2 o = w[i];
+        o.x += sign * re;
+        o.y += sign * im;
+        w[i] = o;
+    }
+}
+
+// ---- host-side tridiagonal helpers ------------------------------------------------------------
+// number of eigenvalues of T(alpha, beta) below x (Sturm count via LDL^T pivots)
+static int sturm_count(const std::vector<double> &a, const std::vector<double> &b, int m, double x) {
+    int count = 0;
+    double d = 1.0;
+    for (int i = 0; i < m; ++i) {
+        const double off = i > 0 ? b[i - 1] * b[i - 1] : 0.0;
+        d = a[i] - x - (i > 0 ? off / d : 0.0);
+        if (fabs(d) < 1e-300) d = -1e-300;
+        if (d < 0) ++count;
+    }
+    return count;
+}
+
+static double lowest_eigenvalue(const std::vector<double> &a, const std::vector<double> &b, int m) {
+    double lo = a[0], hi = a[0];
+    for (int i = 0; i < m; ++i) {
+        const double r = (i > 0 ? fabs(b[i - 1]) : 0.0) + (i < m - 1 ? fabs(b[i]) : 0.0);
+        lo = fmin(lo, a[i] - r);
+        hi = fmax(hi, a[i] + r);
+    }
+    for (int it = 0; it < 200 && hi - lo > 1e-15 * fmax(1.0, fabs(lo) + fabs(hi)); ++it) {
+        const double mid = 0.5 * (lo + hi);
+        if (sturm_count(a, b, m, mid) >= 1) hi = mid; else lo = mid;
+    }
+    return 0.5 * (lo + hi);
+}
+
+// eigenvector of the lowest eigenvalue by inverse iteration (T - shift positive definite -> Thomas is stable)
+static void lowest_eigenvector(const std::vector<double> &a, const std::vector<double> &b, int m, double theta,
+                               std::vector<double> &y) {
+    const double shift = theta - 1e-9 * fmax(1.0, fabs(theta));
+    y.assign(m, 1.0 / sqrt((double)m));
+    std::vector<double> c(m), d(m);
+    for (int it = 0; it < 4; ++it) {
+        // forward elimination
+        double piv = a[0] - shift;
+        c[0] = (m > 1 ? b[0] : 0.0) / piv;
+        d[0] = y[0] / piv;
+        for (int i = 1; i < m; ++i) {
+            piv = a[i] - shift - b[i - 1] * c[i - 1];
+            if (fabs(piv) < 1e-300) piv = 1e-300;
+            c[i] = (i < m - 1 ? b[i] : 0.0) / piv;
+            d[i] = (y[i] - b[i - 1] * d[i - 1]) / piv;
+        }
+        y[m - 1] = d[m - 1];
+        for (int i = m - 2; i >= 0; --i) y[i] = d[i] - c[i] * y[i + 1];
+        double nrm = 0.0;
+        for (int i = 0; i < m; ++i) nrm += y[i] * y[i];
+        nrm = sqrt(nrm);
+        for (int i = 0; i < m; ++i) y[i] /= nrm;
+    }
+}
+
+// ---- driver -------------------------------------------------------------------------------------
+struct LzBuffers {
+    double2 *V = nullptr, *F = nullptr, *w = nullptr, *x = nullptr;
+    double *partials = nullptr, *coef = nullptr, *h_coef = nullptr;
+    ~LzBuffers() {
+        cudaFree(V);
+        cudaFree(F);
+        cudaFree(w);
+        cudaFree(x);
+        cudaFree(partials);
+        cudaFree(coef);
+        cudaFreeHost(h_coef);
+    }
+};
+
+static int project_out(fh_ctx *ctx, double2 *w, const double2 *basis, int nvec, u64 dim, LzBuffers &B) {
+    if (nvec <= 0) return FH_OK;
+    for (int off = 0; off < nvec; off += 32768) {
+        const int cnt = nvec - off < 32768 ? nvec - off : 32768;
+        dim3 grid(MD_CHUNKS, cnt);
+        k_multi_dot<<<grid, 256, 0, ctx->stream>>>(basis + (size_t)off * dim, dim, w, B.partials);
+        k_multi_dot_finalize<<<cnt, 32, 0, ctx->stream>>>(B.partials, B.coef);
+        int g = (int)((dim + 255) / 256);
+        if (g > ctx->sm_count * 8) g = ctx->sm_count * 8;
+        k_multi_axpy<<<g, 256, 0, ctx->stream>>>(w, basis + (size_t)off * dim, dim, B.coef, cnt, -1.0);
+    }
+    FH_CUDA(cudaGetLastError());
+    return FH_OK;
+}
+
+static int device_norm(fh_ctx *ctx, const double2 *v, u64 dim, double *out) {
+    launch_inner(ctx->stream, ctx->sm_count, v, v, dim, ctx->d_partials, ctx->d_result);
+    FH_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FH_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = sqrt(fmax(ctx->h_result[0], 0.0));
+    return FH_OK;
+}
+
+extern "C" int fh_lanczos(const fh_table *tab, int n_up, int n_dn, int k, double tol, int max_iter, uint64_t seed,
+                          double *evals, fh_state *const *evecs, int *iterations) {
+    FH_REQUIRE(tab && evals, "fh_lanczos: NULL argument");
+    FH_REQUIRE(k >= 1 && k <= 64, "fh_lanczos: k=%d outside [1, 64]", k);
+    FH_REQUIRE(max_iter >= 2, "fh_lanczos: max_iter must be >= 2");
+    FH_REQUIRE(tol > 0, "fh_lanczos: tol must be positive");
+    const int n = tab->n;
+    FH_REQUIRE((n_up < 0 && n_dn < 0) || (n_up >= 0 && n_dn >= 0 && n_up <= (n + 1) / 2 && n_dn <= n / 2),
+               "fh_lanczos: bad sector (%d up, %d down) for %d qubits", n_up, n_dn, n);
+    if (evecs)
+        for (int e = 0; e < k; ++e) FH_REQUIRE(evecs[e] && evecs[e]->n == n, "fh_lanczos: evecs[%d] missing or wrong size", e);
+    fh_ctx *ctx = tab->ctx;
+    FH_CUDA(cudaSetDevice(ctx->device));
+    const u64 dim = 1ull << n;
+    const size_t vbytes = dim * sizeof(double2);
+
+    // Krylov basis capacity from free memory
+    size_t free_b = 0, total_b = 0;
+    FH_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t fixed = vbytes * (size_t)(k + 2);
+    FH_REQUIRE(free_b > fixed + 3 * vbytes, "fh_lanczos: not enough device memory for %d-qubit vectors", n);
+    size_t cap = (size_t)((free_b - fixed) * 0.7 / vbytes);
+    if (cap > (size_t)max_iter) cap = max_iter;
+    if (cap > 2000) cap = 2000;
+    FH_REQUIRE(cap >= 3, "fh_lanczos: room for only %zu Krylov vectors", cap);
+    const int mcap = (int)cap;
+
+    LzBuffers B;
+    FH_CUDA(cudaMalloc(&B.V, vbytes * mcap));
+    FH_CUDA(cudaMalloc(&B.F, vbytes * k));
+    FH_CUDA(cudaMalloc(&B.w, vbytes));
+    FH_CUDA(cudaMalloc(&B.x, vbytes));
+    const int maxvec = mcap > k ? mcap : k;
+    FH_CUDA(cudaMalloc(&B.partials, sizeof(double) * 2 * MD_CHUNKS * (size_t)(maxvec < 32768 ? maxvec : 32768)));
+    FH_CUDA(cudaMalloc(&B.coef, sizeof(double) * 2 * maxvec));
+    FH_CUDA(cudaMallocHost(&B.h_coef, sizeof(double) * 2 * maxvec));
+
+    int total_iters = 0;
+    std::vector<double> alpha, beta, y;
+    for (int e = 0; e < k; ++e) {
+        // start vector: random in the sector, orthogonal to the converged eigenvectors
+        launch_sector_random(ctx->stream, ctx->sm_count, B.x, n, n_up, n_dn, seed + 0x9e37ull * (u64)e);
+        FH_TRY(project_out(ctx, B.x, B.F, e, dim, B));
+        double nrm = 0.0;
+        FH_TRY(device_norm(ctx, B.x, dim, &nrm));
+        FH_REQUIRE(nrm > 1e-12, "fh_lanczos: sector is empty or exhausted (eigenpair %d)", e);
+        launch_scale(ctx->stream, ctx->sm_count, B.x, 1.0 / nrm, dim);
+
+        double theta = 0.0, prev_theta = 1e300;
+        bool converged = false;
+        int iters_this = 0;
+        while (!converged && iters_this < max_iter) {
+            // (re)start Lanczos from B.x
+            alpha.clear();
+            beta.clear();
+            FH_CUDA(cudaMemcpyAsync(B.V, B.x, vbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+            int m = 0;
+            for (; m < mcap && iters_this < max_iter; ++iters_this) {
+                double2 *v = B.V + (size_t)m * dim;
+                // w = H v ; alpha = <v|H|v>
+                launch_apply_table(ctx->stream, ctx->sm_count, tab->d_groups, tab->n_groups, tab->d_terms,
+                                   (int)tab->terms.size(), tab->all_real, v, B.w, n, ctx->d_partials, ctx->d_result);
+                // full re-orthogonalisation (covers the three-term recurrence) + deflation, applied twice
+                for (int pass = 0; pass < 2; ++pass) {
+                    FH_TRY(project_out(ctx, B.w, B.V, m + 1, dim, B));
+                    FH_TRY(project_out(ctx, B.w, B.F, e, dim, B));
+                }
+                launch_inner(ctx->stream, ctx->sm_count, B.w, B.w, dim, ctx->d_partials, ctx->d_result + 2);
+                FH_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+                FH_CUDA(cudaStreamSynchronize(ctx->stream));
+                alpha.push_back(ctx->h_result[0]);
+                const double bnorm = sqrt(fmax(ctx->h_result[2], 0.0));
+                ++m;
+                theta = lowest_eigenvalue(alpha, beta, m);
+                lowest_eigenvector(alpha, beta, m, theta, y);
+                const double resid = fabs(bnorm * y[m - 1]);
+                if (resid < tol * fmax(1.0, fabs(theta)) || bnorm < 1e-13) {
+                    converged = true;
+                    ++iters_this;
+                    break;
+                }
+                prev_theta = theta;
+                if (m < mcap) {
+                    beta.push_back(bnorm);
+                    FH_CUDA(cudaMemcpyAsync(B.V + (size_t)m * dim, B.w, vbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+                    launch_scale(ctx->stream, ctx->sm_count, B.V + (size_t)m * dim, 1.0 / bnorm, dim);
+                }
+            }
+            // Ritz vector x = sum_r y_r V_r
+            const int mv = (int)alpha.size();
+            for (int r = 0; r < mv; ++r) {
+                B.h_coef[2 * r] = y[r];
+                B.h_coef[2 * r + 1] = 0.0;
+            }
+            FH_CUDA(cudaMemcpyAsync(B.coef, B.h_coef, sizeof(double) * 2 * mv, cudaMemcpyHostToDevice, ctx->stream));
+            FH_CUDA(cudaMemsetAsync(B.x, 0, vbytes, ctx->stream));
+            int g = (int)((dim + 255) / 256);
+            if (g > ctx->sm_count * 8) g = ctx->sm_count * 8;
+            k_multi_axpy<<<g, 256, 0, ctx->stream>>>(B.x, B.V, dim, B.coef, mv, 1.0);
+            FH_TRY(project_out(ctx, B.x, B.F, e, dim, B));
+            FH_TRY(device_norm(ctx, B.x, dim, &nrm));
+            launch_scale(ctx->stream, ctx->sm_count, B.x, 1.0 / nrm, dim);
+            FH_CUDA(cudaStreamSynchronize(ctx->stream));   // h_coef reused by the next restart
+        }
+        (void)prev_theta;
+        FH_REQUIRE(converged, "fh_lanczos: eigenpair %d not converged to %.1e in %d iterations", e, tol, max_iter);
+        total_iters += iters_this;
+        evals[e] = theta;
+        FH_CUDA(cudaMemcpyAsync(B.F + (size_t)e * dim, B.x, vbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (evecs) FH_CUDA(cudaMemcpyAsync(evecs[e]->d, B.x, vbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    FH_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (iterations) *iterations = total_iters;
+    return FH_OK;
+}

@@ -1,0 +1,589 @@
+// Compiled circuits: ordered pair/diag ops, fused shared-memory tile runs, and the one-call
+// evaluation (forward, observables, adjoint-gradient sweep, pool screening) replayed as a CUDA graph.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+
+int fh_fill_pair(PairOp *op, int n, u64 x, u64 fixmask, u64 fixval, u64 zeta, const double m[8]);
+int fh_enqueue_apply_table(const fh_table *tab, const double2 *in, double2 *out, int result_slot);
+int fh_enqueue_pool(const fh_pool *pool, const double2 *psi, const double2 *lam, int first, int count);
+
+#define FH_MAX_RESULT_TABLES 8
+#define FH_MAX_OVERLAPS 8
+#define FH_GRAD_BLOCKS 256     // partial blocks per parametrised op in the adjoint sweep
+
+struct Item {
+    int type;    // 1 pair, 2 diag, 3 tile
+    int index;   // into pairs / diagops / tiles
+};
+
+struct EvalKey {
+    u64 basis;
+    int n_tables, n_overlaps, want_grads;
+    const void *tables[FH_MAX_RESULT_TABLES];
+    const void *targets[FH_MAX_OVERLAPS];
+    const void *pool;
+    int pool_pos, pool_first, pool_count;
+    const void *state_out;
+    bool operator==(const EvalKey &o) const { return memcmp(this, &o, sizeof(EvalKey)) == 0; }
+};
+
+struct fh_program {
+    fh_ctx *ctx = nullptr;
+    int n = 0, n_params = 0;
+    bool finalized = false, in_tile = false;
+    std::vector<PairOp> pairs;
+    std::vector<DiagOp> diagops;
+    std::vector<DiagTerm> dterms;
+    std::vector<TileOp> tiles;
+    std::vector<TileSub> subs;
+    std::vector<Item> items;
+    // device mirrors + pinned staging of the theta-dependent payload
+    PairOp *d_pairs = nullptr, *h_pairs = nullptr;
+    DiagTerm *d_dterms = nullptr, *h_dterms = nullptr;
+    DiagOp *d_diagops = nullptr;
+    TileOp *d_tiles = nullptr;
+    TileSub *d_subs = nullptr;
+    // workspaces
+    double2 *d_psi = nullptr, *d_lam = nullptr, *d_chk = nullptr;
+    // adjoint-gradient partials: one segment per parametrised op processed
+    double *d_gpart = nullptr, *d_gseg = nullptr, *h_gseg = nullptr;
+    int *d_gfirst = nullptr;
+    int n_param_ops = 0;
+    // results (pinned)
+    double *h_res = nullptr, *d_res = nullptr;
+    // graph cache
+    bool have_graph = false;
+    EvalKey key;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    std::vector<int> seg_param;       // per processed segment: parameter index
+    std::vector<double> seg_scale;    // per processed segment: 2*gscale
+    int n_segments = 0;
+};
+
+static inline int popcnt(u64 v) { return __builtin_popcountll(v); }
+
+// ----------------------------------------------------------------------------------------------
+extern "C" int fh_program_create(fh_ctx *ctx, int n_qubits, int n_params, fh_program **out) {
+    FH_REQUIRE(ctx && out, "fh_program_create: NULL argument");
+    FH_REQUIRE(n_qubits >= 1 && n_qubits <= 33, "fh_program_create: n_qubits=%d outside [1, 33]", n_qubits);
+    FH_REQUIRE(n_params >= 0, "fh_program_create: negative parameter count");
+    fh_program *p = new (std::nothrow) fh_program();
+    if (!p) return FH_ENOMEM;
+    p->ctx = ctx;
+    p->n = n_qubits;
+    p->n_params = n_params;
+    *out = p;
+    return FH_OK;
+}
+
+static void drop_graph(fh_program *p) {
+    if (p->exec) cudaGraphExecDestroy(p->exec);
+    if (p->graph) cudaGraphDestroy(p->graph);
+    p->exec = nullptr;
+    p->graph = nullptr;
+    p->have_graph = false;
+}
+
+extern "C" int fh_program_destroy(fh_program *p) {
+    if (!p) return FH_OK;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    drop_graph(p);
+    cudaFree(p->d_pairs);
+    cudaFree(p->d_dterms);
+    cudaFree(p->d_diagops);
+    cudaFree(p->d_tiles);
+    cudaFree(p->d_subs);
+    cudaFree(p->d_psi);
+    cudaFree(p->d_lam);
+    cudaFree(p->d_chk);
+    cudaFree(p->d_gpart);
+    cudaFree(p->d_gseg);
+    cudaFree(p->d_gfirst);
+    cudaFree(p->d_res);
+    cudaFreeHost(p->h_pairs);
+    cudaFreeHost(p->h_dterms);
+    cudaFreeHost(p->h_gseg);
+    cudaFreeHost(p->h_res);
+    delete p;
+    return FH_OK;
+}
+
+extern "C" int fh_program_add_pair(fh_program *p, uint64_t x, uint64_t fixmask, uint64_t fixval, uint64_t zeta, int kind,
+                                   int param, double scale, double bhat_re, double bhat_im, const double m[8]) {
+    FH_REQUIRE(p, "fh_program_add_pair: program is NULL");
+    FH_REQUIRE(!p->finalized, "fh_program_add_pair: program already finalized");
+    FH_REQUIRE(kind == 0 || kind == 1, "fh_program_add_pair: kind must be 0 (fixed) or 1 (rotation)");
+    PairOp op;
+    FH_TRY(fh_fill_pair(&op, p->n, x, fixmask, fixval, zeta, kind == 0 ? m : nullptr));
+    op.kind = kind;
+    if (kind == 0) {
+        FH_REQUIRE(m != nullptr, "fh_program_add_pair: fixed op needs a matrix");
+        op.param = -1;
+    } else {
+        FH_REQUIRE(param >= -1 && param < p->n_params, "fh_program_add_pair: parameter index %d out of range", param);
+        const double nb = bhat_re * bhat_re + bhat_im * bhat_im;
+        FH_REQUIRE(fabs(nb - 1.0) < 1e-9, "fh_program_add_pair: bhat must have unit modulus");
+        op.param = param;
+        op.gscale = scale;
+        op.bhat[0] = bhat_re;
+        op.bhat[1] = bhat_im;
+    }
+    const int idx = (int)p->pairs.size();
+    p->pairs.push_back(op);
+    if (p->in_tile) {
+        TileOp &t = p->tiles.back();
+        // x must lie inside the tile bits
+        unsigned xlocal = 0;
+        int lpivot = -1;
+        u64 rest = x;
+        for (int b = 0; b < t.nbits; ++b) {
+            if (x >> t.bits[b] & 1) {
+                xlocal |= 1u << b;
+                lpivot = b;
+                rest &= ~(1ull << t.bits[b]);
+            }
+        }
+        FH_REQUIRE(rest == 0, "fh_program_add_pair: x-mask 0x%llx not inside the open tile", (u64)x);
+        TileSub s;
+        s.type = 1;
+        s.index = idx;
+        s.lpivot = lpivot;
+        s.xlocal = xlocal;
+        p->subs.push_back(s);
+        t.nsub++;
+    } else {
+        p->items.push_back({1, idx});
+    }
+    return FH_OK;
+}
+
+extern "C" int fh_program_add_diag(fh_program *p, int n_terms, const uint64_t *z, const double *coef, int param) {
+    FH_REQUIRE(p, "fh_program_add_diag: program is NULL");
+    FH_REQUIRE(!p->finalized, "fh_program_add_diag: program already finalized");
+    FH_REQUIRE(n_terms > 0 && z && coef, "fh_program_add_diag: need at least one term");
+    FH_REQUIRE(n_terms <= 512, "fh_program_add_diag: at most 512 terms per diagonal op (got %d)", n_terms);
+    FH_REQUIRE(param >= -1 && param < p->n_params, "fh_program_add_diag: parameter index %d out of range", param);
+    const u64 full = (1ull << p->n) - 1ull;
+    DiagOp d;
+    d.first = (int)p->dterms.size();
+    d.count = n_terms;
+    d.param = param;
+    d.pad = 0;
+    for (int m = 0; m < n_terms; ++m) {
+        FH_REQUIRE((z[m] & ~full) == 0 && z[m] != 0, "fh_program_add_diag: bad z-mask in term %d", m);
+        DiagTerm t;
+        t.z = z[m];
+        t.coef = param >= 0 ? coef[m] : 0.0;
+        t.angle = param >= 0 ? 0.0 : coef[m];
+        t.c = cos(t.angle);
+        t.s = sin(t.angle);
+        p->dterms.push_back(t);
+    }
+    const int idx = (int)p->diagops.size();
+    p->diagops.push_back(d);
+    if (p->in_tile) {
+        TileSub s;
+        s.type = 2;
+        s.index = idx;
+        s.lpivot = 0;
+        s.xlocal = 0;
+        p->subs.push_back(s);
+        p->tiles.back().nsub++;
+    } else {
+        p->items.push_back({2, idx});
+    }
+    return FH_OK;
+}
+
+extern "C" int fh_program_begin_tile(fh_program *p, int n_bits, const int32_t *bits) {
+    FH_REQUIRE(p && bits, "fh_program_begin_tile: NULL argument");
+    FH_REQUIRE(!p->finalized && !p->in_tile, "fh_program_begin_tile: program finalized or tile already open");
+    FH_REQUIRE(n_bits >= 1 && n_bits <= FH_MAX_TILE_BITS && n_bits <= p->n, "fh_program_begin_tile: n_bits=%d outside [1, %d]",
+               n_bits, FH_MAX_TILE_BITS);
+    FH_REQUIRE(p->n <= 32, "fh_program_begin_tile: tiles support at most 32 qubits");
+    TileOp t;
+    memset(&t, 0, sizeof(t));
+    t.nbits = n_bits;
+    t.first_sub = (int)p->subs.size();
+    t.nsub = 0;
+    for (int b = 0; b < n_bits; ++b) {
+        FH_REQUIRE(bits[b] >= 0 && bits[b] < p->n && (b == 0 || bits[b] > bits[b - 1]),
+                   "fh_program_begin_tile: bits must be ascending and < n_qubits");
+        t.bits[b] = (unsigned char)bits[b];
+    }
+    p->tiles.push_back(t);
+    p->in_tile = true;
+    return FH_OK;
+}
+
+extern "C" int fh_program_end_tile(fh_program *p) {
+    FH_REQUIRE(p && p->in_tile, "fh_program_end_tile: no open tile");
+    p->in_tile = false;
+    if (p->tiles.back().nsub == 0) {
+        p->tiles.pop_back();
+        return FH_OK;
+    }
+    p->items.push_back({3, (int)p->tiles.size() - 1});
+    return FH_OK;
+}
+
+template <typename T>
+static int upload_vec(T **dptr, const std::vector<T> &v, cudaStream_t s) {
+    if (v.empty()) return FH_OK;
+    FH_CUDA(cudaMalloc(dptr, sizeof(T) * v.size()));
+    FH_CUDA(cudaMemcpyAsync(*dptr, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, s));
+    return FH_OK;
+}
+
+extern "C" int fh_program_finalize(fh_program *p) {
+    FH_REQUIRE(p, "fh_program_finalize: program is NULL");
+    FH_REQUIRE(!p->finalized && !p->in_tile, "fh_program_finalize: already finalized or tile still open");
+    fh_ctx *ctx = p->ctx;
+    FH_CUDA(cudaSetDevice(ctx->device));
+    FH_TRY(upload_vec(&p->d_pairs, p->pairs, ctx->stream));
+    FH_TRY(upload_vec(&p->d_dterms, p->dterms, ctx->stream));
+    FH_TRY(upload_vec(&p->d_diagops, p->diagops, ctx->stream));
+    FH_TRY(upload_vec(&p->d_tiles, p->tiles, ctx->stream));
+    FH_TRY(upload_vec(&p->d_subs, p->subs, ctx->stream));
+    if (!p->pairs.empty()) {
+        FH_CUDA(cudaMallocHost(&p->h_pairs, sizeof(PairOp) * p->pairs.size()));
+        memcpy(p->h_pairs, p->pairs.data(), sizeof(PairOp) * p->pairs.size());
+    }
+    if (!p->dterms.empty()) {
+        FH_CUDA(cudaMallocHost(&p->h_dterms, sizeof(DiagTerm) * p->dterms.size()));
+        memcpy(p->h_dterms, p->dterms.data(), sizeof(DiagTerm) * p->dterms.size());
+    }
+    int n_param_ops = 0;
+    for (auto &op : p->pairs) n_param_ops += (op.kind == 1 && op.param >= 0);
+    for (auto &d : p->diagops) n_param_ops += (d.param >= 0);
+    p->n_param_ops = n_param_ops;
+    const int segs = n_param_ops > 0 ? n_param_ops : 1;
+    FH_CUDA(cudaMalloc(&p->d_gpart, sizeof(double) * (size_t)segs * FH_GRAD_BLOCKS));
+    FH_CUDA(cudaMalloc(&p->d_gseg, sizeof(double) * segs));
+    FH_CUDA(cudaMalloc(&p->d_gfirst, sizeof(int) * (segs + 1)));
+    FH_CUDA(cudaMallocHost(&p->h_gseg, sizeof(double) * segs));
+    FH_CUDA(cudaMalloc(&p->d_res, sizeof(double) * 64));
+    FH_CUDA(cudaMallocHost(&p->h_res, sizeof(double) * 64));
+    FH_CUDA(cudaStreamSynchronize(ctx->stream));
+    p->finalized = true;
+    return FH_OK;
+}
+
+extern "C" int fh_program_info(const fh_program *p, int *n_ops, int *n_launches) {
+    FH_REQUIRE(p, "fh_program_info: program is NULL");
+    if (n_ops) *n_ops = (int)(p->pairs.size() + p->diagops.size());
+    if (n_launches) *n_launches = (int)p->items.size();
+    return FH_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// theta -> payload (host, double precision), staged in pinned memory and uploaded on the stream
+// ----------------------------------------------------------------------------------------------
+static int upload_payload(fh_program *p, const double *thetas, int n_thetas) {
+    FH_REQUIRE(n_thetas == p->n_params, "program expects %d parameters, got %d", p->n_params, n_thetas);
+    FH_REQUIRE(n_thetas == 0 || thetas, "thetas is NULL");
+    fh_ctx *ctx = p->ctx;
+    for (size_t k = 0; k < p->pairs.size(); ++k) {
+        PairOp &op = p->h_pairs[k];
+        if (op.kind != 1) continue;
+        const double a = op.param >= 0 ? op.gscale * thetas[op.param] : op.gscale;
+        const double c = cos(a), s = sin(a), br = op.bhat[0], bi = op.bhat[1];
+        op.m[0] = c;       op.m[1] = 0.0;
+        op.m[2] = s * bi;  op.m[3] = -s * br;     // -i s bhat
+        op.m[4] = -s * bi; op.m[5] = -s * br;     // -i s conj(bhat)
+        op.m[6] = c;       op.m[7] = 0.0;
+    }
+    for (auto &d : p->diagops) {
+        if (d.param < 0) continue;
+        for (int m = d.first; m < d.first + d.count; ++m) {
+            DiagTerm &t = p->h_dterms[m];
+            t.angle = thetas[d.param] * t.coef;
+            t.c = cos(t.angle);
+            t.s = sin(t.angle);
+        }
+    }
+    if (!p->pairs.empty())
+        FH_CUDA(cudaMemcpyAsync(p->d_pairs, p->h_pairs, sizeof(PairOp) * p->pairs.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (!p->dterms.empty())
+        FH_CUDA(cudaMemcpyAsync(p->d_dterms, p->h_dterms, sizeof(DiagTerm) * p->dterms.size(), cudaMemcpyHostToDevice,
+                                ctx->stream));
+    return FH_OK;
+}
+
+static bool item_has_param(const fh_program *p, const Item &it) {
+    if (it.type == 1) return p->pairs[it.index].kind == 1 && p->pairs[it.index].param >= 0;
+    if (it.type == 2) return p->diagops[it.index].param >= 0;
+    const TileOp &t = p->tiles[it.index];
+    for (int s = t.first_sub; s < t.first_sub + t.nsub; ++s) {
+        const TileSub &sub = p->subs[s];
+        if (sub.type == 1 && p->pairs[sub.index].kind == 1 && p->pairs[sub.index].param >= 0) return true;
+        if (sub.type == 2 && p->diagops[sub.index].param >= 0) return true;
+    }
+    return false;
+}
+
+static void apply_item(fh_program *p, const Item &it, double2 *st, int dagger) {
+    fh_ctx *ctx = p->ctx;
+    if (it.type == 1) {
+        launch_pair(ctx->stream, ctx->sm_count, st, p->d_pairs + it.index, p->n, p->pairs[it.index].npos, dagger);
+    } else if (it.type == 2) {
+        const DiagOp &d = p->diagops[it.index];
+        launch_diag(ctx->stream, ctx->sm_count, st, p->d_dterms + d.first, d.count, p->n, dagger);
+    } else {
+        launch_tile(ctx->stream, st, p->d_tiles + it.index, p->d_subs, p->d_pairs, p->d_diagops, p->d_dterms, p->n,
+                    p->tiles[it.index].nbits, dagger, nullptr);
+    }
+}
+
+extern "C" int fh_program_run(fh_program *p, fh_state *st, const double *thetas, int n_thetas, int first, int count,
+                              int dagger) {
+    FH_REQUIRE(p && st, "fh_program_run: NULL argument");
+    FH_REQUIRE(p->finalized, "fh_program_run: program not finalized");
+    FH_REQUIRE(st->n == p->n, "fh_program_run: state has %d qubits, program %d", st->n, p->n);
+    FH_REQUIRE(first >= 0 && count >= 0 && first + count <= (int)p->items.size(), "fh_program_run: op range out of bounds");
+    FH_TRY(upload_payload(p, thetas, n_thetas));
+    for (int k = 0; k < count; ++k) {
+        const int idx = dagger ? first + count - 1 - k : first + k;
+        apply_item(p, p->items[idx], st->d, dagger);
+    }
+    FH_CUDA(cudaGetLastError());
+    FH_CUDA(cudaStreamSynchronize(p->ctx->stream));   // pinned payload may be rewritten by the next call
+    return FH_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// adjoint processing of one logical op (gradient partial + undo on psi and lam)
+// ----------------------------------------------------------------------------------------------
+static void adjoint_logical(fh_program *p, int type, int index, double2 *psi, double2 *lam, bool want_grads) {
+    fh_ctx *ctx = p->ctx;
+    int used = 0;
+    if (type == 1) {
+        const PairOp &op = p->pairs[index];
+        if (want_grads && op.kind == 1 && op.param >= 0) {
+            launch_pair_adjoint(ctx->stream, ctx->sm_count, psi, lam, p->d_pairs + index, p->n, op.npos,
+                                p->d_gpart + (size_t)p->n_segments * FH_GRAD_BLOCKS, FH_GRAD_BLOCKS, &used);
+            p->seg_param.push_back(op.param);
+            p->seg_scale.push_back(2.0 * op.gscale);
+            p->n_segments++;
+        } else {
+            launch_pair(ctx->stream, ctx->sm_count, psi, p->d_pairs + index, p->n, op.npos, 1);
+            launch_pair(ctx->stream, ctx->sm_count, lam, p->d_pairs + index, p->n, op.npos, 1);
+        }
+    } else {
+        const DiagOp &d = p->diagops[index];
+        if (want_grads && d.param >= 0) {
+            launch_diag_adjoint(ctx->stream, ctx->sm_count, psi, lam, p->d_dterms + d.first, d.count, p->n,
+                                p->d_gpart + (size_t)p->n_segments * FH_GRAD_BLOCKS, FH_GRAD_BLOCKS, &used);
+            p->seg_param.push_back(d.param);
+            p->seg_scale.push_back(2.0);
+            p->n_segments++;
+        } else {
+            launch_diag(ctx->stream, ctx->sm_count, psi, p->d_dterms + d.first, d.count, p->n, 1);
+            launch_diag(ctx->stream, ctx->sm_count, lam, p->d_dterms + d.first, d.count, p->n, 1);
+        }
+    }
+}
+
+static void adjoint_item(fh_program *p, const Item &it, double2 *psi, double2 *lam, bool want_grads) {
+    if (it.type != 3) {
+        adjoint_logical(p, it.type, it.index, psi, lam, want_grads);
+        return;
+    }
+    if (!want_grads || !item_has_param(p, it)) {
+        apply_item(p, it, psi, 1);
+        apply_item(p, it, lam, 1);
+        return;
+    }
+    const TileOp &t = p->tiles[it.index];
+    for (int s = t.first_sub + t.nsub - 1; s >= t.first_sub; --s)
+        adjoint_logical(p, p->subs[s].type, p->subs[s].index, psi, lam, want_grads);
+}
+
+// Enqueue one whole evaluation on the stream (this is what gets captured into the CUDA graph).
+// Result buffer h_res (doubles): [0, 2T) expvals re/im, [2T, 2T+2V) overlaps re/im.
+static int enqueue_evaluation(fh_program *p, const EvalKey &k, fh_table *const *tables, const fh_pool *pool,
+                              fh_state *const *targets, fh_state *state_out) {
+    fh_ctx *ctx = p->ctx;
+    const int n_items = (int)p->items.size();
+    const size_t bytes = sizeof(double2) << p->n;
+    const bool want_grads = k.want_grads != 0;
+    const bool want_pool = pool != nullptr;
+    const bool need_adjoint = want_grads || want_pool;
+    int first_param = n_items, last_param = -1;
+    for (int i = 0; i < n_items; ++i)
+        if (item_has_param(p, p->items[i])) {
+            if (i < first_param) first_param = i;
+            last_param = i;
+        }
+    // psi after items[0:chk_pos) is checkpointed so the fixed suffix is only unwound on lambda
+    int chk_pos = 0;
+    if (want_grads) chk_pos = last_param + 1;
+    if (want_pool && k.pool_pos > chk_pos) chk_pos = k.pool_pos;
+
+    if (!p->pairs.empty())
+        FH_CUDA(cudaMemcpyAsync(p->d_pairs, p->h_pairs, sizeof(PairOp) * p->pairs.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (!p->dterms.empty())
+        FH_CUDA(cudaMemcpyAsync(p->d_dterms, p->h_dterms, sizeof(DiagTerm) * p->dterms.size(), cudaMemcpyHostToDevice,
+                                ctx->stream));
+    launch_set_basis(ctx->stream, p->d_psi, 1ull << p->n, k.basis);
+    double2 *psi = p->d_psi;
+    for (int i = 0; i < n_items; ++i) {
+        if (need_adjoint && i == chk_pos)
+            FH_CUDA(cudaMemcpyAsync(p->d_chk, psi, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        apply_item(p, p->items[i], psi, 0);
+    }
+    for (int t = 0; t < k.n_tables; ++t) {
+        const fh_table *tab = tables[t];
+        launch_apply_table(ctx->stream, ctx->sm_count, tab->d_groups, tab->n_groups, tab->d_terms, (int)tab->terms.size(),
+                           tab->all_real, psi, (t == 0 && need_adjoint) ? p->d_lam : nullptr, p->n, ctx->d_partials,
+                           p->d_res + 2 * t);
+    }
+    for (int v = 0; v < k.n_overlaps; ++v)
+        launch_inner(ctx->stream, ctx->sm_count, targets[v]->d, psi, 1ull << p->n, ctx->d_partials,
+                     p->d_res + 2 * k.n_tables + 2 * v);
+    if (state_out) FH_CUDA(cudaMemcpyAsync(state_out->d, psi, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    FH_CUDA(cudaMemcpyAsync(p->h_res, p->d_res, sizeof(double) * 2 * (k.n_tables + k.n_overlaps + 1),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+
+    p->n_segments = 0;
+    p->seg_param.clear();
+    p->seg_scale.clear();
+    if (need_adjoint) {
+        double2 *lam = p->d_lam;
+        if (want_grads && p->n_param_ops > 0)
+            FH_CUDA(cudaMemsetAsync(p->d_gpart, 0, sizeof(double) * (size_t)p->n_param_ops * FH_GRAD_BLOCKS, ctx->stream));
+        for (int i = n_items - 1; i >= chk_pos; --i) apply_item(p, p->items[i], lam, 1);
+        if (chk_pos < n_items) psi = p->d_chk;
+        int stop = want_grads ? first_param : n_items;      // lowest item the sweep must undo
+        if (want_pool && k.pool_pos < stop) stop = k.pool_pos;
+        if (want_pool && k.pool_pos == chk_pos) FH_TRY(fh_enqueue_pool(pool, psi, lam, k.pool_first, k.pool_count));
+        for (int i = chk_pos - 1; i >= stop; --i) {
+            adjoint_item(p, p->items[i], psi, lam, want_grads);
+            if (want_pool && k.pool_pos == i) FH_TRY(fh_enqueue_pool(pool, psi, lam, k.pool_first, k.pool_count));
+        }
+        if (p->n_segments > 0) {
+            launch_sum_strided(ctx->stream, p->d_gpart, FH_GRAD_BLOCKS, p->n_segments, p->d_gseg);
+            FH_CUDA(cudaMemcpyAsync(p->h_gseg, p->d_gseg, sizeof(double) * p->n_segments, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (want_pool && k.pool_count > 0)
+            FH_CUDA(cudaMemcpyAsync(pool->h_out, pool->d_out + k.pool_first, sizeof(double) * k.pool_count,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    FH_CUDA(cudaGetLastError());
+    return FH_OK;
+}
+
+static int ensure_workspaces(fh_program *p) {
+    const size_t bytes = sizeof(double2) << p->n;
+    if (!p->d_psi) FH_CUDA(cudaMalloc(&p->d_psi, bytes));
+    if (!p->d_lam) FH_CUDA(cudaMalloc(&p->d_lam, bytes));
+    if (!p->d_chk) FH_CUDA(cudaMalloc(&p->d_chk, bytes));
+    return FH_OK;
+}
+
+extern "C" int fh_program_evaluate(fh_program *p, uint64_t basis_index, const double *thetas, int n_thetas, int n_tables,
+                                   fh_table *const *tables, double *expvals, double *grads, const fh_pool *pool,
+                                   int pool_pos, int pool_first, int pool_count, double *pool_out, int n_overlaps,
+                                   fh_state *const *targets, double *overlaps, fh_state *state_out) {
+    FH_REQUIRE(p, "fh_program_evaluate: program is NULL");
+    FH_REQUIRE(p->finalized, "fh_program_evaluate: program not finalized");
+    FH_REQUIRE(n_thetas == p->n_params && (n_thetas == 0 || thetas), "fh_program_evaluate: expected %d parameters, got %d",
+               p->n_params, n_thetas);
+    FH_REQUIRE(n_tables >= 1 && n_tables <= FH_MAX_RESULT_TABLES && tables && expvals,
+               "fh_program_evaluate: need 1..%d observable tables", FH_MAX_RESULT_TABLES);
+    FH_REQUIRE(n_overlaps >= 0 && n_overlaps <= FH_MAX_OVERLAPS, "fh_program_evaluate: at most %d overlap targets", FH_MAX_OVERLAPS);
+    FH_REQUIRE(n_overlaps == 0 || (targets && overlaps), "fh_program_evaluate: NULL overlap arrays");
+    FH_REQUIRE(basis_index < (1ull << p->n), "fh_program_evaluate: basis index out of range");
+    for (int t = 0; t < n_tables; ++t)
+        FH_REQUIRE(tables[t] && tables[t]->n == p->n, "fh_program_evaluate: table %d missing or wrong qubit count", t);
+    for (int v = 0; v < n_overlaps; ++v)
+        FH_REQUIRE(targets[v] && targets[v]->n == p->n, "fh_program_evaluate: target %d missing or wrong qubit count", v);
+    FH_REQUIRE(!state_out || state_out->n == p->n, "fh_program_evaluate: state_out has wrong qubit count");
+    if (pool) {
+        FH_REQUIRE(pool->n == p->n && pool_out, "fh_program_evaluate: pool mismatch or pool_out NULL");
+        FH_REQUIRE(pool_pos >= 0 && pool_pos <= (int)p->items.size(), "fh_program_evaluate: pool_pos out of range");
+        FH_REQUIRE(pool_first >= 0 && pool_count >= 0 && pool_first + pool_count <= pool->n_out,
+                   "fh_program_evaluate: pool range out of bounds");
+    }
+    fh_ctx *ctx = p->ctx;
+    FH_CUDA(cudaSetDevice(ctx->device));
+    FH_TRY(ensure_workspaces(p));
+
+    // theta -> payload in the pinned staging buffers (the graph's first nodes copy them to the device)
+    for (size_t k = 0; k < p->pairs.size(); ++k) {
+        PairOp &op = p->h_pairs[k];
+        if (op.kind != 1) continue;
+        const double a = op.param >= 0 ? op.gscale * thetas[op.param] : op.gscale;
+        const double c = cos(a), s = sin(a), br = op.bhat[0], bi = op.bhat[1];
+        op.m[0] = c;       op.m[1] = 0.0;
+        op.m[2] = s * bi;  op.m[3] = -s * br;
+        op.m[4] = -s * bi; op.m[5] = -s * br;
+        op.m[6] = c;       op.m[7] = 0.0;
+    }
+    for (auto &d : p->diagops) {
+        if (d.param < 0) continue;
+        for (int m = d.first; m < d.first + d.count; ++m) {
+            DiagTerm &t = p->h_dterms[m];
+            t.angle = thetas[d.param] * t.coef;
+            t.c = cos(t.angle);
+            t.s = sin(t.angle);
+        }
+    }
+
+    EvalKey key;
+    memset(&key, 0, sizeof(key));
+    key.basis = basis_index;
+    key.n_tables = n_tables;
+    key.n_overlaps = n_overlaps;
+    key.want_grads = grads != nullptr;
+    for (int t = 0; t < n_tables; ++t) key.tables[t] = tables[t];
+    for (int v = 0; v < n_overlaps; ++v) key.targets[v] = targets[v];
+    key.pool = pool;
+    key.pool_pos = pool ? pool_pos : 0;
+    key.pool_first = pool ? pool_first : 0;
+    key.pool_count = pool ? pool_count : 0;
+    key.state_out = state_out;
+
+    static const bool no_graph = getenv("FHSIM_NO_GRAPH") != nullptr;
+    if (no_graph) {
+        FH_TRY(enqueue_evaluation(p, key, tables, pool, targets, state_out));
+    } else {
+        if (!p->have_graph || !(p->key == key)) {
+            drop_graph(p);
+            FH_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = enqueue_evaluation(p, key, tables, pool, targets, state_out);
+            cudaGraph_t g = nullptr;
+            const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+            if (rc != FH_OK) {
+                if (g) cudaGraphDestroy(g);
+                return rc;
+            }
+            if (e != cudaSuccess) {
+                fh_set_error("fh_program_evaluate: stream capture failed: %s", cudaGetErrorString(e));
+                return FH_ECUDA;
+            }
+            p->graph = g;
+            FH_CUDA(cudaGraphInstantiate(&p->exec, p->graph, 0));
+            p->key = key;
+            p->have_graph = true;
+        }
+        FH_CUDA(cudaGraphLaunch(p->exec, ctx->stream));
+    }
+    FH_CUDA(cudaStreamSynchronize(ctx->stream));
+
+    for (int t = 0; t < n_tables; ++t) expvals[t] = p->h_res[2 * t];
+    for (int v = 0; v < 2 * n_overlaps; ++v) overlaps[v] = p->h_res[2 * n_tables + v];
+    if (grads) {
+        for (int q = 0; q < p->n_params; ++q) grads[q] = 0.0;
+        for (int s = 0; s < p->n_segments; ++s) grads[p->seg_param[s]] += p->seg_scale[s] * p->h_gseg[s];
+    }
+    if (pool && pool_count > 0) memcpy(pool_out, pool->h_out, sizeof(double) * pool_count);
+    return FH_OK;
+}

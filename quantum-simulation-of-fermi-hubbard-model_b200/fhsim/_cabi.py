@@ -1,0 +1,120 @@
+"""ctypes binding to ``libfhsim.so`` (the C-ABI declared in ``include/fhsim.h``).
+
+There is no CPU fallback: if the shared library is missing this module raises at import of
+:func:`lib`, and every compute call raises when no CUDA device is present (FH_ECUDA).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfhsim.so")
+
+FH_OK, FH_EINVAL, FH_ECUDA, FH_ENOMEM, FH_ESTATE = 0, -1, -2, -3, -4
+
+_u64p = C.POINTER(C.c_uint64)
+_f64p = C.POINTER(C.c_double)
+_i32p = C.POINTER(C.c_int32)
+_vp = C.c_void_p
+_vpp = C.POINTER(C.c_void_p)
+
+# name -> (argtypes); every function returns int unless listed in _SPECIAL
+SIGNATURES = {
+    "fh_ctx_create": [C.c_int, _vp, _vpp],
+    "fh_ctx_destroy": [_vp],
+    "fh_ctx_sync": [_vp],
+    "fh_ctx_info": [_vp, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)],
+    "fh_ctx_flush_l2": [_vp, C.c_size_t],
+    "fh_state_create": [_vp, C.c_int, _vpp],
+    "fh_state_wrap": [_vp, C.c_int, _vp, _vpp],
+    "fh_state_destroy": [_vp],
+    "fh_state_set_basis": [_vp, C.c_uint64],
+    "fh_state_copy": [_vp, _vp],
+    "fh_state_to_host": [_vp, _f64p],
+    "fh_state_from_host": [_vp, _f64p],
+    "fh_state_device_ptr": [_vp, _vpp],
+    "fh_state_inner": [_vp, _vp, _f64p, _f64p],
+    "fh_state_norm2": [_vp, _f64p],
+    "fh_apply_pair": [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _f64p],
+    "fh_apply_diag": [_vp, C.c_int, _u64p, _f64p],
+    "fh_apply_pauli_rot_batch": [_vp, C.c_int, _u64p, _u64p, _f64p],
+    "fh_table_upload": [_vp, C.c_int, C.c_int, _u64p, _u64p, _f64p, _f64p, _vpp],
+    "fh_table_free": [_vp],
+    "fh_table_info": [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "fh_apply_table": [_vp, _vp, _vp, _f64p, _f64p],
+    "fh_pool_upload": [_vp, C.c_int, C.c_int, _u64p, _u64p, _u64p, _u64p, _f64p, _f64p, _i32p, C.c_int, _vpp],
+    "fh_pool_free": [_vp],
+    "fh_pool_gradients": [_vp, _vp, _vp, C.c_int, C.c_int, _f64p],
+    "fh_program_create": [_vp, C.c_int, C.c_int, _vpp],
+    "fh_program_destroy": [_vp],
+    "fh_program_add_pair": [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_double,
+                            C.c_double, C.c_double, _f64p],
+    "fh_program_add_diag": [_vp, C.c_int, _u64p, _f64p, C.c_int],
+    "fh_program_begin_tile": [_vp, C.c_int, _i32p],
+    "fh_program_end_tile": [_vp],
+    "fh_program_finalize": [_vp],
+    "fh_program_info": [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "fh_program_run": [_vp, _vp, _f64p, C.c_int, C.c_int, C.c_int, C.c_int],
+    "fh_program_evaluate": [_vp, C.c_uint64, _f64p, C.c_int, C.c_int, _vpp, _f64p, _f64p, _vp, C.c_int, C.c_int,
+                            C.c_int, _f64p, C.c_int, _vpp, _f64p, _vp],
+    "fh_lanczos": [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint64, _f64p, _vpp, C.POINTER(C.c_int)],
+}
+_SPECIAL = {"fh_version": ([], C.c_int), "fh_last_error": ([], C.c_char_p)}
+
+_lib = None
+
+
+class FhsimError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libfhsim.so once; fail loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FhsimError(
+                f"{LIB_PATH} not found: build it with `make -C quantum-simulation-of-fermi-hubbard-model_b200/csrc` "
+                "(or __graft_entry__.build()).  fhsim has no CPU fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        for name, (argtypes, restype) in _SPECIAL.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = restype
+        _lib = handle
+    return _lib
+
+
+def check(rc: int):
+    """Map a status code to the exception the reference's Python API would raise."""
+    if rc == FH_OK:
+        return
+    msg = lib().fh_last_error().decode("utf-8", "replace")
+    if rc == FH_EINVAL:
+        raise ValueError(msg)
+    if rc == FH_ENOMEM:
+        raise MemoryError(msg)
+    raise FhsimError(msg)
+
+
+def u64_array(values):
+    import numpy as np
+    a = np.ascontiguousarray(values, dtype=np.uint64)
+    return a, a.ctypes.data_as(_u64p)
+
+
+def f64_array(values):
+    import numpy as np
+    a = np.ascontiguousarray(values, dtype=np.float64)
+    return a, a.ctypes.data_as(_f64p)
+
+
+def i32_array(values):
+    import numpy as np
+    a = np.ascontiguousarray(values, dtype=np.int32)
+    return a, a.ctypes.data_as(_i32p)

@@ -1,0 +1,225 @@
+"""Thin object wrappers over the C-ABI handles (context, state, observable table, pool).
+
+PyTorch / numpy arrays are only the host-side buffer types here; all statevector arithmetic
+happens inside ``libfhsim.so``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _cabi
+from .tables import DiagPiece, GeneratorPlan, PauliTable
+
+C = _cabi.C
+
+
+class Context:
+    """One CUDA device + stream (replaces ``qml.device(...)``, reference adapt_vqe.py:299-304)."""
+
+    def __init__(self, device: int = 0, stream=None):
+        self._h = _cabi._vp()
+        _cabi.check(_cabi.lib().fh_ctx_create(int(device), stream, C.byref(self._h)))
+        self.device = int(device)
+
+    def sync(self):
+        _cabi.check(_cabi.lib().fh_ctx_sync(self._h))
+
+    def info(self):
+        sm, free, total = C.c_int(), C.c_size_t(), C.c_size_t()
+        _cabi.check(_cabi.lib().fh_ctx_info(self._h, C.byref(sm), C.byref(free), C.byref(total)))
+        return {"sm_count": sm.value, "free_bytes": free.value, "total_bytes": total.value}
+
+    def flush_l2(self, nbytes=256 << 20):
+        _cabi.check(_cabi.lib().fh_ctx_flush_l2(self._h, int(nbytes)))
+
+    def close(self):
+        if self._h:
+            _cabi.lib().fh_ctx_destroy(self._h)
+            self._h = _cabi._vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_DEFAULT_CTX = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _DEFAULT_CTX:
+        _DEFAULT_CTX[device] = Context(device)
+    return _DEFAULT_CTX[device]
+
+
+class State:
+    """complex128[2^n] on the device."""
+
+    def __init__(self, ctx: Context, n_qubits: int):
+        self.ctx, self.n = ctx, int(n_qubits)
+        self._h = _cabi._vp()
+        _cabi.check(_cabi.lib().fh_state_create(ctx._h, self.n, C.byref(self._h)))
+
+    @classmethod
+    def from_numpy(cls, ctx, vec):
+        vec = np.ascontiguousarray(vec, dtype=np.complex128)
+        n = int(np.log2(vec.size))
+        if 1 << n != vec.size:
+            raise ValueError("state length must be a power of two")
+        st = cls(ctx, n)
+        st.upload(vec)
+        return st
+
+    def upload(self, vec):
+        vec = np.ascontiguousarray(vec, dtype=np.complex128)
+        if vec.size != 1 << self.n:
+            raise ValueError(f"expected {1 << self.n} amplitudes, got {vec.size}")
+        _cabi.check(_cabi.lib().fh_state_from_host(self._h, vec.view(np.float64).ctypes.data_as(_cabi._f64p)))
+
+    def numpy(self):
+        out = np.empty(1 << self.n, dtype=np.complex128)
+        _cabi.check(_cabi.lib().fh_state_to_host(self._h, out.view(np.float64).ctypes.data_as(_cabi._f64p)))
+        return out
+
+    def set_basis(self, index: int):
+        _cabi.check(_cabi.lib().fh_state_set_basis(self._h, int(index)))
+
+    def copy_from(self, other: "State"):
+        _cabi.check(_cabi.lib().fh_state_copy(self._h, other._h))
+
+    def inner(self, other: "State") -> complex:
+        """<self|other>."""
+        re, im = C.c_double(), C.c_double()
+        _cabi.check(_cabi.lib().fh_state_inner(self._h, other._h, C.byref(re), C.byref(im)))
+        return complex(re.value, im.value)
+
+    def norm2(self) -> float:
+        out = C.c_double()
+        _cabi.check(_cabi.lib().fh_state_norm2(self._h, C.byref(out)))
+        return out.value
+
+    # immediate-mode ops ------------------------------------------------------------------------
+    def apply_pair(self, x, fixmask, fixval, zeta, matrix):
+        ma, mp = _cabi.f64_array(matrix)
+        _cabi.check(_cabi.lib().fh_apply_pair(self._h, int(x), int(fixmask), int(fixval), int(zeta), mp))
+
+    def apply_diag(self, z, angles):
+        za, zp = _cabi.u64_array(z)
+        aa, ap = _cabi.f64_array(angles)
+        _cabi.check(_cabi.lib().fh_apply_diag(self._h, len(za), zp, ap))
+
+    def apply_pauli_rotations(self, x, z, half_angles):
+        """prod_m exp(-i half_angles[m] P_m), in order (literal Trotterize_generator)."""
+        xa, xp = _cabi.u64_array(x)
+        za, zp = _cabi.u64_array(z)
+        aa, ap = _cabi.f64_array(half_angles)
+        _cabi.check(_cabi.lib().fh_apply_pauli_rot_batch(self._h, len(xa), xp, zp, ap))
+
+    def close(self):
+        if self._h:
+            _cabi.lib().fh_state_destroy(self._h)
+            self._h = _cabi._vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceTable:
+    """Observable uploaded to the device (K2)."""
+
+    def __init__(self, ctx: Context, table: PauliTable):
+        self.ctx, self.table, self.n = ctx, table, table.n_qubits
+        self._h = _cabi._vp()
+        xa, xp = _cabi.u64_array(table.x)
+        za, zp = _cabi.u64_array(table.z)
+        ra, rp = _cabi.f64_array(table.coeff.real)
+        ia, ip = _cabi.f64_array(table.coeff.imag)
+        _cabi.check(_cabi.lib().fh_table_upload(ctx._h, self.n, len(table), xp, zp, rp, ip, C.byref(self._h)))
+
+    def info(self):
+        nt, ng = C.c_int(), C.c_int()
+        _cabi.check(_cabi.lib().fh_table_info(self._h, C.byref(nt), C.byref(ng)))
+        return {"n_terms": nt.value, "n_groups": ng.value}
+
+    def apply(self, state: State, out: State | None = None) -> complex:
+        """out <- H state (optional); returns <state|H|state>."""
+        re, im = C.c_double(), C.c_double()
+        _cabi.check(_cabi.lib().fh_apply_table(self._h, state._h, out._h if out is not None else None,
+                                                C.byref(re), C.byref(im)))
+        return complex(re.value, im.value)
+
+    def expval(self, state: State) -> float:
+        return self.apply(state).real
+
+    def close(self):
+        if self._h:
+            _cabi.lib().fh_table_free(self._h)
+            self._h = _cabi._vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DevicePool:
+    """Screening pool (K3): one output per generator, entries = its x-mask pair pieces."""
+
+    def __init__(self, ctx: Context, plans: list[GeneratorPlan], n_qubits: int):
+        self.ctx, self.n, self.n_out = ctx, int(n_qubits), len(plans)
+        x, fm, fv, ze, br, bi, out = [], [], [], [], [], [], []
+        for k, plan in enumerate(plans):
+            if not plan.exact:
+                raise NotImplementedError("pool generators must consist of mutually commuting strings")
+            for piece in plan.pieces:
+                if isinstance(piece, DiagPiece):
+                    raise NotImplementedError("diagonal pool generators are not supported by the screening kernel")
+                x.append(piece.x); fm.append(piece.fixmask); fv.append(piece.fixval); ze.append(piece.zeta)
+                br.append(piece.b.real); bi.append(piece.b.imag); out.append(k)
+        self.n_entries = len(x)
+        self._h = _cabi._vp()
+        xa, xp = _cabi.u64_array(x)
+        fa, fp = _cabi.u64_array(fm)
+        va, vp = _cabi.u64_array(fv)
+        za, zp = _cabi.u64_array(ze)
+        ra, rp = _cabi.f64_array(br)
+        ia, ip = _cabi.f64_array(bi)
+        oa, op = _cabi.i32_array(out)
+        _cabi.check(_cabi.lib().fh_pool_upload(ctx._h, self.n, self.n_entries, xp, fp, vp, zp, rp, ip, op, self.n_out,
+                                               C.byref(self._h)))
+
+    def gradients(self, psi: State, lam: State, first=0, count=None) -> np.ndarray:
+        if count is None:
+            count = self.n_out - first
+        out = np.zeros(max(count, 1))
+        _cabi.check(_cabi.lib().fh_pool_gradients(self._h, psi._h, lam._h, int(first), int(count),
+                                                  out.ctypes.data_as(_cabi._f64p)))
+        return out[:count]
+
+    def close(self):
+        if self._h:
+            _cabi.lib().fh_pool_free(self._h)
+            self._h = _cabi._vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def lanczos(table: DeviceTable, k=1, n_up=-1, n_dn=-1, tol=1e-10, max_iter=1000, seed=7, want_vectors=True):
+    """k lowest eigenpairs of the observable in the (n_up, n_dn) sector (-1, -1: full space)."""
+    ctx = table.ctx
+    evals = np.zeros(k)
+    vecs = [State(ctx, table.n) for _ in range(k)] if want_vectors else []
+    arr = (C.c_void_p * max(k, 1))(*[v._h for v in vecs]) if want_vectors else None
+    iters = C.c_int()
+    _cabi.check(_cabi.lib().fh_lanczos(table._h, int(n_up), int(n_dn), int(k), float(tol), int(max_iter), int(seed),
+                                       evals.ctypes.data_as(_cabi._f64p), arr, C.byref(iters)))
+    return evals, vecs, iters.value

@@ -1,0 +1,380 @@
+"""Circuit description on the host and its compilation into a device program.
+
+A :class:`Circuit` is the ordered op list the reference builds by calling ``qml.*`` inside
+``circuit()`` (``models/adapt_vqe.py:325-361``, ``hva.py:273-303``, ``iqcc_hubbard.py:59-80``,
+``vqe_hea.py:43-57``), but already lowered to the two device op kinds:
+
+* pair op  -- a 2x2 block on index pairs (i, i^x) selected by a bit pattern, with a parity sign;
+* diag op  -- a phase exp(-i sum_m a_m (-1)^popcount(i & z_m)).
+
+``compile`` schedules runs of ops into shared-memory tiles (one global read+write per run) and hands
+the result to ``libfhsim`` through the C-ABI.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _cabi
+from .tables import DiagPiece, GeneratorPlan, PairPiece, popcount, qubit_bit, strings_commute
+
+_X = (0.0, 0.0, 1.0, 0.0, 1.0, 0.0, 0.0, 0.0)      # [[0,1],[1,0]] as re/im pairs
+
+
+@dataclass
+class PairOpSpec:
+    x: int
+    fixmask: int
+    fixval: int
+    zeta: int
+    kind: int = 0                 # 0 fixed matrix, 1 rotation exp(-i scale*theta Ghat)
+    param: int = -1
+    scale: float = 0.0
+    bhat: complex = 1.0
+    matrix: tuple = _X
+    strings: list = field(default_factory=list)
+
+    @property
+    def tile_bits(self):
+        return self.x
+
+
+@dataclass
+class DiagOpSpec:
+    z: list
+    coef: list
+    param: int = -1
+    strings: list = field(default_factory=list)
+
+    @property
+    def tile_bits(self):
+        return 0
+
+
+@dataclass
+class Marker:
+    name: str
+
+
+def _ops_commute(a, b) -> bool:
+    for s in a.strings:
+        for t in b.strings:
+            if not strings_commute(s, t):
+                return False
+    return True
+
+
+def _normalise_pair(x, fixmask, fixval, zeta, m):
+    """Make the pattern side the one whose top x bit is 0 (swap roles if needed)."""
+    top = 1 << (x.bit_length() - 1)
+    fixmask |= top
+    if fixval & top:
+        s = -1.0 if popcount(x & zeta) & 1 else 1.0
+        fixval = (fixval ^ x) & fixmask
+        m00, m01, m10, m11 = [complex(m[2 * i], m[2 * i + 1]) for i in range(4)]
+        m00, m01, m10, m11 = m11, s * m10, s * m01, m00
+        m = (m00.real, m00.imag, m01.real, m01.imag, m10.real, m10.imag, m11.real, m11.imag)
+    return x, fixmask, fixval, zeta, tuple(m)
+
+
+class Circuit:
+    """Ordered list of device-level ops over ``n_qubits`` with ``n_params`` real parameters."""
+
+    def __init__(self, n_qubits: int, n_params: int = 0):
+        self.n = int(n_qubits)
+        self.n_params = int(n_params)
+        self.ops = []
+
+    # -- elementary gates (PennyLane conventions, wire 0 = MSB) ---------------------------------
+    def _bit(self, wire):
+        if not 0 <= wire < self.n:
+            raise ValueError(f"wire {wire} outside a {self.n}-qubit register")
+        return qubit_bit(wire, self.n)
+
+    def marker(self, name):
+        self.ops.append(Marker(name))
+
+    def pauli_x(self, wire):
+        b = self._bit(wire)
+        self.ops.append(PairOpSpec(b, b, 0, 0, matrix=_X, strings=[(b, 0)]))
+
+    def cnot(self, control, target):
+        c, t = self._bit(control), self._bit(target)
+        self.ops.append(PairOpSpec(t, t | c, c, 0, matrix=_X, strings=[(t, 0), (0, c)]))
+
+    def rz(self, angle, wire, param=-1, coef=0.5):
+        """exp(-i angle Z/2); with ``param >= 0`` the angle is theta[param] (coef = 1/2)."""
+        b = self._bit(wire)
+        if param >= 0:
+            self.ops.append(DiagOpSpec([b], [coef], param, [(0, b)]))
+        else:
+            self.ops.append(DiagOpSpec([b], [0.5 * float(angle)], -1, [(0, b)]))
+
+    def _rot_1q(self, wire, letter, angle, param):
+        b = self._bit(wire)
+        z = b if letter == "Y" else 0
+        bhat = -1j if letter == "Y" else 1.0
+        if param >= 0:
+            self.ops.append(PairOpSpec(b, b, 0, 0, kind=1, param=param, scale=0.5, bhat=bhat, strings=[(b, z)]))
+        else:
+            c, s = math.cos(0.5 * angle), math.sin(0.5 * angle)
+            m01, m10 = -1j * s * bhat, -1j * s * np.conj(bhat)
+            m = (c, 0.0, m01.real, m01.imag, m10.real, m10.imag, c, 0.0)
+            self.ops.append(PairOpSpec(b, b, 0, 0, matrix=m, strings=[(b, z)]))
+
+    def rx(self, angle, wire, param=-1):
+        self._rot_1q(wire, "X", angle, param)
+
+    def ry(self, angle, wire, param=-1):
+        self._rot_1q(wire, "Y", angle, param)
+
+    def single_excitation(self, phi, wire_i, wire_j):
+        """qml.SingleExcitation(phi, [i, j]): |01> -> c|01> + s|10>, |10> -> -s|01> + c|10>."""
+        bi, bj = self._bit(wire_i), self._bit(wire_j)
+        c, s = math.cos(0.5 * phi), math.sin(0.5 * phi)
+        x = bi | bj
+        # pattern side |q_i q_j> = |01> : q_j set, q_i clear
+        m = (c, 0.0, -s, 0.0, s, 0.0, c, 0.0)
+        x, fixmask, fixval, zeta, m = _normalise_pair(x, x, bj, 0, m)
+        self.ops.append(PairOpSpec(x, fixmask, fixval, zeta, matrix=m, strings=[(x, bi), (x, bj)]))
+
+    def pauli_rotation(self, x, z, coef, angle=0.0, param=-1):
+        """exp(-i a coef P) with a = theta[param] (or the fixed ``angle``) for one string (x, z)."""
+        if x == 0:
+            if z == 0:
+                return
+            if param >= 0:
+                self.ops.append(DiagOpSpec([z], [coef], param, [(0, z)]))
+            else:
+                self.ops.append(DiagOpSpec([z], [coef * angle], -1, [(0, z)]))
+            return
+        k = popcount(x & z)
+        b = (1, 1j, -1, -1j)[k & 3] * (-1) ** k
+        top = 1 << (x.bit_length() - 1)
+        sgn = 1.0 if coef >= 0 else -1.0
+        if param >= 0:
+            self.ops.append(PairOpSpec(x, top, 0, z, kind=1, param=param, scale=abs(coef), bhat=b * sgn, strings=[(x, z)]))
+        else:
+            a = coef * angle
+            c, s = math.cos(a), math.sin(a)
+            m01, m10 = -1j * s * b, -1j * s * np.conj(b)
+            m = (c, 0.0, m01.real, m01.imag, m10.real, m10.imag, c, 0.0)
+            self.ops.append(PairOpSpec(x, top, 0, z, matrix=m, strings=[(x, z)]))
+
+    # -- generators -------------------------------------------------------------------------
+    def generator(self, plan: GeneratorPlan, param=-1, angle=0.0):
+        """exp(-i theta G): theta = theta[param] or the fixed ``angle`` (Trotterize_generator)."""
+        for piece in plan.pieces:
+            if isinstance(piece, DiagPiece):
+                if param >= 0:
+                    self.ops.append(DiagOpSpec(list(piece.z), list(piece.coef), param, piece.strings))
+                else:
+                    self.ops.append(DiagOpSpec(list(piece.z), [c * angle for c in piece.coef], -1, piece.strings))
+                continue
+            r = abs(piece.b)
+            bhat = piece.b / r
+            if param >= 0:
+                self.ops.append(PairOpSpec(piece.x, piece.fixmask, piece.fixval, piece.zeta, kind=1, param=param,
+                                           scale=r, bhat=bhat, strings=piece.strings))
+            else:
+                a = r * angle
+                c, s = math.cos(a), math.sin(a)
+                m01, m10 = -1j * s * bhat, -1j * s * np.conj(bhat)
+                m = (c, 0.0, m01.real, m01.imag, m10.real, m10.imag, c, 0.0)
+                self.ops.append(PairOpSpec(piece.x, piece.fixmask, piece.fixval, piece.zeta, matrix=m,
+                                           strings=piece.strings))
+
+    def basis_change(self, diagonal, circuit_description):
+        """The W network of reference adapt_vqe.py:344-354: RZ(angle(diagonal[q])) on every wire, then for
+        each layer (already reversed by the caller) SingleExcitation(2 theta, [i, j]) and RZ(phi, j)."""
+        for q in range(len(diagonal)):
+            a = float(np.angle(diagonal[q]))
+            if a != 0.0:
+                self.rz(a, q)
+        for layer in circuit_description:
+            for op in layer:
+                i, j, theta, phi = op
+                self.single_excitation(2.0 * theta, i, j)
+                if phi != 0.0:
+                    self.rz(phi, j)
+
+    # -- compilation ------------------------------------------------------------------------
+    def compile(self, ctx, fuse=True, tile_bits=None, low_bits=None):
+        return DeviceProgram(ctx, self, fuse=fuse, tile_bits=tile_bits, low_bits=low_bits)
+
+
+# ---------------------------------------------------------------------------------------------
+# tile scheduling
+# ---------------------------------------------------------------------------------------------
+_LAUNCH_BYTES = 12e6          # bytes of traffic one kernel launch is "worth" (launch latency x bandwidth)
+
+
+def _op_bytes(op, n):
+    if isinstance(op, DiagOpSpec):
+        return 32.0 * 2 ** n
+    return 64.0 * 2 ** (n - popcount(op.fixmask))
+
+
+def schedule(ops, n, tile_bits, low_bits, lookahead=512):
+    """Greedy in-order packing of commuting-compatible ops into tiles.
+
+    Returns a list of launch items: ('tile', [bit positions], [ops]) or ('op', op).  An op may jump
+    ahead of skipped ops only if it commutes with every one of them (string-level check).
+    """
+    items = []
+    remaining = list(ops)
+    base_bits = (1 << low_bits) - 1
+    while remaining:
+        bits = base_bits
+        chosen, skipped = [], []
+        scanned = 0
+        for op in remaining:
+            scanned += 1
+            if skipped and any(not _ops_commute(op, s) for s in skipped):
+                skipped.append(op)
+            else:
+                need = bits | op.tile_bits
+                if popcount(need) <= tile_bits:
+                    bits = need
+                    chosen.append(op)
+                else:
+                    skipped.append(op)
+            if len(skipped) >= lookahead:
+                break
+        rest = skipped + remaining[scanned:]
+        if not chosen:                                   # cannot happen (first op always fits) but stay safe
+            items.append(("op", remaining[0]))
+            remaining = remaining[1:]
+            continue
+        alone = sum(_op_bytes(o, n) + _LAUNCH_BYTES for o in chosen)
+        fused = 32.0 * 2 ** n + _LAUNCH_BYTES
+        if len(chosen) == 1 or fused >= alone:
+            # keep program order: only the leading run of chosen ops is emitted unfused
+            items.extend(("op", o) for o in chosen)
+        else:
+            # pad the tile with the lowest free bits so global accesses stay wide
+            b = 0
+            while popcount(bits) < min(tile_bits, n):
+                if not bits >> b & 1:
+                    bits |= 1 << b
+                b += 1
+            items.append(("tile", [p for p in range(n) if bits >> p & 1], chosen))
+        remaining = rest
+    return items
+
+
+class DeviceProgram:
+    """A finalized ``fh_program`` plus the bookkeeping to call ``fh_program_evaluate``."""
+
+    def __init__(self, ctx, circuit: Circuit, fuse=True, tile_bits=None, low_bits=None):
+        self.ctx = ctx
+        self.n = circuit.n
+        self.n_params = circuit.n_params
+        self.markers = {}
+        self._h = _cabi._vp()
+        L = _cabi.lib()
+        _cabi.check(L.fh_program_create(ctx._h, self.n, self.n_params, _cabi.C.byref(self._h)))
+        n = self.n
+        if tile_bits is None:
+            tile_bits = max(1, min(12, n - 7)) if n > 8 else n
+        tile_bits = min(tile_bits, n, 13)
+        if low_bits is None:
+            low_bits = 1 if n <= 20 else 2
+        low_bits = min(low_bits, tile_bits)
+        self.tile_bits, self.low_bits = tile_bits, low_bits
+        self.n_items = 0
+        self.n_tiles = 0
+        segment = []
+        for op in circuit.ops + [Marker("__end__")]:
+            if isinstance(op, Marker):
+                self._emit_segment(segment, fuse)
+                segment = []
+                self.markers[op.name] = self.n_items
+            else:
+                segment.append(op)
+        _cabi.check(L.fh_program_finalize(self._h))
+
+    def _emit_segment(self, ops, fuse):
+        if not ops:
+            return
+        L = _cabi.lib()
+        if fuse:
+            items = schedule(ops, self.n, self.tile_bits, self.low_bits)
+        else:
+            items = [("op", o) for o in ops]
+        for item in items:
+            if item[0] == "op":
+                self._add_op(item[1])
+            else:
+                _, bits, chosen = item
+                arr, ptr = _cabi.i32_array(bits)
+                _cabi.check(L.fh_program_begin_tile(self._h, len(bits), ptr))
+                for o in chosen:
+                    self._add_op(o)
+                _cabi.check(L.fh_program_end_tile(self._h))
+                self.n_tiles += 1
+            self.n_items += 1
+
+    def _add_op(self, op):
+        L = _cabi.lib()
+        if isinstance(op, DiagOpSpec):
+            za, zp = _cabi.u64_array(op.z)
+            ca, cp = _cabi.f64_array(op.coef)
+            _cabi.check(L.fh_program_add_diag(self._h, len(op.z), zp, cp, op.param))
+        else:
+            ma, mp = _cabi.f64_array(op.matrix)
+            b = complex(op.bhat)
+            _cabi.check(L.fh_program_add_pair(self._h, op.x, op.fixmask, op.fixval, op.zeta, op.kind, op.param,
+                                              float(op.scale), b.real, b.imag, mp))
+
+    def close(self):
+        if self._h:
+            _cabi.lib().fh_program_destroy(self._h)
+            self._h = _cabi._vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, state, thetas=(), first=0, count=None, dagger=False):
+        """Apply launch items [first, first+count) to ``state`` in place."""
+        if count is None:
+            count = self.n_items - first
+        ta, tp = _cabi.f64_array(thetas)
+        _cabi.check(_cabi.lib().fh_program_run(self._h, state._h, tp, len(ta), first, count, int(dagger)))
+
+    def evaluate(self, basis_index, thetas, tables, grads=False, pool=None, pool_pos=0, pool_range=None,
+                 targets=(), state_out=None):
+        """One fused evaluation; returns dict(expvals, grads, pool, overlaps)."""
+        C = _cabi.C
+        ta, tp = _cabi.f64_array(thetas)
+        nt = len(tables)
+        tab_arr = (C.c_void_p * nt)(*[t._h for t in tables])
+        expvals = np.zeros(nt)
+        g = np.zeros(max(self.n_params, 1)) if grads else None
+        nv = len(targets)
+        tgt_arr = (C.c_void_p * max(nv, 1))(*[t._h for t in targets])
+        ov = np.zeros(2 * max(nv, 1))
+        if pool is not None:
+            first, count = pool_range if pool_range is not None else (0, pool.n_out)
+            pout = np.zeros(max(count, 1))
+        else:
+            first = count = 0
+            pout = None
+        _cabi.check(_cabi.lib().fh_program_evaluate(
+            self._h, int(basis_index), tp, len(ta), nt, tab_arr, expvals.ctypes.data_as(_cabi._f64p),
+            g.ctypes.data_as(_cabi._f64p) if grads else None,
+            pool._h if pool is not None else None, int(pool_pos), int(first), int(count),
+            pout.ctypes.data_as(_cabi._f64p) if pool is not None else None,
+            nv, tgt_arr, ov.ctypes.data_as(_cabi._f64p),
+            state_out._h if state_out is not None else None))
+        return {
+            "expvals": expvals,
+            "grads": g[:self.n_params] if grads else None,
+            "pool": pout[:count] if pool is not None else None,
+            "overlaps": (ov[0:2 * nv:2] + 1j * ov[1:2 * nv:2]) if nv else np.zeros(0, complex),
+        }

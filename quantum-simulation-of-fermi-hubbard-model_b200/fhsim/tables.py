@@ -1,0 +1,206 @@
+"""Host compile step: symbolic operators -> packed Pauli tables and pair/diagonal op plans.
+
+"The Jordan-Wigner Hamiltonian and operator pool are compiled once on the host into packed
+Pauli-term tables (x-mask, z-mask, phase, coefficient)".  This replaces
+``QubitOperator_to_qmlHamiltonian`` (reference ``models/utils.py:30-56``) for observables and the
+per-string gate expansion of ``Trotterize_generator`` / ``PauliStringRotation``
+(``models/adapt_vqe.py:87-98``, ``models/utils.py:58-83``) for generators.
+
+Bit convention: qubit/wire q <-> bit (n-1-q).  String (x, z) = i^k X^x Z^z, k = popcount(x&z).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .symbolic import FermionOperator, QubitOperator, jordan_wigner
+
+_I_POW = (1, 1j, -1, -1j)
+_TOL = 1e-12
+
+
+def popcount(v: int) -> int:
+    return bin(v).count("1")
+
+
+def qubit_bit(q: int, n: int) -> int:
+    return 1 << (n - 1 - q)
+
+
+def pack_term(term, n: int):
+    """((q, 'X'|'Y'|'Z'), ...) -> (x, z)."""
+    x = z = 0
+    for q, p in term:
+        if q >= n:
+            raise ValueError(f"qubit {q} outside a {n}-qubit register")
+        b = 1 << (n - 1 - q)
+        if p == "X":
+            x |= b
+        elif p == "Z":
+            z |= b
+        else:
+            x |= b
+            z |= b
+    return x, z
+
+
+class PauliTable:
+    """Packed observable: arrays x, z (uint64), k (uint8 phase exponent), coeff (complex128)
+    in ``QubitOperator.terms`` order (after ``compress()``, as the reference does)."""
+
+    def __init__(self, n_qubits, x, z, coeff):
+        self.n_qubits = int(n_qubits)
+        self.x = np.ascontiguousarray(x, dtype=np.uint64)
+        self.z = np.ascontiguousarray(z, dtype=np.uint64)
+        self.coeff = np.ascontiguousarray(coeff, dtype=np.complex128)
+        self.k = np.array([popcount(int(a) & int(b)) & 3 for a, b in zip(self.x, self.z)], dtype=np.uint8)
+
+    @classmethod
+    def from_operator(cls, op, n_qubits, compress=True):
+        if isinstance(op, FermionOperator):
+            op = jordan_wigner(op)
+        if not isinstance(op, QubitOperator):
+            raise TypeError("PauliTable needs a QubitOperator or FermionOperator")
+        if compress:
+            op = op.copy()
+            op.compress()
+        xs, zs, cs = [], [], []
+        for term, c in op.terms.items():
+            x, z = pack_term(term, n_qubits)
+            xs.append(x)
+            zs.append(z)
+            cs.append(complex(c))
+        return cls(n_qubits, xs, zs, cs)
+
+    def __len__(self):
+        return len(self.x)
+
+    @property
+    def n_groups(self):
+        return len(set(int(v) for v in self.x))
+
+    def as_dict(self):
+        return {(int(a), int(b)): complex(c) for a, b, c in zip(self.x, self.z, self.coeff)}
+
+
+# ---------------------------------------------------------------------------------------------
+# generator plans
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class PairPiece:
+    """On every index i with (i & fixmask) == fixval:  (G psi)[i] = s B psi[i^x], (G psi)[i^x] = s conj(B) psi[i],
+    s = (-1)^popcount(i & zeta).  fixmask contains the top bit of x and fixval has it clear."""
+    x: int
+    fixmask: int
+    fixval: int
+    zeta: int
+    b: complex
+    strings: list = field(default_factory=list)     # [(x, z)] Pauli strings it stands for (commutation checks)
+
+
+@dataclass
+class DiagPiece:
+    """(G psi)[i] = sum_m coef[m] (-1)^popcount(i & z[m]) psi[i]."""
+    z: list
+    coef: list
+    strings: list = field(default_factory=list)
+
+
+def strings_commute(a, b) -> bool:
+    (x1, z1), (x2, z2) = a, b
+    return (popcount(x1 & z2) + popcount(x2 & z1)) % 2 == 0
+
+
+def all_commute(strings) -> bool:
+    for i in range(len(strings)):
+        for j in range(i + 1, len(strings)):
+            if not strings_commute(strings[i], strings[j]):
+                return False
+    return True
+
+
+def _single_string_piece(x, z, c):
+    k = popcount(x & z)
+    d = c * _I_POW[k & 3]
+    b = d * (-1) ** k               # w(i) = B (-1)^popcount(i&z)
+    top = 1 << (x.bit_length() - 1)
+    return PairPiece(x, top, 0, z, b, [(x, z)])
+
+
+def _analyse_group(x, terms, max_patterns=8):
+    """terms: [(z, real coeff)] sharing x != 0 -> list of PairPiece, or None when the group is not
+    a union of simple 2x2 blocks (caller falls back to one piece per string)."""
+    if len(terms) == 1:
+        return [_single_string_piece(x, terms[0][0], terms[0][1])]
+    xbits = [b for b in range(x.bit_length()) if x >> b & 1]
+    if len(xbits) > 10:
+        return None
+    top = 1 << xbits[-1]
+    classes = {}
+    for z, c in terms:
+        classes.setdefault(z & ~x, []).append((z & x, c * _I_POW[popcount(x & z) & 3]))
+    pieces = []
+    strings = [(x, z) for z, _ in terms]
+    for pat in range(1 << (len(xbits) - 1)):          # top bit of the pattern stays 0
+        a = 0
+        for t, b in enumerate(xbits[:-1]):
+            if pat >> t & 1:
+                a |= 1 << b
+        partner_bits = a ^ x
+        active = []
+        for zeta, members in classes.items():
+            val = sum(d * (-1) ** popcount(partner_bits & zin) for zin, d in members)
+            if abs(val) > _TOL:
+                active.append((zeta, val))
+        if not active:
+            continue
+        if len(active) > 1:
+            return None
+        pieces.append(PairPiece(x, x, a, active[0][0], complex(active[0][1]), strings))
+        if len(pieces) > max_patterns:
+            return None
+    assert all(p.fixmask & top for p in pieces)
+    return pieces
+
+
+class GeneratorPlan:
+    """exp(-i theta G) for G = sum_m Re(c_m) P_m as a list of pair / diagonal pieces.
+
+    ``exact`` is True when every string of G commutes with every other: then the product of the
+    pieces (any order) equals the reference's literal Trotter product exactly.  Otherwise the plan
+    holds one piece per string in ``generator.terms`` order, which *is* the reference's product.
+    """
+
+    def __init__(self, generator, n_qubits):
+        if isinstance(generator, FermionOperator):
+            generator = jordan_wigner(generator)
+        self.n_qubits = n_qubits
+        strings = []
+        for term, c in generator.terms.items():
+            if not term:
+                continue                                  # identity: global phase (reference adapt_vqe.py:92-93)
+            x, z = pack_term(term, n_qubits)
+            strings.append((x, z, complex(c).real))
+        self.strings = strings
+        self.exact = all_commute([(x, z) for x, z, _ in strings])
+        self.pieces = []
+        if self.exact:
+            groups = {}
+            for x, z, c in strings:
+                groups.setdefault(x, []).append((z, c))
+            for x, terms in groups.items():
+                if x == 0:
+                    self.pieces.append(DiagPiece([z for z, _ in terms], [c for _, c in terms], [(0, z) for z, _ in terms]))
+                    continue
+                got = _analyse_group(x, terms)
+                if got is None:
+                    got = [_single_string_piece(x, z, c) for z, c in terms]
+                self.pieces.extend(got)
+        else:
+            for x, z, c in strings:
+                if x == 0:
+                    self.pieces.append(DiagPiece([z], [c], [(0, z)]))
+                else:
+                    self.pieces.append(_single_string_piece(x, z, c))
+        self.pieces = [p for p in self.pieces if isinstance(p, DiagPiece) or abs(p.b) > _TOL]

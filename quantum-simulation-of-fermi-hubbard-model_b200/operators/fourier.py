@@ -26,12 +26,15 @@ def fourier_transform_matrix(x_dimension, y_dimension):
     """(2N x 2N) unitary, block diagonal in spin for the interleaved orbital order."""
     Nx, Ny = x_dimension, y_dimension
     n_sites = Nx * Ny
-    sites = np.arange(n_sites)
-    sx, sy = sites % Nx, sites // Nx
-    phase = np.exp(-2j * np.pi * np.outer(sx, sx) / Nx) * np.exp(-2j * np.pi * np.outer(sy, sy) / Ny)
     matrix = np.zeros((2 * n_sites, 2 * n_sites), dtype=complex)
-    matrix[0::2, 0::2] = phase
-    matrix[1::2, 1::2] = phase
+    for n_site in range(n_sites):
+        nx, ny = _site_xy(n_site, Nx)
+        for m_site in range(n_sites):
+            mx, my = _site_xy(m_site, Nx)
+            # same operation order as the reference expression so the entries agree to the last bit
+            value = np.exp(-1j * 2 * np.pi * mx * nx / Nx) * np.exp(-1j * 2 * np.pi * my * ny / Ny)
+            matrix[2 * n_site, 2 * m_site] = value
+            matrix[2 * n_site + 1, 2 * m_site + 1] = value
     return matrix / np.sqrt(n_sites)
 
 

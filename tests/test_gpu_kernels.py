@@ -1,0 +1,209 @@
+"""Parity of the CUDA path (through the C-ABI) against the oracle on the same seeded inputs.
+
+Tolerances: amplitudes 1e-12 abs, energies 1e-10 abs, gradients 1e-9 abs (BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+
+from fhsim.backend import Context, DevicePool, DeviceTable, State, lanczos
+from fhsim.circuit import Circuit
+from fhsim.symbolic import QubitOperator, fermi_hubbard, givens_decomposition_square, jordan_wigner
+from fhsim.tables import GeneratorPlan, PauliTable, pack_term
+from operators.fourier import fourier_transform_matrix
+from operators.pool import hubbard_interaction_pool_simplified
+from oracle import ed, pauli, statevector as sv
+
+pytestmark = pytest.mark.gpu
+
+AMP_TOL, E_TOL, G_TOL = 1e-12, 1e-10, 1e-9
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return Context(0)
+
+
+def rand_state(n, seed):
+    rng = np.random.default_rng(seed)
+    v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    return v / np.linalg.norm(v)
+
+
+def lattice(nx, ny, u):
+    n = 2 * nx * ny
+    h_op = fermi_hubbard(nx, ny, 1.0, u)
+    h_tab = PauliTable.from_operator(h_op, n)
+    pool_ops = [jordan_wigner(g) for g in hubbard_interaction_pool_simplified(nx, ny)]
+    dec, diag = givens_decomposition_square(fourier_transform_matrix(nx, ny))
+    o_h = pauli.compress(pauli.jw_table(pauli.hubbard_fermion_terms(nx, ny, 1.0, u), n))
+    o_pool = [pauli.jw_table(op, n) for op in pauli.pool_fermion_terms(nx, ny)]
+    return n, h_tab, pool_ops, dec, diag, o_h, o_pool
+
+
+@pytest.mark.parametrize("n", [3, 8, 12, 18])
+def test_pauli_rotation_batch_vs_oracle(ctx, n):
+    rng = np.random.default_rng(n)
+    psi = rand_state(n, 100 + n)
+    xs = rng.integers(0, 1 << n, size=12, dtype=np.uint64)
+    zs = rng.integers(0, 1 << n, size=12, dtype=np.uint64)
+    xs[3] = 0                      # a diagonal string
+    xs[5], zs[5] = 0, 0            # identity: skipped
+    xs[7] = 1                      # lowest-bit flip
+    xs[8] = 1 << (n - 1)           # highest-bit flip
+    th = rng.uniform(-3, 3, size=12)
+    st = State.from_numpy(ctx, psi)
+    st.apply_pauli_rotations(xs, zs, 0.5 * th)
+    want = psi
+    for x, z, t in zip(xs, zs, th):
+        if x == 0 and z == 0:
+            continue
+        want = sv.pauli_rotation(want, t, int(x), int(z), n)
+    assert np.abs(st.numpy() - want).max() < AMP_TOL
+    assert abs(st.norm2() - 1.0) < 1e-12
+
+
+def test_rotation_inverse_is_identity(ctx):
+    n = 14
+    psi = rand_state(n, 5)
+    st = State.from_numpy(ctx, psi)
+    x, z = np.array([0b10110000110011], np.uint64), np.array([0b00110100010001], np.uint64)
+    st.apply_pauli_rotations(x, z, [0.731])
+    st.apply_pauli_rotations(x, z, [-0.731])
+    assert np.abs(st.numpy() - psi).max() < 1e-14
+
+
+@pytest.mark.parametrize("lat,u", [((2, 2), 4.0), ((2, 3), 4.0), ((3, 3), 6.0)])
+def test_apply_table_and_expval(ctx, lat, u):
+    n, h_tab, _, _, _, o_h, _ = lattice(*lat, u)
+    psi = rand_state(n, 21)
+    dtab = DeviceTable(ctx, h_tab)
+    info = dtab.info()
+    assert info["n_terms"] == len(o_h)
+    st, out = State.from_numpy(ctx, psi), State(ctx, n)
+    e = dtab.apply(st, out)
+    want = sv.apply_table(psi, o_h, n)
+    assert np.abs(out.numpy() - want).max() < 1e-12
+    assert abs(e - np.vdot(psi, want)) < E_TOL
+    assert abs(dtab.expval(st) - np.vdot(psi, want).real) < E_TOL
+    # Hermiticity <phi|H psi> = conj <psi|H phi>
+    phi = rand_state(n, 22)
+    sp, hp = State.from_numpy(ctx, phi), State(ctx, n)
+    dtab.apply(sp, hp)
+    assert abs(sp.inner(out) - np.conj(st.inner(hp))) < 1e-11
+
+
+def test_complex_coefficient_table(ctx):
+    n = 6
+    op = QubitOperator('X0 Y2', 0.3 + 0.2j) + QubitOperator('Z1 Z5', -0.7) + QubitOperator('Y3', 1.1j) + QubitOperator((), 0.25)
+    tab = PauliTable.from_operator(op, n)
+    psi = rand_state(n, 8)
+    st, out = State.from_numpy(ctx, psi), State(ctx, n)
+    e = DeviceTable(ctx, tab).apply(st, out)
+    want = sv.apply_table(psi, tab.as_dict(), n)
+    assert np.abs(out.numpy() - want).max() < 1e-13
+    assert abs(e - np.vdot(psi, want)) < 1e-12
+
+
+@pytest.mark.parametrize("lat,u,up,dn", [((2, 2), 4.0, 2, 2), ((2, 3), 4.0, 3, 3)])
+def test_pool_gradients_vs_oracle(ctx, lat, u, up, dn):
+    n, h_tab, pool_ops, dec, diag, o_h, o_pool = lattice(*lat, u)
+    rng = np.random.default_rng(1234)
+    occ_up, occ_dn, _ = pauli.k_space_occupation(*lat, 1.0, up, dn)
+    picks = list(range(1, len(o_pool), max(1, len(o_pool) // 6)))[:6]
+    th = rng.uniform(-0.3, 0.3, len(picks))
+    psi = sv.adapt_state(n, occ_up + occ_dn, [o_pool[k] for k in picks], th)
+    g_want, e_want, lam = sv.pool_gradients(psi, o_h, o_pool, diag, dec, n)
+    plans = [GeneratorPlan(g, n) for g in pool_ops]
+    dpool = DevicePool(ctx, plans, n)
+    got = dpool.gradients(State.from_numpy(ctx, psi), State.from_numpy(ctx, lam))
+    assert np.abs(got - g_want).max() < G_TOL
+    part = dpool.gradients(State.from_numpy(ctx, psi), State.from_numpy(ctx, lam), first=5, count=7)
+    assert np.array_equal(part, got[5:12])          # pool sharding gives bit-identical slices
+
+
+@pytest.mark.parametrize("fuse", [False, True])
+@pytest.mark.parametrize("lat,u,up,dn", [((2, 2), 4.0, 2, 2), ((2, 3), 4.0, 3, 3)])
+def test_program_evaluate_energy_grads_pool(ctx, lat, u, up, dn, fuse):
+    n, h_tab, pool_ops, dec, diag, o_h, o_pool = lattice(*lat, u)
+    rng = np.random.default_rng(99)
+    occ_up, occ_dn, _ = pauli.k_space_occupation(*lat, 1.0, up, dn)
+    picks = list(rng.choice(len(pool_ops), size=7, replace=False))
+    th = rng.uniform(-0.4, 0.4, len(picks))
+    plans = [GeneratorPlan(g, n) for g in pool_ops]
+    circ = Circuit(n, len(picks))
+    for p, k in enumerate(picks):
+        circ.generator(plans[k], param=p)
+    circ.marker("ansatz_end")
+    circ.basis_change(diag, list(reversed(dec)))
+    prog = circ.compile(ctx, fuse=fuse)
+    dtab = DeviceTable(ctx, h_tab)
+    dpool = DevicePool(ctx, plans, n)
+    basis = sum(1 << (n - 1 - q) for q in occ_up + occ_dn)
+    out_state = State(ctx, n)
+    res = prog.evaluate(basis, th, [dtab], grads=True, pool=dpool, pool_pos=prog.markers["ansatz_end"],
+                        state_out=out_state)
+    gens = [o_pool[k] for k in picks]
+    e_want, g_want = sv.adjoint_gradient(n, occ_up + occ_dn, gens, th, o_h, diag, dec)
+    psi_k = sv.adapt_state(n, occ_up + occ_dn, gens, th)
+    pg_want, _, _ = sv.pool_gradients(psi_k, o_h, o_pool, diag, dec, n)
+    assert abs(res["expvals"][0] - e_want) < E_TOL
+    assert np.abs(res["grads"] - g_want).max() < G_TOL
+    assert np.abs(res["pool"] - pg_want).max() < G_TOL
+    phi = sv.basis_change(psi_k, diag, dec, n)
+    assert np.abs(out_state.numpy() - phi).max() < 1e-12
+    # replay of the captured graph with new parameters
+    th2 = th + 0.05
+    res2 = prog.evaluate(basis, th2, [dtab], grads=True, pool=dpool, pool_pos=prog.markers["ansatz_end"],
+                         state_out=out_state)
+    e2, g2 = sv.adjoint_gradient(n, occ_up + occ_dn, gens, th2, o_h, diag, dec)
+    assert abs(res2["expvals"][0] - e2) < E_TOL and np.abs(res2["grads"] - g2).max() < G_TOL
+
+
+def test_known_answers_3x3_first_screening(ctx):
+    """E_HF = -5/3 and exactly 52 operators at |g| = 4/3 through the CUDA path."""
+    n, h_tab, pool_ops, dec, diag, _, _ = lattice(3, 3, 6.0)
+    plans = [GeneratorPlan(g, n) for g in pool_ops]
+    circ = Circuit(n, 0)
+    circ.marker("ansatz_end")
+    circ.basis_change(diag, list(reversed(dec)))
+    prog = circ.compile(ctx)
+    occ = [0, 2, 4, 6, 12, 1, 3, 5, 7]
+    basis = sum(1 << (n - 1 - q) for q in occ)
+    res = prog.evaluate(basis, [], [DeviceTable(ctx, h_tab)], pool=DevicePool(ctx, plans, n), pool_pos=0)
+    assert abs(res["expvals"][0] + 5.0 / 3.0) < E_TOL
+    g = np.abs(res["pool"])
+    assert (g > 1e-9).sum() == 52 and np.allclose(g[g > 1e-9], 4.0 / 3.0, atol=G_TOL)
+
+
+def test_lanczos_vs_sector_ed(ctx):
+    for (nx, ny, u, up, dn) in [(2, 2, 4.0, 2, 2), (2, 3, 4.0, 3, 3)]:
+        n, h_tab, _, _, _, o_h, _ = lattice(nx, ny, u)
+        want, _, _ = ed.ground_state(o_h, n, up + dn, up, dn, k=3)
+        dtab = DeviceTable(ctx, h_tab)
+        vals, vecs, iters = lanczos(dtab, k=3, n_up=up, n_dn=dn, tol=1e-11)
+        assert np.abs(np.sort(vals) - want).max() < 1e-9
+        for v, e in zip(vecs, vals):
+            hv = State(ctx, n)
+            assert abs(dtab.apply(v, hv).real - e) < 1e-9
+            assert abs(v.norm2() - 1) < 1e-10
+
+
+def test_lanczos_3x3_degenerate_ground_level(ctx):
+    n, h_tab, _, _, _, _, _ = lattice(3, 3, 6.0)
+    vals, vecs, iters = lanczos(DeviceTable(ctx, h_tab), k=5, n_up=5, n_dn=4, tol=1e-10, max_iter=600)
+    vals = np.sort(vals)
+    assert np.abs(vals[:4] + 5.5623088363).max() < 2e-9
+    assert abs(vals[4] + 4.7084214853) < 2e-9
+
+
+def test_error_paths(ctx):
+    with pytest.raises(ValueError):
+        State(ctx, 0)
+    st = State(ctx, 4)
+    with pytest.raises(ValueError):
+        st.set_basis(16)
+    with pytest.raises(ValueError):
+        st.apply_pair(0, 1, 0, 0, [0, 0, 1, 0, 1, 0, 0, 0])
+    tab = PauliTable(3, [1], [0], [1.0])
+    with pytest.raises(ValueError):
+        DeviceTable(ctx, tab).apply(st)              # qubit-count mismatch
