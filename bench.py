@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- ADAPT pool-gradients/s and <H> evals/s at 3x3 (18 qubits) on B200.
+
+One "step" = one full ADAPT screening evaluation of BASELINE.json config 3
+(3x3 Hubbard, U=6, (5 up, 4 down); k-space HF state evolved by the 52 first-epoch pool
+operators, theta ~ U(-0.1, 0.1), default_rng(1234)):
+    psi_k = U_52..U_1|HF>,  phi = W psi_k,  E = <phi|H|phi>,  lambda = W^dagger H phi,
+    g_k = 2 Im <lambda|G_k|psi_k> for all 324 pool operators
+i.e. what reference ADAPT.select_operator (models/adapt_vqe.py:297-323) computes, through ONE
+C-ABI call (fh_program_evaluate, replayed as a CUDA graph).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 (under torchrun): every rank runs the same workload on its own GPU (independent screenings,
+no data-path collective) -> "scaling": "weak"; time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "quantum-simulation-of-fermi-hubbard-model_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+NX, NY, U, N_UP, N_DN = 3, 3, 6.0, 5, 4
+N_QUBITS = 2 * NX * NY
+WORKLOAD = "cfg3: ADAPT screening, 3x3 Hubbard U=6 (5up,4dn), 18 qubits, 52-operator ansatz, 324-operator pool"
+METRIC = "ADAPT pool-gradients/s at 3x3 (18q)"
+L2_FLUSH_BYTES = 256 << 20
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
+
+    def __init__(self, device):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(device), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons, busy = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                clk, cmax, util = float(parts[0]), float(parts[1]), float(parts[6])
+            except ValueError:
+                continue
+            sm.append(clk)
+            mx.append(cmax)
+            if util > 0:
+                busy.append(clk)
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.tmp.name)
+        if sm:
+            out["sm_mhz"] = statistics.median(busy or sm)
+            out["sm_max_mhz"] = max(mx)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------
+def build_tables():
+    from fhsim.symbolic import fermi_hubbard, givens_decomposition_square, jordan_wigner
+    from fhsim.tables import GeneratorPlan, PauliTable
+    from operators.fourier import fourier_transform_matrix
+    from operators.pool import hubbard_interaction_pool_simplified
+    n = N_QUBITS
+    h_tab = PauliTable.from_operator(fermi_hubbard(NX, NY, 1.0, U), n)
+    plans = [GeneratorPlan(jordan_wigner(g), n) for g in hubbard_interaction_pool_simplified(NX, NY)]
+    dec, diag = givens_decomposition_square(fourier_transform_matrix(NX, NY))
+    occ = [0, 2, 4, 6, 12, 1, 3, 5, 7]        # stable sort of eps_k
+    basis = sum(1 << (n - 1 - q) for q in occ)
+    return h_tab, plans, dec, diag, basis
+
+
+def build_gpu_workload(ctx):
+    from fhsim.backend import DevicePool, DeviceTable
+    from fhsim.circuit import Circuit
+    n = N_QUBITS
+    h_tab, plans, dec, diag, basis = build_tables()
+    dtab = DeviceTable(ctx, h_tab)
+    dpool = DevicePool(ctx, plans, n)
+    # first-epoch screening at the HF state picks the 52 operators with |g| = 2U/N
+    c0 = Circuit(n, 0)
+    c0.marker("ansatz_end")
+    c0.basis_change(diag, list(reversed(dec)))
+    p0 = c0.compile(ctx)
+    g0 = p0.evaluate(basis, [], [dtab], pool=dpool, pool_pos=0)["pool"]
+    picks = [k for k in range(len(plans)) if abs(g0[k]) > 1e-9]
+    assert len(picks) == 52, len(picks)
+    p0.close()
+    thetas = np.random.default_rng(1234).uniform(-0.1, 0.1, len(picks))
+    circ = Circuit(n, len(picks))
+    for j, k in enumerate(picks):
+        circ.generator(plans[k], param=j)
+    circ.marker("ansatz_end")
+    circ.basis_change(diag, list(reversed(dec)))
+    prog = circ.compile(ctx)
+    return dict(prog=prog, dtab=dtab, dpool=dpool, basis=basis, thetas=thetas, picks=picks, circ=circ,
+                plans=plans, dec=dec, diag=diag, h_tab=h_tab)
+
+
+def cpu_reference_sample(n_ops, picks=None, thetas=None):
+    """Reference CPU path (oracle/literal.py: gate-by-gate torch + autograd) on a bounded sample:
+    screening of the first ``n_ops`` pool operators appended to the ansatz state.  The ansatz prefix
+    is prepared untimed by the closed-form oracle (in the reference it is amortised over all 324
+    operators); W, <H> and the backward pass are inside the timed region."""
+    import torch
+    from oracle import literal, pauli, statevector as sv
+    n = N_QUBITS
+    torch.set_num_threads(os.cpu_count() or 1)
+    h = pauli.compress(pauli.jw_table(pauli.hubbard_fermion_terms(NX, NY, 1.0, U), n))
+    opool = [pauli.jw_table(op, n) for op in pauli.pool_fermion_terms(NX, NY)]
+    layers, diag = pauli.givens_network(pauli.ft_matrix(NX, NY))
+    occ = [0, 2, 4, 6, 12, 1, 3, 5, 7]
+    if picks is None:
+        psi = sv.basis_state(n, occ)
+        g0, _, _ = sv.pool_gradients(psi, h, opool, diag, layers, n)
+        picks = [k for k in range(len(opool)) if abs(g0[k]) > 1e-9]
+        thetas = np.random.default_rng(1234).uniform(-0.1, 0.1, len(picks))
+    psi_k = sv.adapt_state(n, occ, [opool[k] for k in picks], thetas)
+    h_terms = [(x, z, c) for (x, z), c in h.items()]
+    sub = [literal.strings_of(p, n) for p in opool[:n_ops]]
+
+    def one_step():
+        t0 = time.perf_counter()
+        e = torch.zeros(len(sub), dtype=torch.float32, requires_grad=True)
+        sim = literal.LiteralSimulator(n)
+        sim.state = torch.from_numpy(psi_k.reshape([2] * n).copy())
+        for i, strings in enumerate(sub):
+            sim.trotterize(e[i], strings)
+        sim.basis_change(diag, layers)
+        loss = sim.expval(h_terms)
+        loss.backward()
+        return time.perf_counter() - t0, e.grad.numpy().copy(), sim.gate_passes
+
+    return one_step, torch.get_num_threads()
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    n_ops = 4
+    one_step, cores = cpu_reference_sample(n_ops)
+    budget_s = 150.0
+    times = []
+    t_first, _, passes = one_step()                       # warm-up / calibration
+    steps = max(1, min(args.steps, int(budget_s / max(t_first, 1e-3))))
+    warm = max(0, min(args.warmup, 1))
+    for _ in range(warm):
+        one_step()
+    for _ in range(steps):
+        dt, _, _ = one_step()
+        times.append(dt)
+    total = sum(times)
+    value = n_ops * len(times) / total
+    sample = (f"{n_ops} of 324 pool operators appended to the 52-operator ansatz state (prefix prepared untimed), "
+              f"W + per-term <H> + autograd backward timed; {passes} gate passes per step")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "gradients/s", "n_gpus": args.gpus,
+        "steps": len(times), "steps_requested": args.steps, "warmup": warm, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": value, "unit": "gradients/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "gradients/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_gpu_arm(args, rank, world, local_rank):
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from fhsim.backend import Context, State
+    ctx = Context(local_rank if world > 1 else 0)
+    wl = build_gpu_workload(ctx)
+    prog, dtab, dpool, basis, thetas = wl["prog"], wl["dtab"], wl["dpool"], wl["basis"], wl["thetas"]
+    marker = prog.markers["ansatz_end"]
+    n_pool = dpool.n_out
+
+    def step():
+        return prog.evaluate(basis, thetas, [dtab], pool=dpool, pool_pos=marker)
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank if world > 1 else 0) if rank == 0 else None
+
+    # ---- value: device-resident, CUDA events around the graph, L2 flushed before every step ----
+    for _ in range(max(args.warmup, 3)):
+        ctx.flush_l2(L2_FLUSH_BYTES)
+        step()
+    barrier()
+    dev_ms = []
+    launches = 0
+    for _ in range(args.steps):
+        ctx.flush_l2(L2_FLUSH_BYTES)
+        ctx.sync()
+        res = step()
+        ms, launches = prog.last_stats()
+        dev_ms.append(ms)
+    barrier()
+    total_ms = sum(dev_ms)
+    if dist is not None:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+
+    # ---- e2e: wall clock around the public call (host theta in, host gradients out) ----
+    wall = []
+    for _ in range(args.steps):
+        ctx.flush_l2(L2_FLUSH_BYTES)
+        ctx.sync()
+        t0 = time.perf_counter()
+        res = step()
+        wall.append(time.perf_counter() - t0)
+    e2e_total = sum(wall)
+    if dist is not None:
+        t = torch.tensor([e2e_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_total = float(t.item())
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- <H> evals/s (energy only: forward + K2 expectation) ----
+    for _ in range(3):
+        prog.evaluate(basis, thetas, [dtab])
+    h_ms = []
+    for _ in range(min(args.steps, 500)):
+        ctx.flush_l2(L2_FLUSH_BYTES)
+        ctx.sync()
+        prog.evaluate(basis, thetas, [dtab])
+        h_ms.append(prog.last_stats()[0])
+    h_launches = prog.last_stats()[1]
+    step()   # restore the screening graph
+
+    # ---- dominant kernel (K3 pool screening) timed alone for the roofline ----
+    n = N_QUBITS
+    psi_k, lam = State(ctx, n), State(ctx, n)
+    psi_k.set_basis(basis)
+    prog.run(psi_k, thetas, 0, marker)
+    lam.copy_from(psi_k)
+    prog.run(lam, thetas, marker, prog.n_items - marker)
+    phi = State(ctx, n)
+    phi.copy_from(lam)
+    dtab.apply(phi, lam)
+    prog.run(lam, thetas, marker, prog.n_items - marker, dagger=True)
+    g_check = dpool.gradients(psi_k, lam)
+    assert np.abs(g_check - res["pool"]).max() < 1e-9
+    k3_ms = []
+    reps = 10
+    for _ in range(10):
+        ctx.flush_l2(L2_FLUSH_BYTES)
+        # in the real step psi and lambda were produced just before the screening kernel, i.e. they are
+        # L2-resident there too: touch them after the flush, then time `reps` back-to-back launches
+        psi_k.norm2(); lam.norm2()
+        ctx.timer_start()
+        for _r in range(reps):
+            dpool.enqueue(psi_k, lam)
+        k3_ms.append(ctx.timer_stop() / reps)
+    k3 = statistics.median(k3_ms) * 1e-3
+    peak, peak_src = measured_peak_gbs()
+    alg_bytes = 4.0 * (1 << n) * n_pool              # 4*2^n B per gradient
+    achieved = alg_bytes / k3 / 1e9
+
+    clocks = sampler.stop() if sampler else {}
+
+    # ---- CPU baseline (bounded sample of the same workload) ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        n_ops = 4
+        one_step, cores = cpu_reference_sample(n_ops, wl["picks"], thetas)
+        one_step()
+        ts, grads_cpu, passes = [], None, 0
+        for _ in range(3):
+            dt, grads_cpu, passes = one_step()
+            ts.append(dt)
+        cpu_val = n_ops / statistics.median(ts)
+        err = float(np.abs(np.abs(grads_cpu) - np.abs(res["pool"][:n_ops]).astype(np.float32)).max())
+        cpu = {"value": cpu_val, "unit": "gradients/s", "cores": cores, "kind": "port",
+               "sample": (f"{n_ops} of 324 pool operators by the reference's append-and-backprop algorithm "
+                          f"(oracle/literal.py, torch CPU, {passes} gate passes/step; ansatz prefix untimed); "
+                          f"max |g_cpu - g_gpu| on the sample = {err:.2e}")}
+
+    value = world * n_pool * args.steps / (total_ms * 1e-3)
+    e2e_value = world * n_pool * args.steps / e2e_total
+    h2d = 160 * len(wl["circ"].ops)            # op payload staged from pinned host memory each step (upper bound)
+    d2h = 8 * (n_pool + 4)
+    line = {
+        "metric": METRIC, "value": value, "unit": "gradients/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "complex128", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "l2": "flushed (256 MiB write) before every timed step",
+                   "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                   "launch_items": prog.n_items, "tile_kernels": prog.n_tiles},
+        "e2e": {"value": e2e_value, "unit": "gradients/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_total / args.steps},
+        "gpu_launches": launches * args.steps,
+        "launches_per_step": launches,
+        "h_evals_per_s": world * len(h_ms) / (sum(h_ms) * 1e-3),
+        "h_eval_ms": statistics.median(h_ms), "h_eval_launches": h_launches,
+        "roofline": {"bound": "hbm", "kernel": "k_pool (K3 pool screening) + k_pool_finalize",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel_ms": k3 * 1e3,
+                     "note": "18-qubit working set (8 MiB) is L2-resident: effective GB/s vs HBM peak; "
+                             "algorithmic bytes = 4*2^n per gradient x 324"},
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+        "energy": float(res["expvals"][0]),
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="fhsim", choices=["fhsim", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks"}))
+        sys.exit(2)
+    run_gpu_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -51,6 +51,10 @@ int fh_ctx_sync(fh_ctx *ctx);
 int fh_ctx_info(fh_ctx *ctx, int *sm_count, size_t *free_bytes, size_t *total_bytes);
 /* write `bytes` of scratch (>= L2 size) so the next kernel starts with a cold L2 (benchmark hygiene) */
 int fh_ctx_flush_l2(fh_ctx *ctx, size_t bytes);
+/* CUDA-event stopwatch on the context's stream (measurement only): start records an event, stop records a
+ * second one, synchronises and returns the elapsed device time in milliseconds */
+int fh_ctx_timer_start(fh_ctx *ctx);
+int fh_ctx_timer_stop(fh_ctx *ctx, double *elapsed_ms);
 
 /* ---- state --------------------------------------------------------------------------------
  * replaces the PennyLane state tensor and qml.state() (models/adapt_vqe.py:358-359, 404-407). */
@@ -137,6 +141,10 @@ int fh_program_evaluate(fh_program *prog, uint64_t basis_index, const double *th
                         const fh_pool *pool, int pool_pos, int pool_first, int pool_count, double *pool_out,
                         int n_overlaps, fh_state *const *targets, double *overlaps,
                         fh_state *state_out);
+
+/* measurement: device time (CUDA events bracketing the graph launch on the context's stream) and number of
+ * kernel launches of the most recent fh_program_evaluate call */
+int fh_program_last_stats(const fh_program *prog, double *elapsed_ms, int *kernel_launches);
 
 /* ---- K4: Lanczos ground states --------------------------------------------------------------
  * replaces linalg/exact_diagonalization.py:34-51, 181-229 (scipy eigsh, which='SA') and

@@ -64,6 +64,8 @@ extern "C" int fh_ctx_destroy(fh_ctx *ctx) {
     cudaFree(ctx->d_result);
     cudaFreeHost(ctx->h_result);
     if (ctx->d_flush) cudaFree(ctx->d_flush);
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return FH_OK;
@@ -99,6 +101,27 @@ extern "C" int fh_ctx_flush_l2(fh_ctx *ctx, size_t bytes) {
     }
     launch_flush(ctx->stream, ctx->d_flush, bytes);
     FH_CUDA(cudaGetLastError());
+    return FH_OK;
+}
+
+extern "C" int fh_ctx_timer_start(fh_ctx *ctx) {
+    FH_REQUIRE(ctx, "fh_ctx_timer_start: ctx is NULL");
+    if (!ctx->ev_start) {
+        FH_CUDA(cudaEventCreate(&ctx->ev_start));
+        FH_CUDA(cudaEventCreate(&ctx->ev_stop));
+    }
+    FH_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
+    return FH_OK;
+}
+
+extern "C" int fh_ctx_timer_stop(fh_ctx *ctx, double *elapsed_ms) {
+    FH_REQUIRE(ctx && elapsed_ms, "fh_ctx_timer_stop: NULL argument");
+    FH_REQUIRE(ctx->ev_start, "fh_ctx_timer_stop: timer not started");
+    FH_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
+    FH_CUDA(cudaEventSynchronize(ctx->ev_stop));
+    float ms = 0.f;
+    FH_CUDA(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
+    *elapsed_ms = ms;
     return FH_OK;
 }
 
@@ -545,13 +568,14 @@ int fh_enqueue_pool(const fh_pool *pool, const double2 *psi, const double2 *lam,
 
 extern "C" int fh_pool_gradients(const fh_pool *pool, const fh_state *psi, const fh_state *lambda, int first, int count,
                                  double *out) {
-    FH_REQUIRE(pool && psi && lambda && out, "fh_pool_gradients: NULL argument");
+    FH_REQUIRE(pool && psi && lambda, "fh_pool_gradients: NULL argument");
     FH_REQUIRE(psi->n == pool->n && lambda->n == pool->n, "fh_pool_gradients: qubit count mismatch");
     FH_REQUIRE(first >= 0 && count >= 0 && first + count <= pool->n_out, "fh_pool_gradients: range [%d, %d) outside pool of %d",
                first, first + count, pool->n_out);
     if (count == 0) return FH_OK;
     fh_ctx *ctx = pool->ctx;
     FH_TRY(fh_enqueue_pool(pool, psi->d, lambda->d, first, count));
+    if (!out) return FH_OK;     // enqueue only (results stay on the device); used to time the kernel alone
     FH_CUDA(cudaMemcpyAsync(pool->h_out, pool->d_out + first, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->stream));
     FH_CUDA(cudaStreamSynchronize(ctx->stream));
     memcpy(out, pool->h_out, sizeof(double) * count);

@@ -120,6 +120,7 @@ struct fh_ctx {
     double *h_result = nullptr;       // pinned mirror
     void *d_flush = nullptr;
     size_t flush_bytes = 0;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
 };
 
 #define FH_MAX_PARTIALS 4096

@@ -15,6 +15,9 @@
 
 #define FULL 0xffffffffu
 
+// number of kernel launches issued through the wrappers below (measurement; read via fh_program_last_stats)
+long long g_fh_launch_count = 0;
+
 // ----------------------------------------------------------------------------------------------
 // small device helpers
 // ----------------------------------------------------------------------------------------------
@@ -530,10 +533,10 @@ void launch_pair(cudaStream_t s, int sm, double2 *psi, const PairOp *d_op, int n
     const u64 npairs = 1ull << (n - nfix);
     if (npairs >= (u64)sm * 128 * 16) {
         const int grid = grid_for(npairs, 128, 4, sm, sm * 32);
-        k_pair<4><<<grid, 128, 0, s>>>(psi, d_op, npairs, dagger);
+        ++g_fh_launch_count; k_pair<4><<<grid, 128, 0, s>>>(psi, d_op, npairs, dagger);
     } else {
         const int grid = grid_for(npairs, 128, 1, sm, sm * 32);
-        k_pair<1><<<grid, 128, 0, s>>>(psi, d_op, npairs, dagger);
+        ++g_fh_launch_count; k_pair<1><<<grid, 128, 0, s>>>(psi, d_op, npairs, dagger);
     }
 }
 
@@ -541,7 +544,7 @@ void launch_pair_adjoint(cudaStream_t s, int sm, double2 *psi, double2 *lam, con
                          double *d_partials, int max_blocks, int *blocks_used) {
     const u64 npairs = 1ull << (n - nfix);
     int grid = grid_for(npairs, 128, npairs >= (u64)sm * 128 * 8 ? 2 : 1, sm, max_blocks);
-    k_pair_adjoint<<<grid, 128, 0, s>>>(psi, lam, d_op, npairs, d_partials);
+    ++g_fh_launch_count; k_pair_adjoint<<<grid, 128, 0, s>>>(psi, lam, d_op, npairs, d_partials);
     *blocks_used = grid;
 }
 
@@ -550,7 +553,7 @@ void launch_diag(cudaStream_t s, int sm, double2 *psi, const DiagTerm *d_terms, 
     for (int off = 0; off < nterms; off += DIAG_SMEM_TERMS) {
         const int cnt = nterms - off < DIAG_SMEM_TERMS ? nterms - off : DIAG_SMEM_TERMS;
         const int grid = grid_for(dim, 256, dim >= (u64)sm * 256 * 8 ? 2 : 1, sm, sm * 16);
-        k_diag<<<grid, 256, 0, s>>>(psi, d_terms + off, cnt, dim, dagger);
+        ++g_fh_launch_count; k_diag<<<grid, 256, 0, s>>>(psi, d_terms + off, cnt, dim, dagger);
     }
 }
 
@@ -558,7 +561,7 @@ void launch_diag_adjoint(cudaStream_t s, int sm, double2 *psi, double2 *lam, con
                          double *d_partials, int max_blocks, int *blocks_used) {
     const u64 dim = 1ull << n;
     int grid = grid_for(dim, 256, 1, sm, max_blocks);
-    k_diag_adjoint<<<grid, 256, 0, s>>>(psi, lam, d_terms, nterms, dim, d_partials);
+    ++g_fh_launch_count; k_diag_adjoint<<<grid, 256, 0, s>>>(psi, lam, d_terms, nterms, dim, d_partials);
     *blocks_used = grid;
 }
 
@@ -573,7 +576,7 @@ void launch_tile(cudaStream_t s, double2 *psi, const TileOp *d_tile, const TileS
     }
     u64 ntiles = 1ull << (n - nbits);
     const int grid = (int)(ntiles > 148ull * 16 ? 148ull * 16 : ntiles);
-    k_tile<<<grid, 256, smem, s>>>(psi, d_tile, d_subs, d_pairs, d_diags, d_terms, n, dagger);
+    ++g_fh_launch_count; k_tile<<<grid, 256, smem, s>>>(psi, d_tile, d_subs, d_pairs, d_diags, d_terms, n, dagger);
     if (psi2) k_tile<<<grid, 256, smem, s>>>(psi2, d_tile, d_subs, d_pairs, d_diags, d_terms, n, dagger);
 }
 
@@ -588,15 +591,18 @@ void launch_apply_table(cudaStream_t s, int sm, const TabGroup *g, int ngroups, 
     const size_t smem = use_smem ? need : 0;
     int grid = grid_for(dim, 256, 1, sm, FH_MAX_PARTIALS);
     if (grid > sm * 8 && dim > (u64)sm * 8 * 256) grid = sm * 8;
-#define LAUNCH_TAB(R, W) \
-    k_apply_table<R, W><<<grid, 256, smem, s>>>(g, ngroups, t, nterms, use_smem, in, out, dim, d_partials)
+#define LAUNCH_TAB(R, W)                                                                                            \
+    do {                                                                                                            \
+        ++g_fh_launch_count;                                                                                        \
+        k_apply_table<R, W><<<grid, 256, smem, s>>>(g, ngroups, t, nterms, use_smem, in, out, dim, d_partials);     \
+    } while (0)
     if (all_real) {
         if (out) LAUNCH_TAB(true, true); else LAUNCH_TAB(true, false);
     } else {
         if (out) LAUNCH_TAB(false, true); else LAUNCH_TAB(false, false);
     }
 #undef LAUNCH_TAB
-    k_finalize_pairs<<<1, 256, 0, s>>>(d_partials, grid, d_result);
+    ++g_fh_launch_count; k_finalize_pairs<<<1, 256, 0, s>>>(d_partials, grid, d_result);
 }
 
 void launch_pool(cudaStream_t s, const PoolEntry *entries, int first_entry, int n_entries, int chunks, int n,
@@ -606,26 +612,26 @@ void launch_pool(cudaStream_t s, const PoolEntry *entries, int first_entry, int 
     for (int off = 0; off < n_entries; off += 32768) {
         const int cnt = n_entries - off < 32768 ? n_entries - off : 32768;
         dim3 grid(chunks, cnt);
-        k_pool<<<grid, 128, 0, s>>>(entries, first_entry + off, n, psi, lam, d_partials);
+        ++g_fh_launch_count; k_pool<<<grid, 128, 0, s>>>(entries, first_entry + off, n, psi, lam, d_partials);
     }
 }
 
 void launch_pool_finalize(cudaStream_t s, const double *d_partials, const int *d_out_first, int chunks, int first_out,
                           int count, double *d_out) {
     if (count <= 0) return;
-    k_pool_finalize<<<count, 32, 0, s>>>(d_partials, d_out_first, chunks, first_out, d_out);
+    ++g_fh_launch_count; k_pool_finalize<<<count, 32, 0, s>>>(d_partials, d_out_first, chunks, first_out, d_out);
 }
 
 void launch_inner(cudaStream_t s, int sm, const double2 *a, const double2 *b, u64 dim, double *d_partials,
                   double *d_result) {
     int grid = grid_for(dim, 256, 4, sm, sm * 8);
-    k_inner<<<grid, 256, 0, s>>>(a, b, dim, d_partials);
-    k_finalize_pairs<<<1, 256, 0, s>>>(d_partials, grid, d_result);
+    ++g_fh_launch_count; k_inner<<<grid, 256, 0, s>>>(a, b, dim, d_partials);
+    ++g_fh_launch_count; k_finalize_pairs<<<1, 256, 0, s>>>(d_partials, grid, d_result);
 }
 
 void launch_sum_segments(cudaStream_t s, const double *d_partials, const int *d_first, int nseg, double *d_out) {
     if (nseg <= 0) return;
-    k_sum_segments<<<nseg, 32, 0, s>>>(d_partials, d_first, d_out);
+    ++g_fh_launch_count; k_sum_segments<<<nseg, 32, 0, s>>>(d_partials, d_first, d_out);
 }
 
 // out[s] = sum_{t < stride} partials[s*stride + t]   (fixed order; unused slots are pre-zeroed)
@@ -640,33 +646,33 @@ __global__ void __launch_bounds__(32) k_sum_strided(const double *__restrict__ p
 
 void launch_sum_strided(cudaStream_t s, const double *d_partials, int stride, int nseg, double *d_out) {
     if (nseg <= 0) return;
-    k_sum_strided<<<nseg, 32, 0, s>>>(d_partials, stride, d_out);
+    ++g_fh_launch_count; k_sum_strided<<<nseg, 32, 0, s>>>(d_partials, stride, d_out);
 }
 
 void launch_set_basis(cudaStream_t s, double2 *psi, u64 dim, u64 index) {
     int grid = (int)((dim + 255) / 256 > 148 * 16 ? 148 * 16 : (dim + 255) / 256);
-    k_set_basis<<<grid, 256, 0, s>>>(psi, dim, index);
+    ++g_fh_launch_count; k_set_basis<<<grid, 256, 0, s>>>(psi, dim, index);
 }
 
 void launch_flush(cudaStream_t s, void *buf, size_t bytes) {
-    k_flush<<<148 * 8, 256, 0, s>>>(reinterpret_cast<double4 *>(buf), bytes / sizeof(double4));
+    ++g_fh_launch_count; k_flush<<<148 * 8, 256, 0, s>>>(reinterpret_cast<double4 *>(buf), bytes / sizeof(double4));
 }
 
 static inline int vec_grid(u64 dim, int sm) { return grid_for(dim, 256, 2, sm, sm * 16); }
 
 void launch_axpby(cudaStream_t s, int sm, double2 *y, double a, const double2 *x, double b, u64 dim) {
-    k_axpby<<<vec_grid(dim, sm), 256, 0, s>>>(y, a, x, b, dim);
+    ++g_fh_launch_count; k_axpby<<<vec_grid(dim, sm), 256, 0, s>>>(y, a, x, b, dim);
 }
 void launch_caxpy(cudaStream_t s, int sm, double2 *y, double ar, double ai, const double2 *x, u64 dim) {
-    k_caxpy<<<vec_grid(dim, sm), 256, 0, s>>>(y, ar, ai, x, dim);
+    ++g_fh_launch_count; k_caxpy<<<vec_grid(dim, sm), 256, 0, s>>>(y, ar, ai, x, dim);
 }
 void launch_lanczos_update(cudaStream_t s, int sm, double2 *w, const double2 *v, const double2 *vprev, double alpha,
                            double beta, u64 dim) {
-    k_lanczos_update<<<vec_grid(dim, sm), 256, 0, s>>>(w, v, vprev, alpha, beta, dim);
+    ++g_fh_launch_count; k_lanczos_update<<<vec_grid(dim, sm), 256, 0, s>>>(w, v, vprev, alpha, beta, dim);
 }
 void launch_scale(cudaStream_t s, int sm, double2 *y, double a, u64 dim) {
-    k_scale<<<vec_grid(dim, sm), 256, 0, s>>>(y, a, dim);
+    ++g_fh_launch_count; k_scale<<<vec_grid(dim, sm), 256, 0, s>>>(y, a, dim);
 }
 void launch_sector_random(cudaStream_t s, int sm, double2 *v, int n, int n_up, int n_dn, u64 seed) {
-    k_sector_random<<<vec_grid(1ull << n, sm), 256, 0, s>>>(v, n, n_up, n_dn, seed);
+    ++g_fh_launch_count; k_sector_random<<<vec_grid(1ull << n, sm), 256, 0, s>>>(v, n, n_up, n_dn, seed);
 }

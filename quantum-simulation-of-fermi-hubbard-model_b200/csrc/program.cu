@@ -64,7 +64,13 @@ struct fh_program {
     std::vector<int> seg_param;       // per processed segment: parameter index
     std::vector<double> seg_scale;    // per processed segment: 2*gscale
     int n_segments = 0;
+    // measurement
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms = 0.0;
+    int last_launches = 0;
 };
+
+extern long long g_fh_launch_count;
 
 static inline int popcnt(u64 v) { return __builtin_popcountll(v); }
 
@@ -95,6 +101,8 @@ extern "C" int fh_program_destroy(fh_program *p) {
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
     drop_graph(p);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
     cudaFree(p->d_pairs);
     cudaFree(p->d_dterms);
     cudaFree(p->d_diagops);
@@ -552,11 +560,20 @@ extern "C" int fh_program_evaluate(fh_program *p, uint64_t basis_index, const do
     key.state_out = state_out;
 
     static const bool no_graph = getenv("FHSIM_NO_GRAPH") != nullptr;
+    if (!p->ev0) {
+        FH_CUDA(cudaEventCreate(&p->ev0));
+        FH_CUDA(cudaEventCreate(&p->ev1));
+    }
     if (no_graph) {
+        const long long before = g_fh_launch_count;
+        FH_CUDA(cudaEventRecord(p->ev0, ctx->stream));
         FH_TRY(enqueue_evaluation(p, key, tables, pool, targets, state_out));
+        FH_CUDA(cudaEventRecord(p->ev1, ctx->stream));
+        p->last_launches = (int)(g_fh_launch_count - before);
     } else {
         if (!p->have_graph || !(p->key == key)) {
             drop_graph(p);
+            const long long before = g_fh_launch_count;
             FH_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
             const int rc = enqueue_evaluation(p, key, tables, pool, targets, state_out);
             cudaGraph_t g = nullptr;
@@ -573,10 +590,18 @@ extern "C" int fh_program_evaluate(fh_program *p, uint64_t basis_index, const do
             FH_CUDA(cudaGraphInstantiate(&p->exec, p->graph, 0));
             p->key = key;
             p->have_graph = true;
+            p->last_launches = (int)(g_fh_launch_count - before);
         }
+        FH_CUDA(cudaEventRecord(p->ev0, ctx->stream));
         FH_CUDA(cudaGraphLaunch(p->exec, ctx->stream));
+        FH_CUDA(cudaEventRecord(p->ev1, ctx->stream));
     }
     FH_CUDA(cudaStreamSynchronize(ctx->stream));
+    {
+        float ms = 0.f;
+        FH_CUDA(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+        p->last_ms = ms;
+    }
 
     for (int t = 0; t < n_tables; ++t) expvals[t] = p->h_res[2 * t];
     for (int v = 0; v < 2 * n_overlaps; ++v) overlaps[v] = p->h_res[2 * n_tables + v];
@@ -585,5 +610,12 @@ extern "C" int fh_program_evaluate(fh_program *p, uint64_t basis_index, const do
         for (int s = 0; s < p->n_segments; ++s) grads[p->seg_param[s]] += p->seg_scale[s] * p->h_gseg[s];
     }
     if (pool && pool_count > 0) memcpy(pool_out, pool->h_out, sizeof(double) * pool_count);
+    return FH_OK;
+}
+
+extern "C" int fh_program_last_stats(const fh_program *p, double *elapsed_ms, int *kernel_launches) {
+    FH_REQUIRE(p, "fh_program_last_stats: program is NULL");
+    if (elapsed_ms) *elapsed_ms = p->last_ms;
+    if (kernel_launches) *kernel_launches = p->last_launches;
     return FH_OK;
 }

@@ -26,6 +26,8 @@ SIGNATURES = {
     "fh_ctx_sync": [_vp],
     "fh_ctx_info": [_vp, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)],
     "fh_ctx_flush_l2": [_vp, C.c_size_t],
+    "fh_ctx_timer_start": [_vp],
+    "fh_ctx_timer_stop": [_vp, _f64p],
     "fh_state_create": [_vp, C.c_int, _vpp],
     "fh_state_wrap": [_vp, C.c_int, _vp, _vpp],
     "fh_state_destroy": [_vp],
@@ -58,6 +60,7 @@ SIGNATURES = {
     "fh_program_run": [_vp, _vp, _f64p, C.c_int, C.c_int, C.c_int, C.c_int],
     "fh_program_evaluate": [_vp, C.c_uint64, _f64p, C.c_int, C.c_int, _vpp, _f64p, _f64p, _vp, C.c_int, C.c_int,
                             C.c_int, _f64p, C.c_int, _vpp, _f64p, _vp],
+    "fh_program_last_stats": [_vp, _f64p, C.POINTER(C.c_int)],
     "fh_lanczos": [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint64, _f64p, _vpp, C.POINTER(C.c_int)],
 }
 _SPECIAL = {"fh_version": ([], C.c_int), "fh_last_error": ([], C.c_char_p)}

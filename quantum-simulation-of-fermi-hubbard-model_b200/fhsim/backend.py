@@ -32,6 +32,15 @@ class Context:
     def flush_l2(self, nbytes=256 << 20):
         _cabi.check(_cabi.lib().fh_ctx_flush_l2(self._h, int(nbytes)))
 
+    def timer_start(self):
+        _cabi.check(_cabi.lib().fh_ctx_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        """Elapsed device time in milliseconds since timer_start (CUDA events on this context's stream)."""
+        ms = C.c_double()
+        _cabi.check(_cabi.lib().fh_ctx_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
     def close(self):
         if self._h:
             _cabi.lib().fh_ctx_destroy(self._h)
@@ -192,6 +201,12 @@ class DevicePool:
         oa, op = _cabi.i32_array(out)
         _cabi.check(_cabi.lib().fh_pool_upload(ctx._h, self.n, self.n_entries, xp, fp, vp, zp, rp, ip, op, self.n_out,
                                                C.byref(self._h)))
+
+    def enqueue(self, psi: State, lam: State, first=0, count=None):
+        """Launch the screening kernels only (no copy-back, no sync); for timing the kernel alone."""
+        if count is None:
+            count = self.n_out - first
+        _cabi.check(_cabi.lib().fh_pool_gradients(self._h, psi._h, lam._h, int(first), int(count), None))
 
     def gradients(self, psi: State, lam: State, first=0, count=None) -> np.ndarray:
         if count is None:

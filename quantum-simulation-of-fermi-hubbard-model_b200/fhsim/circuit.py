@@ -340,6 +340,12 @@ class DeviceProgram:
         except Exception:
             pass
 
+    def last_stats(self):
+        """(device milliseconds, kernel launches) of the most recent ``evaluate`` call."""
+        ms, nl = _cabi.C.c_double(), _cabi.C.c_int()
+        _cabi.check(_cabi.lib().fh_program_last_stats(self._h, _cabi.C.byref(ms), _cabi.C.byref(nl)))
+        return ms.value, nl.value
+
     def run(self, state, thetas=(), first=0, count=None, dagger=False):
         """Apply launch items [first, first+count) to ``state`` in place."""
         if count is None:
