@@ -140,7 +140,7 @@ def build_gpu_workload(ctx):
     for j, k in enumerate(picks):
         circ.generator(plans[k], param=j)
     circ.marker("ansatz_end")
-    circ.basis_change(diag, list(reversed(dec)))
+    circ.basis_change_separable(NX, NY)      # same unitary as the reference W network (tests/test_circuit_host.py)
     prog = circ.compile(ctx)
     return dict(prog=prog, dtab=dtab, dpool=dpool, basis=basis, thetas=thetas, picks=picks, circ=circ,
                 plans=plans, dec=dec, diag=diag, h_tab=h_tab)

@@ -44,6 +44,8 @@ void fh_set_error(const char *fmt, ...);
 // ----------------------------------------------------------------------------------------------
 #define FH_MAX_FIX 16      // max bits in a pair op's fixmask
 #define FH_MAX_TILE_BITS 13
+#define FH_TILE_MAX_SUB 96      // ops per fused tile kernel (descriptors live in shared memory)
+#define FH_TILE_MAX_TERMS 256   // diagonal terms per fused tile kernel
 
 // 2x2 op on index pairs (i, i^x) selected by (i & fixmask) == fixval, sign s = parity(i & zeta).
 struct __align__(16) PairOp {

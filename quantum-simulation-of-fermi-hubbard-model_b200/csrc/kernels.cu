@@ -232,54 +232,179 @@ __global__ void __launch_bounds__(256) k_diag_adjoint(double2 *__restrict__ psi,
 // A tile = all 2^T amplitudes that differ only in the T tile bits.  Each CTA stages one tile in shared
 // memory (plus the global index of every slot), applies the whole run of ops to it with one
 // __syncthreads per op, and writes it back: one global read + one write for the whole run.
-__global__ void __launch_bounds__(256) k_tile(double2 *__restrict__ psi, const TileOp *__restrict__ tilep,
+// The op descriptors of the run are gathered into shared memory by all threads in parallel first, so
+// the per-op loop never waits on global memory.
+#define TILE_MAX_SUB FH_TILE_MAX_SUB
+#define TILE_MAX_TERMS FH_TILE_MAX_TERMS
+
+struct __align__(16) TileRec {      // 112 bytes
+    unsigned fixmask_out, fixval_out;   // pattern bits outside the tile: uniform per tile
+    unsigned zeta, xlocal;
+    unsigned lfixval;                   // pattern bits inside the tile, in tile-local coordinates
+    int type;                           // 1 pair (complex matrix), 3 pair (real matrix), 2 diag
+    int nlfix, term_off, nterms;
+    int pad;
+    unsigned char lfix[8];              // ascending tile-local positions of the pattern bits
+    double m[8];
+};
+
+struct __align__(16) TileTerm {     // 32 bytes
+    u64 z;
+    double angle, c, s;
+};
+
+__device__ __forceinline__ double2 tile_diag_phase(const TileTerm *t, int nterms, unsigned gi) {
+    double2 ph;
+    if (nterms <= 4) {
+        ph = make_double2(1.0, 0.0);
+        for (int m = 0; m < nterms; ++m) {
+            const double sg = (__popc(gi & (unsigned)t[m].z) & 1) ? -1.0 : 1.0;
+            ph = cmul(ph, make_double2(t[m].c, -sg * t[m].s));
+        }
+    } else {
+        double tot = 0.0;
+        for (int m = 0; m < nterms; ++m) tot += ((__popc(gi & (unsigned)t[m].z) & 1) ? -1.0 : 1.0) * t[m].angle;
+        double sn, cs;
+        sincos(tot, &sn, &cs);
+        ph = make_double2(cs, -sn);
+    }
+    return ph;
+}
+
+__global__ void __launch_bounds__(512) k_tile(double2 *__restrict__ psi, const TileOp *__restrict__ tilep,
                                               const TileSub *__restrict__ subs, const PairOp *__restrict__ pairs,
                                               const DiagOp *__restrict__ diags, const DiagTerm *__restrict__ terms,
                                               int n, int dagger) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ TileOp tile;
+    __shared__ TileRec rec[TILE_MAX_SUB];
+    __shared__ TileTerm tterm[TILE_MAX_TERMS];
+    __shared__ unsigned slo[64], shi[128];      // scatter tables: local index bits -> global bit positions
     if (threadIdx.x < sizeof(TileOp) / 4)
         reinterpret_cast<unsigned int *>(&tile)[threadIdx.x] = reinterpret_cast<const unsigned int *>(tilep)[threadIdx.x];
     __syncthreads();
-    const int T = tile.nbits;
+    const int T = tile.nbits, nsub = tile.nsub;
     const unsigned L = 1u << T;
     double2 *buf = reinterpret_cast<double2 *>(smem_raw);
     unsigned int *gidx = reinterpret_cast<unsigned int *>(buf + L);
+
+    if (threadIdx.x < 64) {
+        unsigned g = 0;
+        for (int b = 0; b < 6 && b < T; ++b) g |= ((threadIdx.x >> b) & 1u) << tile.bits[b];
+        slo[threadIdx.x] = g;
+    } else if (threadIdx.x < 192) {
+        const unsigned v = threadIdx.x - 64;
+        unsigned g = 0;
+        for (int b = 6; b < T; ++b) g |= ((v >> (b - 6)) & 1u) << tile.bits[b];
+        shi[v] = g;
+    }
+    unsigned tilemask = 0;
+    for (int b = 0; b < T; ++b) tilemask |= 1u << tile.bits[b];
+
+    // ---- gather the run's descriptors in parallel (execution order, dagger applied) ----
+    for (int sidx = threadIdx.x; sidx < nsub; sidx += blockDim.x) {
+        const TileSub sub = subs[tile.first_sub + (dagger ? nsub - 1 - sidx : sidx)];
+        TileRec r;
+        r.pad = 0;
+        if (sub.type == 1) {
+            const PairOp *op = pairs + sub.index;
+            const Mat2 M = op_matrix(*op, dagger);
+            r.m[0] = M.m00.x; r.m[1] = M.m00.y; r.m[2] = M.m01.x; r.m[3] = M.m01.y;
+            r.m[4] = M.m10.x; r.m[5] = M.m10.y; r.m[6] = M.m11.x; r.m[7] = M.m11.y;
+            const bool real = (M.m00.y == 0.0 && M.m01.y == 0.0 && M.m10.y == 0.0 && M.m11.y == 0.0);
+            r.type = real ? 3 : 1;
+            const unsigned fm = (unsigned)op->fixmask, fv = (unsigned)op->fixval;
+            r.fixmask_out = fm & ~tilemask;
+            r.fixval_out = fv & ~tilemask;
+            r.zeta = (unsigned)op->zeta;
+            r.xlocal = sub.xlocal;
+            int nl = 0;
+            unsigned lv = 0;
+            for (int b = 0; b < T; ++b)
+                if (fm >> tile.bits[b] & 1u) {
+                    if (nl < 8) r.lfix[nl] = (unsigned char)b;
+                    ++nl;
+                    lv |= ((fv >> tile.bits[b]) & 1u) << b;
+                }
+            r.nlfix = nl;
+            r.lfixval = lv;
+            r.term_off = 0;
+            r.nterms = 0;
+        } else {
+            const DiagOp d = diags[sub.index];
+            r.type = 2;
+            r.fixmask_out = r.fixval_out = r.zeta = r.xlocal = r.lfixval = 0;
+            r.nlfix = 0;
+            r.term_off = sub.lpivot;          // tile-local term offset (host-computed)
+            r.nterms = d.count;
+            for (int m = 0; m < d.count; ++m) {
+                const DiagTerm t = terms[d.first + m];
+                TileTerm tt;
+                tt.z = t.z;
+                tt.angle = dagger ? -t.angle : t.angle;
+                tt.c = t.c;
+                tt.s = dagger ? -t.s : t.s;
+                tterm[sub.lpivot + m] = tt;
+            }
+            for (int k = 0; k < 8; ++k) r.m[k] = 0.0;
+        }
+        rec[sidx] = r;
+    }
+    __syncthreads();
+
     const u64 ntiles = 1ull << (n - T);
     for (u64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const u64 base = deposit_zeros(t, tile.bits, T);
+        const unsigned base = (unsigned)deposit_zeros(t, tile.bits, T);
         for (unsigned l = threadIdx.x; l < L; l += blockDim.x) {
-            u64 g = base;
-            for (int b = 0; b < T; ++b) g |= (u64)((l >> b) & 1u) << tile.bits[b];
-            gidx[l] = (unsigned int)g;
+            const unsigned g = base | slo[l & 63u] | shi[l >> 6];
+            gidx[l] = g;
             buf[l] = psi[g];
         }
         __syncthreads();
-        for (int sidx = 0; sidx < tile.nsub; ++sidx) {
-            const TileSub sub = subs[tile.first_sub + (dagger ? tile.nsub - 1 - sidx : sidx)];
-            if (sub.type == 1) {
-                const PairOp *op = pairs + sub.index;
-                const Mat2 M = op_matrix(*op, dagger);
-                const u64 fixmask = op->fixmask, fixval = op->fixval, zeta = op->zeta;
-                const unsigned lowmask = (1u << sub.lpivot) - 1u;
-                for (unsigned k = threadIdx.x; k < (L >> 1); k += blockDim.x) {
-                    const unsigned il = ((k >> sub.lpivot) << (sub.lpivot + 1)) | (k & lowmask);
-                    const u64 gi = gidx[il];
-                    if ((gi & fixmask) == fixval) {
-                        const unsigned jl = il ^ sub.xlocal;
-                        double2 a = buf[il], b = buf[jl];
-                        rot2(M, sign_of(gi & zeta), a, b);
-                        buf[il] = a;
-                        buf[jl] = b;
+        for (int sidx = 0; sidx < nsub; ++sidx) {
+            const TileRec &r = rec[sidx];
+            const int type = r.type;
+            if (type != 2) {
+                if ((base & r.fixmask_out) == r.fixval_out) {
+                    const int nl = r.nlfix;
+                    const unsigned npairs = L >> nl;
+                    if (threadIdx.x < npairs) {
+                        const unsigned zeta = r.zeta, xl = r.xlocal, lv = r.lfixval;
+                        const double m00 = r.m[0], m01 = r.m[2], m10 = r.m[4], m11 = r.m[6];
+                        for (unsigned k = threadIdx.x; k < npairs; k += blockDim.x) {
+                            unsigned il = k;
+                            for (int q = 0; q < nl; ++q) {
+                                const unsigned p = r.lfix[q];
+                                il = ((il >> p) << (p + 1)) | (il & ((1u << p) - 1u));
+                            }
+                            il |= lv;
+                            const unsigned jl = il ^ xl;
+                            const double sg = (__popc(gidx[il] & zeta) & 1) ? -1.0 : 1.0;
+                            double2 a = buf[il], b = buf[jl];
+                            if (type == 3) {
+                                const double s01 = sg * m01, s10 = sg * m10;
+                                const double2 ra = make_double2(m00 * a.x + s01 * b.x, m00 * a.y + s01 * b.y);
+                                const double2 rb = make_double2(s10 * a.x + m11 * b.x, s10 * a.y + m11 * b.y);
+                                a = ra;
+                                b = rb;
+                            } else {
+                                Mat2 M;
+                                M.m00 = make_double2(r.m[0], r.m[1]);
+                                M.m01 = make_double2(r.m[2], r.m[3]);
+                                M.m10 = make_double2(r.m[4], r.m[5]);
+                                M.m11 = make_double2(r.m[6], r.m[7]);
+                                rot2(M, sg, a, b);
+                            }
+                            buf[il] = a;
+                            buf[jl] = b;
+                        }
                     }
                 }
             } else {
-                const DiagOp d = diags[sub.index];
-                const DiagTerm *dt = terms + d.first;
-                for (unsigned l = threadIdx.x; l < L; l += blockDim.x) {
-                    const double2 ph = diag_phase(dt, d.count, (u64)gidx[l], dagger);
-                    buf[l] = cmul(ph, buf[l]);
-                }
+                const TileTerm *dt = tterm + r.term_off;
+                const int cnt = r.nterms;
+                for (unsigned l = threadIdx.x; l < L; l += blockDim.x)
+                    buf[l] = cmul(tile_diag_phase(dt, cnt, gidx[l]), buf[l]);
             }
             __syncthreads();
         }
@@ -571,13 +696,21 @@ void launch_tile(cudaStream_t s, double2 *psi, const TileOp *d_tile, const TileS
                  const DiagOp *d_diags, const DiagTerm *d_terms, int n, int nbits, int dagger, double2 *psi2) {
     const size_t smem = ((size_t)1 << nbits) * (sizeof(double2) + sizeof(unsigned int));
     if (!g_tile_attr_set) {
-        cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
         g_tile_attr_set = true;
     }
     u64 ntiles = 1ull << (n - nbits);
     const int grid = (int)(ntiles > 148ull * 16 ? 148ull * 16 : ntiles);
-    ++g_fh_launch_count; k_tile<<<grid, 256, smem, s>>>(psi, d_tile, d_subs, d_pairs, d_diags, d_terms, n, dagger);
-    if (psi2) k_tile<<<grid, 256, smem, s>>>(psi2, d_tile, d_subs, d_pairs, d_diags, d_terms, n, dagger);
+    // one thread per index pair of the tile (at most 1024); small problems get at least 64 threads
+    int threads = nbits >= 1 ? (1 << (nbits - 1)) : 1;
+    if (threads > 512) threads = 512;
+    if (threads < 192) threads = 192;           // the scatter tables are filled by threads 0..191
+    ++g_fh_launch_count;
+    k_tile<<<grid, threads, smem, s>>>(psi, d_tile, d_subs, d_pairs, d_diags, d_terms, n, dagger);
+    if (psi2) {
+        ++g_fh_launch_count;
+        k_tile<<<grid, threads, smem, s>>>(psi2, d_tile, d_subs, d_pairs, d_diags, d_terms, n, dagger);
+    }
 }
 
 void launch_apply_table(cudaStream_t s, int sm, const TabGroup *g, int ngroups, const TabTerm *t, int nterms,

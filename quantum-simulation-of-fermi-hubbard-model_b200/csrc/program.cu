@@ -143,6 +143,9 @@ extern "C" int fh_program_add_pair(fh_program *p, uint64_t x, uint64_t fixmask, 
         op.bhat[0] = bhat_re;
         op.bhat[1] = bhat_im;
     }
+    if (p->in_tile)
+        FH_REQUIRE(p->tiles.back().nsub < FH_TILE_MAX_SUB, "fh_program_add_pair: more than %d ops in one tile",
+                   FH_TILE_MAX_SUB);
     const int idx = (int)p->pairs.size();
     p->pairs.push_back(op);
     if (p->in_tile) {
@@ -159,6 +162,9 @@ extern "C" int fh_program_add_pair(fh_program *p, uint64_t x, uint64_t fixmask, 
             }
         }
         FH_REQUIRE(rest == 0, "fh_program_add_pair: x-mask 0x%llx not inside the open tile", (u64)x);
+        u64 tmask = 0;
+        for (int b = 0; b < t.nbits; ++b) tmask |= 1ull << t.bits[b];
+        FH_REQUIRE(popcnt(fixmask & tmask) <= 8, "fh_program_add_pair: more than 8 pattern bits inside a tile");
         TileSub s;
         s.type = 1;
         s.index = idx;
@@ -197,13 +203,18 @@ extern "C" int fh_program_add_diag(fh_program *p, int n_terms, const uint64_t *z
     const int idx = (int)p->diagops.size();
     p->diagops.push_back(d);
     if (p->in_tile) {
+        TileOp &t = p->tiles.back();
+        FH_REQUIRE(t.nsub < FH_TILE_MAX_SUB, "fh_program_add_diag: more than %d ops in one tile", FH_TILE_MAX_SUB);
+        FH_REQUIRE(t.pad + n_terms <= FH_TILE_MAX_TERMS, "fh_program_add_diag: more than %d diagonal terms in one tile",
+                   FH_TILE_MAX_TERMS);
         TileSub s;
         s.type = 2;
         s.index = idx;
-        s.lpivot = 0;
+        s.lpivot = t.pad;          // tile-local offset of this op's terms
         s.xlocal = 0;
         p->subs.push_back(s);
-        p->tiles.back().nsub++;
+        t.pad += n_terms;
+        t.nsub++;
     } else {
         p->items.push_back({2, idx});
     }

@@ -140,6 +140,79 @@ class Circuit:
         x, fixmask, fixval, zeta, m = _normalise_pair(x, x, bj, 0, m)
         self.ops.append(PairOpSpec(x, fixmask, fixval, zeta, matrix=m, strings=[(x, bi), (x, bj)]))
 
+    def fermionic_single_excitation(self, phi, wire_i, wire_j):
+        """exp((phi/2)(a†_i a_j - a†_j a_i)): the Givens rotation between two *modes* under Jordan-Wigner.
+        Same 2x2 block as ``single_excitation`` on |q_i q_j> = |01>, |10>, times the parity of the
+        occupied modes strictly between i and j (for adjacent modes the two gates coincide)."""
+        bi, bj = self._bit(wire_i), self._bit(wire_j)
+        c, s = math.cos(0.5 * phi), math.sin(0.5 * phi)
+        x = bi | bj
+        hi, lo = max(bi, bj), min(bi, bj)
+        between = (hi - 1) & ~((lo << 1) - 1)
+        m = (c, 0.0, -s, 0.0, s, 0.0, c, 0.0)
+        x, fixmask, fixval, zeta, m = _normalise_pair(x, x, bj, between, m)
+        self.ops.append(PairOpSpec(x, fixmask, fixval, zeta, matrix=m,
+                                   strings=[(x, between | bi), (x, between | bj)]))
+
+    def gaussian(self, unitary, wires):
+        """Fermionic Gaussian unitary W with W a†_p W† = sum_q U[p,q] a†_q on the listed modes: the
+        Givens network of ``givens_decomposition_square(U)`` with fermionic rotations, i.e. the recipe
+        of reference adapt_vqe.py:344-354 for an arbitrary (not necessarily adjacent) set of modes.
+        Returns the phase the network puts on the vacuum."""
+        from .symbolic import givens_decomposition_square
+        decomposition, diagonal = givens_decomposition_square(np.asarray(unitary, dtype=complex))
+        total = 0.0
+        phases = []
+        for i, w in enumerate(wires):
+            a = float(np.angle(diagonal[i]))
+            if a != 0.0:
+                phases.append((self._bit(w), 0.5 * a))
+                total += a
+        if phases:
+            zs = [b for b, _ in phases]
+            self.ops.append(DiagOpSpec(zs, [a for _, a in phases], -1, [(0, b) for b in zs]))
+        for layer in reversed(decomposition):
+            phases = []
+            for (i, j, theta, phi) in layer:
+                self.fermionic_single_excitation(2.0 * theta, wires[i], wires[j])
+                if phi != 0.0:
+                    phases.append((self._bit(wires[j]), 0.5 * float(phi)))
+                    total += float(phi)
+            if phases:
+                zs = [b for b, _ in phases]
+                self.ops.append(DiagOpSpec(zs, [a for _, a in phases], -1, [(0, b) for b in zs]))
+        return -0.5 * total            # vacuum picks up exp(-i/2 sum of RZ angles)
+
+    def basis_change_separable(self, x_dimension, y_dimension):
+        """Same unitary as ``basis_change`` for ``fourier_transform_matrix`` (up to a global phase), compiled
+        from its tensor structure: the matrix is F_x (x) F_y per spin, so W factorises into commuting row
+        and column transforms -- N(Nx+Ny-2)... Givens rotations instead of n(n-1)/2 (3x3: 36 vs 144).
+        Returns the vacuum phase of this network (see ``basis_change_vacuum_phase``)."""
+        Nx, Ny = x_dimension, y_dimension
+
+        def dft(L):
+            k = np.arange(L)
+            return np.exp(-1j * 2 * np.pi * np.outer(k, k) / L) / np.sqrt(L)
+
+        phase = 0.0
+        for spin in (0, 1):
+            if Nx > 1:
+                for y in range(Ny):
+                    phase += self.gaussian(dft(Nx), [2 * (x + y * Nx) + spin for x in range(Nx)])
+            if Ny > 1:
+                for x in range(Nx):
+                    phase += self.gaussian(dft(Ny), [2 * (x + y * Nx) + spin for y in range(Ny)])
+        return phase
+
+    @staticmethod
+    def basis_change_vacuum_phase(diagonal, circuit_description):
+        """Phase (radians) the reference W network (``basis_change``) puts on the vacuum."""
+        total = sum(float(np.angle(d)) for d in diagonal)
+        for layer in circuit_description:
+            for (_, _, _, phi) in layer:
+                total += float(phi)
+        return -0.5 * total
+
     def pauli_rotation(self, x, z, coef, angle=0.0, param=-1):
         """exp(-i a coef P) with a = theta[param] (or the fixed ``angle``) for one string (x, z)."""
         if x == 0:
@@ -189,16 +262,23 @@ class Circuit:
     def basis_change(self, diagonal, circuit_description):
         """The W network of reference adapt_vqe.py:344-354: RZ(angle(diagonal[q])) on every wire, then for
         each layer (already reversed by the caller) SingleExcitation(2 theta, [i, j]) and RZ(phi, j)."""
-        for q in range(len(diagonal)):
-            a = float(np.angle(diagonal[q]))
-            if a != 0.0:
-                self.rz(a, q)
+        first = [(self._bit(q), 0.5 * float(np.angle(diagonal[q]))) for q in range(len(diagonal))
+                 if float(np.angle(diagonal[q])) != 0.0]
+        if first:
+            zs = [b for b, _ in first]
+            self.ops.append(DiagOpSpec(zs, [a for _, a in first], -1, [(0, b) for b in zs]))
         for layer in circuit_description:
+            phases = []
             for op in layer:
                 i, j, theta, phi = op
                 self.single_excitation(2.0 * theta, i, j)
                 if phi != 0.0:
-                    self.rz(phi, j)
+                    phases.append((self._bit(j), 0.5 * float(phi)))
+            if phases:
+                # the RZs of one layer sit on disjoint wires and commute with the layer's other rotations:
+                # one diagonal op per layer
+                zs = [b for b, _ in phases]
+                self.ops.append(DiagOpSpec(zs, [a for _, a in phases], -1, [(0, b) for b in zs]))
 
     # -- compilation ------------------------------------------------------------------------
     def compile(self, ctx, fuse=True, tile_bits=None, low_bits=None):
@@ -208,6 +288,8 @@ class Circuit:
 # ---------------------------------------------------------------------------------------------
 # tile scheduling
 # ---------------------------------------------------------------------------------------------
+MAX_TILE_OPS = 96             # FH_TILE_MAX_SUB
+MAX_TILE_TERMS = 256          # FH_TILE_MAX_TERMS
 _LAUNCH_BYTES = 12e6          # bytes of traffic one kernel launch is "worth" (launch latency x bandwidth)
 
 
@@ -229,15 +311,17 @@ def schedule(ops, n, tile_bits, low_bits, lookahead=512):
     while remaining:
         bits = base_bits
         chosen, skipped = [], []
-        scanned = 0
+        scanned = n_terms = 0
         for op in remaining:
             scanned += 1
             if skipped and any(not _ops_commute(op, s) for s in skipped):
                 skipped.append(op)
             else:
                 need = bits | op.tile_bits
-                if popcount(need) <= tile_bits:
+                nt = len(op.z) if isinstance(op, DiagOpSpec) else 0
+                if popcount(need) <= tile_bits and len(chosen) < MAX_TILE_OPS and n_terms + nt <= MAX_TILE_TERMS:
                     bits = need
+                    n_terms += nt
                     chosen.append(op)
                 else:
                     skipped.append(op)

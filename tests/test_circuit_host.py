@@ -132,3 +132,22 @@ def test_scheduler_preserves_the_unitary(tile_bits, low_bits):
     assert sum(1 if it[0] == "op" else len(it[2]) for it in items) == len(ops)
     assert any(it[0] == "tile" for it in items)
     assert np.abs(run_items(items, psi, th, n) - want).max() < 1e-12
+
+
+@pytest.mark.parametrize("lat", [(2, 2), (3, 1), (2, 3), (3, 2), (3, 3)])
+def test_separable_basis_change_equals_reference_network(lat):
+    """W compiled from the tensor structure of the FT matrix (36 fermionic Givens at 3x3) is the
+    reference's 144-rotation network up to the global phase both vacuum phases predict."""
+    nx, ny = lat
+    n = 2 * nx * ny
+    dec, diag = givens_decomposition_square(fourier_transform_matrix(nx, ny))
+    ref = Circuit(n)
+    ref.basis_change(diag, list(reversed(dec)))
+    fast = Circuit(n)
+    ph_fast = fast.basis_change_separable(nx, ny)
+    ph_ref = Circuit.basis_change_vacuum_phase(diag, dec)
+    assert len(fast.ops) < len(ref.ops)
+    psi = rand_state(n, 17)
+    want = sv.basis_change(psi, diag, dec, n)
+    got = run_circuit(fast, psi) * np.exp(-1j * (ph_fast - ph_ref))
+    assert np.abs(got - want).max() < 1e-12

@@ -121,9 +121,9 @@ def test_pool_gradients_vs_oracle(ctx, lat, u, up, dn):
     assert np.array_equal(part, got[5:12])          # pool sharding gives bit-identical slices
 
 
-@pytest.mark.parametrize("fuse", [False, True])
+@pytest.mark.parametrize("fuse,separable", [(False, False), (True, False), (True, True)])
 @pytest.mark.parametrize("lat,u,up,dn", [((2, 2), 4.0, 2, 2), ((2, 3), 4.0, 3, 3)])
-def test_program_evaluate_energy_grads_pool(ctx, lat, u, up, dn, fuse):
+def test_program_evaluate_energy_grads_pool(ctx, lat, u, up, dn, fuse, separable):
     n, h_tab, pool_ops, dec, diag, o_h, o_pool = lattice(*lat, u)
     rng = np.random.default_rng(99)
     occ_up, occ_dn, _ = pauli.k_space_occupation(*lat, 1.0, up, dn)
@@ -134,7 +134,11 @@ def test_program_evaluate_energy_grads_pool(ctx, lat, u, up, dn, fuse):
     for p, k in enumerate(picks):
         circ.generator(plans[k], param=p)
     circ.marker("ansatz_end")
-    circ.basis_change(diag, list(reversed(dec)))
+    phase = 0.0
+    if separable:
+        phase = circ.basis_change_separable(*lat) - Circuit.basis_change_vacuum_phase(diag, dec)
+    else:
+        circ.basis_change(diag, list(reversed(dec)))
     prog = circ.compile(ctx, fuse=fuse)
     dtab = DeviceTable(ctx, h_tab)
     dpool = DevicePool(ctx, plans, n)
@@ -150,7 +154,7 @@ def test_program_evaluate_energy_grads_pool(ctx, lat, u, up, dn, fuse):
     assert np.abs(res["grads"] - g_want).max() < G_TOL
     assert np.abs(res["pool"] - pg_want).max() < G_TOL
     phi = sv.basis_change(psi_k, diag, dec, n)
-    assert np.abs(out_state.numpy() - phi).max() < 1e-12
+    assert np.abs(out_state.numpy() * np.exp(-1j * phase) - phi).max() < 1e-12
     # replay of the captured graph with new parameters
     th2 = th + 0.05
     res2 = prog.evaluate(basis, th2, [dtab], grads=True, pool=dpool, pool_pos=prog.markers["ansatz_end"],
@@ -165,7 +169,7 @@ def test_known_answers_3x3_first_screening(ctx):
     plans = [GeneratorPlan(g, n) for g in pool_ops]
     circ = Circuit(n, 0)
     circ.marker("ansatz_end")
-    circ.basis_change(diag, list(reversed(dec)))
+    circ.basis_change_separable(3, 3)
     prog = circ.compile(ctx)
     occ = [0, 2, 4, 6, 12, 1, 3, 5, 7]
     basis = sum(1 << (n - 1 - q) for q in occ)
