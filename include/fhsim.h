@@ -145,6 +145,8 @@ int fh_program_evaluate(fh_program *prog, uint64_t basis_index, const double *th
 /* measurement: device time (CUDA events bracketing the graph launch on the context's stream) and number of
  * kernel launches of the most recent fh_program_evaluate call */
 int fh_program_last_stats(const fh_program *prog, double *elapsed_ms, int *kernel_launches);
+/* measurement: average device milliseconds of launching items [first, first+count) `reps` times back to back */
+int fh_program_time_items(fh_program *prog, fh_state *st, int first, int count, int dagger, int reps, double *ms_per_rep);
 
 /* ---- K4: Lanczos ground states --------------------------------------------------------------
  * replaces linalg/exact_diagonalization.py:34-51, 181-229 (scipy eigsh, which='SA') and

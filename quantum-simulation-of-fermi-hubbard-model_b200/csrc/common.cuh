@@ -73,19 +73,47 @@ struct DiagOp {
     int pad;
 };
 
-// one entry of a fused tile kernel's op list
+// one entry of a fused tile kernel's op list (host bookkeeping)
 struct TileSub {
     int type;        // 1 pair, 2 diag
     int index;       // index into PairOp / DiagOp arrays
-    int lpivot;      // local (tile) position of the top x bit (pair)
+    int lpivot;      // diag: tile-local offset of its terms
     unsigned int xlocal;   // x in tile-local coordinates (pair)
 };
 
-struct TileOp {
+// geometry of one fused tile kernel: passed BY VALUE as a kernel argument (constant bank, no latency)
+struct TileLaunch {
     int nbits;                          // T
-    int first_sub, nsub;
-    int pad;
+    int nsub;                           // records in this run
+    int first_rec;                      // offset into the record array of the chosen direction
+    int first_term, nterms;             // range in the tile-term array of the chosen direction
     unsigned char bits[16];             // ascending global bit positions of the tile
+};
+
+// ready-to-execute record of one op inside a tile (built on the host, one array per direction)
+struct __align__(16) TileRec {          // 112 bytes
+    unsigned fixmask_out, fixval_out;   // pattern bits outside the tile: uniform per tile
+    unsigned zeta, xlocal;
+    unsigned lfixval;                   // pattern bits inside the tile, in tile-local coordinates
+    int type;                           // 1 pair (complex matrix), 3 pair (real matrix), 2 diag
+    int nlfix, term_off, nterms;
+    int pad;
+    unsigned char lfix[8];              // ascending tile-local positions of the pattern bits
+    double m[8];
+};
+
+struct __align__(16) TileTerm {         // 32 bytes
+    u64 z;
+    double angle, c, s;
+};
+
+struct TileOp {                         // host bookkeeping of one tile run
+    int nbits;
+    int first_sub, nsub;
+    int pad;                            // running count of diagonal terms while the tile is open
+    unsigned char bits[16];
+    int first_rec_fwd, first_rec_dag;   // offsets into the two record arrays
+    int first_term_fwd, first_term_dag, nterms;
 };
 
 struct TabGroup {
@@ -170,8 +198,8 @@ void launch_pair_adjoint(cudaStream_t s, int sm, double2 *psi, double2 *lam, con
 void launch_diag(cudaStream_t s, int sm, double2 *psi, const DiagTerm *d_terms, int nterms, int n, int dagger);
 void launch_diag_adjoint(cudaStream_t s, int sm, double2 *psi, double2 *lam, const DiagTerm *d_terms, int nterms, int n,
                          double *d_partials, int max_blocks, int *blocks_used);
-void launch_tile(cudaStream_t s, double2 *psi, const TileOp *d_tile, const TileSub *d_subs, const PairOp *d_pairs,
-                 const DiagOp *d_diags, const DiagTerm *d_terms, int n, int nbits, int dagger, double2 *psi2);
+void launch_tile(cudaStream_t s, double2 *psi, const TileLaunch &tl, const TileRec *d_recs, const TileTerm *d_terms,
+                 int n);
 void launch_apply_table(cudaStream_t s, int sm, const TabGroup *g, int ngroups, const TabTerm *t, int nterms,
                         bool all_real, const double2 *in, double2 *out, int n, double *d_partials, double *d_result);
 void launch_pool(cudaStream_t s, const PoolEntry *entries, int first_entry, int n_entries, int chunks, int n,

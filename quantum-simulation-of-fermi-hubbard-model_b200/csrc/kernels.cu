@@ -237,22 +237,6 @@ __global__ void __launch_bounds__(256) k_diag_adjoint(double2 *__restrict__ psi,
 #define TILE_MAX_SUB FH_TILE_MAX_SUB
 #define TILE_MAX_TERMS FH_TILE_MAX_TERMS
 
-struct __align__(16) TileRec {      // 112 bytes
-    unsigned fixmask_out, fixval_out;   // pattern bits outside the tile: uniform per tile
-    unsigned zeta, xlocal;
-    unsigned lfixval;                   // pattern bits inside the tile, in tile-local coordinates
-    int type;                           // 1 pair (complex matrix), 3 pair (real matrix), 2 diag
-    int nlfix, term_off, nterms;
-    int pad;
-    unsigned char lfix[8];              // ascending tile-local positions of the pattern bits
-    double m[8];
-};
-
-struct __align__(16) TileTerm {     // 32 bytes
-    u64 z;
-    double angle, c, s;
-};
-
 __device__ __forceinline__ double2 tile_diag_phase(const TileTerm *t, int nterms, unsigned gi) {
     double2 ph;
     if (nterms <= 4) {
@@ -271,90 +255,44 @@ __device__ __forceinline__ double2 tile_diag_phase(const TileTerm *t, int nterms
     return ph;
 }
 
-__global__ void __launch_bounds__(512) k_tile(double2 *__restrict__ psi, const TileOp *__restrict__ tilep,
-                                              const TileSub *__restrict__ subs, const PairOp *__restrict__ pairs,
-                                              const DiagOp *__restrict__ diags, const DiagTerm *__restrict__ terms,
-                                              int n, int dagger) {
+__global__ void __launch_bounds__(512) k_tile(double2 *__restrict__ psi, const TileLaunch tl,
+                                              const TileRec *__restrict__ recs, const TileTerm *__restrict__ terms,
+                                              int n) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ TileOp tile;
     __shared__ TileRec rec[TILE_MAX_SUB];
     __shared__ TileTerm tterm[TILE_MAX_TERMS];
     __shared__ unsigned slo[64], shi[128];      // scatter tables: local index bits -> global bit positions
-    if (threadIdx.x < sizeof(TileOp) / 4)
-        reinterpret_cast<unsigned int *>(&tile)[threadIdx.x] = reinterpret_cast<const unsigned int *>(tilep)[threadIdx.x];
-    __syncthreads();
-    const int T = tile.nbits, nsub = tile.nsub;
+    const int T = tl.nbits, nsub = tl.nsub;
     const unsigned L = 1u << T;
     double2 *buf = reinterpret_cast<double2 *>(smem_raw);
     unsigned int *gidx = reinterpret_cast<unsigned int *>(buf + L);
 
+    // ---- prologue: one coalesced copy of the run's records (issued first, consumed after the tile load) ----
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(recs + tl.first_rec);
+        uint4 *dst = reinterpret_cast<uint4 *>(rec);
+        const int chunks = nsub * (int)(sizeof(TileRec) / 16);
+        for (int c = threadIdx.x; c < chunks; c += blockDim.x) dst[c] = __ldg(src + c);
+        const uint4 *tsrc = reinterpret_cast<const uint4 *>(terms + tl.first_term);
+        uint4 *tdst = reinterpret_cast<uint4 *>(tterm);
+        const int tchunks = tl.nterms * (int)(sizeof(TileTerm) / 16);
+        for (int c = threadIdx.x; c < tchunks; c += blockDim.x) tdst[c] = __ldg(tsrc + c);
+    }
     if (threadIdx.x < 64) {
         unsigned g = 0;
-        for (int b = 0; b < 6 && b < T; ++b) g |= ((threadIdx.x >> b) & 1u) << tile.bits[b];
+        for (int b = 0; b < 6 && b < T; ++b) g |= ((threadIdx.x >> b) & 1u) << tl.bits[b];
         slo[threadIdx.x] = g;
     } else if (threadIdx.x < 192) {
         const unsigned v = threadIdx.x - 64;
         unsigned g = 0;
-        for (int b = 6; b < T; ++b) g |= ((v >> (b - 6)) & 1u) << tile.bits[b];
+        for (int b = 6; b < T; ++b) g |= ((v >> (b - 6)) & 1u) << tl.bits[b];
         shi[v] = g;
-    }
-    unsigned tilemask = 0;
-    for (int b = 0; b < T; ++b) tilemask |= 1u << tile.bits[b];
-
-    // ---- gather the run's descriptors in parallel (execution order, dagger applied) ----
-    for (int sidx = threadIdx.x; sidx < nsub; sidx += blockDim.x) {
-        const TileSub sub = subs[tile.first_sub + (dagger ? nsub - 1 - sidx : sidx)];
-        TileRec r;
-        r.pad = 0;
-        if (sub.type == 1) {
-            const PairOp *op = pairs + sub.index;
-            const Mat2 M = op_matrix(*op, dagger);
-            r.m[0] = M.m00.x; r.m[1] = M.m00.y; r.m[2] = M.m01.x; r.m[3] = M.m01.y;
-            r.m[4] = M.m10.x; r.m[5] = M.m10.y; r.m[6] = M.m11.x; r.m[7] = M.m11.y;
-            const bool real = (M.m00.y == 0.0 && M.m01.y == 0.0 && M.m10.y == 0.0 && M.m11.y == 0.0);
-            r.type = real ? 3 : 1;
-            const unsigned fm = (unsigned)op->fixmask, fv = (unsigned)op->fixval;
-            r.fixmask_out = fm & ~tilemask;
-            r.fixval_out = fv & ~tilemask;
-            r.zeta = (unsigned)op->zeta;
-            r.xlocal = sub.xlocal;
-            int nl = 0;
-            unsigned lv = 0;
-            for (int b = 0; b < T; ++b)
-                if (fm >> tile.bits[b] & 1u) {
-                    if (nl < 8) r.lfix[nl] = (unsigned char)b;
-                    ++nl;
-                    lv |= ((fv >> tile.bits[b]) & 1u) << b;
-                }
-            r.nlfix = nl;
-            r.lfixval = lv;
-            r.term_off = 0;
-            r.nterms = 0;
-        } else {
-            const DiagOp d = diags[sub.index];
-            r.type = 2;
-            r.fixmask_out = r.fixval_out = r.zeta = r.xlocal = r.lfixval = 0;
-            r.nlfix = 0;
-            r.term_off = sub.lpivot;          // tile-local term offset (host-computed)
-            r.nterms = d.count;
-            for (int m = 0; m < d.count; ++m) {
-                const DiagTerm t = terms[d.first + m];
-                TileTerm tt;
-                tt.z = t.z;
-                tt.angle = dagger ? -t.angle : t.angle;
-                tt.c = t.c;
-                tt.s = dagger ? -t.s : t.s;
-                tterm[sub.lpivot + m] = tt;
-            }
-            for (int k = 0; k < 8; ++k) r.m[k] = 0.0;
-        }
-        rec[sidx] = r;
     }
     __syncthreads();
 
     const u64 ntiles = 1ull << (n - T);
     for (u64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const unsigned base = (unsigned)deposit_zeros(t, tile.bits, T);
+        const unsigned base = (unsigned)deposit_zeros(t, tl.bits, T);
         for (unsigned l = threadIdx.x; l < L; l += blockDim.x) {
             const unsigned g = base | slo[l & 63u] | shi[l >> 6];
             gidx[l] = g;
@@ -692,8 +630,9 @@ void launch_diag_adjoint(cudaStream_t s, int sm, double2 *psi, double2 *lam, con
 
 static bool g_tile_attr_set = false;
 
-void launch_tile(cudaStream_t s, double2 *psi, const TileOp *d_tile, const TileSub *d_subs, const PairOp *d_pairs,
-                 const DiagOp *d_diags, const DiagTerm *d_terms, int n, int nbits, int dagger, double2 *psi2) {
+void launch_tile(cudaStream_t s, double2 *psi, const TileLaunch &tl, const TileRec *d_recs, const TileTerm *d_terms,
+                 int n) {
+    const int nbits = tl.nbits;
     const size_t smem = ((size_t)1 << nbits) * (sizeof(double2) + sizeof(unsigned int));
     if (!g_tile_attr_set) {
         cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
@@ -701,16 +640,12 @@ void launch_tile(cudaStream_t s, double2 *psi, const TileOp *d_tile, const TileS
     }
     u64 ntiles = 1ull << (n - nbits);
     const int grid = (int)(ntiles > 148ull * 16 ? 148ull * 16 : ntiles);
-    // one thread per index pair of the tile (at most 1024); small problems get at least 64 threads
+    // one thread per index pair of the tile (at most 512); the scatter tables are filled by threads 0..191
     int threads = nbits >= 1 ? (1 << (nbits - 1)) : 1;
     if (threads > 512) threads = 512;
-    if (threads < 192) threads = 192;           // the scatter tables are filled by threads 0..191
+    if (threads < 192) threads = 192;
     ++g_fh_launch_count;
-    k_tile<<<grid, threads, smem, s>>>(psi, d_tile, d_subs, d_pairs, d_diags, d_terms, n, dagger);
-    if (psi2) {
-        ++g_fh_launch_count;
-        k_tile<<<grid, threads, smem, s>>>(psi2, d_tile, d_subs, d_pairs, d_diags, d_terms, n, dagger);
-    }
+    k_tile<<<grid, threads, smem, s>>>(psi, tl, d_recs, d_terms, n);
 }
 
 void launch_apply_table(cudaStream_t s, int sm, const TabGroup *g, int ngroups, const TabTerm *t, int nterms,

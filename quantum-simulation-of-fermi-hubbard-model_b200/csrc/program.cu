@@ -46,8 +46,13 @@ struct fh_program {
     PairOp *d_pairs = nullptr, *h_pairs = nullptr;
     DiagTerm *d_dterms = nullptr, *h_dterms = nullptr;
     DiagOp *d_diagops = nullptr;
-    TileOp *d_tiles = nullptr;
-    TileSub *d_subs = nullptr;
+    // fused-tile records, one array per direction (host-built, theta-dependent parts refreshed per call)
+    std::vector<TileRec> recs_fwd, recs_dag;
+    std::vector<TileTerm> tterms_fwd, tterms_dag;
+    std::vector<int> pair_rec_fwd, pair_rec_dag;       // pair index -> record index (or -1)
+    std::vector<int> dterm_tt_fwd, dterm_tt_dag;       // diag term index -> tile-term index (or -1)
+    TileRec *d_recs_fwd = nullptr, *d_recs_dag = nullptr, *h_recs_fwd = nullptr, *h_recs_dag = nullptr;
+    TileTerm *d_tterms_fwd = nullptr, *d_tterms_dag = nullptr, *h_tterms_fwd = nullptr, *h_tterms_dag = nullptr;
     // workspaces
     double2 *d_psi = nullptr, *d_lam = nullptr, *d_chk = nullptr;
     // adjoint-gradient partials: one segment per parametrised op processed
@@ -106,8 +111,14 @@ extern "C" int fh_program_destroy(fh_program *p) {
     cudaFree(p->d_pairs);
     cudaFree(p->d_dterms);
     cudaFree(p->d_diagops);
-    cudaFree(p->d_tiles);
-    cudaFree(p->d_subs);
+    cudaFree(p->d_recs_fwd);
+    cudaFree(p->d_recs_dag);
+    cudaFree(p->d_tterms_fwd);
+    cudaFree(p->d_tterms_dag);
+    cudaFreeHost(p->h_recs_fwd);
+    cudaFreeHost(p->h_recs_dag);
+    cudaFreeHost(p->h_tterms_fwd);
+    cudaFreeHost(p->h_tterms_dag);
     cudaFree(p->d_psi);
     cudaFree(p->d_lam);
     cudaFree(p->d_chk);
@@ -253,6 +264,86 @@ extern "C" int fh_program_end_tile(fh_program *p) {
     return FH_OK;
 }
 
+// ----------------------------------------------------------------------------------------------
+// fused-tile records (host): everything k_tile needs per op, in execution order, for both directions
+// ----------------------------------------------------------------------------------------------
+static void set_rec_matrix(TileRec &r, const double m[8], bool dagger) {
+    if (!dagger) {
+        for (int k = 0; k < 8; ++k) r.m[k] = m[k];
+    } else {   // conjugate transpose
+        r.m[0] = m[0]; r.m[1] = -m[1];
+        r.m[2] = m[4]; r.m[3] = -m[5];
+        r.m[4] = m[2]; r.m[5] = -m[3];
+        r.m[6] = m[6]; r.m[7] = -m[7];
+    }
+    const bool real = (r.m[1] == 0.0 && r.m[3] == 0.0 && r.m[5] == 0.0 && r.m[7] == 0.0);
+    r.type = real ? 3 : 1;
+}
+
+static void set_tile_term(TileTerm &tt, const DiagTerm &t, bool dagger) {
+    tt.z = t.z;
+    tt.angle = dagger ? -t.angle : t.angle;
+    tt.c = t.c;
+    tt.s = dagger ? -t.s : t.s;
+}
+
+static void build_tile_records(fh_program *p) {
+    p->pair_rec_fwd.assign(p->pairs.size(), -1);
+    p->pair_rec_dag.assign(p->pairs.size(), -1);
+    p->dterm_tt_fwd.assign(p->dterms.size(), -1);
+    p->dterm_tt_dag.assign(p->dterms.size(), -1);
+    for (auto &t : p->tiles) {
+        unsigned tilemask = 0;
+        for (int b = 0; b < t.nbits; ++b) tilemask |= 1u << t.bits[b];
+        for (int dir = 0; dir < 2; ++dir) {
+            std::vector<TileRec> &recs = dir ? p->recs_dag : p->recs_fwd;
+            std::vector<TileTerm> &tts = dir ? p->tterms_dag : p->tterms_fwd;
+            (dir ? t.first_rec_dag : t.first_rec_fwd) = (int)recs.size();
+            (dir ? t.first_term_dag : t.first_term_fwd) = (int)tts.size();
+            int term_off = 0;
+            for (int k = 0; k < t.nsub; ++k) {
+                const TileSub &sub = p->subs[t.first_sub + (dir ? t.nsub - 1 - k : k)];
+                TileRec r;
+                memset(&r, 0, sizeof(r));
+                if (sub.type == 1) {
+                    const PairOp &op = p->pairs[sub.index];
+                    set_rec_matrix(r, op.m, dir != 0);
+                    const unsigned fm = (unsigned)op.fixmask, fv = (unsigned)op.fixval;
+                    r.fixmask_out = fm & ~tilemask;
+                    r.fixval_out = fv & ~tilemask;
+                    r.zeta = (unsigned)op.zeta;
+                    r.xlocal = sub.xlocal;
+                    int nl = 0;
+                    unsigned lv = 0;
+                    for (int b = 0; b < t.nbits; ++b)
+                        if (fm >> t.bits[b] & 1u) {
+                            if (nl < 8) r.lfix[nl] = (unsigned char)b;
+                            ++nl;
+                            lv |= ((fv >> t.bits[b]) & 1u) << b;
+                        }
+                    r.nlfix = nl;
+                    r.lfixval = lv;
+                    (dir ? p->pair_rec_dag : p->pair_rec_fwd)[sub.index] = (int)recs.size();
+                } else {
+                    const DiagOp &d = p->diagops[sub.index];
+                    r.type = 2;
+                    r.term_off = term_off;
+                    r.nterms = d.count;
+                    for (int m = 0; m < d.count; ++m) {
+                        TileTerm tt;
+                        set_tile_term(tt, p->dterms[d.first + m], dir != 0);
+                        (dir ? p->dterm_tt_dag : p->dterm_tt_fwd)[d.first + m] = (int)tts.size();
+                        tts.push_back(tt);
+                    }
+                    term_off += d.count;
+                }
+                recs.push_back(r);
+            }
+            t.nterms = term_off;
+        }
+    }
+}
+
 template <typename T>
 static int upload_vec(T **dptr, const std::vector<T> &v, cudaStream_t s) {
     if (v.empty()) return FH_OK;
@@ -269,8 +360,23 @@ extern "C" int fh_program_finalize(fh_program *p) {
     FH_TRY(upload_vec(&p->d_pairs, p->pairs, ctx->stream));
     FH_TRY(upload_vec(&p->d_dterms, p->dterms, ctx->stream));
     FH_TRY(upload_vec(&p->d_diagops, p->diagops, ctx->stream));
-    FH_TRY(upload_vec(&p->d_tiles, p->tiles, ctx->stream));
-    FH_TRY(upload_vec(&p->d_subs, p->subs, ctx->stream));
+    build_tile_records(p);
+    FH_TRY(upload_vec(&p->d_recs_fwd, p->recs_fwd, ctx->stream));
+    FH_TRY(upload_vec(&p->d_recs_dag, p->recs_dag, ctx->stream));
+    FH_TRY(upload_vec(&p->d_tterms_fwd, p->tterms_fwd, ctx->stream));
+    FH_TRY(upload_vec(&p->d_tterms_dag, p->tterms_dag, ctx->stream));
+    if (!p->recs_fwd.empty()) {
+        FH_CUDA(cudaMallocHost(&p->h_recs_fwd, sizeof(TileRec) * p->recs_fwd.size()));
+        FH_CUDA(cudaMallocHost(&p->h_recs_dag, sizeof(TileRec) * p->recs_dag.size()));
+        memcpy(p->h_recs_fwd, p->recs_fwd.data(), sizeof(TileRec) * p->recs_fwd.size());
+        memcpy(p->h_recs_dag, p->recs_dag.data(), sizeof(TileRec) * p->recs_dag.size());
+    }
+    if (!p->tterms_fwd.empty()) {
+        FH_CUDA(cudaMallocHost(&p->h_tterms_fwd, sizeof(TileTerm) * p->tterms_fwd.size()));
+        FH_CUDA(cudaMallocHost(&p->h_tterms_dag, sizeof(TileTerm) * p->tterms_dag.size()));
+        memcpy(p->h_tterms_fwd, p->tterms_fwd.data(), sizeof(TileTerm) * p->tterms_fwd.size());
+        memcpy(p->h_tterms_dag, p->tterms_dag.data(), sizeof(TileTerm) * p->tterms_dag.size());
+    }
     if (!p->pairs.empty()) {
         FH_CUDA(cudaMallocHost(&p->h_pairs, sizeof(PairOp) * p->pairs.size()));
         memcpy(p->h_pairs, p->pairs.data(), sizeof(PairOp) * p->pairs.size());
@@ -305,10 +411,7 @@ extern "C" int fh_program_info(const fh_program *p, int *n_ops, int *n_launches)
 // ----------------------------------------------------------------------------------------------
 // theta -> payload (host, double precision), staged in pinned memory and uploaded on the stream
 // ----------------------------------------------------------------------------------------------
-static int upload_payload(fh_program *p, const double *thetas, int n_thetas) {
-    FH_REQUIRE(n_thetas == p->n_params, "program expects %d parameters, got %d", p->n_params, n_thetas);
-    FH_REQUIRE(n_thetas == 0 || thetas, "thetas is NULL");
-    fh_ctx *ctx = p->ctx;
+static void refresh_payload(fh_program *p, const double *thetas) {
     for (size_t k = 0; k < p->pairs.size(); ++k) {
         PairOp &op = p->h_pairs[k];
         if (op.kind != 1) continue;
@@ -318,6 +421,10 @@ static int upload_payload(fh_program *p, const double *thetas, int n_thetas) {
         op.m[2] = s * bi;  op.m[3] = -s * br;     // -i s bhat
         op.m[4] = -s * bi; op.m[5] = -s * br;     // -i s conj(bhat)
         op.m[6] = c;       op.m[7] = 0.0;
+        if (p->pair_rec_fwd[k] >= 0) {
+            set_rec_matrix(p->h_recs_fwd[p->pair_rec_fwd[k]], op.m, false);
+            set_rec_matrix(p->h_recs_dag[p->pair_rec_dag[k]], op.m, true);
+        }
     }
     for (auto &d : p->diagops) {
         if (d.param < 0) continue;
@@ -326,14 +433,39 @@ static int upload_payload(fh_program *p, const double *thetas, int n_thetas) {
             t.angle = thetas[d.param] * t.coef;
             t.c = cos(t.angle);
             t.s = sin(t.angle);
+            if (p->dterm_tt_fwd[m] >= 0) {
+                set_tile_term(p->h_tterms_fwd[p->dterm_tt_fwd[m]], t, false);
+                set_tile_term(p->h_tterms_dag[p->dterm_tt_dag[m]], t, true);
+            }
         }
     }
+}
+
+// copy the pinned payload to the device (these become the first nodes of the captured graph)
+static int enqueue_payload_upload(fh_program *p) {
+    cudaStream_t s = p->ctx->stream;
     if (!p->pairs.empty())
-        FH_CUDA(cudaMemcpyAsync(p->d_pairs, p->h_pairs, sizeof(PairOp) * p->pairs.size(), cudaMemcpyHostToDevice, ctx->stream));
+        FH_CUDA(cudaMemcpyAsync(p->d_pairs, p->h_pairs, sizeof(PairOp) * p->pairs.size(), cudaMemcpyHostToDevice, s));
     if (!p->dterms.empty())
-        FH_CUDA(cudaMemcpyAsync(p->d_dterms, p->h_dterms, sizeof(DiagTerm) * p->dterms.size(), cudaMemcpyHostToDevice,
-                                ctx->stream));
+        FH_CUDA(cudaMemcpyAsync(p->d_dterms, p->h_dterms, sizeof(DiagTerm) * p->dterms.size(), cudaMemcpyHostToDevice, s));
+    if (!p->recs_fwd.empty()) {
+        FH_CUDA(cudaMemcpyAsync(p->d_recs_fwd, p->h_recs_fwd, sizeof(TileRec) * p->recs_fwd.size(), cudaMemcpyHostToDevice, s));
+        FH_CUDA(cudaMemcpyAsync(p->d_recs_dag, p->h_recs_dag, sizeof(TileRec) * p->recs_dag.size(), cudaMemcpyHostToDevice, s));
+    }
+    if (!p->tterms_fwd.empty()) {
+        FH_CUDA(cudaMemcpyAsync(p->d_tterms_fwd, p->h_tterms_fwd, sizeof(TileTerm) * p->tterms_fwd.size(),
+                                cudaMemcpyHostToDevice, s));
+        FH_CUDA(cudaMemcpyAsync(p->d_tterms_dag, p->h_tterms_dag, sizeof(TileTerm) * p->tterms_dag.size(),
+                                cudaMemcpyHostToDevice, s));
+    }
     return FH_OK;
+}
+
+static int upload_payload(fh_program *p, const double *thetas, int n_thetas) {
+    FH_REQUIRE(n_thetas == p->n_params, "program expects %d parameters, got %d", p->n_params, n_thetas);
+    FH_REQUIRE(n_thetas == 0 || thetas, "thetas is NULL");
+    refresh_payload(p, thetas);
+    return enqueue_payload_upload(p);
 }
 
 static bool item_has_param(const fh_program *p, const Item &it) {
@@ -356,8 +488,16 @@ static void apply_item(fh_program *p, const Item &it, double2 *st, int dagger) {
         const DiagOp &d = p->diagops[it.index];
         launch_diag(ctx->stream, ctx->sm_count, st, p->d_dterms + d.first, d.count, p->n, dagger);
     } else {
-        launch_tile(ctx->stream, st, p->d_tiles + it.index, p->d_subs, p->d_pairs, p->d_diagops, p->d_dterms, p->n,
-                    p->tiles[it.index].nbits, dagger, nullptr);
+        const TileOp &t = p->tiles[it.index];
+        TileLaunch tl;
+        tl.nbits = t.nbits;
+        tl.nsub = t.nsub;
+        tl.first_rec = dagger ? t.first_rec_dag : t.first_rec_fwd;
+        tl.first_term = dagger ? t.first_term_dag : t.first_term_fwd;
+        tl.nterms = t.nterms;
+        memcpy(tl.bits, t.bits, 16);
+        launch_tile(ctx->stream, st, tl, dagger ? p->d_recs_dag : p->d_recs_fwd,
+                    dagger ? p->d_tterms_dag : p->d_tterms_fwd, p->n);
     }
 }
 
@@ -446,11 +586,7 @@ static int enqueue_evaluation(fh_program *p, const EvalKey &k, fh_table *const *
     if (want_grads) chk_pos = last_param + 1;
     if (want_pool && k.pool_pos > chk_pos) chk_pos = k.pool_pos;
 
-    if (!p->pairs.empty())
-        FH_CUDA(cudaMemcpyAsync(p->d_pairs, p->h_pairs, sizeof(PairOp) * p->pairs.size(), cudaMemcpyHostToDevice, ctx->stream));
-    if (!p->dterms.empty())
-        FH_CUDA(cudaMemcpyAsync(p->d_dterms, p->h_dterms, sizeof(DiagTerm) * p->dterms.size(), cudaMemcpyHostToDevice,
-                                ctx->stream));
+    FH_TRY(enqueue_payload_upload(p));
     launch_set_basis(ctx->stream, p->d_psi, 1ull << p->n, k.basis);
     double2 *psi = p->d_psi;
     for (int i = 0; i < n_items; ++i) {
@@ -536,25 +672,7 @@ extern "C" int fh_program_evaluate(fh_program *p, uint64_t basis_index, const do
     FH_TRY(ensure_workspaces(p));
 
     // theta -> payload in the pinned staging buffers (the graph's first nodes copy them to the device)
-    for (size_t k = 0; k < p->pairs.size(); ++k) {
-        PairOp &op = p->h_pairs[k];
-        if (op.kind != 1) continue;
-        const double a = op.param >= 0 ? op.gscale * thetas[op.param] : op.gscale;
-        const double c = cos(a), s = sin(a), br = op.bhat[0], bi = op.bhat[1];
-        op.m[0] = c;       op.m[1] = 0.0;
-        op.m[2] = s * bi;  op.m[3] = -s * br;
-        op.m[4] = -s * bi; op.m[5] = -s * br;
-        op.m[6] = c;       op.m[7] = 0.0;
-    }
-    for (auto &d : p->diagops) {
-        if (d.param < 0) continue;
-        for (int m = d.first; m < d.first + d.count; ++m) {
-            DiagTerm &t = p->h_dterms[m];
-            t.angle = thetas[d.param] * t.coef;
-            t.c = cos(t.angle);
-            t.s = sin(t.angle);
-        }
-    }
+    refresh_payload(p, thetas);
 
     EvalKey key;
     memset(&key, 0, sizeof(key));
@@ -628,5 +746,30 @@ extern "C" int fh_program_last_stats(const fh_program *p, double *elapsed_ms, in
     FH_REQUIRE(p, "fh_program_last_stats: program is NULL");
     if (elapsed_ms) *elapsed_ms = p->last_ms;
     if (kernel_launches) *kernel_launches = p->last_launches;
+    return FH_OK;
+}
+
+// measurement: average device time (ms) of launching items [first, first+count) `reps` times back to back
+// (payload must already be on the device, e.g. after fh_program_run / fh_program_evaluate)
+extern "C" int fh_program_time_items(fh_program *p, fh_state *st, int first, int count, int dagger, int reps,
+                                     double *ms_per_rep) {
+    FH_REQUIRE(p && st && ms_per_rep, "fh_program_time_items: NULL argument");
+    FH_REQUIRE(p->finalized && st->n == p->n, "fh_program_time_items: program not finalized or qubit mismatch");
+    FH_REQUIRE(first >= 0 && count >= 0 && first + count <= (int)p->items.size() && reps >= 1,
+               "fh_program_time_items: bad range");
+    fh_ctx *ctx = p->ctx;
+    if (!p->ev0) {
+        FH_CUDA(cudaEventCreate(&p->ev0));
+        FH_CUDA(cudaEventCreate(&p->ev1));
+    }
+    FH_CUDA(cudaEventRecord(p->ev0, ctx->stream));
+    for (int r = 0; r < reps; ++r)
+        for (int k = 0; k < count; ++k) apply_item(p, p->items[dagger ? first + count - 1 - k : first + k], st->d, dagger);
+    FH_CUDA(cudaEventRecord(p->ev1, ctx->stream));
+    FH_CUDA(cudaGetLastError());
+    FH_CUDA(cudaEventSynchronize(p->ev1));
+    float ms = 0.f;
+    FH_CUDA(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+    *ms_per_rep = ms / reps;
     return FH_OK;
 }

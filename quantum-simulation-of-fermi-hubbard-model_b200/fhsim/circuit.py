@@ -430,6 +430,15 @@ class DeviceProgram:
         _cabi.check(_cabi.lib().fh_program_last_stats(self._h, _cabi.C.byref(ms), _cabi.C.byref(nl)))
         return ms.value, nl.value
 
+    def time_items(self, state, first=0, count=None, dagger=False, reps=20):
+        """Average device milliseconds of items [first, first+count) launched back to back (measurement)."""
+        if count is None:
+            count = self.n_items - first
+        ms = _cabi.C.c_double()
+        _cabi.check(_cabi.lib().fh_program_time_items(self._h, state._h, first, count, int(dagger), reps,
+                                                      _cabi.C.byref(ms)))
+        return ms.value
+
     def run(self, state, thetas=(), first=0, count=None, dagger=False):
         """Apply launch items [first, first+count) to ``state`` in place."""
         if count is None:
