@@ -91,14 +91,20 @@ struct TileLaunch {
 };
 
 // ready-to-execute record of one op inside a tile (built on the host, one array per direction)
-struct __align__(16) TileRec {          // 112 bytes
+struct __align__(16) TileRec {          // 128 bytes = 8 x 16 B; k_tile reads it as uint4 / double2 words
+    // word 0
     unsigned fixmask_out, fixval_out;   // pattern bits outside the tile: uniform per tile
     unsigned zeta, xlocal;
+    // word 1
     unsigned lfixval;                   // pattern bits inside the tile, in tile-local coordinates
     int type;                           // 1 pair (complex matrix), 3 pair (real matrix), 2 diag
-    int nlfix, term_off, nterms;
-    int pad;
-    unsigned char lfix[8];              // ascending tile-local positions of the pattern bits
+    int nlfix, term_off;
+    // word 2: bit-insertion masks (1<<p)-1 of the (at most 4) pattern bits inside the tile, ascending;
+    // unused slots hold 0xffffffff (insertion is then a no-op)
+    unsigned lowmask[4];
+    // word 3
+    int nterms, pad[3];
+    // words 4..7
     double m[8];
 };
 

@@ -255,6 +255,8 @@ __device__ __forceinline__ double2 tile_diag_phase(const TileTerm *t, int nterms
     return ph;
 }
 
+__device__ __forceinline__ int n_terms_of(const TileRec &r) { return r.nterms; }
+
 __global__ void __launch_bounds__(512) k_tile(double2 *__restrict__ psi, const TileLaunch tl,
                                               const TileRec *__restrict__ recs, const TileTerm *__restrict__ terms,
                                               int n) {
@@ -293,58 +295,86 @@ __global__ void __launch_bounds__(512) k_tile(double2 *__restrict__ psi, const T
     const u64 ntiles = 1ull << (n - T);
     for (u64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const unsigned base = (unsigned)deposit_zeros(t, tl.bits, T);
-        for (unsigned l = threadIdx.x; l < L; l += blockDim.x) {
-            const unsigned g = base | slo[l & 63u] | shi[l >> 6];
-            gidx[l] = g;
-            buf[l] = psi[g];
+        // four independent 128-bit loads in flight per thread before anything is written to shared memory
+        for (unsigned l0 = threadIdx.x; l0 < L; l0 += 4 * blockDim.x) {
+            unsigned gg[4];
+            double2 vv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned l = l0 + u * blockDim.x;
+                if (l < L) {
+                    gg[u] = base | slo[l & 63u] | shi[l >> 6];
+                    vv[u] = psi[gg[u]];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned l = l0 + u * blockDim.x;
+                if (l < L) {
+                    gidx[l] = gg[u];
+                    buf[l] = vv[u];
+                }
+            }
         }
         __syncthreads();
+        // Per-op loop.  Each record is pulled into registers with a few 128-bit shared loads issued
+        // together, and the NEXT record is fetched before the barrier so its latency is off the chain.
+        uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0;
+        double2 ma = make_double2(0, 0), mb = ma, mc = ma, md = ma;
+        if (nsub > 0) {
+            const uint4 *rp = reinterpret_cast<const uint4 *>(&rec[0]);
+            q0 = rp[0]; q1 = rp[1]; q2 = rp[2];
+            const double2 *mp = reinterpret_cast<const double2 *>(rec[0].m);
+            ma = mp[0]; mb = mp[1]; mc = mp[2]; md = mp[3];
+        }
         for (int sidx = 0; sidx < nsub; ++sidx) {
-            const TileRec &r = rec[sidx];
-            const int type = r.type;
+            uint4 n0 = q0, n1 = q1, n2 = q2;
+            double2 na = ma, nb = mb, nc = mc, nd = md;
+            if (sidx + 1 < nsub) {
+                const uint4 *rp = reinterpret_cast<const uint4 *>(&rec[sidx + 1]);
+                n0 = rp[0]; n1 = rp[1]; n2 = rp[2];
+                const double2 *mp = reinterpret_cast<const double2 *>(rec[sidx + 1].m);
+                na = mp[0]; nb = mp[1]; nc = mp[2]; nd = mp[3];
+            }
+            // q0 = {fixmask_out, fixval_out, zeta, xlocal}; q1 = {lfixval, type, nlfix, term_off}; q2 = insertion masks
+            const int type = (int)q1.y;
             if (type != 2) {
-                if ((base & r.fixmask_out) == r.fixval_out) {
-                    const int nl = r.nlfix;
-                    const unsigned npairs = L >> nl;
-                    if (threadIdx.x < npairs) {
-                        const unsigned zeta = r.zeta, xl = r.xlocal, lv = r.lfixval;
-                        const double m00 = r.m[0], m01 = r.m[2], m10 = r.m[4], m11 = r.m[6];
-                        for (unsigned k = threadIdx.x; k < npairs; k += blockDim.x) {
-                            unsigned il = k;
-                            for (int q = 0; q < nl; ++q) {
-                                const unsigned p = r.lfix[q];
-                                il = ((il >> p) << (p + 1)) | (il & ((1u << p) - 1u));
-                            }
-                            il |= lv;
-                            const unsigned jl = il ^ xl;
-                            const double sg = (__popc(gidx[il] & zeta) & 1) ? -1.0 : 1.0;
-                            double2 a = buf[il], b = buf[jl];
-                            if (type == 3) {
-                                const double s01 = sg * m01, s10 = sg * m10;
-                                const double2 ra = make_double2(m00 * a.x + s01 * b.x, m00 * a.y + s01 * b.y);
-                                const double2 rb = make_double2(s10 * a.x + m11 * b.x, s10 * a.y + m11 * b.y);
-                                a = ra;
-                                b = rb;
-                            } else {
-                                Mat2 M;
-                                M.m00 = make_double2(r.m[0], r.m[1]);
-                                M.m01 = make_double2(r.m[2], r.m[3]);
-                                M.m10 = make_double2(r.m[4], r.m[5]);
-                                M.m11 = make_double2(r.m[6], r.m[7]);
-                                rot2(M, sg, a, b);
-                            }
-                            buf[il] = a;
-                            buf[jl] = b;
+                if ((base & q0.x) == q0.y) {
+                    const unsigned npairs = L >> q1.z;
+                    for (unsigned k = threadIdx.x; k < npairs; k += blockDim.x) {
+                        unsigned il = k;
+                        il = ((il & ~q2.x) << 1) | (il & q2.x);
+                        il = ((il & ~q2.y) << 1) | (il & q2.y);
+                        il = ((il & ~q2.z) << 1) | (il & q2.z);
+                        il = ((il & ~q2.w) << 1) | (il & q2.w);
+                        il |= q1.x;
+                        const unsigned jl = il ^ q0.w;
+                        double2 a = buf[il], b = buf[jl];
+                        const double sg = (__popc(gidx[il] & q0.z) & 1) ? -1.0 : 1.0;
+                        if (type == 3) {
+                            const double s01 = sg * mb.x, s10 = sg * mc.x;
+                            const double2 ra = make_double2(ma.x * a.x + s01 * b.x, ma.x * a.y + s01 * b.y);
+                            const double2 rb = make_double2(s10 * a.x + md.x * b.x, s10 * a.y + md.x * b.y);
+                            a = ra;
+                            b = rb;
+                        } else {
+                            Mat2 M;
+                            M.m00 = ma; M.m01 = mb; M.m10 = mc; M.m11 = md;
+                            rot2(M, sg, a, b);
                         }
+                        buf[il] = a;
+                        buf[jl] = b;
                     }
                 }
             } else {
-                const TileTerm *dt = tterm + r.term_off;
-                const int cnt = r.nterms;
+                const TileTerm *dt = tterm + (int)q1.w;
+                const int cnt = (int)n_terms_of(rec[sidx]);
                 for (unsigned l = threadIdx.x; l < L; l += blockDim.x)
                     buf[l] = cmul(tile_diag_phase(dt, cnt, gidx[l]), buf[l]);
             }
             __syncthreads();
+            q0 = n0; q1 = n1; q2 = n2;
+            ma = na; mb = nb; mc = nc; md = nd;
         }
         for (unsigned l = threadIdx.x; l < L; l += blockDim.x) psi[gidx[l]] = buf[l];
         __syncthreads();

@@ -175,7 +175,7 @@ extern "C" int fh_program_add_pair(fh_program *p, uint64_t x, uint64_t fixmask, 
         FH_REQUIRE(rest == 0, "fh_program_add_pair: x-mask 0x%llx not inside the open tile", (u64)x);
         u64 tmask = 0;
         for (int b = 0; b < t.nbits; ++b) tmask |= 1ull << t.bits[b];
-        FH_REQUIRE(popcnt(fixmask & tmask) <= 8, "fh_program_add_pair: more than 8 pattern bits inside a tile");
+        FH_REQUIRE(popcnt(fixmask & tmask) <= 4, "fh_program_add_pair: more than 4 pattern bits inside a tile");
         TileSub s;
         s.type = 1;
         s.index = idx;
@@ -315,9 +315,10 @@ static void build_tile_records(fh_program *p) {
                     r.xlocal = sub.xlocal;
                     int nl = 0;
                     unsigned lv = 0;
+                    for (int q = 0; q < 4; ++q) r.lowmask[q] = 0xffffffffu;
                     for (int b = 0; b < t.nbits; ++b)
                         if (fm >> t.bits[b] & 1u) {
-                            if (nl < 8) r.lfix[nl] = (unsigned char)b;
+                            if (nl < 4) r.lowmask[nl] = (1u << b) - 1u;
                             ++nl;
                             lv |= ((fv >> t.bits[b]) & 1u) << b;
                         }

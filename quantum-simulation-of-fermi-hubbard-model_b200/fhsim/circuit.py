@@ -281,8 +281,8 @@ class Circuit:
                 self.ops.append(DiagOpSpec(zs, [a for _, a in phases], -1, [(0, b) for b in zs]))
 
     # -- compilation ------------------------------------------------------------------------
-    def compile(self, ctx, fuse=True, tile_bits=None, low_bits=None):
-        return DeviceProgram(ctx, self, fuse=fuse, tile_bits=tile_bits, low_bits=low_bits)
+    def compile(self, ctx, fuse=True, tile_bits=None, low_bits=None, absorb=True):
+        return DeviceProgram(ctx, self, fuse=fuse, tile_bits=tile_bits, low_bits=low_bits, absorb=absorb)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -290,6 +290,7 @@ class Circuit:
 # ---------------------------------------------------------------------------------------------
 MAX_TILE_OPS = 96             # FH_TILE_MAX_SUB
 MAX_TILE_TERMS = 256          # FH_TILE_MAX_TERMS
+MAX_TILE_PATTERN_BITS = 4     # pattern bits a pair op may have to be fused into a tile
 _LAUNCH_BYTES = 12e6          # bytes of traffic one kernel launch is "worth" (launch latency x bandwidth)
 
 
@@ -297,6 +298,65 @@ def _op_bytes(op, n):
     if isinstance(op, DiagOpSpec):
         return 32.0 * 2 ** n
     return 64.0 * 2 ** (n - popcount(op.fixmask))
+
+
+def absorb_phases(ops):
+    """Push fixed single-qubit Z phases (RZ-type diagonal terms) through the pair ops that follow them.
+
+    With D = exp(-i sum_w a_w Z_w) pending after the ops seen so far, a pair op G whose pattern fixes
+    every bit of its x-mask obeys G D = D (D^dagger G D), and D^dagger G D is the same op with its
+    off-diagonal entries multiplied by a unit phase.  All absorbed phases end up in ONE diagonal op at
+    the end of the segment instead of one diagonal pass per layer.  Exact (no approximation); ops that
+    cannot absorb (pattern does not pin the x bits) first flush the pending phase.
+    """
+    import cmath
+    pending = {}                                     # bit mask (single bit) -> angle a_w
+    out = []
+
+    def flush():
+        if pending:
+            zs = sorted(pending)
+            out.append(DiagOpSpec(zs, [pending[b] for b in zs], -1, [(0, b) for b in zs]))
+            pending.clear()
+
+    for op in ops:
+        if isinstance(op, DiagOpSpec):
+            if op.param < 0 and all(popcount(z) == 1 for z in op.z):
+                for z, a in zip(op.z, op.coef):
+                    pending[z] = pending.get(z, 0.0) + a
+            else:
+                out.append(op)                       # diagonal ops commute with the pending phase
+            continue
+        touched = [b for b in pending if b & op.x]
+        if not touched:
+            out.append(op)
+            continue
+        if op.fixmask & op.x != op.x or popcount(op.x) > 6:
+            flush()
+            out.append(op)
+            continue
+        # rho = d(j)/d(i) for the pattern side i:  exp(+2i sum_{w in x} a_w (-1)^{i_w})
+        expo = sum(pending[b] * (-1.0 if op.fixval & b else 1.0) for b in touched)
+        rho = cmath.exp(2j * expo)
+        # conjugation by Z phases on the x bits turns each Pauli string (x, z) of the op into a mix of
+        # (x, z ^ s), s subset of x: keep all of them so the scheduler's commutation test stays valid
+        xbits = [1 << b for b in range(op.x.bit_length()) if op.x >> b & 1]
+        subsets = [0]
+        for b in xbits:
+            subsets += [s | b for s in subsets]
+        strings = sorted({(sx, sz ^ s) for (sx, sz) in op.strings for s in subsets})
+        new = PairOpSpec(op.x, op.fixmask, op.fixval, op.zeta, op.kind, op.param, op.scale, op.bhat, op.matrix,
+                         strings)
+        if op.kind == 1:
+            new.bhat = complex(op.bhat) * rho
+        else:
+            m = [complex(op.matrix[2 * i], op.matrix[2 * i + 1]) for i in range(4)]
+            m[1] *= rho
+            m[2] *= rho.conjugate()
+            new.matrix = tuple(v for c in m for v in (c.real, c.imag))
+        out.append(new)
+    flush()
+    return out
 
 
 def schedule(ops, n, tile_bits, low_bits, lookahead=512):
@@ -319,7 +379,9 @@ def schedule(ops, n, tile_bits, low_bits, lookahead=512):
             else:
                 need = bits | op.tile_bits
                 nt = len(op.z) if isinstance(op, DiagOpSpec) else 0
-                if popcount(need) <= tile_bits and len(chosen) < MAX_TILE_OPS and n_terms + nt <= MAX_TILE_TERMS:
+                fusable = isinstance(op, DiagOpSpec) or popcount(op.fixmask) <= MAX_TILE_PATTERN_BITS
+                if (fusable and popcount(need) <= tile_bits and len(chosen) < MAX_TILE_OPS
+                        and n_terms + nt <= MAX_TILE_TERMS):
                     bits = need
                     n_terms += nt
                     chosen.append(op)
@@ -352,7 +414,8 @@ def schedule(ops, n, tile_bits, low_bits, lookahead=512):
 class DeviceProgram:
     """A finalized ``fh_program`` plus the bookkeeping to call ``fh_program_evaluate``."""
 
-    def __init__(self, ctx, circuit: Circuit, fuse=True, tile_bits=None, low_bits=None):
+    def __init__(self, ctx, circuit: Circuit, fuse=True, tile_bits=None, low_bits=None, absorb=True):
+        self.absorb = absorb
         self.ctx = ctx
         self.n = circuit.n
         self.n_params = circuit.n_params
@@ -384,6 +447,8 @@ class DeviceProgram:
         if not ops:
             return
         L = _cabi.lib()
+        if self.absorb:
+            ops = absorb_phases(ops)
         if fuse:
             items = schedule(ops, self.n, self.tile_bits, self.low_bits)
         else:

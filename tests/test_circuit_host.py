@@ -151,3 +151,29 @@ def test_separable_basis_change_equals_reference_network(lat):
     want = sv.basis_change(psi, diag, dec, n)
     got = run_circuit(fast, psi) * np.exp(-1j * (ph_fast - ph_ref))
     assert np.abs(got - want).max() < 1e-12
+
+
+@pytest.mark.parametrize("lat", [(2, 2), (2, 3), (3, 3)])
+def test_phase_absorption_is_exact(lat):
+    from fhsim.circuit import absorb_phases, DiagOpSpec
+    nx, ny = lat
+    n = 2 * nx * ny
+    c = Circuit(n, 2)
+    c.rz(0.37, 1)
+    c.basis_change_separable(nx, ny)
+    c.ry(0.0, 2, param=0)                       # cannot absorb (pattern does not pin x): forces a flush
+    c.rz(-0.61, 2)
+    pool = hubbard_interaction_pool_simplified(nx, ny)
+    c.generator(GeneratorPlan(jordan_wigner(pool[3]), n), param=1)
+    psi = rand_state(n, 23)
+    th = [0.4, -0.3]
+    want = run_circuit(c, psi, th)
+    ops = [o for o in c.ops if not isinstance(o, Marker)]
+    fused = absorb_phases(ops)
+    assert sum(isinstance(o, DiagOpSpec) for o in fused) < sum(isinstance(o, DiagOpSpec) for o in ops)
+    d = Circuit(n, 2)
+    d.ops = fused
+    assert np.abs(run_circuit(d, psi, th) - want).max() < 1e-13
+    # and scheduling the absorbed ops still preserves the unitary
+    items = schedule(fused, n, min(8, n), 1)
+    assert np.abs(run_items(items, psi, th, n) - want).max() < 1e-12
