@@ -25,7 +25,7 @@ import torch.optim as optim
 from linalg.exact_diagonalization import jw_get_ground_state
 from operators.pool import hubbard_interaction_pool_simplified
 
-from .common import (Circuit, DevicePool, HubbardProblem, Param, Trotterize_generator, ensure_parent,
+from .common import (Circuit, DevicePool, HubbardProblem, Param, State, Trotterize_generator, ensure_parent,
                      evaluate_with_grad, generator_plan, get_non_interacting_ground_state_index,
                      get_particle_number_operator, get_spin_operators, get_total_spin, print_list, recording,
                      try_pyplot)

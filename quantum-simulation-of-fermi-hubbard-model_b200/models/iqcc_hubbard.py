@@ -150,6 +150,7 @@ class IQCC:
     def dress_hamiltonian(self, operators, taus):
         """H <- H + sin(tau)(-i/2)[H, P] + (1/2)(1 - cos tau)(P H P - H), last entangler first."""
         for P_k, tau_k in zip(operators[::-1], taus[::-1]):
+            tau_k = float(tau_k)        # float32 parameter, promoted exactly: keeps the algebra in double precision
             H = self.currentHamiltonian
             first = np.sin(tau_k) * (-1j / 2) * (H * P_k - P_k * H)
             second = 1 / 2 * (1 - np.cos(tau_k)) * (P_k * H * P_k - H)
