@@ -94,6 +94,8 @@ int fh_table_free(fh_table *tab);
 int fh_table_info(const fh_table *tab, int *n_terms, int *n_groups);
 /* out <- H in (out may be NULL: expectation only); *e = <in|H|in>.  in and out must differ. */
 int fh_apply_table(const fh_table *tab, const fh_state *in, fh_state *out, double *e_re, double *e_im);
+/* out <- out + H in  (sum of partial Hamiltonians, e.g. one table per qubit layout of a sharded state); *e = <in|H|in> */
+int fh_apply_table_accumulate(const fh_table *tab, const fh_state *in, fh_state *out, double *e_re, double *e_im);
 
 /* ---- K3: pool screening ---------------------------------------------------------------------
  * replaces ADAPT.select_operator's append-and-backprop (models/adapt_vqe.py:297-310):

@@ -370,7 +370,8 @@ extern "C" int fh_table_upload(fh_ctx *ctx, int n_qubits, int n_terms, const uin
     tab->n_terms = n_terms;
     tab->all_real = true;
     tab->d_groups = nullptr;
-    tab->d_terms = nullptr;
+    tab->d_classes = nullptr;
+    tab->d_vals = nullptr;
     // group by x-mask in first-seen order; term order inside a group = table order
     std::map<u64, int> group_of;
     std::vector<std::vector<TabTerm>> buckets;
@@ -405,22 +406,88 @@ extern "C" int fh_table_upload(fh_ctx *ctx, int n_qubits, int n_terms, const uin
         buckets[g].push_back(tt);
     }
     for (size_t g = 0; g < buckets.size(); ++g) {
+        const u64 gx = group_x[g];
+        const std::vector<TabTerm> &bt = buckets[g];
         TabGroup grp;
-        grp.x = group_x[g];
-        grp.first = (int)tab->terms.size();
-        grp.count = (int)buckets[g].size();
+        memset(&grp, 0, sizeof(grp));
+        grp.x = gx;
+        grp.first_class = (int)tab->classes.size();
+        for (int q = 0; q < 4; ++q) grp.pos[q] = 63;
+        const int kx = popcnt(gx);
+        if (kx >= 1 && kx <= 4) {
+            // classes by zeta = z & ~x (first-seen order); per class a 2^kx table over the x-bit pattern of j
+            grp.kbits = kx;
+            int q = 0;
+            for (int b = 0; b < n_qubits; ++b)
+                if (gx >> b & 1ull) grp.pos[q++] = (unsigned char)b;
+            std::vector<u64> zetas;
+            for (const TabTerm &tt : bt) {
+                const u64 zeta = tt.z & ~gx;
+                bool seen = false;
+                for (u64 v : zetas) seen = seen || v == zeta;
+                if (!seen) zetas.push_back(zeta);
+            }
+            for (u64 zeta : zetas) {
+                std::vector<double2> tbl((size_t)1 << kx, make_double2(0.0, 0.0));
+                bool any = false;
+                for (int pat = 0; pat < (1 << kx); ++pat) {
+                    u64 dep = 0;
+                    for (int b = 0; b < kx; ++b)
+                        if (pat >> b & 1) dep |= 1ull << grp.pos[b];
+                    double vr = 0.0, vi = 0.0;
+                    for (const TabTerm &tt : bt) {
+                        if ((tt.z & ~gx) != zeta) continue;
+                        const double sg = (popcnt(dep & tt.z) & 1) ? -1.0 : 1.0;
+                        vr += sg * tt.dr;
+                        vi += sg * tt.di;
+                    }
+                    tbl[pat] = make_double2(vr, vi);
+                    any = any || vr != 0.0 || vi != 0.0;
+                }
+                if (!any) continue;
+                TabClass cl;
+                cl.zeta = zeta;
+                cl.vofs = (int)tab->vals.size();
+                cl.pad = 0;
+                tab->classes.push_back(cl);
+                tab->vals.insert(tab->vals.end(), tbl.begin(), tbl.end());
+            }
+        } else {
+            grp.kbits = 0;
+            for (const TabTerm &tt : bt) {
+                TabClass cl;
+                cl.zeta = tt.z;
+                cl.vofs = (int)tab->vals.size();
+                cl.pad = 0;
+                tab->classes.push_back(cl);
+                tab->vals.push_back(make_double2(tt.dr, tt.di));
+            }
+        }
+        grp.n_class = (int)tab->classes.size() - grp.first_class;
+        for (int r = 0; r < 8; ++r) {                 // how bits 8, 9, 10 of the index move the x-bit pattern
+            unsigned d = 0;
+            for (int q = 0; q < grp.kbits; ++q)
+                if ((grp.pos[q] == 8 && (r & 1)) || (grp.pos[q] == 9 && (r & 2)) || (grp.pos[q] == 10 && (r & 4)))
+                    d |= 1u << q;
+            grp.rpat |= d << (4 * r);
+        }
         tab->groups.push_back(grp);
-        tab->terms.insert(tab->terms.end(), buckets[g].begin(), buckets[g].end());
+        tab->terms.insert(tab->terms.end(), bt.begin(), bt.end());
     }
     tab->n_groups = (int)tab->groups.size();
     FH_CUDA(cudaSetDevice(ctx->device));
     if (tab->n_groups) {
         FH_CUDA(cudaMalloc(&tab->d_groups, sizeof(TabGroup) * tab->groups.size()));
-        FH_CUDA(cudaMalloc(&tab->d_terms, sizeof(TabTerm) * tab->terms.size()));
+        FH_CUDA(cudaMalloc(&tab->d_classes, sizeof(TabClass) * (tab->classes.size() + 1)));
+        FH_CUDA(cudaMalloc(&tab->d_vals, sizeof(double2) * (tab->vals.size() + 1)));
         FH_CUDA(cudaMemcpyAsync(tab->d_groups, tab->groups.data(), sizeof(TabGroup) * tab->groups.size(),
                                 cudaMemcpyHostToDevice, ctx->stream));
-        FH_CUDA(cudaMemcpyAsync(tab->d_terms, tab->terms.data(), sizeof(TabTerm) * tab->terms.size(),
-                                cudaMemcpyHostToDevice, ctx->stream));
+        if (!tab->classes.empty())
+            FH_CUDA(cudaMemcpyAsync(tab->d_classes, tab->classes.data(), sizeof(TabClass) * tab->classes.size(),
+                                    cudaMemcpyHostToDevice, ctx->stream));
+        if (!tab->vals.empty())
+            FH_CUDA(cudaMemcpyAsync(tab->d_vals, tab->vals.data(), sizeof(double2) * tab->vals.size(),
+                                    cudaMemcpyHostToDevice, ctx->stream));
         FH_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     *out = tab;
@@ -432,7 +499,8 @@ extern "C" int fh_table_free(fh_table *tab) {
     cudaSetDevice(tab->ctx->device);
     cudaStreamSynchronize(tab->ctx->stream);
     cudaFree(tab->d_groups);
-    cudaFree(tab->d_terms);
+    cudaFree(tab->d_classes);
+    cudaFree(tab->d_vals);
     delete tab;
     return FH_OK;
 }
@@ -447,8 +515,8 @@ extern "C" int fh_table_info(const fh_table *tab, int *n_terms, int *n_groups) {
 // enqueue K2 without synchronising; result lands in ctx->d_result[slot*2 .. slot*2+1]
 int fh_enqueue_apply_table(const fh_table *tab, const double2 *in, double2 *out, int result_slot) {
     fh_ctx *ctx = tab->ctx;
-    launch_apply_table(ctx->stream, ctx->sm_count, tab->d_groups, tab->n_groups, tab->d_terms, (int)tab->terms.size(),
-                       tab->all_real, in, out, tab->n, ctx->d_partials, ctx->d_result + 2 * result_slot);
+    launch_apply_table(ctx->stream, ctx->sm_count, tab, in, out, out ? 1 : 0, ctx->d_partials,
+                       ctx->d_result + 2 * result_slot);
     FH_CUDA(cudaGetLastError());
     return FH_OK;
 }
@@ -460,6 +528,21 @@ extern "C" int fh_apply_table(const fh_table *tab, const fh_state *in, fh_state 
     FH_REQUIRE(!out || out->d != in->d, "fh_apply_table: in and out must be different buffers");
     fh_ctx *ctx = tab->ctx;
     FH_TRY(fh_enqueue_apply_table(tab, in->d, out ? out->d : nullptr, 0));
+    FH_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FH_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (e_re) *e_re = ctx->h_result[0];
+    if (e_im) *e_im = ctx->h_result[1];
+    return FH_OK;
+}
+
+extern "C" int fh_apply_table_accumulate(const fh_table *tab, const fh_state *in, fh_state *out, double *e_re,
+                                         double *e_im) {
+    FH_REQUIRE(tab && in && out, "fh_apply_table_accumulate: NULL argument");
+    FH_REQUIRE(in->n == tab->n && out->n == in->n, "fh_apply_table_accumulate: qubit counts differ");
+    FH_REQUIRE(out->d != in->d, "fh_apply_table_accumulate: in and out must be different buffers");
+    fh_ctx *ctx = tab->ctx;
+    launch_apply_table(ctx->stream, ctx->sm_count, tab, in->d, out->d, 2, ctx->d_partials, ctx->d_result);
+    FH_CUDA(cudaGetLastError());
     FH_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     FH_CUDA(cudaStreamSynchronize(ctx->stream));
     if (e_re) *e_re = ctx->h_result[0];

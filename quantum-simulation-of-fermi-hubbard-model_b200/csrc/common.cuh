@@ -122,14 +122,28 @@ struct TileOp {                         // host bookkeeping of one tile run
     int first_term_fwd, first_term_dag, nterms;
 };
 
-struct TabGroup {
-    u64 x;
-    int first, count;
-};
-
 struct TabTerm {
     u64 z;
     double dr, di;    // coefficient * i^k  (weight of psi[i^x] is sum_m d_m (-1)^popcount((i^x)&z_m))
+};
+
+// K2 device form.  Inside one x-mask group the terms are split into classes by zeta = z & ~x; within a class
+// the weight only depends on the bits of j = i^x at the (at most 4) x positions, so it is tabulated:
+//     w_g(j) = sum_c (-1)^popcount(j & zeta_c) * V_c[pattern(j)],   pattern = bits of j at pos[0..kbits)
+// Groups with x = 0 or more than 4 x bits use kbits = 0 and one class per term (V = the coefficient).
+struct __align__(16) TabGroup {     // 32 bytes
+    u64 x;
+    int first_class, n_class;
+    unsigned char pos[4];           // ascending bit positions of x; unused slots = 63 (that bit of j is always 0)
+    int kbits;
+    unsigned rpat;                  // 8 x 4 bits: pattern(j ^ (r << 8)) = pattern(j) ^ ((rpat >> 4r) & 15)   (k_apply_table4)
+    int pad;
+};
+
+struct __align__(16) TabClass {     // 16 bytes
+    u64 zeta;
+    int vofs;                       // first entry of this class's table in the V array
+    int pad;
 };
 
 struct PoolEntry {
@@ -175,9 +189,12 @@ struct fh_table {
     int n_terms, n_groups;
     bool all_real;
     TabGroup *d_groups;
-    TabTerm *d_terms;
+    TabClass *d_classes;
+    double2 *d_vals;
     std::vector<TabGroup> groups;
-    std::vector<TabTerm> terms;
+    std::vector<TabClass> classes;
+    std::vector<double2> vals;
+    std::vector<TabTerm> terms;     // host copy in table order (grouped by x-mask)
 };
 
 struct fh_pool {
@@ -206,8 +223,9 @@ void launch_diag_adjoint(cudaStream_t s, int sm, double2 *psi, double2 *lam, con
                          double *d_partials, int max_blocks, int *blocks_used);
 void launch_tile(cudaStream_t s, double2 *psi, const TileLaunch &tl, const TileRec *d_recs, const TileTerm *d_terms,
                  int n);
-void launch_apply_table(cudaStream_t s, int sm, const TabGroup *g, int ngroups, const TabTerm *t, int nterms,
-                        bool all_real, const double2 *in, double2 *out, int n, double *d_partials, double *d_result);
+// mode 0: expectation only; 1: out = H in; 2: out += H in.   Result (re, im of <in|H|in>) -> d_result[0..1]
+void launch_apply_table(cudaStream_t s, int sm, const fh_table *tab, const double2 *in, double2 *out, int mode,
+                        double *d_partials, double *d_result);
 void launch_pool(cudaStream_t s, const PoolEntry *entries, int first_entry, int n_entries, int chunks, int n,
                  const double2 *psi, const double2 *lam, double *d_partials);
 void launch_pool_finalize(cudaStream_t s, const double *d_partials, const int *d_out_first, int chunks, int first_out,

@@ -384,55 +384,203 @@ __global__ void __launch_bounds__(512) k_tile(double2 *__restrict__ psi, const T
 // ----------------------------------------------------------------------------------------------
 // K2: out = H in, e = <in|H|in>
 // ----------------------------------------------------------------------------------------------
-// One thread owns output index i and walks the x-mask groups: weight of in[i^x_g] is
-// w_g = sum_m d_m (-1)^popcount((i^x_g) & z_m) (pure integer work on chip), so the memory traffic is
-// one gather per group plus one store -- independent of the term count.
-template <bool REAL, bool WRITE>
+// One thread owns output index i and walks the x-mask groups.  The weight of in[i^x_g] is a sum over
+// the group's classes of (-1)^popcount(j & zeta_c) * V_c[pattern(j)] (see TabGroup in common.cuh):
+// for a hopping group that is one parity + one 4-entry table lookup, and half of all (i, group)
+// combinations have weight 0 and skip the gather.  Tables live in shared memory.  Memory traffic is
+// one (mostly L1/L2-resident) gather per contributing group plus one store -- independent of the
+// term count.
+template <bool REAL, int MODE>
 __global__ void __launch_bounds__(256) k_apply_table(const TabGroup *__restrict__ groups, int ngroups,
-                                                     const TabTerm *__restrict__ terms, int nterms, int use_smem,
+                                                     const TabClass *__restrict__ classes, int nclasses,
+                                                     const double2 *__restrict__ vals, int nvals, int use_smem,
                                                      const double2 *__restrict__ in, double2 *__restrict__ out, u64 dim,
                                                      double *__restrict__ partials) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[8];
     const TabGroup *G = groups;
-    const TabTerm *Tm = terms;
+    const TabClass *Cl = classes;
+    const double2 *V = vals;
     if (use_smem) {
-        TabGroup *sg = reinterpret_cast<TabGroup *>(smem_raw);
-        TabTerm *stm = reinterpret_cast<TabTerm *>(sg + ngroups);
-        for (int t = threadIdx.x; t < ngroups; t += blockDim.x) sg[t] = groups[t];
-        for (int t = threadIdx.x; t < nterms; t += blockDim.x) stm[t] = terms[t];
+        uint4 *dst = reinterpret_cast<uint4 *>(smem_raw);
+        const int ng4 = ngroups * (int)(sizeof(TabGroup) / 16), nc4 = nclasses, nv4 = nvals;
+        const uint4 *sg = reinterpret_cast<const uint4 *>(groups);
+        const uint4 *sc = reinterpret_cast<const uint4 *>(classes);
+        const uint4 *sv = reinterpret_cast<const uint4 *>(vals);
+        for (int t = threadIdx.x; t < ng4; t += blockDim.x) dst[t] = __ldg(sg + t);
+        for (int t = threadIdx.x; t < nc4; t += blockDim.x) dst[ng4 + t] = __ldg(sc + t);
+        for (int t = threadIdx.x; t < nv4; t += blockDim.x) dst[ng4 + nc4 + t] = __ldg(sv + t);
         __syncthreads();
-        G = sg;
-        Tm = stm;
+        G = reinterpret_cast<const TabGroup *>(dst);
+        Cl = reinterpret_cast<const TabClass *>(dst + ng4);
+        V = reinterpret_cast<const double2 *>(dst + ng4 + nc4);
     }
     const u64 stride = (u64)gridDim.x * blockDim.x;
     double er = 0.0, ei = 0.0;
+    constexpr int B = 8;          // groups per batch: weights first, then B independent gathers in flight, then the FMAs
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += stride) {
         double2 acc = make_double2(0.0, 0.0);
-        for (int g = 0; g < ngroups; ++g) {
-            const TabGroup grp = G[g];
-            const u64 j = i ^ grp.x;
-            double wr = 0.0, wi = 0.0;
-            for (int m = grp.first; m < grp.first + grp.count; ++m) {
-                const TabTerm tt = Tm[m];
-                const double sg = sign_of(j & tt.z);
-                wr += sg * tt.dr;
-                if (!REAL) wi += sg * tt.di;
-            }
-            if (REAL) {
-                if (wr != 0.0) {
-                    const double2 v = in[j];
-                    acc.x += wr * v.x;
-                    acc.y += wr * v.y;
+        for (int gb = 0; gb < ngroups; gb += B) {
+            u64 jj[B];
+            double wr[B], wi[B];
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                wr[u] = 0.0;
+                wi[u] = 0.0;
+                jj[u] = i;
+                if (gb + u < ngroups) {
+                    const uint4 g0 = reinterpret_cast<const uint4 *>(G + gb + u)[0];   // x (lo, hi), first_class, n_class
+                    const unsigned p = reinterpret_cast<const uint2 *>(G + gb + u)[2].x;   // pos[4]
+                    const u64 j = i ^ ((u64)g0.x | ((u64)g0.y << 32));
+                    const unsigned pat = (unsigned)((j >> (p & 63u)) & 1ull) |
+                                         ((unsigned)((j >> ((p >> 8) & 63u)) & 1ull) << 1) |
+                                         ((unsigned)((j >> ((p >> 16) & 63u)) & 1ull) << 2) |
+                                         ((unsigned)((j >> ((p >> 24) & 63u)) & 1ull) << 3);
+                    const int c0 = (int)g0.z, c1 = c0 + (int)g0.w;
+                    for (int c = c0; c < c1; ++c) {
+                        const TabClass cl = Cl[c];
+                        const double sg = sign_of(j & cl.zeta);
+                        if (REAL) {
+                            wr[u] += sg * V[cl.vofs + pat].x;
+                        } else {
+                            const double2 v = V[cl.vofs + pat];
+                            wr[u] += sg * v.x;
+                            wi[u] += sg * v.y;
+                        }
+                    }
+                    jj[u] = j;
                 }
-            } else {
-                if (wr != 0.0 || wi != 0.0) acc = cadd(acc, cmul(make_double2(wr, wi), in[j]));
+            }
+            double2 vv[B];
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                const bool live = REAL ? (wr[u] != 0.0) : (wr[u] != 0.0 || wi[u] != 0.0);
+                vv[u] = live ? in[jj[u]] : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                if (REAL) {
+                    acc.x += wr[u] * vv[u].x;
+                    acc.y += wr[u] * vv[u].y;
+                } else {
+                    acc = cadd(acc, cmul(make_double2(wr[u], wi[u]), vv[u]));
+                }
             }
         }
         const double2 self = in[i];
         er += self.x * acc.x + self.y * acc.y;     // conj(self) * acc
         ei += self.x * acc.y - self.y * acc.x;
-        if (WRITE) out[i] = acc;
+        if (MODE == 1) out[i] = acc;
+        if (MODE == 2) out[i] = cadd(out[i], acc);
+    }
+    const double sr = block_sum<256>(er, red);
+    const double si = block_sum<256>(ei, red);
+    if (threadIdx.x == 0) {
+        partials[2 * blockIdx.x] = sr;
+        partials[2 * blockIdx.x + 1] = si;
+    }
+}
+
+// K2, main variant (n >= 10): each thread owns the FOUR outputs i0 | (r << 8), r = 0..3 (i0 has bits 8, 9 clear),
+// so everything that does not depend on bits 8/9 of the index -- group decode, partner index, x-bit pattern,
+// the parity over zeta -- is computed once per four amplitudes; per amplitude only a sign flip, the table
+// entry (shared unless the group's x-mask contains bit 8 or 9) and the gather remain.  Consecutive lanes own
+// consecutive indices, so every gather of a warp is one contiguous 512-byte run.
+template <typename IDX, bool REAL, int MODE, int RL>
+__global__ void __launch_bounds__(256) k_apply_table4(const TabGroup *__restrict__ groups, int ngroups,
+                                                      const TabClass *__restrict__ classes, int nclasses,
+                                                      const double2 *__restrict__ vals, int nvals,
+                                                      const double2 *__restrict__ in, double2 *__restrict__ out,
+                                                      unsigned nblk, double *__restrict__ partials) {
+    constexpr int R = 1 << RL;                    // outputs per thread: i0 | (r << 8), r < R
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[8];
+    uint4 *dst = reinterpret_cast<uint4 *>(smem_raw);
+    const int ng4 = ngroups * 2, nc4 = nclasses, nv4 = nvals;
+    {
+        const uint4 *sg = reinterpret_cast<const uint4 *>(groups);
+        const uint4 *sc = reinterpret_cast<const uint4 *>(classes);
+        const uint4 *sv = reinterpret_cast<const uint4 *>(vals);
+        for (int t = threadIdx.x; t < ng4; t += blockDim.x) dst[t] = __ldg(sg + t);
+        for (int t = threadIdx.x; t < nc4; t += blockDim.x) dst[ng4 + t] = __ldg(sc + t);
+        for (int t = threadIdx.x; t < nv4; t += blockDim.x) dst[ng4 + nc4 + t] = __ldg(sv + t);
+        __syncthreads();
+    }
+    const uint4 *G = dst;
+    const uint4 *Cl = dst + ng4;
+    const double2 *V = reinterpret_cast<const double2 *>(dst + ng4 + nc4);
+    double er = 0.0, ei = 0.0;
+    for (unsigned blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const IDX i0 = ((IDX)blk << (8 + RL)) | (IDX)threadIdx.x;
+        double ar[R], ai[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) ar[r] = ai[r] = 0.0;
+        for (int g = 0; g < ngroups; ++g) {
+            const uint4 g0 = G[2 * g];            // x lo, x hi, first_class, n_class
+            const uint4 g1 = G[2 * g + 1];        // pos[4], kbits, rpat (8 x 4 bits), -
+            const IDX j0 = i0 ^ (sizeof(IDX) == 4 ? (IDX)g0.x : (IDX)((u64)g0.x | ((u64)g0.y << 32)));
+            const unsigned p = g1.x;
+            const unsigned pat0 = (unsigned)((j0 >> (p & 63u)) & 1u) | ((unsigned)((j0 >> ((p >> 8) & 63u)) & 1u) << 1) |
+                                  ((unsigned)((j0 >> ((p >> 16) & 63u)) & 1u) << 2) |
+                                  ((unsigned)((j0 >> ((p >> 24) & 63u)) & 1u) << 3);
+            const unsigned rpat = g1.z;
+            double wr[R], wi[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) wr[r] = wi[r] = 0.0;
+            const int c0 = (int)g0.z, c1 = c0 + (int)g0.w;
+            for (int c = c0; c < c1; ++c) {
+                const uint4 cl = Cl[c];           // zeta lo, zeta hi, vofs, -
+                unsigned sb;
+                if (sizeof(IDX) == 4) sb = __popc((unsigned)j0 & cl.x);
+                else sb = __popcll((u64)j0 & ((u64)cl.x | ((u64)cl.y << 32)));
+                const unsigned zr = cl.x >> 8;    // zeta bits 8.. decide the sign flips between the R outputs
+                if (rpat == 0u) {
+                    const double2 v = V[cl.z + pat0];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int f = (int)((sb + __popc(zr & (unsigned)r)) << 31);
+                        wr[r] += __hiloint2double(__double2hiint(v.x) ^ f, __double2loint(v.x));
+                        if (!REAL) wi[r] += __hiloint2double(__double2hiint(v.y) ^ f, __double2loint(v.y));
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const double2 v = V[cl.z + (pat0 ^ ((rpat >> (4 * r)) & 15u))];
+                        const int f = (int)((sb + __popc(zr & (unsigned)r)) << 31);
+                        wr[r] += __hiloint2double(__double2hiint(v.x) ^ f, __double2loint(v.x));
+                        if (!REAL) wi[r] += __hiloint2double(__double2hiint(v.y) ^ f, __double2loint(v.y));
+                    }
+                }
+            }
+            double2 vv[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const bool live = REAL ? (wr[r] != 0.0) : (wr[r] != 0.0 || wi[r] != 0.0);
+                vv[r] = live ? in[j0 ^ ((IDX)r << 8)] : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (REAL) {
+                    ar[r] += wr[r] * vv[r].x;
+                    ai[r] += wr[r] * vv[r].y;
+                } else {
+                    ar[r] += wr[r] * vv[r].x - wi[r] * vv[r].y;
+                    ai[r] += wr[r] * vv[r].y + wi[r] * vv[r].x;
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const IDX i = i0 | ((IDX)r << 8);
+            const double2 self = in[i];
+            er += self.x * ar[r] + self.y * ai[r];     // conj(self) * acc
+            ei += self.x * ai[r] - self.y * ar[r];
+            if (MODE == 1) out[i] = make_double2(ar[r], ai[r]);
+            if (MODE == 2) {
+                const double2 o = out[i];
+                out[i] = make_double2(o.x + ar[r], o.y + ai[r]);
+            }
+        }
     }
     const double sr = block_sum<256>(er, red);
     const double si = block_sum<256>(ei, red);
@@ -678,26 +826,54 @@ void launch_tile(cudaStream_t s, double2 *psi, const TileLaunch &tl, const TileR
     k_tile<<<grid, threads, smem, s>>>(psi, tl, d_recs, d_terms, n);
 }
 
-void launch_apply_table(cudaStream_t s, int sm, const TabGroup *g, int ngroups, const TabTerm *t, int nterms,
-                        bool all_real, const double2 *in, double2 *out, int n, double *d_partials, double *d_result);
-
-void launch_apply_table(cudaStream_t s, int sm, const TabGroup *g, int ngroups, const TabTerm *t, int nterms,
-                        bool all_real, const double2 *in, double2 *out, int n, double *d_partials, double *d_result) {
-    const u64 dim = 1ull << n;
-    const size_t need = (size_t)ngroups * sizeof(TabGroup) + (size_t)nterms * sizeof(TabTerm);
+void launch_apply_table(cudaStream_t s, int sm, const fh_table *tab, const double2 *in, double2 *out, int mode,
+                        double *d_partials, double *d_result) {
+    const u64 dim = 1ull << tab->n;
+    const int ngroups = (int)tab->groups.size(), nclasses = (int)tab->classes.size(), nvals = (int)tab->vals.size();
+    const size_t need = (size_t)ngroups * sizeof(TabGroup) + (size_t)nclasses * sizeof(TabClass) +
+                        (size_t)nvals * sizeof(double2);
     const int use_smem = need <= 40 * 1024;
     const size_t smem = use_smem ? need : 0;
-    int grid = grid_for(dim, 256, 1, sm, FH_MAX_PARTIALS);
-    if (grid > sm * 8 && dim > (u64)sm * 8 * 256) grid = sm * 8;
-#define LAUNCH_TAB(R, W)                                                                                            \
+    if (!out) mode = 0;
+    int grid;
+    if (tab->n >= 11 && use_smem) {
+        const int rl = tab->n >= 22 ? 3 : 2;          // 8 outputs per thread once there is parallelism to spare
+        const unsigned nblk = (unsigned)(dim >> (8 + rl));
+        grid = nblk < (unsigned)(sm * 8) ? (int)nblk : sm * 8;
+#define LAUNCH_TAB4(I, R, M, RLV)                                                                                   \
     do {                                                                                                            \
         ++g_fh_launch_count;                                                                                        \
-        k_apply_table<R, W><<<grid, 256, smem, s>>>(g, ngroups, t, nterms, use_smem, in, out, dim, d_partials);     \
+        k_apply_table4<I, R, M, RLV><<<grid, 256, smem, s>>>(tab->d_groups, ngroups, tab->d_classes, nclasses,      \
+                                                             tab->d_vals, nvals, in, out, nblk, d_partials);        \
     } while (0)
-    if (all_real) {
-        if (out) LAUNCH_TAB(true, true); else LAUNCH_TAB(true, false);
+#define LAUNCH_TAB4_M(I, R, RLV)                                                                                    \
+    do {                                                                                                            \
+        if (mode == 0) LAUNCH_TAB4(I, R, 0, RLV); else if (mode == 1) LAUNCH_TAB4(I, R, 1, RLV); else LAUNCH_TAB4(I, R, 2, RLV); \
+    } while (0)
+#define LAUNCH_TAB4_I(I)                                                                                            \
+    do {                                                                                                            \
+        if (tab->all_real) { if (rl == 3) LAUNCH_TAB4_M(I, true, 3); else LAUNCH_TAB4_M(I, true, 2); }              \
+        else { if (rl == 3) LAUNCH_TAB4_M(I, false, 3); else LAUNCH_TAB4_M(I, false, 2); }                          \
+    } while (0)
+        if (tab->n <= 31) LAUNCH_TAB4_I(unsigned); else LAUNCH_TAB4_I(u64);
+#undef LAUNCH_TAB4_I
+#undef LAUNCH_TAB4_M
+#undef LAUNCH_TAB4
+        ++g_fh_launch_count; k_finalize_pairs<<<1, 256, 0, s>>>(d_partials, grid, d_result);
+        return;
+    }
+    grid = grid_for(dim, 256, 1, sm, FH_MAX_PARTIALS);
+    if (grid > sm * 8 && dim > (u64)sm * 8 * 256) grid = sm * 8;
+#define LAUNCH_TAB(R, M)                                                                                           \
+    do {                                                                                                           \
+        ++g_fh_launch_count;                                                                                       \
+        k_apply_table<R, M><<<grid, 256, smem, s>>>(tab->d_groups, ngroups, tab->d_classes, nclasses, tab->d_vals, \
+                                                    nvals, use_smem, in, out, dim, d_partials);                    \
+    } while (0)
+    if (tab->all_real) {
+        if (mode == 0) LAUNCH_TAB(true, 0); else if (mode == 1) LAUNCH_TAB(true, 1); else LAUNCH_TAB(true, 2);
     } else {
-        if (out) LAUNCH_TAB(false, true); else LAUNCH_TAB(false, false);
+        if (mode == 0) LAUNCH_TAB(false, 0); else if (mode == 1) LAUNCH_TAB(false, 1); else LAUNCH_TAB(false, 2);
     }
 #undef LAUNCH_TAB
     ++g_fh_launch_count; k_finalize_pairs<<<1, 256, 0, s>>>(d_partials, grid, d_result);

@@ -240,8 +240,7 @@ extern "C" int fh_lanczos(const fh_table *tab, int n_up, int n_dn, int k, double
             for (; m < mcap && iters_this < max_iter; ++iters_this) {
                 double2 *v = B.V + (size_t)m * dim;
                 // w = H v ; alpha = <v|H|v>
-                launch_apply_table(ctx->stream, ctx->sm_count, tab->d_groups, tab->n_groups, tab->d_terms,
-                                   (int)tab->terms.size(), tab->all_real, v, B.w, n, ctx->d_partials, ctx->d_result);
+                launch_apply_table(ctx->stream, ctx->sm_count, tab, v, B.w, 1, ctx->d_partials, ctx->d_result);
                 // full re-orthogonalisation (covers the three-term recurrence) + deflation, applied twice
                 for (int pass = 0; pass < 2; ++pass) {
                     FH_TRY(project_out(ctx, B.w, B.V, m + 1, dim, B));

@@ -597,9 +597,8 @@ static int enqueue_evaluation(fh_program *p, const EvalKey &k, fh_table *const *
     }
     for (int t = 0; t < k.n_tables; ++t) {
         const fh_table *tab = tables[t];
-        launch_apply_table(ctx->stream, ctx->sm_count, tab->d_groups, tab->n_groups, tab->d_terms, (int)tab->terms.size(),
-                           tab->all_real, psi, (t == 0 && need_adjoint) ? p->d_lam : nullptr, p->n, ctx->d_partials,
-                           p->d_res + 2 * t);
+        double2 *h_out = (t == 0 && need_adjoint) ? p->d_lam : nullptr;
+        launch_apply_table(ctx->stream, ctx->sm_count, tab, psi, h_out, h_out ? 1 : 0, ctx->d_partials, p->d_res + 2 * t);
     }
     for (int v = 0; v < k.n_overlaps; ++v)
         launch_inner(ctx->stream, ctx->sm_count, targets[v]->d, psi, 1ull << p->n, ctx->d_partials,

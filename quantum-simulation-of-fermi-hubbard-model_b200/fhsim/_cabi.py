@@ -45,6 +45,7 @@ SIGNATURES = {
     "fh_table_free": [_vp],
     "fh_table_info": [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "fh_apply_table": [_vp, _vp, _vp, _f64p, _f64p],
+    "fh_apply_table_accumulate": [_vp, _vp, _vp, _f64p, _f64p],
     "fh_pool_upload": [_vp, C.c_int, C.c_int, _u64p, _u64p, _u64p, _u64p, _f64p, _f64p, _i32p, C.c_int, _vpp],
     "fh_pool_free": [_vp],
     "fh_pool_gradients": [_vp, _vp, _vp, C.c_int, C.c_int, _f64p],

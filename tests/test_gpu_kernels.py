@@ -104,6 +104,104 @@ def test_complex_coefficient_table(ctx):
     assert abs(e - np.vdot(psi, want)) < 1e-12
 
 
+@pytest.mark.parametrize("n,seed", [(5, 1), (9, 2), (12, 3), (14, 4)])
+def test_random_tables_all_group_shapes(ctx, n, seed):
+    """K2 on random Hermitian-free (complex coefficient) tables: x-masks of weight 0..n (both the tabulated
+    <=4-bit groups and the per-term fallback), several zeta classes per group, repeated x-masks."""
+    rng = np.random.default_rng(seed)
+    full = (1 << n) - 1
+    xs = [0, 0, 0]
+    for w in (1, 2, 2, 3, 4, 4, 5, min(7, n)):
+        bits = rng.choice(n, size=w, replace=False)
+        xs.append(int(sum(1 << int(b) for b in bits)))
+    table = {}
+    for x in xs:
+        for _ in range(int(rng.integers(1, 6))):
+            z = int(rng.integers(0, full + 1))
+            if x == 0 and z == 0:
+                continue
+            table[(x, z)] = complex(rng.normal(), rng.normal())
+    table[(0, 0)] = 0.37
+    keys = list(table)
+    tab = PauliTable(n, [k[0] for k in keys], [k[1] for k in keys], [table[k] for k in keys])
+    psi = rand_state(n, 100 + seed)
+    st, out = State.from_numpy(ctx, psi), State(ctx, n)
+    e = DeviceTable(ctx, tab).apply(st, out)
+    want = sv.apply_table(psi, table, n)
+    assert np.abs(out.numpy() - want).max() < 1e-12
+    assert abs(e - np.vdot(psi, want)) < 1e-11
+    # real coefficients only -> the REAL kernel instantiation; only strings with an even number of Y's
+    # have a real weight table, so keep those
+    rtable = {k: v.real for k, v in table.items() if bin(k[0] & k[1]).count("1") % 2 == 0}
+    rkeys = list(rtable)
+    rtab = PauliTable(n, [k[0] for k in rkeys], [k[1] for k in rkeys], [rtable[k] for k in rkeys])
+    e2 = DeviceTable(ctx, rtab).apply(st, out)
+    want2 = sv.apply_table(psi, rtable, n)
+    assert np.abs(out.numpy() - want2).max() < 1e-12
+    assert abs(e2 - np.vdot(psi, want2)) < 1e-11
+
+
+def test_apply_table_22_qubits_eight_outputs_per_thread(ctx):
+    """n >= 22 switches K2 to 8 outputs per thread (index bits 8..10): 1x11 Hubbard chain + a complex random table
+    whose x / z masks hit bits 8, 9, 10."""
+    n = 22
+    o_h = pauli.compress(pauli.jw_table(pauli.hubbard_fermion_terms(11, 1, 1.0, 4.0), n))
+    rng = np.random.default_rng(9)
+    psi = rand_state(n, 31)
+    st, out = State.from_numpy(ctx, psi), State(ctx, n)
+    keys = list(o_h)
+    tab = PauliTable(n, [k[0] for k in keys], [k[1] for k in keys], [o_h[k] for k in keys])
+    e = DeviceTable(ctx, tab).apply(st, out)
+    want = sv.apply_table(psi, o_h, n)
+    assert np.abs(out.numpy() - want).max() < 1e-12
+    assert abs(e - np.vdot(psi, want)) < E_TOL
+    table = {}
+    for x in (0, 1 << 8, (1 << 9) | (1 << 3), (1 << 10) | (1 << 8) | (1 << 20), (1 << 9) | (1 << 10) | 1 | (1 << 15),
+              (1 << 21) | (1 << 2), 0b11111 << 7):
+        for _ in range(3):
+            z = int(rng.integers(0, 1 << n)) | (int(rng.integers(0, 8)) << 8)
+            if x or z:
+                table[(x, z)] = complex(rng.normal(), rng.normal())
+    keys = list(table)
+    tab = PauliTable(n, [k[0] for k in keys], [k[1] for k in keys], [table[k] for k in keys])
+    e = DeviceTable(ctx, tab).apply(st, out)
+    want = sv.apply_table(psi, table, n)
+    assert np.abs(out.numpy() - want).max() < 1e-12
+    assert abs(e - np.vdot(psi, want)) < 1e-10
+
+
+def test_apply_table_accumulate_splits(ctx):
+    """out = H1 psi, then out += H2 psi equals (H1+H2) psi: the sum-of-partial-tables mode used by the sharded path."""
+    from fhsim import _cabi
+    n, h_tab, _, _, _, o_h, _ = lattice(2, 3, 4.0)
+    keys = list(o_h)
+    half = len(keys) // 2
+    parts = [dict((k, o_h[k]) for k in keys[:half]), dict((k, o_h[k]) for k in keys[half:])]
+    psi = rand_state(n, 77)
+    st, out = State.from_numpy(ctx, psi), State(ctx, n)
+    tabs = [DeviceTable(ctx, PauliTable(n, [k[0] for k in p], [k[1] for k in p], [p[k] for k in p])) for p in parts]
+    e1 = tabs[0].apply(st, out)
+    re, im = _cabi.C.c_double(), _cabi.C.c_double()
+    _cabi.check(_cabi.lib().fh_apply_table_accumulate(tabs[1]._h, st._h, out._h, _cabi.C.byref(re), _cabi.C.byref(im)))
+    want = sv.apply_table(psi, o_h, n)
+    assert np.abs(out.numpy() - want).max() < 1e-12
+    assert abs(e1 + complex(re.value, im.value) - np.vdot(psi, want)) < E_TOL
+
+
+def test_spin_squared_table(ctx):
+    """S^2 (442 terms at 3x3 in the reference; 187 here at 2x3): 4-bit x-mask groups, <S^2> of a sector state."""
+    from models.common import get_spin_operators
+    n = 12
+    s2 = jordan_wigner(get_spin_operators(6, 'S^2'))
+    tab = PauliTable.from_operator(s2, n)
+    psi = rand_state(n, 5)
+    st, out = State.from_numpy(ctx, psi), State(ctx, n)
+    e = DeviceTable(ctx, tab).apply(st, out)
+    want = sv.apply_table(psi, tab.as_dict(), n)
+    assert np.abs(out.numpy() - want).max() < 1e-11
+    assert abs(e - np.vdot(psi, want)) < E_TOL
+
+
 @pytest.mark.parametrize("lat,u,up,dn", [((2, 2), 4.0, 2, 2), ((2, 3), 4.0, 3, 3)])
 def test_pool_gradients_vs_oracle(ctx, lat, u, up, dn):
     n, h_tab, pool_ops, dec, diag, o_h, o_pool = lattice(*lat, u)
