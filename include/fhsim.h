@@ -69,6 +69,11 @@ int fh_state_from_host(fh_state *st, const double *in_re_im);
 int fh_state_device_ptr(const fh_state *st, void **ptr);
 int fh_state_inner(const fh_state *a, const fh_state *b, double *re, double *im);   /* <a|b>, fidelity (adapt_vqe.py:408) */
 int fh_state_norm2(const fh_state *st, double *out);
+/* dst[i] = src[i with bits a[k] <-> b[k] exchanged] (disjoint pairs, out of place, stream-ordered, no sync): the
+ * local half of a global<->local qubit swap of a state sharded over ranks by its top index bits (the other half is
+ * an all-to-all of the 2^g top-local chunks, done by the host with NCCL).  No reference counterpart: the reference
+ * is single-device (models/adapt_vqe.py:156). */
+int fh_state_swap_bits(fh_state *dst, const fh_state *src, int n_pairs, const int32_t *a, const int32_t *b);
 
 /* ---- K1: rotations, immediate mode ----------------------------------------------------------
  * pair op: for every index i with (i & fixmask) == fixval, j = i ^ x, s = (-1)^popcount(i & zeta):

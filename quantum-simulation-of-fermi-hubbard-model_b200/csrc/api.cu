@@ -271,6 +271,27 @@ extern "C" int fh_apply_pair(fh_state *st, uint64_t x, uint64_t fixmask, uint64_
     return FH_OK;
 }
 
+extern "C" int fh_state_swap_bits(fh_state *dst, const fh_state *src, int n_pairs, const int32_t *a, const int32_t *b) {
+    FH_REQUIRE(dst && src && (n_pairs == 0 || (a && b)), "fh_state_swap_bits: NULL argument");
+    FH_REQUIRE(dst->n == src->n && dst->d != src->d, "fh_state_swap_bits: states must have equal size and distinct buffers");
+    FH_REQUIRE(n_pairs >= 0 && n_pairs <= 8, "fh_state_swap_bits: at most 8 bit pairs");
+    int aa[8], bb[8];
+    u64 seen = 0;
+    for (int k = 0; k < n_pairs; ++k) {
+        FH_REQUIRE(a[k] >= 0 && a[k] < src->n && b[k] >= 0 && b[k] < src->n && a[k] != b[k],
+                   "fh_state_swap_bits: bit positions out of range");
+        FH_REQUIRE(!(seen >> a[k] & 1ull) && !(seen >> b[k] & 1ull), "fh_state_swap_bits: bit pairs must be disjoint");
+        seen |= (1ull << a[k]) | (1ull << b[k]);
+        aa[k] = a[k];
+        bb[k] = b[k];
+    }
+    fh_ctx *ctx = src->ctx;
+    FH_CUDA(cudaSetDevice(ctx->device));
+    launch_swap_bits(ctx->stream, ctx->sm_count, src->d, dst->d, src->n, n_pairs, aa, bb);
+    FH_CUDA(cudaGetLastError());
+    return FH_OK;
+}
+
 extern "C" int fh_apply_diag(fh_state *st, int n_terms, const uint64_t *z, const double *angle) {
     FH_REQUIRE(st && (n_terms == 0 || (z && angle)), "fh_apply_diag: NULL argument");
     FH_REQUIRE(n_terms >= 0, "fh_apply_diag: negative term count");

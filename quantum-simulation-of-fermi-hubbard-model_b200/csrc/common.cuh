@@ -236,6 +236,8 @@ void launch_sum_segments(cudaStream_t s, const double *d_partials, const int *d_
 void launch_sum_strided(cudaStream_t s, const double *d_partials, int stride, int nseg, double *d_out);
 void launch_set_basis(cudaStream_t s, double2 *psi, u64 dim, u64 index);
 void launch_flush(cudaStream_t s, void *buf, size_t bytes);
+void launch_swap_bits(cudaStream_t s, int sm, const double2 *src, double2 *dst, int n, int npairs, const int *a,
+                      const int *b);
 // Lanczos helpers
 void launch_axpby(cudaStream_t s, int sm, double2 *y, double a, const double2 *x, double b, u64 dim);          // y = a*x + b*y
 void launch_lanczos_update(cudaStream_t s, int sm, double2 *w, const double2 *v, const double2 *vprev, double alpha,

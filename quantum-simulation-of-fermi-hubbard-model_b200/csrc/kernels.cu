@@ -257,7 +257,7 @@ __device__ __forceinline__ double2 tile_diag_phase(const TileTerm *t, int nterms
 
 __device__ __forceinline__ int n_terms_of(const TileRec &r) { return r.nterms; }
 
-__global__ void __launch_bounds__(512) k_tile(double2 *__restrict__ psi, const TileLaunch tl,
+__global__ void __launch_bounds__(512, 2) k_tile(double2 *__restrict__ psi, const TileLaunch tl,
                                               const TileRec *__restrict__ recs, const TileTerm *__restrict__ terms,
                                               int n) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -757,6 +757,43 @@ __global__ void __launch_bounds__(256) k_sector_random(double2 *v, int n, int n_
         }
         v[i] = make_double2(val, 0.0);
     }
+}
+
+// dst[i] = src[i with bit a[k] and bit b[k] exchanged, k < npairs]: the local half of a global<->local qubit
+// swap of a sharded state (the other half is an all-to-all over the top local bits).  Writes are consecutive;
+// reads stay in >= 2^min(a,b)-amplitude runs.
+struct SwapPairs {
+    int n;
+    unsigned char a[8], b[8];
+};
+
+__global__ void __launch_bounds__(256) k_swap_bits(const double2 *__restrict__ src, double2 *__restrict__ dst, u64 dim,
+                                                   const SwapPairs sp) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += stride) {
+        u64 j = i;
+#pragma unroll 1
+        for (int k = 0; k < sp.n; ++k) {
+            const u64 t = ((j >> sp.a[k]) ^ (j >> sp.b[k])) & 1ull;
+            j ^= (t << sp.a[k]) | (t << sp.b[k]);
+        }
+        dst[i] = src[j];
+    }
+}
+
+void launch_swap_bits(cudaStream_t s, int sm, const double2 *src, double2 *dst, int n, int npairs, const int *a,
+                      const int *b) {
+    SwapPairs sp;
+    sp.n = npairs;
+    for (int k = 0; k < npairs; ++k) {
+        sp.a[k] = (unsigned char)a[k];
+        sp.b[k] = (unsigned char)b[k];
+    }
+    const u64 dim = 1ull << n;
+    u64 blocks = (dim + 255) / 256;
+    if (blocks > (u64)sm * 32) blocks = (u64)sm * 32;
+    ++g_fh_launch_count;
+    k_swap_bits<<<(int)blocks, 256, 0, s>>>(src, dst, dim, sp);
 }
 
 // ----------------------------------------------------------------------------------------------

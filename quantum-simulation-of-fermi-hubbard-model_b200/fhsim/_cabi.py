@@ -38,6 +38,7 @@ SIGNATURES = {
     "fh_state_device_ptr": [_vp, _vpp],
     "fh_state_inner": [_vp, _vp, _f64p, _f64p],
     "fh_state_norm2": [_vp, _f64p],
+    "fh_state_swap_bits": [_vp, _vp, C.c_int, _i32p, _i32p],
     "fh_apply_pair": [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _f64p],
     "fh_apply_diag": [_vp, C.c_int, _u64p, _f64p],
     "fh_apply_pauli_rot_batch": [_vp, C.c_int, _u64p, _u64p, _f64p],

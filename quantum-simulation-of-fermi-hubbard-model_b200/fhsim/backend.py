@@ -190,6 +190,20 @@ class DevicePool:
                     raise NotImplementedError("diagonal pool generators are not supported by the screening kernel")
                 x.append(piece.x); fm.append(piece.fixmask); fv.append(piece.fixval); ze.append(piece.zeta)
                 br.append(piece.b.real); bi.append(piece.b.imag); out.append(k)
+        self._upload(x, fm, fv, ze, br, bi, out)
+
+    @classmethod
+    def from_entries(cls, ctx: Context, n_qubits: int, entries, n_out: int):
+        """entries: [(x, fixmask, fixval, zeta, b, out)] sorted by ``out`` (outputs without entries give 0)."""
+        self = cls.__new__(cls)
+        self.ctx, self.n, self.n_out = ctx, int(n_qubits), int(n_out)
+        cols = list(zip(*entries)) if entries else [[] for _ in range(6)]
+        self._upload(list(cols[0]), list(cols[1]), list(cols[2]), list(cols[3]), [complex(b).real for b in cols[4]],
+                     [complex(b).imag for b in cols[4]], list(cols[5]))
+        return self
+
+    def _upload(self, x, fm, fv, ze, br, bi, out):
+        ctx = self.ctx
         self.n_entries = len(x)
         self._h = _cabi._vp()
         xa, xp = _cabi.u64_array(x)
