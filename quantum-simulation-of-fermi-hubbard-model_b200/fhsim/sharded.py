@@ -536,6 +536,23 @@ class ShardedSimulator:
 # ---------------------------------------------------------------------------------------------
 # CUDA engine: libfhsim through the C-ABI, torch tensors as slab memory, torch.distributed for the collectives
 # ---------------------------------------------------------------------------------------------
+def pairwise_all_to_all(dist, chunks_in):
+    """all-to-all of equal CPU chunks by ordered pairwise send/recv (gloo has no alltoall)."""
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    outs = [torch.empty_like(c) for c in chunks_in]
+    for peer in range(world):
+        if peer == rank:
+            outs[peer].copy_(chunks_in[peer])
+        elif peer > rank:
+            dist.send(chunks_in[peer].contiguous(), peer)
+            dist.recv(outs[peer], peer)
+        else:
+            dist.recv(outs[peer], peer)
+            dist.send(chunks_in[peer].contiguous(), peer)
+    return outs
+
+
 class CudaEngine:
     """One rank's slab engine.  ``dist`` is an initialised torch.distributed (NCCL) or None for world = 1."""
 
@@ -550,10 +567,14 @@ class CudaEngine:
         self.n_local = int(n_local)
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
-        # everything (our kernels and NCCL) is ordered on torch's current stream
-        self.ctx = Context(device, stream=_cabi.C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        # everything (our kernels, torch copies and NCCL) is ordered on ONE explicit stream.  torch's default
+        # current stream is the legacy NULL stream, which fh_ctx_create would replace by a private one.
+        self.stream = torch.cuda.Stream(self.device)
+        torch.cuda.set_stream(self.stream)
+        self.ctx = Context(device, stream=_cabi.C.c_void_p(self.stream.cuda_stream))
         self._spare = None
         self.a2a_ms = 0.0
+        self._host_staged = dist is not None and dist.get_backend() == "gloo"
 
     # slabs are torch tensors wrapped (borrowed) as fh_state handles
     class _Slab:
@@ -619,7 +640,12 @@ class CudaEngine:
         dst = torch.view_as_real(spare.t).reshape(-1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        self.dist.all_to_all_single(dst, src)
+        if self._host_staged:
+            # ranks sharing one GPU (tests): NCCL refuses duplicate devices, so exchange through the host with gloo
+            hs = src.cpu()
+            dst.copy_(torch.cat(pairwise_all_to_all(self.dist, list(hs.chunk(self.world)))))
+        else:
+            self.dist.all_to_all_single(dst, src)
         e1.record()
         e1.synchronize()
         self.a2a_ms += e0.elapsed_time(e1)
@@ -655,14 +681,15 @@ class CudaEngine:
     def all_reduce(self, arr):
         if self.world == 1:
             return np.asarray(arr, dtype=np.float64)
-        t = self.torch.as_tensor(np.asarray(arr, dtype=np.float64), device=self.device)
+        t = self.torch.as_tensor(np.asarray(arr, dtype=np.float64), device="cpu" if self._host_staged else self.device)
         self.dist.all_reduce(t)
         return t.cpu().numpy()
 
     def all_gather_slab(self, h):
         if self.world == 1:
             return [h[0].t.cpu().numpy()]
-        outs = [self.torch.empty_like(h[0].t) for _ in range(self.world)]
+        mine = h[0].t.cpu() if self._host_staged else h[0].t
+        outs = [self.torch.empty_like(mine) for _ in range(self.world)]
         flat = [self.torch.view_as_real(o).reshape(-1) for o in outs]
-        self.dist.all_gather(flat, self.torch.view_as_real(h[0].t).reshape(-1))
+        self.dist.all_gather(flat, self.torch.view_as_real(mine).reshape(-1))
         return [o.cpu().numpy() for o in outs]

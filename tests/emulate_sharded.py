@@ -76,21 +76,8 @@ class NumpyEngine:
             return
         import torch
         src = torch.from_numpy(np.ascontiguousarray(h[0]).view(np.float64).copy())
-        chunks_in = list(src.chunk(self.world))
-        chunks_out = [torch.empty_like(c) for c in chunks_in]
-        try:
-            self.dist.all_to_all(chunks_out, chunks_in)
-        except RuntimeError:
-            # gloo builds without alltoall: pairwise exchange
-            for peer in range(self.world):
-                if peer == self.rank:
-                    chunks_out[peer].copy_(chunks_in[peer])
-                elif peer > self.rank:
-                    self.dist.send(chunks_in[peer], peer)
-                    self.dist.recv(chunks_out[peer], peer)
-                else:
-                    self.dist.recv(chunks_out[peer], peer)
-                    self.dist.send(chunks_in[peer], peer)
+        from fhsim.sharded import pairwise_all_to_all
+        chunks_out = pairwise_all_to_all(self.dist, list(src.chunk(self.world)))
         h[0] = torch.cat(chunks_out).numpy().view(np.complex128).copy()
 
     def apply_table(self, table, h_in, h_out, accumulate):
