@@ -259,9 +259,23 @@ def choose_globals_belady(ops, start, layout: QubitLayout):
     # farthest next use first; among equals prefer qubits already sitting at the top of the slab (no local pass)
     cand.sort(key=lambda b: (-(next_use[b] if next_use[b] is not None else inf), -layout.perm[b]))
     chosen = cand[:g]
-    if any(next_use[b] == start for b in chosen):
+    if start < len(ops) and any(next_use[b] == start for b in chosen) and layout.nl < layout.n:
         raise ValueError("op needs more local qubits than the slab has")
     return chosen
+
+
+def best_initial_layout(ops, n_qubits: int, g: int) -> QubitLayout:
+    """Layout for a state that starts as a basis state (so its layout is free): the rank qubits are the g qubits
+    whose first use as an x-bit lies farthest in the future, the rest keep their relative order."""
+    ops = [o for o in ops if not isinstance(o, Marker)]
+    probe = QubitLayout(n_qubits, 0)
+    probe.g = g
+    chosen = sorted(choose_globals_belady(ops, 0, probe)) if g else []
+    rest = [b for b in range(n_qubits) if b not in chosen]
+    perm = [0] * n_qubits
+    for p, b in enumerate(rest + chosen):
+        perm[b] = p
+    return QubitLayout(n_qubits, g, perm)
 
 
 def plan_circuit(ops, layout: QubitLayout):
@@ -334,6 +348,10 @@ class ShardedSimulator:
             raise ValueError("engine slab size does not match n_qubits - log2(world)")
         if self.nl < 2 * g:
             raise ValueError("slab too small for a global<->local swap")
+        self.profiling = False         # True: adapt_screening syncs after every phase and fills self.profile (seconds)
+        self.profile = {}
+        self._keepalive = {}           # op lists whose ids key the engine's compiled-program cache
+        self._dagger_cache = {}
         self.swap_count = 0            # all-to-alls issued (per state)
         self.pass_count = {"table": 0, "pool": 0}
 
@@ -427,7 +445,9 @@ class ShardedSimulator:
                     local.extend(lower_pair(op, lay, rank))
             # every rank runs its (possibly shorter) local segment; no collective inside
             if local:
-                self.engine.run_ops(st.h, local, thetas, n_params)
+                key = (tuple(id(o) for o in seg), tuple(lay.perm), int(n_params))
+                self._keepalive[key] = seg
+                self.engine.run_ops(st.h, local, thetas, n_params, key=key)
 
     # -- K2 --------------------------------------------------------------------------------------
     def apply_table(self, table: PauliTable, phi: ShardedState, out: ShardedState | None = None) -> complex:
@@ -512,20 +532,39 @@ class ShardedSimulator:
                         n_params=0, want_gradients=True):
         """psi_k = ansatz|basis>, phi = W psi_k, E = <phi|H|phi>, lam = W^dagger H phi, g = pool gradients
         (reference ADAPT.select_operator, models/adapt_vqe.py:297-323, on a sharded state)."""
-        psi = self.new_state()
+        import time
+        prof = self.profile = {}
+
+        def lap(name, t0):
+            if self.profiling:
+                self.engine.sync()
+                prof[name] = prof.get(name, 0.0) + time.perf_counter() - t0
+            return time.perf_counter()
+
+        t = time.perf_counter()
+        psi = self.new_state(best_initial_layout(list(ansatz_ops) + list(basis_change_ops), self.n, self.g))
         self.set_basis(psi, basis_index)
         self.apply_ops(psi, ansatz_ops, thetas, n_params)
+        t = lap("ansatz", t)
         phi = self.new_state()
         self.copy(phi, psi)
         self.apply_ops(phi, basis_change_ops, thetas, n_params)
+        t = lap("W", t)
         lam = self.new_state(phi.layout) if want_gradients else None
         energy = self.apply_table(h_table, phi, lam)
+        t = lap("H_apply", t)
         grads = None
         if want_gradients:
             phi.close()
-            self.apply_ops(lam, dagger_ops(basis_change_ops), thetas, n_params)
+            wd = self._dagger_cache.get(id(basis_change_ops))
+            if wd is None:
+                wd = self._dagger_cache[id(basis_change_ops)] = (dagger_ops(basis_change_ops), basis_change_ops)
+            self.apply_ops(lam, wd[0], thetas, n_params)
+            t = lap("W_dagger", t)
             self.to_layout(lam, psi.layout)
+            t = lap("align_layouts", t)
             grads = self.pool_gradients(plans, psi, lam)
+            t = lap("pool_scan", t)
             lam.close()
         else:
             phi.close()
@@ -573,6 +612,7 @@ class CudaEngine:
         torch.cuda.set_stream(self.stream)
         self.ctx = Context(device, stream=_cabi.C.c_void_p(self.stream.cuda_stream))
         self._spare = None
+        self._programs = {}             # compiled local segments, keyed by the planner
         self.a2a_ms = 0.0
         self._host_staged = dist is not None and dist.get_backend() == "gloo"
 
@@ -614,15 +654,20 @@ class CudaEngine:
     def copy(self, dst, src):
         dst[0].st.copy_from(src[0].st)
 
-    def run_ops(self, h, ops, thetas, n_params):
+    def run_ops(self, h, ops, thetas, n_params, key=None):
         from .circuit import Circuit
-        circ = Circuit(self.n_local, n_params)
-        circ.ops = list(ops)
-        prog = circ.compile(self.ctx)
+        prog = self._programs.get(key) if key is not None else None
+        if prog is None:
+            circ = Circuit(self.n_local, n_params)
+            circ.ops = list(ops)
+            prog = circ.compile(self.ctx)
+            if key is not None:
+                self._programs[key] = prog
         try:
             prog.run(h[0].st, thetas)
         finally:
-            prog.close()
+            if key is None:
+                prog.close()
 
     def swap_bits(self, h, pairs):
         spare = self._spare_slab()
@@ -677,6 +722,9 @@ class CudaEngine:
 
     def inner(self, ha, hb):
         return ha[0].st.inner(hb[0].st)
+
+    def sync(self):
+        self.stream.synchronize()
 
     def all_reduce(self, arr):
         if self.world == 1:

@@ -45,7 +45,7 @@ class NumpyEngine:
     def copy(self, dst, src):
         dst[0] = src[0].copy()
 
-    def run_ops(self, h, ops, thetas, n_params):
+    def run_ops(self, h, ops, thetas, n_params, key=None):
         self.calls["run_ops"] += 1
         psi = h[0]
         for op in ops:
@@ -114,6 +114,9 @@ class NumpyEngine:
             val = np.sum(np.conj(lam[i]) * s * b * psi[j] + np.conj(lam[j]) * s * np.conj(b) * psi[i])
             out[o] += 2.0 * val.imag
         return out
+
+    def sync(self):
+        pass
 
     def inner(self, ha, hb):
         return complex(np.vdot(ha[0], hb[0]))
