@@ -212,3 +212,42 @@ def test_planner_keeps_every_op_local_and_cover_choice_progresses():
     assert remaining
     _, lay2 = swap_steps(lay, choose_globals_cover(remaining, lay))
     assert all(lay2.is_local(m) for m in remaining)
+
+
+def _pool_worker(rank, world, port, n_out):
+    import torch.distributed as dist
+    sys.path[:0] = [HERE, os.path.dirname(HERE), os.path.join(os.path.dirname(HERE), "quantum-simulation-of-fermi-hubbard-model_b200")]
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fhsim.parallel import pool_ranges, screen_pool_sharded
+        truth = np.sin(np.arange(n_out) * 0.37)
+
+        class FakePool:
+            pass
+
+        class FakeProgram:                       # stands in for DeviceProgram.evaluate (needs a GPU)
+            def evaluate(self, basis, thetas, tables, pool=None, pool_pos=0, pool_range=None):
+                first, count = pool_range
+                return {"expvals": np.array([1.5]), "pool": truth[first:first + count].copy()}
+
+        pool = FakePool()
+        pool.n_out = n_out
+        res = screen_pool_sharded(FakeProgram(), 0, [], [], pool, 0, dist)
+        assert np.array_equal(res["pool"], truth)
+        assert sum(c for _, c in pool_ranges(n_out, world)) == n_out
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_out", [(2, 324), (3, 24), (2, 1)])
+def test_pool_sharded_gather_gloo(world, n_out):
+    import torch.multiprocessing as mp
+    mp.spawn(_pool_worker, args=(world, _free_port(), n_out), nprocs=world, join=True)
+
+
+def test_pool_ranges_match_survey_split():
+    from fhsim.parallel import pool_ranges
+    assert [c for _, c in pool_ranges(324, 8)] == [41, 41, 41, 41, 40, 40, 40, 40]
+    assert pool_ranges(5, 8)[5:] == [(5, 0), (5, 0), (5, 0)]
