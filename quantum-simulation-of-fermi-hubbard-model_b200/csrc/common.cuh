@@ -97,7 +97,7 @@ struct __align__(16) TileRec {          // 128 bytes = 8 x 16 B; k_tile reads it
     unsigned zeta, xlocal;
     // word 1
     unsigned lfixval;                   // pattern bits inside the tile, in tile-local coordinates
-    int type;                           // 1 pair (complex matrix), 3 pair (real matrix), 2 diag
+    int type;                           // 1 pair (complex matrix), 3 pair (real matrix), 6 pair (real diagonal), 2 diag
     int nlfix, term_off;
     // word 2: bit-insertion masks (1<<p)-1 of the (at most 4) pattern bits inside the tile, ascending;
     // unused slots hold 0xffffffff (insertion is then a no-op)

@@ -257,6 +257,13 @@ __device__ __forceinline__ double2 tile_diag_phase(const TileTerm *t, int nterms
 
 __device__ __forceinline__ int n_terms_of(const TileRec &r) { return r.nterms; }
 
+// Shared-memory slot of tile-local index l.  The three low bits (the 128-bit bank group) are XOR-folded with every
+// higher 3-bit group, so eight lanes that differ in ANY three bit positions of distinct residue mod 3 hit eight
+// different bank groups: consecutive indices (tile load/store) and the strided accesses of the register runs alike.
+__device__ __forceinline__ unsigned tile_slot(unsigned l) {
+    return l ^ ((l >> 3) & 7u) ^ ((l >> 6) & 7u) ^ ((l >> 9) & 7u) ^ ((l >> 12) & 7u);
+}
+
 __global__ void __launch_bounds__(512, 2) k_tile(double2 *__restrict__ psi, const TileLaunch tl,
                                               const TileRec *__restrict__ recs, const TileTerm *__restrict__ terms,
                                               int n) {
@@ -264,12 +271,18 @@ __global__ void __launch_bounds__(512, 2) k_tile(double2 *__restrict__ psi, cons
     __shared__ TileRec rec[TILE_MAX_SUB];
     __shared__ TileTerm tterm[TILE_MAX_TERMS];
     __shared__ unsigned slo[64], shi[128];      // scatter tables: local index bits -> global bit positions
+    __shared__ double2 ph[192];                 // diagonal ops: phase factor tables over local bits 0..5 / 6..12
     const int T = tl.nbits, nsub = tl.nsub;
+    unsigned lomask_g = 0, himask_g = 0;        // global masks of the tile's local bits 0..5 / 6..
+    for (int b = 0; b < T; ++b) {
+        if (b < 6) lomask_g |= 1u << tl.bits[b];
+        else himask_g |= 1u << tl.bits[b];
+    }
     const unsigned L = 1u << T;
     double2 *buf = reinterpret_cast<double2 *>(smem_raw);
     unsigned int *gidx = reinterpret_cast<unsigned int *>(buf + L);
 
-    // ---- prologue: one coalesced copy of the run's records (issued first, consumed after the tile load) ----
+    // ---- prologue: one coalesced copy of the launch's records (issued first, consumed after the tile load) ----
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(recs + tl.first_rec);
         uint4 *dst = reinterpret_cast<uint4 *>(rec);
@@ -280,12 +293,12 @@ __global__ void __launch_bounds__(512, 2) k_tile(double2 *__restrict__ psi, cons
         const int tchunks = tl.nterms * (int)(sizeof(TileTerm) / 16);
         for (int c = threadIdx.x; c < tchunks; c += blockDim.x) tdst[c] = __ldg(tsrc + c);
     }
-    if (threadIdx.x < 64) {
+    for (unsigned v = threadIdx.x; v < 64u; v += blockDim.x) {
         unsigned g = 0;
-        for (int b = 0; b < 6 && b < T; ++b) g |= ((threadIdx.x >> b) & 1u) << tl.bits[b];
-        slo[threadIdx.x] = g;
-    } else if (threadIdx.x < 192) {
-        const unsigned v = threadIdx.x - 64;
+        for (int b = 0; b < 6 && b < T; ++b) g |= ((v >> b) & 1u) << tl.bits[b];
+        slo[v] = g;
+    }
+    for (unsigned v = threadIdx.x; v < 128u; v += blockDim.x) {
         unsigned g = 0;
         for (int b = 6; b < T; ++b) g |= ((v >> (b - 6)) & 1u) << tl.bits[b];
         shi[v] = g;
@@ -311,35 +324,23 @@ __global__ void __launch_bounds__(512, 2) k_tile(double2 *__restrict__ psi, cons
             for (int u = 0; u < 4; ++u) {
                 const unsigned l = l0 + u * blockDim.x;
                 if (l < L) {
-                    gidx[l] = gg[u];
-                    buf[l] = vv[u];
+                    const unsigned sl = tile_slot(l);
+                    gidx[sl] = gg[u];
+                    buf[sl] = vv[u];
                 }
             }
         }
         __syncthreads();
-        // Per-op loop.  Each record is pulled into registers with a few 128-bit shared loads issued
-        // together, and the NEXT record is fetched before the barrier so its latency is off the chain.
-        uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0;
-        double2 ma = make_double2(0, 0), mb = ma, mc = ma, md = ma;
-        if (nsub > 0) {
-            const uint4 *rp = reinterpret_cast<const uint4 *>(&rec[0]);
-            q0 = rp[0]; q1 = rp[1]; q2 = rp[2];
-            const double2 *mp = reinterpret_cast<const double2 *>(rec[0].m);
-            ma = mp[0]; mb = mp[1]; mc = mp[2]; md = mp[3];
-        }
-        for (int sidx = 0; sidx < nsub; ++sidx) {
-            uint4 n0 = q0, n1 = q1, n2 = q2;
-            double2 na = ma, nb = mb, nc = mc, nd = md;
-            if (sidx + 1 < nsub) {
-                const uint4 *rp = reinterpret_cast<const uint4 *>(&rec[sidx + 1]);
-                n0 = rp[0]; n1 = rp[1]; n2 = rp[2];
-                const double2 *mp = reinterpret_cast<const double2 *>(rec[sidx + 1].m);
-                na = mp[0]; nb = mp[1]; nc = mp[2]; nd = mp[3];
-            }
-            // q0 = {fixmask_out, fixval_out, zeta, xlocal}; q1 = {lfixval, type, nlfix, term_off}; q2 = insertion masks
+        int sidx = 0;
+        while (sidx < nsub) {
+            const uint4 *rp = reinterpret_cast<const uint4 *>(&rec[sidx]);
+            const uint4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
+            // q0 = {fixmask_out, fixval_out, zeta, xlocal}; q1 = {lfixval, type, nlfix, term_off}; q2 = lowmask[4]
             const int type = (int)q1.y;
             if (type != 2) {
                 if ((base & q0.x) == q0.y) {
+                    const double2 *mp = reinterpret_cast<const double2 *>(rec[sidx].m);
+                    const double2 ma = mp[0], mb = mp[1], mc = mp[2], md = mp[3];
                     const unsigned npairs = L >> q1.z;
                     for (unsigned k = threadIdx.x; k < npairs; k += blockDim.x) {
                         unsigned il = k;
@@ -348,13 +349,23 @@ __global__ void __launch_bounds__(512, 2) k_tile(double2 *__restrict__ psi, cons
                         il = ((il & ~q2.z) << 1) | (il & q2.z);
                         il = ((il & ~q2.w) << 1) | (il & q2.w);
                         il |= q1.x;
-                        const unsigned jl = il ^ q0.w;
+                        const unsigned jl = tile_slot(il ^ q0.w);
+                        il = tile_slot(il);
                         double2 a = buf[il], b = buf[jl];
                         const double sg = (__popc(gidx[il] & q0.z) & 1) ? -1.0 : 1.0;
                         if (type == 3) {
                             const double s01 = sg * mb.x, s10 = sg * mc.x;
                             const double2 ra = make_double2(ma.x * a.x + s01 * b.x, ma.x * a.y + s01 * b.y);
                             const double2 rb = make_double2(s10 * a.x + md.x * b.x, s10 * a.y + md.x * b.y);
+                            a = ra;
+                            b = rb;
+                        } else if (type == 6) {
+                            // real diagonal (every rotation): ra = c a + s m01 b, rb = s m10 a + c' b
+                            const double2 sb = cscale(b, sg), sa = cscale(a, sg);
+                            const double2 ra = make_double2(ma.x * a.x + (mb.x * sb.x - mb.y * sb.y),
+                                                            ma.x * a.y + (mb.x * sb.y + mb.y * sb.x));
+                            const double2 rb = make_double2(md.x * b.x + (mc.x * sa.x - mc.y * sa.y),
+                                                            md.x * b.y + (mc.x * sa.y + mc.y * sa.x));
                             a = ra;
                             b = rb;
                         } else {
@@ -366,17 +377,49 @@ __global__ void __launch_bounds__(512, 2) k_tile(double2 *__restrict__ psi, cons
                         buf[jl] = b;
                     }
                 }
+                sidx += 1;
             } else {
+                // diagonal op: exp(-i sum_m angle_m sgn_m(index)).  Terms whose in-tile z bits sit entirely in local
+                // bits 0..5 (or entirely in 6..) are folded into two small phase tables built once per tile; only
+                // terms straddling both halves are evaluated per amplitude.
                 const TileTerm *dt = tterm + (int)q1.w;
                 const int cnt = (int)n_terms_of(rec[sidx]);
-                for (unsigned l = threadIdx.x; l < L; l += blockDim.x)
-                    buf[l] = cmul(tile_diag_phase(dt, cnt, gidx[l]), buf[l]);
+                for (unsigned v = threadIdx.x; v < 192u; v += blockDim.x) {
+                    const bool lo = v < 64u;
+                    const unsigned gl = base | (lo ? slo[v] : shi[v - 64u]);
+                    double tot = 0.0;
+                    for (int m = 0; m < cnt; ++m) {
+                        const unsigned z = (unsigned)dt[m].z;
+                        const bool in_lo = (z & himask_g) == 0u;
+                        const bool in_hi = (z & lomask_g) == 0u && !in_lo;
+                        if (lo ? in_lo : in_hi) tot += ((__popc(gl & z) & 1) ? -1.0 : 1.0) * dt[m].angle;
+                    }
+                    double sn, cs;
+                    sincos(tot, &sn, &cs);
+                    ph[v] = make_double2(cs, -sn);
+                }
+                __syncthreads();
+                for (unsigned sl = threadIdx.x; sl < L; sl += blockDim.x) {
+                    const unsigned l = tile_slot(sl);
+                    double2 f = cmul(ph[l & 63u], ph[64u + (l >> 6)]);
+                    const unsigned gi = gidx[sl];
+                    for (int m = 0; m < cnt; ++m) {
+                        const unsigned z = (unsigned)dt[m].z;
+                        if ((z & himask_g) != 0u && (z & lomask_g) != 0u) {
+                            const double sg = (__popc(gi & z) & 1) ? -1.0 : 1.0;
+                            f = cmul(f, make_double2(dt[m].c, -sg * dt[m].s));
+                        }
+                    }
+                    buf[sl] = cmul(f, buf[sl]);
+                }
+                sidx += 1;
             }
             __syncthreads();
-            q0 = n0; q1 = n1; q2 = n2;
-            ma = na; mb = nb; mc = nc; md = nd;
         }
-        for (unsigned l = threadIdx.x; l < L; l += blockDim.x) psi[gidx[l]] = buf[l];
+        for (unsigned l = threadIdx.x; l < L; l += blockDim.x) {
+            const unsigned sl = tile_slot(l);
+            psi[gidx[sl]] = buf[sl];
+        }
         __syncthreads();
     }
 }
@@ -855,10 +898,10 @@ void launch_tile(cudaStream_t s, double2 *psi, const TileLaunch &tl, const TileR
     }
     u64 ntiles = 1ull << (n - nbits);
     const int grid = (int)(ntiles > 148ull * 16 ? 148ull * 16 : ntiles);
-    // one thread per index pair of the tile (at most 512); the scatter tables are filled by threads 0..191
+    // one thread per index pair of the tile (at most 512, at least two warps)
     int threads = nbits >= 1 ? (1 << (nbits - 1)) : 1;
     if (threads > 512) threads = 512;
-    if (threads < 192) threads = 192;
+    if (threads < 64) threads = 64;
     ++g_fh_launch_count;
     k_tile<<<grid, threads, smem, s>>>(psi, tl, d_recs, d_terms, n);
 }

@@ -278,7 +278,8 @@ static void set_rec_matrix(TileRec &r, const double m[8], bool dagger) {
         r.m[6] = m[6]; r.m[7] = -m[7];
     }
     const bool real = (r.m[1] == 0.0 && r.m[3] == 0.0 && r.m[5] == 0.0 && r.m[7] == 0.0);
-    r.type = real ? 3 : 1;
+    const bool rdiag = (r.m[1] == 0.0 && r.m[7] == 0.0);       // every rotation exp(-i a G) has a real diagonal
+    r.type = real ? 3 : (rdiag ? 6 : 1);
 }
 
 static void set_tile_term(TileTerm &tt, const DiagTerm &t, bool dagger) {

@@ -12,15 +12,17 @@ from fhsim.tables import GeneratorPlan
 from operators.tools import get_interacting_term
 
 lat = sys.argv[1] if len(sys.argv) > 1 else "3x4"
-tbs = [int(v) for v in sys.argv[2:]] or [None]
+tbs = [tuple(int(x) for x in v.split(":")) for v in sys.argv[2:]] or [(None,)]
 nx, ny = map(int, lat.split("x"))
 n = 2 * nx * ny
 ctx = Context(0)
 st = State(ctx, n)
-for tb in tbs:
+for spec in tbs:
+    tb = spec[0]
+    lb = spec[1] if len(spec) > 1 else None
     c = Circuit(n, 0)
     c.basis_change_separable(nx, ny)
-    prog = c.compile(ctx, tile_bits=tb)
+    prog = c.compile(ctx, tile_bits=tb, low_bits=lb)
     st.set_basis(3)
     prog.run(st, [])
     reps = 20 if n <= 24 else 3
@@ -28,7 +30,7 @@ for tb in tbs:
     per = [1e3 * prog.time_items(st, i, 1, False, reps) for i in range(prog.n_items)]
     tot = 1e3 * prog.time_items(st, 0, prog.n_items, False, reps)
     ideal = 32.0 * (1 << n) / 6552.6e9 * 1e6
-    print(f"{lat} n={n} tile_bits={prog.tile_bits} W: {prog.n_items} launches, total {tot:.1f} us, per launch "
+    print(f"{lat} n={n} tile_bits={prog.tile_bits} low_bits={prog.low_bits} W: {prog.n_items} launches, total {tot:.1f} us, per launch "
           f"{[round(p, 1) for p in per]} us; one streaming pass = {ideal:.1f} us; norm2={st.norm2():.12f}")
     prog.close()
     # Coulomb layer as a single diagonal op (k_diag) and fused in a tile together with ry's
