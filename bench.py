@@ -38,6 +38,9 @@ N_QUBITS = 2 * NX * NY
 WORKLOAD = "cfg3: ADAPT screening, 3x3 Hubbard U=6 (5up,4dn), 18 qubits, 52-operator ansatz, 324-operator pool"
 METRIC = "ADAPT pool-gradients/s at 3x3 (18q)"
 L2_FLUSH_BYTES = 256 << 20
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_pool launch of this workload (ncu --set full,
+# profiles/r01_s2_ncu_full_18q.md rows "k_pool"): psi and lambda (8 MiB) are read from HBM once, everything else hits L2
+K3_DRAM_BYTES_PER_LAUNCH = 8431360
 
 
 def measured_peak_gbs():
@@ -345,6 +348,24 @@ def run_gpu_arm(args, rank, world, local_rank):
     alg_bytes = 4.0 * (1 << n) * n_pool              # 4*2^n B per gradient
     achieved = alg_bytes / k3 / 1e9
 
+    # ---- the same kernels where the state no longer fits L2 (3x4 lattice, 24 qubits, 256 MiB): true HBM rooflines ----
+    hbm = None
+    if world == 1 and not args.no_hbm_regime:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from sweep_roofline import measure_lattice
+        row = measure_lattice(ctx, "3x4", peak, pool_cap=400, verbose=False)
+        hbm = {"workload": "3x4 Hubbard, 24 qubits, state 256 MiB (> L2), back-to-back launches, CUDA events",
+               "unit": "GB/s", "peak": peak}
+        for key, label in (("screening", "k_pool: 400 gradients, 4*2^n B each"),
+                           ("pair_dense", "k_pair: Pauli-string rotation, 32*2^n B"),
+                           ("givens", "k_pair: Givens rotation, 16*2^n B"),
+                           ("pair_fermi4", "k_pair: fermionic double excitation, 4*2^n B"),
+                           ("diag_coulomb", "k_diag: Coulomb layer, 32*2^n B"),
+                           ("tile_W", "k_tile: one fused launch of W, 32*2^n B"),
+                           ("h_apply", "k_apply_table4: H psi + <H>, 32*2^n B")):
+            hbm[key] = {"what": label, "us": round(row[key]["us"], 2), "achieved": round(row[key]["GBps"], 1),
+                        "frac": round(row[key]["frac"], 4)}
+
     clocks = sampler.stop() if sampler else {}
 
     # ---- CPU baseline (bounded sample of the same workload) ----
@@ -383,9 +404,10 @@ def run_gpu_arm(args, rank, world, local_rank):
         "h_eval_ms": statistics.median(h_ms), "h_eval_launches": h_launches,
         "roofline": {"bound": "hbm", "kernel": "k_pool (K3 pool screening) + k_pool_finalize",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel_ms": k3 * 1e3,
+                     "traffic": K3_DRAM_BYTES_PER_LAUNCH, "peak_source": peak_src, "kernel_ms": k3 * 1e3,
                      "note": "18-qubit working set (8 MiB) is L2-resident: effective GB/s vs HBM peak; "
                              "algorithmic bytes = 4*2^n per gradient x 324"},
+        "hbm_regime": hbm,
         "cpu_baseline": cpu,
         "pool_sharded": pool_sharded,
         "clocks": clocks,
@@ -404,6 +426,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="fhsim", choices=["fhsim", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hbm-regime", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

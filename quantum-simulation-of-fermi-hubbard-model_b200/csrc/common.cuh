@@ -91,7 +91,7 @@ struct TileLaunch {
 };
 
 // ready-to-execute record of one op inside a tile (built on the host, one array per direction)
-struct __align__(16) TileRec {          // 128 bytes = 8 x 16 B; k_tile reads it as uint4 / double2 words
+struct __align__(16) TileRec {          // 144 bytes = 9 x 16 B; k_tile reads it as uint4 / double2 words
     // word 0
     unsigned fixmask_out, fixval_out;   // pattern bits outside the tile: uniform per tile
     unsigned zeta, xlocal;
@@ -102,15 +102,20 @@ struct __align__(16) TileRec {          // 128 bytes = 8 x 16 B; k_tile reads it
     // word 2: bit-insertion masks (1<<p)-1 of the (at most 4) pattern bits inside the tile, ascending;
     // unused slots hold 0xffffffff (insertion is then a no-op)
     unsigned lowmask[4];
-    // word 3
-    int nterms, pad[3];
+    // word 3: nterms (diag); seg = index of this op among the tile's parametrised ops in execution order of this
+    // direction, or -1 (used by the fused adjoint sweep, which runs the dagger records)
+    int nterms, seg, pad[2];
     // words 4..7
     double m[8];
+    // word 8: normalised generator element of a rotation op (gradient of the adjoint sweep)
+    double bhat[2];
 };
 
-struct __align__(16) TileTerm {         // 32 bytes
+struct __align__(16) TileTerm {         // 48 bytes
     u64 z;
     double angle, c, s;
+    double coef;                        // d(angle)/d(theta) (0 for fixed terms)
+    double pad;
 };
 
 struct TileOp {                         // host bookkeeping of one tile run
@@ -120,6 +125,7 @@ struct TileOp {                         // host bookkeeping of one tile run
     unsigned char bits[16];
     int first_rec_fwd, first_rec_dag;   // offsets into the two record arrays
     int first_term_fwd, first_term_dag, nterms;
+    int n_param_subs;                   // parametrised ops inside this tile
 };
 
 struct TabTerm {
@@ -223,6 +229,12 @@ void launch_diag_adjoint(cudaStream_t s, int sm, double2 *psi, double2 *lam, con
                          double *d_partials, int max_blocks, int *blocks_used);
 void launch_tile(cudaStream_t s, double2 *psi, const TileLaunch &tl, const TileRec *d_recs, const TileTerm *d_terms,
                  int n);
+// fused adjoint step of a whole tile run (dagger records): gradient partials of every parametrised op into
+// gpart[(seg_base + rec.seg) * FH_GRAD_BLOCKS + block], then the inverse op on psi AND lam
+void launch_tile_adjoint(cudaStream_t s, double2 *psi, double2 *lam, const TileLaunch &tl, const TileRec *d_recs,
+                         const TileTerm *d_terms, int n, double *d_gpart, int seg_base);
+#define FH_GRAD_BLOCKS 256     // partial blocks per parametrised op in the adjoint sweep
+#define FH_TILE_ADJOINT_MAX_BITS 12   // two tiles + index table must fit in shared memory
 // mode 0: expectation only; 1: out = H in; 2: out += H in.   Result (re, im of <in|H|in>) -> d_result[0..1]
 void launch_apply_table(cudaStream_t s, int sm, const fh_table *tab, const double2 *in, double2 *out, int mode,
                         double *d_partials, double *d_result);

@@ -424,6 +424,178 @@ __global__ void __launch_bounds__(512, 2) k_tile(double2 *__restrict__ psi, cons
     }
 }
 
+// Fused adjoint sweep of one tile run.  Both psi and lambda tiles are staged in shared memory; the run's records
+// (already inverted: dagger order, dagger matrices) are walked once.  For every parametrised op the partial
+// Im <lambda| Ghat |psi> over the tile is taken at the op's output side (before undoing it), then the inverse op is
+// applied to both states.  Partials: warp sums go to shared memory without extra barriers, are folded per tile in a
+// fixed order, accumulated over the CTA's tiles, and written once per (op, CTA): deterministic.
+#define TILE_ADJ_WARPS 16
+__global__ void __launch_bounds__(512, 1) k_tile_adjoint(double2 *__restrict__ psi, double2 *__restrict__ lam,
+                                                         const TileLaunch tl, const TileRec *__restrict__ recs,
+                                                         const TileTerm *__restrict__ terms, int n,
+                                                         double *__restrict__ gpart, int seg_base) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ TileRec rec[TILE_MAX_SUB];
+    __shared__ TileTerm tterm[TILE_MAX_TERMS];
+    __shared__ unsigned slo[64], shi[128];
+    __shared__ double2 ph[192];
+    __shared__ double dsum[192];                          // diagonal generator value tables (sum of coef * sign)
+    __shared__ double wsum[TILE_MAX_SUB][TILE_ADJ_WARPS];  // per-op warp partials of the current tile
+    __shared__ double cacc[TILE_MAX_SUB];                 // per-op partial of this CTA over all its tiles
+    const int T = tl.nbits, nsub = tl.nsub;
+    const unsigned L = 1u << T;
+    double2 *bufp = reinterpret_cast<double2 *>(smem_raw);
+    double2 *bufl = bufp + L;
+    unsigned int *gidx = reinterpret_cast<unsigned int *>(bufl + L);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    unsigned lomask_g = 0, himask_g = 0;
+    for (int b = 0; b < T; ++b) {
+        if (b < 6) lomask_g |= 1u << tl.bits[b];
+        else himask_g |= 1u << tl.bits[b];
+    }
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(recs + tl.first_rec);
+        uint4 *dst = reinterpret_cast<uint4 *>(rec);
+        const int chunks = nsub * (int)(sizeof(TileRec) / 16);
+        for (int c = threadIdx.x; c < chunks; c += blockDim.x) dst[c] = __ldg(src + c);
+        const uint4 *tsrc = reinterpret_cast<const uint4 *>(terms + tl.first_term);
+        uint4 *tdst = reinterpret_cast<uint4 *>(tterm);
+        const int tchunks = tl.nterms * (int)(sizeof(TileTerm) / 16);
+        for (int c = threadIdx.x; c < tchunks; c += blockDim.x) tdst[c] = __ldg(tsrc + c);
+    }
+    for (unsigned v = threadIdx.x; v < 64u; v += blockDim.x) {
+        unsigned g = 0;
+        for (int b = 0; b < 6 && b < T; ++b) g |= ((v >> b) & 1u) << tl.bits[b];
+        slo[v] = g;
+    }
+    for (unsigned v = threadIdx.x; v < 128u; v += blockDim.x) {
+        unsigned g = 0;
+        for (int b = 6; b < T; ++b) g |= ((v >> (b - 6)) & 1u) << tl.bits[b];
+        shi[v] = g;
+    }
+    for (int o = threadIdx.x; o < TILE_MAX_SUB; o += blockDim.x) cacc[o] = 0.0;
+    __syncthreads();
+
+    const u64 ntiles = 1ull << (n - T);
+    for (u64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const unsigned base = (unsigned)deposit_zeros(t, tl.bits, T);
+        for (unsigned l = threadIdx.x; l < L; l += blockDim.x) {
+            const unsigned g = base | slo[l & 63u] | shi[l >> 6];
+            const unsigned sl = tile_slot(l);
+            const double2 a = psi[g], b = lam[g];
+            gidx[sl] = g;
+            bufp[sl] = a;
+            bufl[sl] = b;
+        }
+        __syncthreads();
+        for (int sidx = 0; sidx < nsub; ++sidx) {
+            const uint4 *rp = reinterpret_cast<const uint4 *>(&rec[sidx]);
+            const uint4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
+            const int type = (int)q1.y;
+            const int seg = (int)rp[3].y;
+            double acc = 0.0;
+            if (type != 2) {
+                if ((base & q0.x) == q0.y) {
+                    const double2 *mp = reinterpret_cast<const double2 *>(rec[sidx].m);
+                    Mat2 M;
+                    M.m00 = mp[0]; M.m01 = mp[1]; M.m10 = mp[2]; M.m11 = mp[3];
+                    const double2 bh = mp[4];
+                    const double2 bhc = cconj(bh);
+                    const unsigned npairs = L >> q1.z;
+                    for (unsigned k = threadIdx.x; k < npairs; k += blockDim.x) {
+                        unsigned il = k;
+                        il = ((il & ~q2.x) << 1) | (il & q2.x);
+                        il = ((il & ~q2.y) << 1) | (il & q2.y);
+                        il = ((il & ~q2.z) << 1) | (il & q2.z);
+                        il = ((il & ~q2.w) << 1) | (il & q2.w);
+                        il |= q1.x;
+                        const unsigned jl = tile_slot(il ^ q0.w);
+                        il = tile_slot(il);
+                        double2 a = bufp[il], b = bufp[jl], la = bufl[il], lb = bufl[jl];
+                        const double sg = (__popc(gidx[il] & q0.z) & 1) ? -1.0 : 1.0;
+                        if (seg >= 0) {
+                            const double2 gi = cscale(cmul(bh, b), sg);      // (Ghat psi)_i
+                            const double2 gj = cscale(cmul(bhc, a), sg);     // (Ghat psi)_j
+                            acc += im_conj_mul(la, gi) + im_conj_mul(lb, gj);
+                        }
+                        rot2(M, sg, a, b);
+                        rot2(M, sg, la, lb);
+                        bufp[il] = a;
+                        bufp[jl] = b;
+                        bufl[il] = la;
+                        bufl[jl] = lb;
+                    }
+                }
+            } else {
+                const TileTerm *dt = tterm + (int)q1.w;
+                const int cnt = (int)n_terms_of(rec[sidx]);
+                for (unsigned v = threadIdx.x; v < 192u; v += blockDim.x) {
+                    const bool lo = v < 64u;
+                    const unsigned gl = base | (lo ? slo[v] : shi[v - 64u]);
+                    double tot = 0.0, dv = 0.0;
+                    for (int m = 0; m < cnt; ++m) {
+                        const unsigned z = (unsigned)dt[m].z;
+                        const bool in_lo = (z & himask_g) == 0u;
+                        const bool in_hi = (z & lomask_g) == 0u && !in_lo;
+                        if (lo ? in_lo : in_hi) {
+                            const double sg = (__popc(gl & z) & 1) ? -1.0 : 1.0;
+                            tot += sg * dt[m].angle;
+                            dv += sg * dt[m].coef;
+                        }
+                    }
+                    double sn, cs;
+                    sincos(tot, &sn, &cs);
+                    ph[v] = make_double2(cs, -sn);
+                    dsum[v] = dv;
+                }
+                __syncthreads();
+                for (unsigned sl = threadIdx.x; sl < L; sl += blockDim.x) {
+                    const unsigned l = tile_slot(sl);
+                    double2 f = cmul(ph[l & 63u], ph[64u + (l >> 6)]);
+                    double d = dsum[l & 63u] + dsum[64u + (l >> 6)];
+                    const unsigned gi = gidx[sl];
+                    for (int m = 0; m < cnt; ++m) {
+                        const unsigned z = (unsigned)dt[m].z;
+                        if ((z & himask_g) != 0u && (z & lomask_g) != 0u) {
+                            const double sg = (__popc(gi & z) & 1) ? -1.0 : 1.0;
+                            f = cmul(f, make_double2(dt[m].c, -sg * dt[m].s));
+                            d += sg * dt[m].coef;
+                        }
+                    }
+                    const double2 a = bufp[sl], la = bufl[sl];
+                    if (seg >= 0) acc += d * im_conj_mul(la, a);
+                    bufp[sl] = cmul(f, a);
+                    bufl[sl] = cmul(f, la);
+                }
+            }
+            if (seg >= 0) {
+                acc = warp_sum(acc);
+                if (lane == 0) wsum[sidx][warp] = acc;
+            }
+            __syncthreads();
+        }
+        for (unsigned l = threadIdx.x; l < L; l += blockDim.x) {
+            const unsigned sl = tile_slot(l);
+            const unsigned g = gidx[sl];
+            psi[g] = bufp[sl];
+            lam[g] = bufl[sl];
+        }
+        // fold this tile's warp partials (fixed order) into the CTA accumulators
+        for (int o = threadIdx.x; o < nsub; o += blockDim.x) {
+            if (reinterpret_cast<const uint4 *>(&rec[o])[3].y != 0xffffffffu) {
+                double v = 0.0;
+                for (int w = 0; w < nwarps; ++w) v += wsum[o][w];
+                cacc[o] += v;
+            }
+        }
+        __syncthreads();
+    }
+    for (int o = threadIdx.x; o < nsub; o += blockDim.x) {
+        const int seg = (int)reinterpret_cast<const uint4 *>(&rec[o])[3].y;
+        if (seg >= 0) gpart[(size_t)(seg_base + seg) * FH_GRAD_BLOCKS + blockIdx.x] = cacc[o];
+    }
+}
+
 // ----------------------------------------------------------------------------------------------
 // K2: out = H in, e = <in|H|in>
 // ----------------------------------------------------------------------------------------------
@@ -904,6 +1076,25 @@ void launch_tile(cudaStream_t s, double2 *psi, const TileLaunch &tl, const TileR
     if (threads < 64) threads = 64;
     ++g_fh_launch_count;
     k_tile<<<grid, threads, smem, s>>>(psi, tl, d_recs, d_terms, n);
+}
+
+static bool g_tile_adj_attr_set = false;
+
+void launch_tile_adjoint(cudaStream_t s, double2 *psi, double2 *lam, const TileLaunch &tl, const TileRec *d_recs,
+                         const TileTerm *d_terms, int n, double *d_gpart, int seg_base) {
+    const int nbits = tl.nbits;
+    const size_t smem = ((size_t)1 << nbits) * (2 * sizeof(double2) + sizeof(unsigned int));
+    if (!g_tile_adj_attr_set) {
+        cudaFuncSetAttribute(k_tile_adjoint, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        g_tile_adj_attr_set = true;
+    }
+    const u64 ntiles = 1ull << (n - nbits);
+    const int grid = (int)(ntiles > (u64)FH_GRAD_BLOCKS ? (u64)FH_GRAD_BLOCKS : ntiles);
+    int threads = nbits >= 1 ? (1 << (nbits - 1)) : 1;
+    if (threads > 512) threads = 512;
+    if (threads < 64) threads = 64;
+    ++g_fh_launch_count;
+    k_tile_adjoint<<<grid, threads, smem, s>>>(psi, lam, tl, d_recs, d_terms, n, d_gpart, seg_base);
 }
 
 void launch_apply_table(cudaStream_t s, int sm, const fh_table *tab, const double2 *in, double2 *out, int mode,

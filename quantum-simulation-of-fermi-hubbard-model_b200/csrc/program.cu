@@ -14,7 +14,6 @@ int fh_enqueue_pool(const fh_pool *pool, const double2 *psi, const double2 *lam,
 
 #define FH_MAX_RESULT_TABLES 8
 #define FH_MAX_OVERLAPS 8
-#define FH_GRAD_BLOCKS 256     // partial blocks per parametrised op in the adjoint sweep
 
 struct Item {
     int type;    // 1 pair, 2 diag, 3 tile
@@ -287,6 +286,8 @@ static void set_tile_term(TileTerm &tt, const DiagTerm &t, bool dagger) {
     tt.angle = dagger ? -t.angle : t.angle;
     tt.c = t.c;
     tt.s = dagger ? -t.s : t.s;
+    tt.coef = t.coef;
+    tt.pad = 0.0;
 }
 
 static void build_tile_records(fh_program *p) {
@@ -302,14 +303,18 @@ static void build_tile_records(fh_program *p) {
             std::vector<TileTerm> &tts = dir ? p->tterms_dag : p->tterms_fwd;
             (dir ? t.first_rec_dag : t.first_rec_fwd) = (int)recs.size();
             (dir ? t.first_term_dag : t.first_term_fwd) = (int)tts.size();
-            int term_off = 0;
+            int term_off = 0, seg = 0;
             for (int k = 0; k < t.nsub; ++k) {
                 const TileSub &sub = p->subs[t.first_sub + (dir ? t.nsub - 1 - k : k)];
                 TileRec r;
                 memset(&r, 0, sizeof(r));
+                r.seg = -1;
                 if (sub.type == 1) {
                     const PairOp &op = p->pairs[sub.index];
                     set_rec_matrix(r, op.m, dir != 0);
+                    r.bhat[0] = op.bhat[0];
+                    r.bhat[1] = op.bhat[1];
+                    if (op.kind == 1 && op.param >= 0) r.seg = seg++;
                     const unsigned fm = (unsigned)op.fixmask, fv = (unsigned)op.fixval;
                     r.fixmask_out = fm & ~tilemask;
                     r.fixval_out = fv & ~tilemask;
@@ -332,6 +337,7 @@ static void build_tile_records(fh_program *p) {
                     r.type = 2;
                     r.term_off = term_off;
                     r.nterms = d.count;
+                    if (d.param >= 0) r.seg = seg++;
                     for (int m = 0; m < d.count; ++m) {
                         TileTerm tt;
                         set_tile_term(tt, p->dterms[d.first + m], dir != 0);
@@ -343,6 +349,7 @@ static void build_tile_records(fh_program *p) {
                 recs.push_back(r);
             }
             t.nterms = term_off;
+            t.n_param_subs = seg;
         }
     }
 }
@@ -564,6 +571,34 @@ static void adjoint_item(fh_program *p, const Item &it, double2 *psi, double2 *l
         return;
     }
     const TileOp &t = p->tiles[it.index];
+    static const bool unfused = getenv("FHSIM_UNFUSED_ADJOINT") != nullptr;
+    if (!unfused && t.nbits <= FH_TILE_ADJOINT_MAX_BITS) {
+        // one launch: gradient partials of every parametrised op of the run + the inverse run on psi and lam
+        TileLaunch tl;
+        tl.nbits = t.nbits;
+        tl.nsub = t.nsub;
+        tl.first_rec = t.first_rec_dag;
+        tl.first_term = t.first_term_dag;
+        tl.nterms = t.nterms;
+        memcpy(tl.bits, t.bits, 16);
+        launch_tile_adjoint(p->ctx->stream, psi, lam, tl, p->d_recs_dag, p->d_tterms_dag, p->n, p->d_gpart, p->n_segments);
+        for (int s = t.first_sub + t.nsub - 1; s >= t.first_sub; --s) {
+            const TileSub &sub = p->subs[s];
+            if (sub.type == 1) {
+                const PairOp &op = p->pairs[sub.index];
+                if (op.kind == 1 && op.param >= 0) {
+                    p->seg_param.push_back(op.param);
+                    p->seg_scale.push_back(2.0 * op.gscale);
+                    p->n_segments++;
+                }
+            } else if (p->diagops[sub.index].param >= 0) {
+                p->seg_param.push_back(p->diagops[sub.index].param);
+                p->seg_scale.push_back(2.0);
+                p->n_segments++;
+            }
+        }
+        return;
+    }
     for (int s = t.first_sub + t.nsub - 1; s >= t.first_sub; --s)
         adjoint_logical(p, p->subs[s].type, p->subs[s].index, psi, lam, want_grads);
 }

@@ -58,6 +58,76 @@ def time_single(ctx, n, build, reps, fuse=False):
     return ms * 1e-3, items
 
 
+def measure_lattice(ctx, lat, pk, pool_cap=400, verbose=True):
+    """Time every kernel class on one lattice; returns the result row (see module docstring for the byte counts)."""
+    nx, ny = (int(v) for v in lat.split("x"))
+    n = 2 * nx * ny
+    dim = 1 << n
+    t0 = time.time()
+    h_tab = PauliTable.from_operator(fermi_hubbard(nx, ny, 1.0, 4.0), n)
+    pool_ops = hubbard_interaction_pool_simplified(nx, ny)
+    plans = [GeneratorPlan(jordan_wigner(g), n) for g in pool_ops[:pool_cap]]
+    coulomb = GeneratorPlan(jordan_wigner(get_interacting_term(fermi_hubbard(nx, ny, 1.0, 4.0))), n)
+    reps = 20 if n <= 24 else (8 if n <= 28 else 3)
+    res = {"lattice": lat, "n": n, "state_MiB": dim * 16 / 2 ** 20, "pool": len(pool_ops), "h_terms": len(h_tab),
+           "h_groups": h_tab.n_groups, "host_compile_s": round(time.time() - t0, 2)}
+
+    def rec(name, seconds, alg_bytes, extra=None):
+        gbs = alg_bytes / seconds / 1e9
+        res[name] = {"us": seconds * 1e6, "GBps": gbs, "frac": gbs / pk}
+        if extra:
+            res[name].update(extra)
+
+    mid = plans[len(plans) // 2]
+    s, _ = time_single(ctx, n, lambda c: c.generator(mid, angle=0.3), reps)
+    rec("pair_fermi4", s, 4.0 * dim)
+    x = (1 << (n - 1)) | (1 << (n // 2)) | 0b110
+    z = (1 << (n - 2)) | 0b011
+    s, _ = time_single(ctx, n, lambda c: c.pauli_rotation(x, z, 0.5, angle=0.7), reps)
+    rec("pair_dense", s, 32.0 * dim)
+    s, _ = time_single(ctx, n, lambda c: c.single_excitation(0.4, n // 2, n // 2 + 1), reps)
+    rec("givens", s, 16.0 * dim)
+    s, _ = time_single(ctx, n, lambda c: c.generator(coulomb, angle=0.2), reps)
+    rec("diag_coulomb", s, 32.0 * dim, {"terms": sum(len(p.z) for p in coulomb.pieces)})
+    s, items = time_single(ctx, n, lambda c: c.basis_change_separable(nx, ny), reps, fuse=True)
+    rec("tile_W", s / items, 32.0 * dim, {"launches": items, "total_us": s * 1e6})
+
+    # K2 and K3 on a generic (dense) state
+    psi, lam = State(ctx, n), State(ctx, n)
+    c = Circuit(n, 0)
+    for q in range(n):
+        c.ry(0.3 + 0.1 * q, q)
+    prog = c.compile(ctx, fuse=True)
+    psi.set_basis(0)
+    prog.run(psi, [])
+    prog.close()
+    dtab = DeviceTable(ctx, h_tab)
+    dtab.apply(psi, lam)
+    ts = []
+    for _ in range(max(3, reps // 2)):
+        ctx.timer_start()
+        dtab.apply(psi, lam)
+        ts.append(ctx.timer_stop())
+    rec("h_apply", min(ts) * 1e-3, 32.0 * dim)
+    dpool = DevicePool(ctx, plans, n)
+    dpool.gradients(psi, lam)
+    ts = []
+    for _ in range(3):
+        ctx.timer_start()
+        dpool.enqueue(psi, lam)
+        ts.append(ctx.timer_stop())
+    rec("screening", min(ts) * 1e-3, 4.0 * dim * len(plans), {"ops": len(plans), "per_gradient_us": min(ts) * 1e3 / len(plans)})
+    for o in (dpool, dtab, psi, lam):
+        o.close()
+    if verbose:
+        print(f"--- {lat}  n={n}  state={res['state_MiB']:.0f} MiB  pool={res['pool']}  H terms/groups={res['h_terms']}/{res['h_groups']}")
+        for k in ("pair_fermi4", "pair_dense", "givens", "diag_coulomb", "tile_W", "h_apply", "screening"):
+            v = res[k]
+            print(f"    {k:13s} {v['us']:12.1f} us  {v['GBps']:9.1f} GB/s  {100 * v['frac']:6.1f} % of {pk:.0f}")
+        sys.stdout.flush()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--lattices", default="3x3,2x5,2x6,3x4,2x7")
@@ -66,73 +136,7 @@ def main():
     args = ap.parse_args()
     ctx = Context(0)
     pk = peak()
-    rows = []
-    for lat in args.lattices.split(","):
-        nx, ny = (int(v) for v in lat.split("x"))
-        n = 2 * nx * ny
-        dim = 1 << n
-        t0 = time.time()
-        h_tab = PauliTable.from_operator(fermi_hubbard(nx, ny, 1.0, 4.0), n)
-        pool_ops = hubbard_interaction_pool_simplified(nx, ny)
-        plans = [GeneratorPlan(jordan_wigner(g), n) for g in pool_ops[:args.pool_cap]]
-        coulomb = GeneratorPlan(jordan_wigner(get_interacting_term(fermi_hubbard(nx, ny, 1.0, 4.0))), n)
-        reps = 20 if n <= 24 else (8 if n <= 28 else 3)
-        res = {"lattice": lat, "n": n, "state_MiB": dim * 16 / 2 ** 20, "pool": len(pool_ops), "h_terms": len(h_tab),
-               "h_groups": h_tab.n_groups, "host_compile_s": round(time.time() - t0, 2)}
-
-        def rec(name, seconds, alg_bytes, extra=None):
-            gbs = alg_bytes / seconds / 1e9
-            res[name] = {"us": seconds * 1e6, "GBps": gbs, "frac": gbs / pk}
-            if extra:
-                res[name].update(extra)
-
-        mid = plans[len(plans) // 2]
-        s, _ = time_single(ctx, n, lambda c: c.generator(mid, angle=0.3), reps)
-        rec("pair_fermi4", s, 4.0 * dim)
-        x = (1 << (n - 1)) | (1 << (n // 2)) | 0b110
-        z = (1 << (n - 2)) | 0b011
-        s, _ = time_single(ctx, n, lambda c: c.pauli_rotation(x, z, 0.5, angle=0.7), reps)
-        rec("pair_dense", s, 32.0 * dim)
-        s, _ = time_single(ctx, n, lambda c: c.single_excitation(0.4, n // 2, n // 2 + 1), reps)
-        rec("givens", s, 16.0 * dim)
-        s, _ = time_single(ctx, n, lambda c: c.generator(coulomb, angle=0.2), reps)
-        rec("diag_coulomb", s, 32.0 * dim, {"terms": sum(len(p.z) for p in coulomb.pieces)})
-        s, items = time_single(ctx, n, lambda c: c.basis_change_separable(nx, ny), reps, fuse=True)
-        rec("tile_W", s / items, 32.0 * dim, {"launches": items, "total_us": s * 1e6})
-
-        # K2 and K3 on a generic (dense) state
-        psi, lam = State(ctx, n), State(ctx, n)
-        c = Circuit(n, 0)
-        for q in range(n):
-            c.ry(0.3 + 0.1 * q, q)
-        prog = c.compile(ctx, fuse=True)
-        psi.set_basis(0)
-        prog.run(psi, [])
-        prog.close()
-        dtab = DeviceTable(ctx, h_tab)
-        dtab.apply(psi, lam)
-        ts = []
-        for _ in range(max(3, reps // 2)):
-            ctx.timer_start()
-            dtab.apply(psi, lam)
-            ts.append(ctx.timer_stop())
-        rec("h_apply", min(ts) * 1e-3, 32.0 * dim)
-        dpool = DevicePool(ctx, plans, n)
-        dpool.gradients(psi, lam)
-        ts = []
-        for _ in range(3):
-            ctx.timer_start()
-            dpool.enqueue(psi, lam)
-            ts.append(ctx.timer_stop())
-        rec("screening", min(ts) * 1e-3, 4.0 * dim * len(plans), {"ops": len(plans), "per_gradient_us": min(ts) * 1e3 / len(plans)})
-        for o in (dpool, dtab, psi, lam):
-            o.close()
-        rows.append(res)
-        print(f"--- {lat}  n={n}  state={res['state_MiB']:.0f} MiB  pool={res['pool']}  H terms/groups={res['h_terms']}/{res['h_groups']}")
-        for k in ("pair_fermi4", "pair_dense", "givens", "diag_coulomb", "tile_W", "h_apply", "screening"):
-            v = res[k]
-            print(f"    {k:13s} {v['us']:12.1f} us  {v['GBps']:9.1f} GB/s  {100 * v['frac']:6.1f} % of {pk:.0f}")
-        sys.stdout.flush()
+    rows = [measure_lattice(ctx, lat, pk, args.pool_cap) for lat in args.lattices.split(",")]
     if args.json:
         os.makedirs(os.path.dirname(os.path.abspath(args.json)), exist_ok=True)
         json.dump({"peak_GBps": pk, "rows": rows}, open(args.json, "w"), indent=1)
