@@ -574,6 +574,102 @@ extern "C" int fh_apply_table_accumulate(const fh_table *tab, const fh_state *in
 // ----------------------------------------------------------------------------------------------
 // pool
 // ----------------------------------------------------------------------------------------------
+// Greedy cover of the pool's x-masks by sets of T index bits (one pass each).  A pass is only worth a full read of
+// psi and lambda (32 * 2^n B) if it serves enough entries (each costs 4 * 2^n B through k_pool): small tails stay
+// on the per-entry kernel.
+static void build_pool_passes(fh_pool *pool) {
+    const int n = pool->n;
+    // measured (tools/run_k3.py, profiles/): 12-bit tiles win 13-16 % once the states exceed L2 (n >= 22); below that
+    // the per-entry kernel reading straight from L2 is faster, so tiles are off unless FHSIM_POOL_TILE_BITS asks
+    int T = n >= 22 ? 12 : 0;
+    if (const char *env = getenv("FHSIM_POOL_TILE_BITS")) T = atoi(env);
+    pool->tile_bits = 0;
+    pool->tile_grid = 0;
+    const int n_entries = (int)pool->entries.size();
+    std::vector<int> todo;
+    if (T >= 6 && T <= 12 && n >= T + 4 && n <= 32)
+        for (int e = 0; e < n_entries; ++e)
+            if (popcnt(pool->entries[e].x) <= T) todo.push_back(e);
+    std::vector<char> covered(n_entries, 0);
+    const int min_pass = 10;
+    while ((int)todo.size() >= min_pass) {
+        u64 bits = 0;
+        while (popcnt(bits) < T) {
+            int best = -1;
+            double best_score = -1.0;
+            for (int b = 0; b < n; ++b) {
+                if (bits >> b & 1ull) continue;
+                const u64 nb = bits | (1ull << b);
+                const int room = T - popcnt(nb);
+                double score = 0.0;
+                for (int e : todo) {
+                    const u64 x = pool->entries[e].x;
+                    if (popcnt(x & ~nb) <= room) score += (double)(1u << (2 * popcnt(x & nb)));
+                }
+                if (score > best_score) {
+                    best_score = score;
+                    best = b;
+                }
+            }
+            bits |= 1ull << best;
+        }
+        std::vector<int> got;
+        for (int e : todo) {
+            const PoolEntry &pe = pool->entries[e];
+            if ((pe.x & ~bits) == 0 && popcnt(pe.fixmask & bits) <= 4) got.push_back(e);
+        }
+        if ((int)got.size() < min_pass) break;
+        int tb[16], nb = 0;
+        for (int b = 0; b < n; ++b)
+            if (bits >> b & 1ull) tb[nb++] = b;
+        for (size_t off = 0; off < got.size(); off += FH_POOL_PASS_MAX_RECS) {
+            PoolPass ps;
+            memset(&ps, 0, sizeof(ps));
+            ps.nbits = T;
+            ps.first_rec = (int)pool->tile_recs.size();
+            for (int q = 0; q < T; ++q) ps.bits[q] = (unsigned char)tb[q];
+            const size_t end = off + FH_POOL_PASS_MAX_RECS < got.size() ? off + FH_POOL_PASS_MAX_RECS : got.size();
+            for (size_t k = off; k < end; ++k) {
+                const PoolEntry &pe = pool->entries[got[k]];
+                PoolTileRec r;
+                memset(&r, 0, sizeof(r));
+                r.fixmask_out = (unsigned)(pe.fixmask & ~bits);
+                r.fixval_out = (unsigned)(pe.fixval & ~bits);
+                r.zeta = (unsigned)pe.zeta;
+                r.entry = got[k];
+                r.br = pe.br;
+                r.bi = pe.bi;
+                for (int q = 0; q < 4; ++q) r.lowmask[q] = 0xffffffffu;
+                int nl = 0;
+                for (int q = 0; q < T; ++q) {
+                    const u64 g = 1ull << tb[q];
+                    if (pe.x & g) r.xlocal |= 1u << q;
+                    if (pe.fixmask & g) {
+                        r.lowmask[nl++] = (1u << q) - 1u;
+                        if (pe.fixval & g) r.lfixval |= 1u << q;
+                    }
+                }
+                r.nlfix = nl;
+                pool->tile_recs.push_back(r);
+                covered[got[k]] = 1;
+            }
+            ps.nrec = (int)pool->tile_recs.size() - ps.first_rec;
+            pool->passes.push_back(ps);
+        }
+        std::vector<int> left;
+        for (int e : todo)
+            if (!covered[e]) left.push_back(e);
+        todo.swap(left);
+    }
+    if (!pool->passes.empty()) {
+        pool->tile_bits = T;
+        const u64 ntiles = 1ull << (n - T);
+        pool->tile_grid = (int)(ntiles < 1024 ? ntiles : 1024);
+        for (int e = 0; e < n_entries; ++e)
+            if (!covered[e]) pool->rest.push_back(e);
+    }
+}
+
 extern "C" int fh_pool_upload(fh_ctx *ctx, int n_qubits, int n_entries, const uint64_t *x, const uint64_t *fixmask,
                               const uint64_t *fixval, const uint64_t *zeta, const double *b_re, const double *b_im,
                               const int32_t *out_index, int n_out, fh_pool **out) {
@@ -629,13 +725,30 @@ extern "C" int fh_pool_upload(fh_ctx *ctx, int n_qubits, int n_entries, const ui
     u64 chunks = (max_pairs + 128 * 8 - 1) / (128 * 8);
     if (chunks < 1) chunks = 1;
     if (chunks > 1024) chunks = 1024;
-    pool->chunks = (int)chunks;
+    pool->kchunks = (int)chunks;
+    build_pool_passes(pool);
+    pool->chunks = pool->kchunks > pool->tile_grid ? pool->kchunks : pool->tile_grid;
     FH_CUDA(cudaSetDevice(ctx->device));
     if (n_entries) {
         FH_CUDA(cudaMalloc(&pool->d_entries, sizeof(PoolEntry) * n_entries));
         FH_CUDA(cudaMemcpyAsync(pool->d_entries, pool->entries.data(), sizeof(PoolEntry) * n_entries,
                                 cudaMemcpyHostToDevice, ctx->stream));
         FH_CUDA(cudaMalloc(&pool->d_partials, sizeof(double) * (size_t)n_entries * pool->chunks));
+        // slots a kernel never writes (k_pool: [kchunks, chunks), k_pool_tile: [tile_grid, chunks)) stay zero
+        FH_CUDA(cudaMemsetAsync(pool->d_partials, 0, sizeof(double) * (size_t)n_entries * pool->chunks, ctx->stream));
+    }
+    if (!pool->passes.empty()) {
+        FH_CUDA(cudaMalloc(&pool->d_passes, sizeof(PoolPass) * pool->passes.size()));
+        FH_CUDA(cudaMemcpyAsync(pool->d_passes, pool->passes.data(), sizeof(PoolPass) * pool->passes.size(),
+                                cudaMemcpyHostToDevice, ctx->stream));
+        FH_CUDA(cudaMalloc(&pool->d_tile_recs, sizeof(PoolTileRec) * pool->tile_recs.size()));
+        FH_CUDA(cudaMemcpyAsync(pool->d_tile_recs, pool->tile_recs.data(), sizeof(PoolTileRec) * pool->tile_recs.size(),
+                                cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (!pool->rest.empty()) {
+        FH_CUDA(cudaMalloc(&pool->d_rest, sizeof(int) * pool->rest.size()));
+        FH_CUDA(cudaMemcpyAsync(pool->d_rest, pool->rest.data(), sizeof(int) * pool->rest.size(), cudaMemcpyHostToDevice,
+                                ctx->stream));
     }
     FH_CUDA(cudaMalloc(&pool->d_out_first, sizeof(int) * (n_out + 1)));
     FH_CUDA(cudaMemcpyAsync(pool->d_out_first, pool->out_first.data(), sizeof(int) * (n_out + 1), cudaMemcpyHostToDevice,
@@ -652,6 +765,9 @@ extern "C" int fh_pool_free(fh_pool *pool) {
     cudaSetDevice(pool->ctx->device);
     cudaStreamSynchronize(pool->ctx->stream);
     cudaFree(pool->d_entries);
+    cudaFree(pool->d_passes);
+    cudaFree(pool->d_tile_recs);
+    cudaFree(pool->d_rest);
     cudaFree(pool->d_out_first);
     cudaFree(pool->d_partials);
     cudaFree(pool->d_out);
@@ -664,7 +780,15 @@ extern "C" int fh_pool_free(fh_pool *pool) {
 int fh_enqueue_pool(const fh_pool *pool, const double2 *psi, const double2 *lam, int first, int count) {
     fh_ctx *ctx = pool->ctx;
     const int e0 = pool->out_first[first], e1 = pool->out_first[first + count];
-    launch_pool(ctx->stream, pool->d_entries, e0, e1 - e0, pool->chunks, pool->n, psi, lam, pool->d_partials);
+    if (pool->passes.empty()) {
+        launch_pool(ctx->stream, pool->d_entries, e0, e1 - e0, pool->kchunks, pool->n, psi, lam, pool->d_partials, nullptr,
+                    e0, e1, pool->chunks);
+    } else {
+        launch_pool_tiles(ctx->stream, pool->d_passes, (int)pool->passes.size(), pool->d_tile_recs, pool->tile_bits,
+                          pool->tile_grid, pool->chunks, pool->n, psi, lam, pool->d_partials, e0, e1);
+        launch_pool(ctx->stream, pool->d_entries, 0, (int)pool->rest.size(), pool->kchunks, pool->n, psi, lam,
+                    pool->d_partials, pool->d_rest, e0, e1, pool->chunks);
+    }
     launch_pool_finalize(ctx->stream, pool->d_partials, pool->d_out_first, pool->chunks, first, count, pool->d_out);
     FH_CUDA(cudaGetLastError());
     return FH_OK;

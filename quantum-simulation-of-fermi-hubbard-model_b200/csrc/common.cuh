@@ -161,6 +161,25 @@ struct PoolEntry {
     unsigned char pad[3];
 };
 
+// K3, tiled form.  A *pass* fixes a set of T index bits; every pool entry whose x-mask lies inside those bits is
+// served from psi / lambda tiles staged in shared memory, so one read of both states feeds many gradients.
+#define FH_POOL_PASS_MAX_RECS 256
+struct __align__(16) PoolTileRec {      // 64 bytes
+    unsigned fixmask_out, fixval_out;   // pattern bits outside the tile (uniform per tile)
+    unsigned zeta, xlocal;
+    unsigned lfixval;                   // in-tile pattern, tile-local coordinates
+    int nlfix;                          // number of in-tile pattern bits (<= 4)
+    int entry;                          // index into the pool's entry array (partials row)
+    int pad;
+    unsigned lowmask[4];                // bit-insertion masks of the in-tile pattern bits (ascending; unused = ~0)
+    double br, bi;
+};
+
+struct PoolPass {
+    int nbits, first_rec, nrec, pad;
+    unsigned char bits[16];
+};
+
 // ----------------------------------------------------------------------------------------------
 // host objects behind the opaque handles
 // ----------------------------------------------------------------------------------------------
@@ -207,7 +226,8 @@ struct fh_pool {
     fh_ctx *ctx;
     int n;
     int n_entries, n_out;
-    int chunks;                 // blocks per entry
+    int chunks;                 // row width of the partials array (slots per entry)
+    int kchunks;                // blocks per entry of the per-entry kernel (k_pool)
     PoolEntry *d_entries;
     int *d_out_first;           // [n_out+1] entry ranges per output (entries sorted by out)
     double *d_partials;         // [n_entries * chunks]
@@ -215,6 +235,14 @@ struct fh_pool {
     double *h_out;              // pinned [n_out]
     std::vector<PoolEntry> entries;
     std::vector<int> out_first;
+    // tiled scan: passes + their records; entries not covered by a pass go through k_pool via `rest`
+    int tile_bits = 0, tile_grid = 0;
+    std::vector<PoolPass> passes;
+    std::vector<PoolTileRec> tile_recs;
+    std::vector<int> rest;
+    PoolPass *d_passes = nullptr;
+    PoolTileRec *d_tile_recs = nullptr;
+    int *d_rest = nullptr;
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -239,7 +267,12 @@ void launch_tile_adjoint(cudaStream_t s, double2 *psi, double2 *lam, const TileL
 void launch_apply_table(cudaStream_t s, int sm, const fh_table *tab, const double2 *in, double2 *out, int mode,
                         double *d_partials, double *d_result);
 void launch_pool(cudaStream_t s, const PoolEntry *entries, int first_entry, int n_entries, int chunks, int n,
-                 const double2 *psi, const double2 *lam, double *d_partials);
+                 const double2 *psi, const double2 *lam, double *d_partials, const int *entry_ids = nullptr,
+                 int e0 = 0, int e1 = 0x7fffffff, int row = 0);
+// tiled scan of the entries covered by passes; only entries in [e0, e1) are evaluated
+void launch_pool_tiles(cudaStream_t s, const PoolPass *d_passes, int npasses, const PoolTileRec *d_recs, int tile_bits,
+                       int grid_x, int chunks, int n, const double2 *psi, const double2 *lam, double *d_partials, int e0,
+                       int e1);
 void launch_pool_finalize(cudaStream_t s, const double *d_partials, const int *d_out_first, int chunks, int first_out,
                           int count, double *d_out);
 void launch_inner(cudaStream_t s, int sm, const double2 *a, const double2 *b, u64 dim, double *d_partials,

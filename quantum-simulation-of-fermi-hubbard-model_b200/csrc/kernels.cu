@@ -829,12 +829,15 @@ __global__ void __launch_bounds__(256) k_finalize_pairs(const double *__restrict
 // (bit-deposit of the free bits around the fixed pattern), never all 2^n.
 __global__ void __launch_bounds__(128) k_pool(const PoolEntry *__restrict__ entries, int first_entry, int n,
                                               const double2 *__restrict__ psi, const double2 *__restrict__ lam,
-                                              double *__restrict__ partials) {
+                                              double *__restrict__ partials, const int *__restrict__ entry_ids, int e0,
+                                              int e1, int row) {
     __shared__ PoolEntry e;
     __shared__ double red[4];
+    const int eid = entry_ids ? entry_ids[first_entry + blockIdx.y] : first_entry + (int)blockIdx.y;
+    if (eid < e0 || eid >= e1) return;          // outside the requested output range (uniform per block)
     {
         const int words = sizeof(PoolEntry) / 8;
-        const u64 *src = reinterpret_cast<const u64 *>(entries + first_entry + blockIdx.y);
+        const u64 *src = reinterpret_cast<const u64 *>(entries + eid);
         for (int t = threadIdx.x; t < words; t += blockDim.x) reinterpret_cast<u64 *>(&e)[t] = __ldg(src + t);
         __syncthreads();
     }
@@ -859,7 +862,106 @@ __global__ void __launch_bounds__(128) k_pool(const PoolEntry *__restrict__ entr
         acc += sign_of(i0 & e.zeta) * (im_conj_mul(la0, cmul(B, b0)) + im_conj_mul(lb0, cmul(Bc, a0)));
     }
     const double r = block_sum<128>(acc, red);
-    if (threadIdx.x == 0) partials[(size_t)(first_entry + blockIdx.y) * gridDim.x + blockIdx.x] = 2.0 * r;
+    if (threadIdx.x == 0) partials[(size_t)eid * row + blockIdx.x] = 2.0 * r;
+}
+
+// K3 on shared-memory tiles: blockIdx.y = pass (a set of T index bits), blockIdx.x strides over the 2^(n-T) tiles.
+// psi and lambda tiles are loaded once and every entry of the pass is evaluated from them, one warp per entry
+// (its lanes cover the entry's in-tile pairs), so a gradient costs shared-memory instead of L2/HBM traffic.
+// Per-entry partials: lane sums -> warp shuffle -> shared accumulator owned by that warp -> one store per (entry, CTA).
+__global__ void __launch_bounds__(512) k_pool_tile(const PoolPass *__restrict__ passes, const PoolTileRec *__restrict__ recs,
+                                                   int n, int chunks, const double2 *__restrict__ psi,
+                                                   const double2 *__restrict__ lam, double *__restrict__ partials, int e0,
+                                                   int e1) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ PoolTileRec rec[FH_POOL_PASS_MAX_RECS];
+    __shared__ double accE[FH_POOL_PASS_MAX_RECS];
+    __shared__ unsigned slo[64], shi[128];
+    __shared__ PoolPass pass;
+    if (threadIdx.x < sizeof(PoolPass) / 4)
+        reinterpret_cast<unsigned *>(&pass)[threadIdx.x] = reinterpret_cast<const unsigned *>(passes + blockIdx.y)[threadIdx.x];
+    __syncthreads();
+    const int T = pass.nbits, nrec = pass.nrec;
+    const unsigned L = 1u << T;
+    double2 *bufp = reinterpret_cast<double2 *>(smem_raw);
+    double2 *bufl = bufp + L;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(recs + pass.first_rec);
+        uint4 *dst = reinterpret_cast<uint4 *>(rec);
+        const int chunks16 = nrec * (int)(sizeof(PoolTileRec) / 16);
+        for (int c = threadIdx.x; c < chunks16; c += blockDim.x) dst[c] = __ldg(src + c);
+    }
+    for (unsigned v = threadIdx.x; v < 64u; v += blockDim.x) {
+        unsigned g = 0;
+        for (int b = 0; b < 6 && b < T; ++b) g |= ((v >> b) & 1u) << pass.bits[b];
+        slo[v] = g;
+    }
+    for (unsigned v = threadIdx.x; v < 128u; v += blockDim.x) {
+        unsigned g = 0;
+        for (int b = 6; b < T; ++b) g |= ((v >> (b - 6)) & 1u) << pass.bits[b];
+        shi[v] = g;
+    }
+    for (int o = threadIdx.x; o < nrec; o += blockDim.x) accE[o] = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const u64 ntiles = 1ull << (n - T);
+    for (u64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const unsigned base = (unsigned)deposit_zeros(t, pass.bits, T);
+        for (unsigned l0 = threadIdx.x; l0 < L; l0 += 2 * blockDim.x) {
+            unsigned gg[2];
+            double2 va[2], vb[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const unsigned l = l0 + u * blockDim.x;
+                if (l < L) {
+                    gg[u] = base | slo[l & 63u] | shi[l >> 6];
+                    va[u] = psi[gg[u]];
+                    vb[u] = lam[gg[u]];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const unsigned l = l0 + u * blockDim.x;
+                if (l < L) {
+                    const unsigned sl = tile_slot(l);
+                    bufp[sl] = va[u];
+                    bufl[sl] = vb[u];
+                }
+            }
+        }
+        __syncthreads();
+        for (int o = warp; o < nrec; o += nwarps) {
+            const uint4 *rp = reinterpret_cast<const uint4 *>(&rec[o]);
+            const uint4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
+            // q0 = {fixmask_out, fixval_out, zeta, xlocal}; q1 = {lfixval, nlfix, entry, -}; q2 = lowmask[4]
+            if ((int)q1.z < e0 || (int)q1.z >= e1) continue;
+            if ((base & q0.x) != q0.y) continue;
+            const double2 B = reinterpret_cast<const double2 *>(&rec[o])[3];
+            const double2 Bc = make_double2(B.x, -B.y);
+            const unsigned npairs = L >> q1.y;
+            double acc = 0.0;
+            for (unsigned k = lane; k < npairs; k += 32) {
+                unsigned il = k;
+                il = ((il & ~q2.x) << 1) | (il & q2.x);
+                il = ((il & ~q2.y) << 1) | (il & q2.y);
+                il = ((il & ~q2.z) << 1) | (il & q2.z);
+                il = ((il & ~q2.w) << 1) | (il & q2.w);
+                il |= q1.x;
+                const unsigned gi = base | slo[il & 63u] | shi[il >> 6];
+                const unsigned si = tile_slot(il), sj = tile_slot(il ^ q0.w);
+                const double2 a = bufp[si], b = bufp[sj], la = bufl[si], lb = bufl[sj];
+                const double sg = (__popc(gi & q0.z) & 1) ? -1.0 : 1.0;
+                acc += sg * (im_conj_mul(la, cmul(B, b)) + im_conj_mul(lb, cmul(Bc, a)));
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) accE[o] += acc;
+        }
+        __syncthreads();
+    }
+    for (int o = threadIdx.x; o < nrec; o += blockDim.x) {
+        const int entry = rec[o].entry;
+        if (entry >= e0 && entry < e1) partials[(size_t)entry * chunks + blockIdx.x] = 2.0 * accE[o];
+    }
 }
 
 // one warp per output: fixed-order sum over its entries' chunk partials
@@ -1151,13 +1253,38 @@ void launch_apply_table(cudaStream_t s, int sm, const fh_table *tab, const doubl
 }
 
 void launch_pool(cudaStream_t s, const PoolEntry *entries, int first_entry, int n_entries, int chunks, int n,
-                 const double2 *psi, const double2 *lam, double *d_partials) {
+                 const double2 *psi, const double2 *lam, double *d_partials, const int *entry_ids, int e0, int e1,
+                 int row) {
     if (n_entries <= 0) return;
+    if (row <= 0) row = chunks;
     // gridDim.y is limited to 65535
     for (int off = 0; off < n_entries; off += 32768) {
         const int cnt = n_entries - off < 32768 ? n_entries - off : 32768;
         dim3 grid(chunks, cnt);
-        ++g_fh_launch_count; k_pool<<<grid, 128, 0, s>>>(entries, first_entry + off, n, psi, lam, d_partials);
+        ++g_fh_launch_count;
+        k_pool<<<grid, 128, 0, s>>>(entries, first_entry + off, n, psi, lam, d_partials, entry_ids, e0, e1, row);
+    }
+}
+
+static bool g_pool_tile_attr_set = false;
+
+void launch_pool_tiles(cudaStream_t s, const PoolPass *d_passes, int npasses, const PoolTileRec *d_recs, int tile_bits,
+                       int grid_x, int chunks, int n, const double2 *psi, const double2 *lam, double *d_partials, int e0,
+                       int e1) {
+    if (npasses <= 0) return;
+    if (!g_pool_tile_attr_set) {
+        cudaFuncSetAttribute(k_pool_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
+        g_pool_tile_attr_set = true;
+    }
+    const size_t smem = ((size_t)1 << tile_bits) * 2 * sizeof(double2);
+    int threads = 1 << (tile_bits > 3 ? tile_bits - 3 : 0);
+    if (threads > 512) threads = 512;
+    if (threads < 64) threads = 64;
+    for (int off = 0; off < npasses; off += 32768) {
+        const int cnt = npasses - off < 32768 ? npasses - off : 32768;
+        dim3 grid(grid_x, cnt);
+        ++g_fh_launch_count;
+        k_pool_tile<<<grid, threads, smem, s>>>(d_passes + off, d_recs, n, chunks, psi, lam, d_partials, e0, e1);
     }
 }
 
