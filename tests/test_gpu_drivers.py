@@ -248,3 +248,104 @@ def test_linalg_dropin_vs_scipy_sector_ed():
     assert abs(e0b - want[0]) < 1e-9 and len(basis) == 4
     gram = np.array([[np.vdot(a, b) for b in basis] for a in basis])
     assert np.abs(gram - np.eye(4)).max() < 1e-8
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE configs 3 and 4 through the drop-in drivers (18 qubits)
+# ---------------------------------------------------------------------------------------------
+def test_adapt_3x3_first_epoch_matches_oracle():
+    """models/adapt_vqe_for_3x3.ADAPT (reference adapt_vqe_for_3x3.py): 4-fold degenerate ED level, first screening
+    (52 operators at |g| = 4/3) in the oracle's order, E_HF = -5/3, projected fidelity, and one
+    energy + gradient evaluation with the 52 new parameters."""
+    from models.adapt_vqe_for_3x3 import ADAPT
+    nx, ny, u = 3, 3, 6.0
+    n, h, pool, layers, diag = oracle_lattice(nx, ny, u)
+    vqe = ADAPT(n_epoch=1, threshold1=1e-2, threshold2=1e-2, x_dimension=nx, y_dimension=ny, n_electrons=9,
+                n_spin_up=5, n_spin_down=4, tunneling=1, coulomb=u, verbose=False)
+    assert abs(vqe.ground_state_energy + 5.5623088363) < 1e-8
+    wfs = np.array(vqe.ground_state_wfs)
+    assert wfs.shape == (4, 1 << n)
+    assert np.abs(wfs.conj() @ wfs.T - np.eye(4)).max() < 1e-9              # orthonormal degenerate subspace
+    occ = vqe.spin_up_indices + vqe.spin_down_indices
+    assert occ == [0, 2, 4, 6, 12, 1, 3, 5, 7]
+    ops, gates, max_grads = vqe.select_operator()
+    psi0 = sv.basis_state(n, occ)
+    g0, e0, _ = sv.pool_gradients(psi0, h, pool, diag, layers, n)
+    assert abs(e0 + 5.0 / 3.0) < 1e-12
+    want = select_like_reference(g0.astype(np.float32), 0.1, 1e-2)
+    assert len(want) == 52 and vqe.last_selected_indices == want
+    assert np.allclose(max_grads, 4.0 / 3.0, atol=1e-6)
+    # append them as run() does (reference adapt_vqe.py:388-389) and evaluate once at small random parameters
+    vqe.selected_gates += gates
+    rng = np.random.default_rng(1234)
+    th = rng.uniform(-0.1, 0.1, len(gates)).astype(np.float32)
+    vqe.params['t'] = torch.from_numpy(th)
+    loss, sz, s2 = vqe.circuit(mode='train')
+    loss.backward()
+    th64 = th.astype(np.float64)
+    e_or, g_or = sv.adjoint_gradient(n, occ, [pool[k] for k in want], th64, h, diag, layers)
+    assert abs(loss.item() - e_or) < 1e-10
+    assert np.abs(vqe.params['t'].grad.numpy() - g_or.astype(np.float32)).max() < 1e-6
+    assert abs(sz.item() - 0.5) < 1e-10
+    phi = sv.basis_change(sv.adapt_state(n, occ, [pool[k] for k in want], th64), diag, layers, n)
+    fid = vqe.calculate_fidelity(vqe.ground_state_wfs, phi)
+    assert abs(vqe._fidelity() - fid) < 1e-9 and 0.0 <= fid <= 1.0 + 1e-12
+    state = vqe.circuit(mode='state').numpy()
+    assert np.abs(state - phi).max() < 1e-11
+    # second screening at these parameters: same sequence as the oracle
+    vqe.select_operator()
+    g1, _, _ = sv.pool_gradients(sv.adapt_state(n, occ, [pool[k] for k in want], th64), h, pool, diag, layers, n)
+    assert vqe.last_selected_indices == select_like_reference(g1.astype(np.float32), 0.1, 1e-2)
+
+
+def test_hva_3x3_energy_state_and_projected_fidelity():
+    from models.hva_for_3x3 import HVA
+    nx, ny, u = 3, 3, 6.0
+    n, h, pool, layers, diag = oracle_lattice(nx, ny, u)
+    vqe = HVA(n_epoch=1, reps=1, lr=1e-2, threshold=1e-2, x_dimension=nx, y_dimension=ny, n_electrons=9, n_spin_up=5,
+              n_spin_down=4, tunneling=1, coulomb=u, verbose=False)
+    assert (vqe.Nh, vqe.Nv) == (3, 3)                       # odd periodic length: even / odd / wrap-around bonds
+    rng = np.random.default_rng(20260)
+    with torch.no_grad():
+        for k in ('theta_U', 'theta_h', 'theta_v'):
+            vqe.params[k].copy_(torch.from_numpy(rng.uniform(-0.3, 0.3, vqe.params[k].numel()).astype(np.float32)))
+    tu, thh, tv = (vqe.params[k].detach().to(torch.float64).numpy() for k in ('theta_U', 'theta_h', 'theta_v'))
+    loss, sz, s2 = vqe.circuit(vqe.params['theta_U'], vqe.params['theta_h'], vqe.params['theta_v'], mode='train')
+    loss.backward()
+    e_or, psi_or = hva_oracle_energy(vqe, tu, thh, tv, n, h, diag, layers)
+    assert abs(loss.item() - e_or) < 1e-10
+    assert abs(sz.item() - 0.5) < 1e-10
+    state = vqe.circuit(vqe.params['theta_U'], vqe.params['theta_h'], vqe.params['theta_v'], mode='state').numpy()
+    assert np.abs(state - psi_or).max() < 1e-11
+    fid = vqe.calculate_fidelity(vqe.ground_state_wfs, psi_or)
+    assert abs(vqe.fidelity_from_overlaps(vqe._last_overlaps) - fid) < 1e-9
+    # one gradient component by central differences of the oracle
+    hstep = 1e-5
+    plus, minus = tu.copy(), tu.copy()
+    plus[0] += hstep
+    minus[0] -= hstep
+    fd = (hva_oracle_energy(vqe, plus, thh, tv, n, h, diag, layers)[0]
+          - hva_oracle_energy(vqe, minus, thh, tv, n, h, diag, layers)[0]) / (2 * hstep)
+    assert abs(vqe.params['theta_U'].grad[0].item() - fd) < 2e-6
+
+
+def test_iqcc_3x3_partition_and_full_space_lanczos():
+    """cfg 4: iQCC on 3x3 -- 36 non-zero x-mask groups of the Hubbard Hamiltonian (reference iqcc_hubbard.py:82-101),
+    screening gradients of the YX..X generators at the QMF start state vs the oracle, and the Lanczos replacement
+    of openfermion.get_ground_state over the FULL 2^18 space (iqcc_hubbard.py:57) vs sector ED minima."""
+    from fhsim.symbolic import fermi_hubbard
+    from models.iqcc_hubbard import IQCC
+    nx, ny, u = 3, 3, 6.0
+    n = 18
+    model = IQCC(fermi_hubbard(nx, ny, 1.0, u), n_epoch=1, lr=1e-2, threshold=1e-2, verbose=False)
+    groups = model.partition_hamiltonian()
+    assert len([flip for flip in groups if len(flip)]) == 36
+    # the global ground level of 3x3, U = 6 without a chemical potential lies at 6 electrons (degenerate in Sz:
+    # (3,3), (4,2), (5,1) all give -9.7352272458, oracle/ed.py over all 55 (N_up >= N_dn) sectors)
+    o_h = pauli.compress(pauli.jw_table(pauli.hubbard_fermion_terms(nx, ny, 1.0, u), n))
+    best = ed.ground_state(o_h, n, 6, 3, 3, k=1)[0][0]
+    assert abs(best + 9.735227245787) < 1e-9
+    assert abs(model.ground_state_energy - best) < 1e-8
+    wf = np.asarray(model.ground_state_wf)
+    assert abs(np.linalg.norm(wf) - 1.0) < 1e-9
+    assert abs(np.vdot(wf, sv.apply_table(wf, o_h, n)).real - best) < 1e-7      # it is an eigenvector of that level
