@@ -370,7 +370,7 @@ def run_gpu_arm(args, rank, world, local_rank):
 
     # ---- CPU baseline (bounded sample of the same workload) ----
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # rank 0 at N=1 only
         n_ops = 4
         one_step, cores = cpu_reference_sample(n_ops, wl["picks"], thetas)
         one_step()
