@@ -51,6 +51,7 @@ extern "C" int fh_ctx_create(int device, void *stream, fh_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     FH_CUDA(cudaMalloc(&ctx->d_partials, sizeof(double) * 2 * FH_MAX_PARTIALS));
     FH_CUDA(cudaMalloc(&ctx->d_result, sizeof(double) * 64));
+    FH_CUDA(cudaMalloc(&ctx->d_diag, fh_diag_scratch_bytes()));
     FH_CUDA(cudaMallocHost(&ctx->h_result, sizeof(double) * 64));
     *out = ctx;
     return FH_OK;
@@ -64,6 +65,7 @@ extern "C" int fh_ctx_destroy(fh_ctx *ctx) {
     cudaFree(ctx->d_result);
     cudaFreeHost(ctx->h_result);
     if (ctx->d_flush) cudaFree(ctx->d_flush);
+    if (ctx->d_diag) cudaFree(ctx->d_diag);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -94,6 +96,7 @@ extern "C" int fh_ctx_flush_l2(fh_ctx *ctx, size_t bytes) {
     bytes = (bytes + 31) & ~(size_t)31;
     if (bytes > ctx->flush_bytes) {
         if (ctx->d_flush) cudaFree(ctx->d_flush);
+    if (ctx->d_diag) cudaFree(ctx->d_diag);
         ctx->d_flush = nullptr;
         ctx->flush_bytes = 0;
         FH_CUDA(cudaMalloc(&ctx->d_flush, bytes));
@@ -308,7 +311,7 @@ extern "C" int fh_apply_diag(fh_state *st, int n_terms, const uint64_t *z, const
     DiagTerm *d = nullptr;
     FH_CUDA(cudaMallocAsync(&d, sizeof(DiagTerm) * n_terms, ctx->stream));
     FH_CUDA(cudaMemcpyAsync(d, terms.data(), sizeof(DiagTerm) * n_terms, cudaMemcpyHostToDevice, ctx->stream));
-    launch_diag(ctx->stream, ctx->sm_count, st->d, d, n_terms, st->n, 0);
+    launch_diag(ctx->stream, ctx->sm_count, st->d, d, n_terms, st->n, 0, ctx->d_diag);
     FH_CUDA(cudaGetLastError());
     FH_CUDA(cudaFreeAsync(d, ctx->stream));
     FH_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -193,6 +193,7 @@ struct fh_ctx {
     unsigned int *d_counter = nullptr;
     double *d_result = nullptr;       // small device result buffer (64 doubles)
     double *h_result = nullptr;       // pinned mirror
+    void *d_diag = nullptr;           // factor tables of the standalone diagonal kernel (fh_diag_scratch_bytes())
     void *d_flush = nullptr;
     size_t flush_bytes = 0;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
@@ -252,7 +253,9 @@ void launch_pair(cudaStream_t s, int sm, double2 *psi, const PairOp *d_op, int n
 // adjoint step: grad partial of Ghat at (psi, lam), then apply op^dagger to both
 void launch_pair_adjoint(cudaStream_t s, int sm, double2 *psi, double2 *lam, const PairOp *d_op, int n, int nfix,
                          double *d_partials, int max_blocks, int *blocks_used);
-void launch_diag(cudaStream_t s, int sm, double2 *psi, const DiagTerm *d_terms, int nterms, int n, int dagger);
+void launch_diag(cudaStream_t s, int sm, double2 *psi, const DiagTerm *d_terms, int nterms, int n, int dagger,
+                 void *scratch = nullptr);
+size_t fh_diag_scratch_bytes();
 void launch_diag_adjoint(cudaStream_t s, int sm, double2 *psi, double2 *lam, const DiagTerm *d_terms, int nterms, int n,
                          double *d_partials, int max_blocks, int *blocks_used);
 void launch_tile(cudaStream_t s, double2 *psi, const TileLaunch &tl, const TileRec *d_recs, const TileTerm *d_terms,

@@ -1143,14 +1143,107 @@ void launch_pair_adjoint(cudaStream_t s, int sm, double2 *psi, double2 *lam, con
     *blocks_used = grid;
 }
 
-void launch_diag(cudaStream_t s, int sm, double2 *psi, const DiagTerm *d_terms, int nterms, int n, int dagger) {
+// Diagonal op through factor tables (large states): the phase of index i is the product of three table entries
+// (index bits 0..11, 12..23, 24..) times the few terms whose z-mask straddles two chunks.  k_diag_build fills the
+// tables and compacts the straddling terms; k_diag_tab streams the state once with three L1-resident lookups.
+#define DIAG_TAB_A 4096
+#define DIAG_TAB_B 4096
+#define DIAG_TAB_C 1024
+#define DIAG_TAB_ENTRIES (DIAG_TAB_A + DIAG_TAB_B + DIAG_TAB_C)
+#define DIAG_MAX_CROSS 512
+struct DiagCross {
+    u64 z;
+    double c, s;
+    double pad;
+};
+
+__device__ __forceinline__ int diag_chunk_of(u64 z) {     // 0 / 1 / 2: z inside that chunk; -1: straddles
+    const u64 ma = 0xfffull, mb = 0xfffull << 12;
+    if ((z & ~ma) == 0) return 0;
+    if ((z & ~mb) == 0) return 1;
+    if ((z & (ma | mb)) == 0) return 2;
+    return -1;
+}
+
+__global__ void __launch_bounds__(256) k_diag_build(const DiagTerm *__restrict__ terms, int nterms, int dagger,
+                                                    double2 *__restrict__ tab, int *__restrict__ ncross,
+                                                    DiagCross *__restrict__ cross) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < DIAG_TAB_ENTRIES) {
+        const int chunk = v < DIAG_TAB_A ? 0 : (v < DIAG_TAB_A + DIAG_TAB_B ? 1 : 2);
+        const u64 idx = (u64)(v - (chunk == 0 ? 0 : (chunk == 1 ? DIAG_TAB_A : DIAG_TAB_A + DIAG_TAB_B)));
+        const u64 gl = idx << (12 * chunk);
+        double tot = 0.0;
+        for (int m = 0; m < nterms; ++m) {
+            const u64 z = terms[m].z;
+            if (diag_chunk_of(z) == chunk) tot += sign_of(gl & z) * terms[m].angle;
+        }
+        double sn, cs;
+        sincos(tot, &sn, &cs);
+        tab[v] = make_double2(cs, dagger ? sn : -sn);
+    }
+    if (v == 0) {
+        int k = 0;
+        for (int m = 0; m < nterms; ++m)
+            if (diag_chunk_of(terms[m].z) < 0) {
+                cross[k].z = terms[m].z;
+                cross[k].c = terms[m].c;
+                cross[k].s = dagger ? -terms[m].s : terms[m].s;
+                ++k;
+            }
+        *ncross = k;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_diag_tab(double2 *__restrict__ psi, const double2 *__restrict__ tab,
+                                                  const int *__restrict__ ncross, const DiagCross *__restrict__ cross,
+                                                  u64 dim) {
+    const int nc = *ncross;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i0 = ((u64)blockIdx.x * blockDim.x + threadIdx.x); i0 < dim; i0 += 2 * stride) {
+        const u64 i1 = i0 + stride;
+        const bool two = i1 < dim;
+        const double2 a0 = psi[i0];
+        const double2 a1 = two ? psi[i1] : make_double2(0.0, 0.0);
+        double2 f0 = cmul(cmul(__ldg(tab + (i0 & 0xfffull)), __ldg(tab + DIAG_TAB_A + ((i0 >> 12) & 0xfffull))),
+                          __ldg(tab + DIAG_TAB_A + DIAG_TAB_B + (i0 >> 24)));
+        double2 f1 = make_double2(1.0, 0.0);
+        if (two)
+            f1 = cmul(cmul(__ldg(tab + (i1 & 0xfffull)), __ldg(tab + DIAG_TAB_A + ((i1 >> 12) & 0xfffull))),
+                      __ldg(tab + DIAG_TAB_A + DIAG_TAB_B + (i1 >> 24)));
+        for (int m = 0; m < nc; ++m) {
+            const u64 z = cross[m].z;
+            const double c = cross[m].c, sn = cross[m].s;
+            f0 = cmul(f0, make_double2(c, -sign_of(i0 & z) * sn));
+            if (two) f1 = cmul(f1, make_double2(c, -sign_of(i1 & z) * sn));
+        }
+        psi[i0] = cmul(f0, a0);
+        if (two) psi[i1] = cmul(f1, a1);
+    }
+}
+
+void launch_diag(cudaStream_t s, int sm, double2 *psi, const DiagTerm *d_terms, int nterms, int n, int dagger,
+                 void *scratch) {
     const u64 dim = 1ull << n;
+    if (scratch && n >= 20 && n <= 34 && nterms > 4 && nterms <= DIAG_MAX_CROSS) {
+        double2 *tab = reinterpret_cast<double2 *>(scratch);
+        int *ncross = reinterpret_cast<int *>(tab + DIAG_TAB_ENTRIES);
+        DiagCross *cross = reinterpret_cast<DiagCross *>(tab + DIAG_TAB_ENTRIES + 1);
+        ++g_fh_launch_count;
+        k_diag_build<<<(DIAG_TAB_ENTRIES + 255) / 256, 256, 0, s>>>(d_terms, nterms, dagger, tab, ncross, cross);
+        const int grid = grid_for(dim, 256, 4, sm, sm * 16);
+        ++g_fh_launch_count;
+        k_diag_tab<<<grid, 256, 0, s>>>(psi, tab, ncross, cross, dim);
+        return;
+    }
     for (int off = 0; off < nterms; off += DIAG_SMEM_TERMS) {
         const int cnt = nterms - off < DIAG_SMEM_TERMS ? nterms - off : DIAG_SMEM_TERMS;
         const int grid = grid_for(dim, 256, dim >= (u64)sm * 256 * 8 ? 2 : 1, sm, sm * 16);
         ++g_fh_launch_count; k_diag<<<grid, 256, 0, s>>>(psi, d_terms + off, cnt, dim, dagger);
     }
 }
+
+size_t fh_diag_scratch_bytes() { return sizeof(double2) * (DIAG_TAB_ENTRIES + 1) + sizeof(DiagCross) * DIAG_MAX_CROSS; }
 
 void launch_diag_adjoint(cudaStream_t s, int sm, double2 *psi, double2 *lam, const DiagTerm *d_terms, int nterms, int n,
                          double *d_partials, int max_blocks, int *blocks_used) {

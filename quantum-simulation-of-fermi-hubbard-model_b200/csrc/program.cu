@@ -496,7 +496,7 @@ static void apply_item(fh_program *p, const Item &it, double2 *st, int dagger) {
         launch_pair(ctx->stream, ctx->sm_count, st, p->d_pairs + it.index, p->n, p->pairs[it.index].npos, dagger);
     } else if (it.type == 2) {
         const DiagOp &d = p->diagops[it.index];
-        launch_diag(ctx->stream, ctx->sm_count, st, p->d_dterms + d.first, d.count, p->n, dagger);
+        launch_diag(ctx->stream, ctx->sm_count, st, p->d_dterms + d.first, d.count, p->n, dagger, ctx->d_diag);
     } else {
         const TileOp &t = p->tiles[it.index];
         TileLaunch tl;
@@ -554,8 +554,8 @@ static void adjoint_logical(fh_program *p, int type, int index, double2 *psi, do
             p->seg_scale.push_back(2.0);
             p->n_segments++;
         } else {
-            launch_diag(ctx->stream, ctx->sm_count, psi, p->d_dterms + d.first, d.count, p->n, 1);
-            launch_diag(ctx->stream, ctx->sm_count, lam, p->d_dterms + d.first, d.count, p->n, 1);
+            launch_diag(ctx->stream, ctx->sm_count, psi, p->d_dterms + d.first, d.count, p->n, 1, ctx->d_diag);
+            launch_diag(ctx->stream, ctx->sm_count, lam, p->d_dterms + d.first, d.count, p->n, 1, ctx->d_diag);
         }
     }
 }

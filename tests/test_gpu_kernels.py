@@ -141,6 +141,34 @@ def test_random_tables_all_group_shapes(ctx, n, seed):
     assert abs(e2 - np.vdot(psi, want2)) < 1e-11
 
 
+def test_diag_factor_tables_20_qubits(ctx):
+    """n >= 20 and > 4 terms: the standalone diagonal kernel goes through three factor tables (index bits 0-11, 12-23,
+    24-) plus per-amplitude evaluation of the terms that straddle two chunks."""
+    from fhsim.circuit import DiagOpSpec
+    n = 20
+    rng = np.random.default_rng(17)
+    zs = [1 << 3, (1 << 11) | (1 << 10), (1 << 12) | (1 << 11), (1 << 19) | 1, (1 << 13) | (1 << 15), 0b111 << 10,
+          (1 << 19) | (1 << 18), 1 << 12, (1 << 5) | (1 << 17) | (1 << 2)]
+    angles = rng.uniform(-1.0, 1.0, len(zs))
+    psi = rand_state(n, 23)
+    st = State.from_numpy(ctx, psi)
+    st.apply_diag(zs, angles)
+    idx = np.arange(1 << n, dtype=np.uint64)
+    tot = np.zeros(1 << n)
+    for z, a in zip(zs, angles):
+        tot += a * (1 - 2 * (np.bitwise_count(idx & np.uint64(z)) & 1).astype(np.int64))
+    assert np.abs(st.numpy() - psi * np.exp(-1j * tot)).max() < AMP_TOL
+    # through a compiled program, forward then inverse
+    c = Circuit(n, 1)
+    c.ops.append(DiagOpSpec(zs, list(angles), 0, [(0, z) for z in zs]))
+    prog = c.compile(ctx, fuse=False)
+    st.upload(psi)
+    prog.run(st, [0.7])
+    assert np.abs(st.numpy() - psi * np.exp(-0.7j * tot)).max() < AMP_TOL
+    prog.run(st, [0.7], dagger=True)
+    assert np.abs(st.numpy() - psi).max() < AMP_TOL
+
+
 def test_apply_table_22_qubits_eight_outputs_per_thread(ctx):
     """n >= 22 switches K2 to 8 outputs per thread (index bits 8..10): 1x11 Hubbard chain + a complex random table
     whose x / z masks hit bits 8, 9, 10."""
