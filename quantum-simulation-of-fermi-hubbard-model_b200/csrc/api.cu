@@ -488,6 +488,12 @@ extern "C" int fh_table_upload(fh_ctx *ctx, int n_qubits, int n_terms, const uin
             }
         }
         grp.n_class = (int)tab->classes.size() - grp.first_class;
+        grp.live = 0;
+        for (int c = grp.first_class; c < grp.first_class + grp.n_class; ++c)
+            for (int pat = 0; pat < (1 << grp.kbits); ++pat) {
+                const double2 v = tab->vals[tab->classes[c].vofs + pat];
+                if (v.x != 0.0 || v.y != 0.0) grp.live |= 1u << pat;
+            }
         for (int r = 0; r < 8; ++r) {                 // how bits 8, 9, 10 of the index move the x-bit pattern
             unsigned d = 0;
             for (int q = 0; q < grp.kbits; ++q)

@@ -143,7 +143,7 @@ struct __align__(16) TabGroup {     // 32 bytes
     unsigned char pos[4];           // ascending bit positions of x; unused slots = 63 (that bit of j is always 0)
     int kbits;
     unsigned rpat;                  // 8 x 4 bits: pattern(j ^ (r << 8)) = pattern(j) ^ ((rpat >> 4r) & 15)   (k_apply_table4)
-    int pad;
+    unsigned live;                  // bit p set: some class has a non-zero table entry for pattern p
 };
 
 struct __align__(16) TabClass {     // 16 bytes

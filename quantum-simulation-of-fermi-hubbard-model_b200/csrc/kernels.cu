@@ -739,6 +739,9 @@ __global__ void __launch_bounds__(256) k_apply_table4(const TabGroup *__restrict
                                   ((unsigned)((j0 >> ((p >> 16) & 63u)) & 1u) << 2) |
                                   ((unsigned)((j0 >> ((p >> 24) & 63u)) & 1u) << 3);
             const unsigned rpat = g1.z;
+            // all R outputs see the same x-bit pattern unless the mask contains bit 8..10: a pattern no class has a
+            // weight for (half of all cases for a hopping group) skips the class loop and the gathers
+            if (rpat == 0u && !((g1.w >> pat0) & 1u)) continue;
             double wr[R], wi[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) wr[r] = wi[r] = 0.0;
