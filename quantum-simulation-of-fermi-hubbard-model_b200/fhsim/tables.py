@@ -83,6 +83,57 @@ class PauliTable:
     def as_dict(self):
         return {(int(a), int(b)): complex(c) for a, b, c in zip(self.x, self.z, self.coeff)}
 
+    # -- iQCC dressing on packed masks (reference models/iqcc_hubbard.py:184-189) -----------------------------
+    def dressed(self, xp: int, zp: int, tau: float, tol: float = 1e-12) -> "PauliTable":
+        """exp(i tau P / 2) H exp(-i tau P / 2) for the Pauli string P = (xp, zp), i.e. the reference's
+        ``H + sin(tau)(-i/2)[H, P] + (1/2)(1 - cos tau)(P H P - H)``, on the packed table.
+
+        A term that commutes with P is unchanged; a term c_t P_t that anticommutes becomes
+        ``cos(tau) c_t P_t - i sin(tau) c_t P_t P``, and P_t P = i^(k_t + k_P - k_3) (-1)^popcount(z_t & x_P) P_3
+        with P_3 = (x_t ^ x_P, z_t ^ z_P).  Duplicate strings are merged and |c| < tol dropped.  Vectorised: the
+        term table can grow to 10^5..10^6 entries."""
+        xp64, zp64 = np.uint64(xp), np.uint64(zp)
+        x, z, c = self.x, self.z, self.coeff
+        par = (np.bitwise_count(x & zp64) + np.bitwise_count(z & xp64)) & 1      # 1: anticommutes with P
+        anti = par.astype(bool)
+        cs, sn = np.cos(tau), np.sin(tau)
+        keep_c = np.where(anti, cs * c, c)
+        xa, za, ca = x[anti], z[anti], c[anti]
+        x3, z3 = xa ^ xp64, za ^ zp64
+        k1 = np.bitwise_count(xa & za).astype(np.int64)
+        k2 = int(bin(xp & zp).count("1"))
+        k3 = np.bitwise_count(x3 & z3).astype(np.int64)
+        phase = np.array(_I_POW)[(k1 + k2 - k3) & 3] * (1 - 2 * (np.bitwise_count(za & xp64) & 1).astype(np.int64))
+        new_c = -1j * sn * ca * phase
+        ax = np.concatenate([x, x3])
+        az = np.concatenate([z, z3])
+        ac = np.concatenate([keep_c, new_c])
+        # merge equal strings, keeping first-seen order (as the reference's dict-based += does)
+        keys = np.stack([ax, az], axis=1)
+        uniq, first, inv = np.unique(keys, axis=0, return_index=True, return_inverse=True)
+        summed = np.zeros(len(uniq), dtype=np.complex128)
+        np.add.at(summed, inv.reshape(-1), ac)
+        order = np.argsort(first, kind="stable")
+        live = np.abs(summed[order]) > tol
+        sel = order[live]
+        return PauliTable(self.n_qubits, uniq[sel, 0], uniq[sel, 1], summed[sel])
+
+    def to_operator(self):
+        """QubitOperator with this table's terms (table order)."""
+        op = QubitOperator()
+        n = self.n_qubits
+        for x, z, c in zip(self.x, self.z, self.coeff):
+            x, z = int(x), int(z)
+            term = []
+            for q in range(n):
+                b = 1 << (n - 1 - q)
+                if x & b:
+                    term.append((q, "Y" if z & b else "X"))
+                elif z & b:
+                    term.append((q, "Z"))
+            op.terms[tuple(term)] = complex(c)
+        return op
+
 
 # ---------------------------------------------------------------------------------------------
 # generator plans

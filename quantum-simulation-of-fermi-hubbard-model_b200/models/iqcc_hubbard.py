@@ -148,13 +148,22 @@ class IQCC:
         return ([DIS_gates[i] for i in maxIndicies], [DIS_strings[i] for i in maxIndicies], grads[maxIndicies])
 
     def dress_hamiltonian(self, operators, taus):
-        """H <- H + sin(tau)(-i/2)[H, P] + (1/2)(1 - cos tau)(P H P - H), last entangler first."""
+        """H <- H + sin(tau)(-i/2)[H, P] + (1/2)(1 - cos tau)(P H P - H), last entangler first (reference :184-189).
+
+        Evaluated on the packed (x-mask, z-mask, coefficient) table (``PauliTable.dressed``: anticommuting terms pick
+        up cos/sin copies, duplicates are hash-merged), not by symbolic operator products: the term table grows
+        geometrically with the number of entanglers.  ``currentHamiltonian`` stays a QubitOperator for the callers
+        that iterate its terms (``partition_hamiltonian``)."""
+        from fhsim.tables import PauliTable, pack_term
+        table = PauliTable.from_operator(self.currentHamiltonian, self.n_qubits, compress=False)
         for P_k, tau_k in zip(operators[::-1], taus[::-1]):
-            tau_k = float(tau_k)        # float32 parameter, promoted exactly: keeps the algebra in double precision
-            H = self.currentHamiltonian
-            first = np.sin(tau_k) * (-1j / 2) * (H * P_k - P_k * H)
-            second = 1 / 2 * (1 - np.cos(tau_k)) * (P_k * H * P_k - H)
-            self.currentHamiltonian += first + second
+            (term, coeff), = P_k.terms.items()
+            if abs(coeff - 1.0) > 1e-12:
+                raise ValueError('entanglers must be bare Pauli strings')
+            xp, zp = pack_term(term, self.n_qubits)
+            # float32 parameter, promoted exactly: keeps the algebra in double precision
+            table = table.dressed(xp, zp, float(tau_k))
+        self.currentHamiltonian = table.to_operator()
         self.qmlHamiltonian = QubitOperator_to_qmlHamiltonian(self.currentHamiltonian)
 
     def run(self):

@@ -103,3 +103,33 @@ def test_k_space_occupation_matches_oracle():
         oup, odn, _ = pauli.k_space_occupation(nx, ny, 1.0, up, dn)
         assert got_up == oup and got_dn == odn
         assert len(get_interacting_term(h).terms) == nx * ny
+
+
+def test_packed_iqcc_dressing_equals_symbolic():
+    """PauliTable.dressed == the reference's symbolic update H + sin(t)(-i/2)[H,P] + (1/2)(1-cos t)(PHP - H)
+    (models/iqcc_hubbard.py:184-189), chained over several generators, on the 2x3 Hubbard Hamiltonian."""
+    import numpy as np
+    from fhsim.symbolic import QubitOperator, fermi_hubbard, jordan_wigner
+    from fhsim.tables import PauliTable, pack_term
+    n = 12
+    h = jordan_wigner(fermi_hubbard(2, 3, 1.0, 4.0))
+    tab = PauliTable.from_operator(h, n)
+    gens = [("Y0 X1 X4 X5", 0.37), ("Y2 X8", -0.81), ("Y3 X5 X6 X10", 1.3), ("Y0 X1 X4 X5", -0.2)]
+    for string, tau in gens:
+        P = QubitOperator(string)
+        first = np.sin(tau) * (-1j / 2) * (h * P - P * h)
+        second = 1 / 2 * (1 - np.cos(tau)) * (P * h * P - h)
+        h = h + first + second
+        (term, _), = P.terms.items()
+        xp, zp = pack_term(term, n)
+        tab = tab.dressed(xp, zp, tau)
+    want = {}
+    for term, c in h.terms.items():
+        if abs(c) > 1e-12:
+            want[pack_term(term, n)] = complex(c)
+    got = tab.as_dict()
+    assert set(got) == set(want)
+    assert max(abs(got[k] - want[k]) for k in want) < 1e-13
+    assert max(abs(complex(c).imag) for c in got.values()) < 1e-13          # stays Hermitian with real coefficients
+    back = PauliTable.from_operator(tab.to_operator(), n, compress=False).as_dict()
+    assert back == got
