@@ -699,6 +699,7 @@ extern "C" int fh_pool_upload(fh_ctx *ctx, int n_qubits, int n_entries, const ui
     pool->h_out = nullptr;
     int min_fix = 64;
     int prev_out = 0;
+    pool->narrow = 1;
     pool->out_first.assign(n_out + 1, 0);
     for (int e = 0; e < n_entries; ++e) {
         PairOp tmp;
@@ -726,6 +727,7 @@ extern "C" int fh_pool_upload(fh_ctx *ctx, int n_qubits, int n_entries, const ui
         pool->entries.push_back(pe);
         pool->out_first[out_index[e] + 1] = e + 1;
         if (tmp.npos < min_fix) min_fix = tmp.npos;
+        if (tmp.npos > 4) pool->narrow = 0;
     }
     for (int o = 1; o <= n_out; ++o)
         if (pool->out_first[o] < pool->out_first[o - 1]) pool->out_first[o] = pool->out_first[o - 1];
@@ -791,12 +793,12 @@ int fh_enqueue_pool(const fh_pool *pool, const double2 *psi, const double2 *lam,
     const int e0 = pool->out_first[first], e1 = pool->out_first[first + count];
     if (pool->passes.empty()) {
         launch_pool(ctx->stream, pool->d_entries, e0, e1 - e0, pool->kchunks, pool->n, psi, lam, pool->d_partials, nullptr,
-                    e0, e1, pool->chunks);
+                    e0, e1, pool->chunks, pool->narrow);
     } else {
         launch_pool_tiles(ctx->stream, pool->d_passes, (int)pool->passes.size(), pool->d_tile_recs, pool->tile_bits,
                           pool->tile_grid, pool->chunks, pool->n, psi, lam, pool->d_partials, e0, e1);
         launch_pool(ctx->stream, pool->d_entries, 0, (int)pool->rest.size(), pool->kchunks, pool->n, psi, lam,
-                    pool->d_partials, pool->d_rest, e0, e1, pool->chunks);
+                    pool->d_partials, pool->d_rest, e0, e1, pool->chunks, pool->narrow);
     }
     launch_pool_finalize(ctx->stream, pool->d_partials, pool->d_out_first, pool->chunks, first, count, pool->d_out);
     FH_CUDA(cudaGetLastError());

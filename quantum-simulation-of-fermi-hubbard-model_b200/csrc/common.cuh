@@ -229,6 +229,7 @@ struct fh_pool {
     int n_entries, n_out;
     int chunks;                 // row width of the partials array (slots per entry)
     int kchunks;                // blocks per entry of the per-entry kernel (k_pool)
+    int narrow;                 // 1: every entry pins <= 4 bits (k_pool32 applies)
     PoolEntry *d_entries;
     int *d_out_first;           // [n_out+1] entry ranges per output (entries sorted by out)
     double *d_partials;         // [n_entries * chunks]
@@ -271,7 +272,7 @@ void launch_apply_table(cudaStream_t s, int sm, const fh_table *tab, const doubl
                         double *d_partials, double *d_result);
 void launch_pool(cudaStream_t s, const PoolEntry *entries, int first_entry, int n_entries, int chunks, int n,
                  const double2 *psi, const double2 *lam, double *d_partials, const int *entry_ids = nullptr,
-                 int e0 = 0, int e1 = 0x7fffffff, int row = 0);
+                 int e0 = 0, int e1 = 0x7fffffff, int row = 0, int narrow = 0);   // narrow: every pattern pins <= 4 bits
 // tiled scan of the entries covered by passes; only entries in [e0, e1) are evaluated
 void launch_pool_tiles(cudaStream_t s, const PoolPass *d_passes, int npasses, const PoolTileRec *d_recs, int tile_bits,
                        int grid_x, int chunks, int n, const double2 *psi, const double2 *lam, double *d_partials, int e0,

@@ -868,6 +868,57 @@ __global__ void __launch_bounds__(128) k_pool(const PoolEntry *__restrict__ entr
     if (threadIdx.x == 0) partials[(size_t)eid * row + blockIdx.x] = 2.0 * r;
 }
 
+// K3, 32-bit index variant for n <= 31 and patterns of at most 4 pinned bits (every pool the drivers build): the
+// bit-deposit is four register mask insertions instead of a loop over a position array, and all index math is 32-bit.
+__global__ void __launch_bounds__(128) k_pool32(const PoolEntry *__restrict__ entries, int first_entry, int n,
+                                                const double2 *__restrict__ psi, const double2 *__restrict__ lam,
+                                                double *__restrict__ partials, const int *__restrict__ entry_ids, int e0,
+                                                int e1, int row) {
+    __shared__ PoolEntry e;
+    __shared__ double red[4];
+    const int eid = entry_ids ? entry_ids[first_entry + blockIdx.y] : first_entry + (int)blockIdx.y;
+    if (eid < e0 || eid >= e1) return;
+    {
+        const int words = sizeof(PoolEntry) / 8;
+        const u64 *src = reinterpret_cast<const u64 *>(entries + eid);
+        for (int t = threadIdx.x; t < words; t += blockDim.x) reinterpret_cast<u64 *>(&e)[t] = __ldg(src + t);
+        __syncthreads();
+    }
+    const int npos = e.npos;
+    const unsigned m0 = npos > 0 ? (1u << e.pos[0]) - 1u : 0xffffffffu, m1 = npos > 1 ? (1u << e.pos[1]) - 1u : 0xffffffffu,
+                   m2 = npos > 2 ? (1u << e.pos[2]) - 1u : 0xffffffffu, m3 = npos > 3 ? (1u << e.pos[3]) - 1u : 0xffffffffu;
+    const unsigned fixval = (unsigned)e.fixval, x = (unsigned)e.x, zeta = (unsigned)e.zeta;
+    const unsigned npairs = 1u << (n - npos);
+    const unsigned stride = gridDim.x * blockDim.x;
+    const double2 B = make_double2(e.br, e.bi);
+    const double2 Bc = make_double2(e.br, -e.bi);
+    double acc = 0.0;
+    auto place = [&](unsigned v) {
+        v = ((v & ~m0) << 1) | (v & m0);
+        v = ((v & ~m1) << 1) | (v & m1);
+        v = ((v & ~m2) << 1) | (v & m2);
+        v = ((v & ~m3) << 1) | (v & m3);
+        return v | fixval;
+    };
+    unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; idx + stride < npairs; idx += 2 * stride) {
+        const unsigned i0 = place(idx), j0 = i0 ^ x, i1 = place(idx + stride), j1 = i1 ^ x;
+        const double2 a0 = psi[i0], b0 = psi[j0], la0 = lam[i0], lb0 = lam[j0];
+        const double2 a1 = psi[i1], b1 = psi[j1], la1 = lam[i1], lb1 = lam[j1];
+        const double s0 = (__popc(i0 & zeta) & 1) ? -1.0 : 1.0, s1 = (__popc(i1 & zeta) & 1) ? -1.0 : 1.0;
+        acc += s0 * (im_conj_mul(la0, cmul(B, b0)) + im_conj_mul(lb0, cmul(Bc, a0)));
+        acc += s1 * (im_conj_mul(la1, cmul(B, b1)) + im_conj_mul(lb1, cmul(Bc, a1)));
+    }
+    for (; idx < npairs; idx += stride) {
+        const unsigned i0 = place(idx), j0 = i0 ^ x;
+        const double2 a0 = psi[i0], b0 = psi[j0], la0 = lam[i0], lb0 = lam[j0];
+        const double s0 = (__popc(i0 & zeta) & 1) ? -1.0 : 1.0;
+        acc += s0 * (im_conj_mul(la0, cmul(B, b0)) + im_conj_mul(lb0, cmul(Bc, a0)));
+    }
+    const double r = block_sum<128>(acc, red);
+    if (threadIdx.x == 0) partials[(size_t)eid * row + blockIdx.x] = 2.0 * r;
+}
+
 // K3 on shared-memory tiles: blockIdx.y = pass (a set of T index bits), blockIdx.x strides over the 2^(n-T) tiles.
 // psi and lambda tiles are loaded once and every entry of the pass is evaluated from them, one warp per entry
 // (its lanes cover the entry's in-tile pairs), so a gradient costs shared-memory instead of L2/HBM traffic.
@@ -1350,7 +1401,7 @@ void launch_apply_table(cudaStream_t s, int sm, const fh_table *tab, const doubl
 
 void launch_pool(cudaStream_t s, const PoolEntry *entries, int first_entry, int n_entries, int chunks, int n,
                  const double2 *psi, const double2 *lam, double *d_partials, const int *entry_ids, int e0, int e1,
-                 int row) {
+                 int row, int narrow) {
     if (n_entries <= 0) return;
     if (row <= 0) row = chunks;
     // gridDim.y is limited to 65535
@@ -1358,7 +1409,10 @@ void launch_pool(cudaStream_t s, const PoolEntry *entries, int first_entry, int 
         const int cnt = n_entries - off < 32768 ? n_entries - off : 32768;
         dim3 grid(chunks, cnt);
         ++g_fh_launch_count;
-        k_pool<<<grid, 128, 0, s>>>(entries, first_entry + off, n, psi, lam, d_partials, entry_ids, e0, e1, row);
+        if (narrow && n <= 31)
+            k_pool32<<<grid, 128, 0, s>>>(entries, first_entry + off, n, psi, lam, d_partials, entry_ids, e0, e1, row);
+        else
+            k_pool<<<grid, 128, 0, s>>>(entries, first_entry + off, n, psi, lam, d_partials, entry_ids, e0, e1, row);
     }
 }
 
