@@ -429,6 +429,7 @@ extern "C" int fh_table_upload(fh_ctx *ctx, int n_qubits, int n_terms, const uin
         if (tt.di != 0.0) tab->all_real = false;
         buckets[g].push_back(tt);
     }
+    std::vector<TabTerm> diag_tab_terms;
     for (size_t g = 0; g < buckets.size(); ++g) {
         const u64 gx = group_x[g];
         const std::vector<TabTerm> &bt = buckets[g];
@@ -479,6 +480,12 @@ extern "C" int fh_table_upload(fh_ctx *ctx, int n_qubits, int n_terms, const uin
         } else {
             grp.kbits = 0;
             for (const TabTerm &tt : bt) {
+                // diagonal terms whose z-mask lies inside one 12-bit chunk of the index go into three additive
+                // factor tables (built below); only chunk-straddling ones stay per-term classes
+                if (gx == 0 && ((tt.z & ~0xfffull) == 0 || (tt.z & ~(0xfffull << 12)) == 0 || (tt.z & 0xffffffull) == 0)) {
+                    diag_tab_terms.push_back(tt);
+                    continue;
+                }
                 TabClass cl;
                 cl.zeta = tt.z;
                 cl.vofs = (int)tab->vals.size();
@@ -506,6 +513,21 @@ extern "C" int fh_table_upload(fh_ctx *ctx, int n_qubits, int n_terms, const uin
     }
     tab->n_groups = (int)tab->groups.size();
     FH_CUDA(cudaSetDevice(ctx->device));
+    if (!diag_tab_terms.empty()) {
+        std::vector<double2> dt(4096 + 4096 + 1024, make_double2(0.0, 0.0));
+        for (const TabTerm &tt : diag_tab_terms) {
+            const int chunk = (tt.z & ~0xfffull) == 0 ? 0 : ((tt.z & ~(0xfffull << 12)) == 0 ? 1 : 2);
+            const int base = chunk == 0 ? 0 : (chunk == 1 ? 4096 : 8192), len = chunk == 2 ? 1024 : 4096;
+            for (int v = 0; v < len; ++v) {
+                const u64 gl = (u64)v << (12 * chunk);
+                const double sg = (popcnt(gl & tt.z) & 1) ? -1.0 : 1.0;
+                dt[base + v].x += sg * tt.dr;
+                dt[base + v].y += sg * tt.di;
+            }
+        }
+        FH_CUDA(cudaMalloc(&tab->d_diag, sizeof(double2) * dt.size()));
+        FH_CUDA(cudaMemcpy(tab->d_diag, dt.data(), sizeof(double2) * dt.size(), cudaMemcpyHostToDevice));
+    }
     if (tab->n_groups) {
         FH_CUDA(cudaMalloc(&tab->d_groups, sizeof(TabGroup) * tab->groups.size()));
         FH_CUDA(cudaMalloc(&tab->d_classes, sizeof(TabClass) * (tab->classes.size() + 1)));
@@ -531,6 +553,7 @@ extern "C" int fh_table_free(fh_table *tab) {
     cudaFree(tab->d_groups);
     cudaFree(tab->d_classes);
     cudaFree(tab->d_vals);
+    cudaFree(tab->d_diag);
     delete tab;
     return FH_OK;
 }

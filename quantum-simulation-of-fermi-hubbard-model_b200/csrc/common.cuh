@@ -217,6 +217,7 @@ struct fh_table {
     TabGroup *d_groups;
     TabClass *d_classes;
     double2 *d_vals;
+    double2 *d_diag = nullptr;      // diagonal part D(i) = DA[i & 4095] + DB[(i >> 12) & 4095] + DC[i >> 24], or NULL
     std::vector<TabGroup> groups;
     std::vector<TabClass> classes;
     std::vector<double2> vals;

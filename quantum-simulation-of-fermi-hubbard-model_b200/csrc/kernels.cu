@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(256) k_apply_table(const TabGroup *__restrict_
                                                      const TabClass *__restrict__ classes, int nclasses,
                                                      const double2 *__restrict__ vals, int nvals, int use_smem,
                                                      const double2 *__restrict__ in, double2 *__restrict__ out, u64 dim,
-                                                     double *__restrict__ partials) {
+                                                     double *__restrict__ partials, const double2 *__restrict__ dtab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[8];
     const TabGroup *G = groups;
@@ -683,6 +683,11 @@ __global__ void __launch_bounds__(256) k_apply_table(const TabGroup *__restrict_
             }
         }
         const double2 self = in[i];
+        if (dtab) {     // tabulated diagonal part
+            const double2 d = cadd(cadd(__ldg(dtab + (i & 0xfffull)), __ldg(dtab + 4096 + ((i >> 12) & 0xfffull))),
+                                   __ldg(dtab + 8192 + (i >> 24)));
+            acc = cadd(acc, cmul(d, self));
+        }
         er += self.x * acc.x + self.y * acc.y;     // conj(self) * acc
         ei += self.x * acc.y - self.y * acc.x;
         if (MODE == 1) out[i] = acc;
@@ -706,7 +711,8 @@ __global__ void __launch_bounds__(256) k_apply_table4(const TabGroup *__restrict
                                                       const TabClass *__restrict__ classes, int nclasses,
                                                       const double2 *__restrict__ vals, int nvals,
                                                       const double2 *__restrict__ in, double2 *__restrict__ out,
-                                                      unsigned nblk, double *__restrict__ partials) {
+                                                      unsigned nblk, double *__restrict__ partials,
+                                                      const double2 *__restrict__ dtab) {
     constexpr int R = 1 << RL;                    // outputs per thread: i0 | (r << 8), r < R
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[8];
@@ -791,6 +797,17 @@ __global__ void __launch_bounds__(256) k_apply_table4(const TabGroup *__restrict
         for (int r = 0; r < R; ++r) {
             const IDX i = i0 | ((IDX)r << 8);
             const double2 self = in[i];
+            if (dtab) {     // tabulated diagonal part: three additive factor tables over 12-bit chunks of the index
+                const double2 d = cadd(cadd(__ldg(dtab + (i & (IDX)0xfff)), __ldg(dtab + 4096 + ((i >> 12) & (IDX)0xfff))),
+                                       __ldg(dtab + 8192 + (unsigned)((u64)i >> 24)));
+                if (REAL) {
+                    ar[r] += d.x * self.x;
+                    ai[r] += d.x * self.y;
+                } else {
+                    ar[r] += d.x * self.x - d.y * self.y;
+                    ai[r] += d.x * self.y + d.y * self.x;
+                }
+            }
             er += self.x * ar[r] + self.y * ai[r];     // conj(self) * acc
             ei += self.x * ai[r] - self.y * ar[r];
             if (MODE == 1) out[i] = make_double2(ar[r], ai[r]);
@@ -1364,7 +1381,8 @@ void launch_apply_table(cudaStream_t s, int sm, const fh_table *tab, const doubl
     do {                                                                                                            \
         ++g_fh_launch_count;                                                                                        \
         k_apply_table4<I, R, M, RLV><<<grid, 256, smem, s>>>(tab->d_groups, ngroups, tab->d_classes, nclasses,      \
-                                                             tab->d_vals, nvals, in, out, nblk, d_partials);        \
+                                                             tab->d_vals, nvals, in, out, nblk, d_partials,         \
+                                                             tab->d_diag);                                          \
     } while (0)
 #define LAUNCH_TAB4_M(I, R, RLV)                                                                                    \
     do {                                                                                                            \
@@ -1388,7 +1406,7 @@ void launch_apply_table(cudaStream_t s, int sm, const fh_table *tab, const doubl
     do {                                                                                                           \
         ++g_fh_launch_count;                                                                                       \
         k_apply_table<R, M><<<grid, 256, smem, s>>>(tab->d_groups, ngroups, tab->d_classes, nclasses, tab->d_vals, \
-                                                    nvals, use_smem, in, out, dim, d_partials);                    \
+                                                    nvals, use_smem, in, out, dim, d_partials, tab->d_diag);       \
     } while (0)
     if (tab->all_real) {
         if (mode == 0) LAUNCH_TAB(true, 0); else if (mode == 1) LAUNCH_TAB(true, 1); else LAUNCH_TAB(true, 2);

@@ -52,6 +52,10 @@ struct fh_program {
     std::vector<int> dterm_tt_fwd, dterm_tt_dag;       // diag term index -> tile-term index (or -1)
     TileRec *d_recs_fwd = nullptr, *d_recs_dag = nullptr, *h_recs_fwd = nullptr, *h_recs_dag = nullptr;
     TileTerm *d_tterms_fwd = nullptr, *d_tterms_dag = nullptr, *h_tterms_fwd = nullptr, *h_tterms_dag = nullptr;
+    // the theta-dependent payload above lives in ONE pinned arena mirrored by ONE device arena (a single copy node
+    // at the head of the captured graph); the typed pointers are views into them
+    unsigned char *h_arena = nullptr, *d_arena = nullptr;
+    size_t arena_bytes = 0;
     // workspaces
     double2 *d_psi = nullptr, *d_lam = nullptr, *d_chk = nullptr;
     // adjoint-gradient partials: one segment per parametrised op processed
@@ -107,17 +111,9 @@ extern "C" int fh_program_destroy(fh_program *p) {
     drop_graph(p);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
-    cudaFree(p->d_pairs);
-    cudaFree(p->d_dterms);
+    cudaFree(p->d_arena);
+    cudaFreeHost(p->h_arena);
     cudaFree(p->d_diagops);
-    cudaFree(p->d_recs_fwd);
-    cudaFree(p->d_recs_dag);
-    cudaFree(p->d_tterms_fwd);
-    cudaFree(p->d_tterms_dag);
-    cudaFreeHost(p->h_recs_fwd);
-    cudaFreeHost(p->h_recs_dag);
-    cudaFreeHost(p->h_tterms_fwd);
-    cudaFreeHost(p->h_tterms_dag);
     cudaFree(p->d_psi);
     cudaFree(p->d_lam);
     cudaFree(p->d_chk);
@@ -125,8 +121,6 @@ extern "C" int fh_program_destroy(fh_program *p) {
     cudaFree(p->d_gseg);
     cudaFree(p->d_gfirst);
     cudaFree(p->d_res);
-    cudaFreeHost(p->h_pairs);
-    cudaFreeHost(p->h_dterms);
     cudaFreeHost(p->h_gseg);
     cudaFreeHost(p->h_res);
     delete p;
@@ -367,33 +361,44 @@ extern "C" int fh_program_finalize(fh_program *p) {
     FH_REQUIRE(!p->finalized && !p->in_tile, "fh_program_finalize: already finalized or tile still open");
     fh_ctx *ctx = p->ctx;
     FH_CUDA(cudaSetDevice(ctx->device));
-    FH_TRY(upload_vec(&p->d_pairs, p->pairs, ctx->stream));
-    FH_TRY(upload_vec(&p->d_dterms, p->dterms, ctx->stream));
     FH_TRY(upload_vec(&p->d_diagops, p->diagops, ctx->stream));
     build_tile_records(p);
-    FH_TRY(upload_vec(&p->d_recs_fwd, p->recs_fwd, ctx->stream));
-    FH_TRY(upload_vec(&p->d_recs_dag, p->recs_dag, ctx->stream));
-    FH_TRY(upload_vec(&p->d_tterms_fwd, p->tterms_fwd, ctx->stream));
-    FH_TRY(upload_vec(&p->d_tterms_dag, p->tterms_dag, ctx->stream));
-    if (!p->recs_fwd.empty()) {
-        FH_CUDA(cudaMallocHost(&p->h_recs_fwd, sizeof(TileRec) * p->recs_fwd.size()));
-        FH_CUDA(cudaMallocHost(&p->h_recs_dag, sizeof(TileRec) * p->recs_dag.size()));
-        memcpy(p->h_recs_fwd, p->recs_fwd.data(), sizeof(TileRec) * p->recs_fwd.size());
-        memcpy(p->h_recs_dag, p->recs_dag.data(), sizeof(TileRec) * p->recs_dag.size());
-    }
-    if (!p->tterms_fwd.empty()) {
-        FH_CUDA(cudaMallocHost(&p->h_tterms_fwd, sizeof(TileTerm) * p->tterms_fwd.size()));
-        FH_CUDA(cudaMallocHost(&p->h_tterms_dag, sizeof(TileTerm) * p->tterms_dag.size()));
-        memcpy(p->h_tterms_fwd, p->tterms_fwd.data(), sizeof(TileTerm) * p->tterms_fwd.size());
-        memcpy(p->h_tterms_dag, p->tterms_dag.data(), sizeof(TileTerm) * p->tterms_dag.size());
-    }
-    if (!p->pairs.empty()) {
-        FH_CUDA(cudaMallocHost(&p->h_pairs, sizeof(PairOp) * p->pairs.size()));
-        memcpy(p->h_pairs, p->pairs.data(), sizeof(PairOp) * p->pairs.size());
-    }
-    if (!p->dterms.empty()) {
-        FH_CUDA(cudaMallocHost(&p->h_dterms, sizeof(DiagTerm) * p->dterms.size()));
-        memcpy(p->h_dterms, p->dterms.data(), sizeof(DiagTerm) * p->dterms.size());
+    {
+        // carve the payload arena: [pairs | dterms | recs_fwd | recs_dag | tterms_fwd | tterms_dag], 256-byte aligned
+        auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        const size_t sz[6] = {sizeof(PairOp) * p->pairs.size(),       sizeof(DiagTerm) * p->dterms.size(),
+                              sizeof(TileRec) * p->recs_fwd.size(),   sizeof(TileRec) * p->recs_dag.size(),
+                              sizeof(TileTerm) * p->tterms_fwd.size(), sizeof(TileTerm) * p->tterms_dag.size()};
+        size_t off[6], total = 0;
+        for (int k = 0; k < 6; ++k) {
+            off[k] = total;
+            total += align(sz[k]);
+        }
+        p->arena_bytes = total;
+        if (total) {
+            FH_CUDA(cudaMalloc(&p->d_arena, total));
+            FH_CUDA(cudaMallocHost(&p->h_arena, total));
+            memset(p->h_arena, 0, total);
+        }
+        p->h_pairs = reinterpret_cast<PairOp *>(p->h_arena + off[0]);
+        p->d_pairs = reinterpret_cast<PairOp *>(p->d_arena + off[0]);
+        p->h_dterms = reinterpret_cast<DiagTerm *>(p->h_arena + off[1]);
+        p->d_dterms = reinterpret_cast<DiagTerm *>(p->d_arena + off[1]);
+        p->h_recs_fwd = reinterpret_cast<TileRec *>(p->h_arena + off[2]);
+        p->d_recs_fwd = reinterpret_cast<TileRec *>(p->d_arena + off[2]);
+        p->h_recs_dag = reinterpret_cast<TileRec *>(p->h_arena + off[3]);
+        p->d_recs_dag = reinterpret_cast<TileRec *>(p->d_arena + off[3]);
+        p->h_tterms_fwd = reinterpret_cast<TileTerm *>(p->h_arena + off[4]);
+        p->d_tterms_fwd = reinterpret_cast<TileTerm *>(p->d_arena + off[4]);
+        p->h_tterms_dag = reinterpret_cast<TileTerm *>(p->h_arena + off[5]);
+        p->d_tterms_dag = reinterpret_cast<TileTerm *>(p->d_arena + off[5]);
+        if (sz[0]) memcpy(p->h_pairs, p->pairs.data(), sz[0]);
+        if (sz[1]) memcpy(p->h_dterms, p->dterms.data(), sz[1]);
+        if (sz[2]) memcpy(p->h_recs_fwd, p->recs_fwd.data(), sz[2]);
+        if (sz[3]) memcpy(p->h_recs_dag, p->recs_dag.data(), sz[3]);
+        if (sz[4]) memcpy(p->h_tterms_fwd, p->tterms_fwd.data(), sz[4]);
+        if (sz[5]) memcpy(p->h_tterms_dag, p->tterms_dag.data(), sz[5]);
+        if (total) FH_CUDA(cudaMemcpyAsync(p->d_arena, p->h_arena, total, cudaMemcpyHostToDevice, ctx->stream));
     }
     int n_param_ops = 0;
     for (auto &op : p->pairs) n_param_ops += (op.kind == 1 && op.param >= 0);
@@ -453,21 +458,8 @@ static void refresh_payload(fh_program *p, const double *thetas) {
 
 // copy the pinned payload to the device (these become the first nodes of the captured graph)
 static int enqueue_payload_upload(fh_program *p) {
-    cudaStream_t s = p->ctx->stream;
-    if (!p->pairs.empty())
-        FH_CUDA(cudaMemcpyAsync(p->d_pairs, p->h_pairs, sizeof(PairOp) * p->pairs.size(), cudaMemcpyHostToDevice, s));
-    if (!p->dterms.empty())
-        FH_CUDA(cudaMemcpyAsync(p->d_dterms, p->h_dterms, sizeof(DiagTerm) * p->dterms.size(), cudaMemcpyHostToDevice, s));
-    if (!p->recs_fwd.empty()) {
-        FH_CUDA(cudaMemcpyAsync(p->d_recs_fwd, p->h_recs_fwd, sizeof(TileRec) * p->recs_fwd.size(), cudaMemcpyHostToDevice, s));
-        FH_CUDA(cudaMemcpyAsync(p->d_recs_dag, p->h_recs_dag, sizeof(TileRec) * p->recs_dag.size(), cudaMemcpyHostToDevice, s));
-    }
-    if (!p->tterms_fwd.empty()) {
-        FH_CUDA(cudaMemcpyAsync(p->d_tterms_fwd, p->h_tterms_fwd, sizeof(TileTerm) * p->tterms_fwd.size(),
-                                cudaMemcpyHostToDevice, s));
-        FH_CUDA(cudaMemcpyAsync(p->d_tterms_dag, p->h_tterms_dag, sizeof(TileTerm) * p->tterms_dag.size(),
-                                cudaMemcpyHostToDevice, s));
-    }
+    if (p->arena_bytes)
+        FH_CUDA(cudaMemcpyAsync(p->d_arena, p->h_arena, p->arena_bytes, cudaMemcpyHostToDevice, p->ctx->stream));
     return FH_OK;
 }
 
