@@ -52,6 +52,8 @@ extern "C" int fh_ctx_create(int device, void *stream, fh_ctx **out) {
     FH_CUDA(cudaMalloc(&ctx->d_partials, sizeof(double) * 2 * FH_MAX_PARTIALS));
     FH_CUDA(cudaMalloc(&ctx->d_result, sizeof(double) * 64));
     FH_CUDA(cudaMalloc(&ctx->d_diag, fh_diag_scratch_bytes()));
+    FH_CUDA(cudaMalloc(&ctx->d_counter, sizeof(unsigned int) * 4));
+    FH_CUDA(cudaMemset(ctx->d_counter, 0, sizeof(unsigned int) * 4));
     FH_CUDA(cudaMallocHost(&ctx->h_result, sizeof(double) * 64));
     *out = ctx;
     return FH_OK;
@@ -66,6 +68,7 @@ extern "C" int fh_ctx_destroy(fh_ctx *ctx) {
     cudaFreeHost(ctx->h_result);
     if (ctx->d_flush) cudaFree(ctx->d_flush);
     if (ctx->d_diag) cudaFree(ctx->d_diag);
+    if (ctx->d_counter) cudaFree(ctx->d_counter);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -96,7 +99,6 @@ extern "C" int fh_ctx_flush_l2(fh_ctx *ctx, size_t bytes) {
     bytes = (bytes + 31) & ~(size_t)31;
     if (bytes > ctx->flush_bytes) {
         if (ctx->d_flush) cudaFree(ctx->d_flush);
-    if (ctx->d_diag) cudaFree(ctx->d_diag);
         ctx->d_flush = nullptr;
         ctx->flush_bytes = 0;
         FH_CUDA(cudaMalloc(&ctx->d_flush, bytes));
@@ -811,7 +813,8 @@ extern "C" int fh_pool_free(fh_pool *pool) {
 }
 
 // enqueue K3 for outputs [first, first+count) without synchronising; results in pool->d_out[first..]
-int fh_enqueue_pool(const fh_pool *pool, const double2 *psi, const double2 *lam, int first, int count) {
+int fh_enqueue_pool(const fh_pool *pool, const double2 *psi, const double2 *lam, int first, int count,
+                    double *d_out_override) {
     fh_ctx *ctx = pool->ctx;
     const int e0 = pool->out_first[first], e1 = pool->out_first[first + count];
     if (pool->passes.empty()) {
@@ -823,7 +826,8 @@ int fh_enqueue_pool(const fh_pool *pool, const double2 *psi, const double2 *lam,
         launch_pool(ctx->stream, pool->d_entries, 0, (int)pool->rest.size(), pool->kchunks, pool->n, psi, lam,
                     pool->d_partials, pool->d_rest, e0, e1, pool->chunks, pool->narrow);
     }
-    launch_pool_finalize(ctx->stream, pool->d_partials, pool->d_out_first, pool->chunks, first, count, pool->d_out);
+    launch_pool_finalize(ctx->stream, pool->d_partials, pool->d_out_first, pool->chunks, first, count,
+                         d_out_override ? d_out_override : pool->d_out);
     FH_CUDA(cudaGetLastError());
     return FH_OK;
 }
@@ -836,7 +840,7 @@ extern "C" int fh_pool_gradients(const fh_pool *pool, const fh_state *psi, const
                first, first + count, pool->n_out);
     if (count == 0) return FH_OK;
     fh_ctx *ctx = pool->ctx;
-    FH_TRY(fh_enqueue_pool(pool, psi->d, lambda->d, first, count));
+    FH_TRY(fh_enqueue_pool(pool, psi->d, lambda->d, first, count, nullptr));
     if (!out) return FH_OK;     // enqueue only (results stay on the device); used to time the kernel alone
     FH_CUDA(cudaMemcpyAsync(pool->h_out, pool->d_out + first, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->stream));
     FH_CUDA(cudaStreamSynchronize(ctx->stream));

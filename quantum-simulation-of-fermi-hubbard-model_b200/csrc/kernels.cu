@@ -712,7 +712,8 @@ __global__ void __launch_bounds__(256) k_apply_table4(const TabGroup *__restrict
                                                       const double2 *__restrict__ vals, int nvals,
                                                       const double2 *__restrict__ in, double2 *__restrict__ out,
                                                       unsigned nblk, double *__restrict__ partials,
-                                                      const double2 *__restrict__ dtab) {
+                                                      const double2 *__restrict__ dtab, unsigned *__restrict__ counter,
+                                                      double *__restrict__ result) {
     constexpr int R = 1 << RL;                    // outputs per thread: i0 | (r << 8), r < R
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[8];
@@ -819,9 +820,29 @@ __global__ void __launch_bounds__(256) k_apply_table4(const TabGroup *__restrict
     }
     const double sr = block_sum<256>(er, red);
     const double si = block_sum<256>(ei, red);
+    // the last CTA to finish folds all per-CTA partials in slot order (deterministic) -- no separate finalize launch
+    __shared__ unsigned is_last;
     if (threadIdx.x == 0) {
         partials[2 * blockIdx.x] = sr;
         partials[2 * blockIdx.x + 1] = si;
+        __threadfence();
+        is_last = (atomicAdd(counter, 1u) == gridDim.x - 1u) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double r = 0.0, im = 0.0;
+        for (int t = threadIdx.x; t < (int)gridDim.x; t += blockDim.x) {
+            r += __ldcg(partials + 2 * t);
+            im += __ldcg(partials + 2 * t + 1);
+        }
+        const double fr = block_sum<256>(r, red);
+        const double fi = block_sum<256>(im, red);
+        if (threadIdx.x == 0) {
+            result[0] = fr;
+            result[1] = fi;
+            *counter = 0u;
+        }
     }
 }
 
@@ -1382,7 +1403,7 @@ void launch_apply_table(cudaStream_t s, int sm, const fh_table *tab, const doubl
         ++g_fh_launch_count;                                                                                        \
         k_apply_table4<I, R, M, RLV><<<grid, 256, smem, s>>>(tab->d_groups, ngroups, tab->d_classes, nclasses,      \
                                                              tab->d_vals, nvals, in, out, nblk, d_partials,         \
-                                                             tab->d_diag);                                          \
+                                                             tab->d_diag, tab->ctx->d_counter, d_result);           \
     } while (0)
 #define LAUNCH_TAB4_M(I, R, RLV)                                                                                    \
     do {                                                                                                            \
@@ -1397,7 +1418,6 @@ void launch_apply_table(cudaStream_t s, int sm, const fh_table *tab, const doubl
 #undef LAUNCH_TAB4_I
 #undef LAUNCH_TAB4_M
 #undef LAUNCH_TAB4
-        ++g_fh_launch_count; k_finalize_pairs<<<1, 256, 0, s>>>(d_partials, grid, d_result);
         return;
     }
     grid = grid_for(dim, 256, 1, sm, FH_MAX_PARTIALS);

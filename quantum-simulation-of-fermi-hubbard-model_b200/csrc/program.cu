@@ -10,7 +10,8 @@
 
 int fh_fill_pair(PairOp *op, int n, u64 x, u64 fixmask, u64 fixval, u64 zeta, const double m[8]);
 int fh_enqueue_apply_table(const fh_table *tab, const double2 *in, double2 *out, int result_slot);
-int fh_enqueue_pool(const fh_pool *pool, const double2 *psi, const double2 *lam, int first, int count);
+int fh_enqueue_pool(const fh_pool *pool, const double2 *psi, const double2 *lam, int first, int count,
+                    double *d_out_override);
 
 #define FH_MAX_RESULT_TABLES 8
 #define FH_MAX_OVERLAPS 8
@@ -63,7 +64,9 @@ struct fh_program {
     int *d_gfirst = nullptr;
     int n_param_ops = 0;
     // results (pinned)
+    // results: [0, 64) scalars (expvals, overlaps) | [64, 64 + segs) gradient segments | pool outputs; ONE D2H copy
     double *h_res = nullptr, *d_res = nullptr;
+    int res_segs = 0, res_pool_cap = 0;
     // graph cache
     bool have_graph = false;
     EvalKey key;
@@ -118,10 +121,8 @@ extern "C" int fh_program_destroy(fh_program *p) {
     cudaFree(p->d_lam);
     cudaFree(p->d_chk);
     cudaFree(p->d_gpart);
-    cudaFree(p->d_gseg);
     cudaFree(p->d_gfirst);
     cudaFree(p->d_res);
-    cudaFreeHost(p->h_gseg);
     cudaFreeHost(p->h_res);
     delete p;
     return FH_OK;
@@ -406,11 +407,13 @@ extern "C" int fh_program_finalize(fh_program *p) {
     p->n_param_ops = n_param_ops;
     const int segs = n_param_ops > 0 ? n_param_ops : 1;
     FH_CUDA(cudaMalloc(&p->d_gpart, sizeof(double) * (size_t)segs * FH_GRAD_BLOCKS));
-    FH_CUDA(cudaMalloc(&p->d_gseg, sizeof(double) * segs));
     FH_CUDA(cudaMalloc(&p->d_gfirst, sizeof(int) * (segs + 1)));
-    FH_CUDA(cudaMallocHost(&p->h_gseg, sizeof(double) * segs));
-    FH_CUDA(cudaMalloc(&p->d_res, sizeof(double) * 64));
-    FH_CUDA(cudaMallocHost(&p->h_res, sizeof(double) * 64));
+    p->res_segs = segs;
+    p->res_pool_cap = 0;
+    FH_CUDA(cudaMalloc(&p->d_res, sizeof(double) * (64 + segs)));
+    FH_CUDA(cudaMallocHost(&p->h_res, sizeof(double) * (64 + segs)));
+    p->d_gseg = p->d_res + 64;
+    p->h_gseg = p->h_res + 64;
     FH_CUDA(cudaStreamSynchronize(ctx->stream));
     p->finalized = true;
     return FH_OK;
@@ -633,8 +636,10 @@ static int enqueue_evaluation(fh_program *p, const EvalKey &k, fh_table *const *
         launch_inner(ctx->stream, ctx->sm_count, targets[v]->d, psi, 1ull << p->n, ctx->d_partials,
                      p->d_res + 2 * k.n_tables + 2 * v);
     if (state_out) FH_CUDA(cudaMemcpyAsync(state_out->d, psi, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
-    FH_CUDA(cudaMemcpyAsync(p->h_res, p->d_res, sizeof(double) * 2 * (k.n_tables + k.n_overlaps + 1),
-                            cudaMemcpyDeviceToHost, ctx->stream));
+    if (!need_adjoint)
+        FH_CUDA(cudaMemcpyAsync(p->h_res, p->d_res, sizeof(double) * 2 * (k.n_tables + k.n_overlaps + 1),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    double *d_pool_out = p->d_res + 64 + p->res_segs;          // pool outputs land next to the other results
 
     p->n_segments = 0;
     p->seg_param.clear();
@@ -647,18 +652,17 @@ static int enqueue_evaluation(fh_program *p, const EvalKey &k, fh_table *const *
         if (chk_pos < n_items) psi = p->d_chk;
         int stop = want_grads ? first_param : n_items;      // lowest item the sweep must undo
         if (want_pool && k.pool_pos < stop) stop = k.pool_pos;
-        if (want_pool && k.pool_pos == chk_pos) FH_TRY(fh_enqueue_pool(pool, psi, lam, k.pool_first, k.pool_count));
+        if (want_pool && k.pool_pos == chk_pos)
+            FH_TRY(fh_enqueue_pool(pool, psi, lam, k.pool_first, k.pool_count, d_pool_out));
         for (int i = chk_pos - 1; i >= stop; --i) {
             adjoint_item(p, p->items[i], psi, lam, want_grads);
-            if (want_pool && k.pool_pos == i) FH_TRY(fh_enqueue_pool(pool, psi, lam, k.pool_first, k.pool_count));
+            if (want_pool && k.pool_pos == i)
+                FH_TRY(fh_enqueue_pool(pool, psi, lam, k.pool_first, k.pool_count, d_pool_out));
         }
-        if (p->n_segments > 0) {
-            launch_sum_strided(ctx->stream, p->d_gpart, FH_GRAD_BLOCKS, p->n_segments, p->d_gseg);
-            FH_CUDA(cudaMemcpyAsync(p->h_gseg, p->d_gseg, sizeof(double) * p->n_segments, cudaMemcpyDeviceToHost, ctx->stream));
-        }
-        if (want_pool && k.pool_count > 0)
-            FH_CUDA(cudaMemcpyAsync(pool->h_out, pool->d_out + k.pool_first, sizeof(double) * k.pool_count,
-                                    cudaMemcpyDeviceToHost, ctx->stream));
+        if (p->n_segments > 0) launch_sum_strided(ctx->stream, p->d_gpart, FH_GRAD_BLOCKS, p->n_segments, p->d_gseg);
+        // scalars, gradient segments and pool outputs in one copy
+        const size_t n_res = 64 + (size_t)p->res_segs + (want_pool ? (size_t)(k.pool_first + k.pool_count) : 0);
+        FH_CUDA(cudaMemcpyAsync(p->h_res, p->d_res, sizeof(double) * n_res, cudaMemcpyDeviceToHost, ctx->stream));
     }
     FH_CUDA(cudaGetLastError());
     return FH_OK;
@@ -699,6 +703,20 @@ extern "C" int fh_program_evaluate(fh_program *p, uint64_t basis_index, const do
     fh_ctx *ctx = p->ctx;
     FH_CUDA(cudaSetDevice(ctx->device));
     FH_TRY(ensure_workspaces(p));
+    if (pool && pool->n_out > p->res_pool_cap) {
+        // grow the result buffers so the pool outputs fit behind the scalars and gradient segments
+        FH_CUDA(cudaStreamSynchronize(ctx->stream));
+        drop_graph(p);
+        cudaFree(p->d_res);
+        cudaFreeHost(p->h_res);
+        p->d_res = p->h_res = nullptr;
+        const size_t n_res = 64 + (size_t)p->res_segs + (size_t)pool->n_out;
+        FH_CUDA(cudaMalloc(&p->d_res, sizeof(double) * n_res));
+        FH_CUDA(cudaMallocHost(&p->h_res, sizeof(double) * n_res));
+        p->d_gseg = p->d_res + 64;
+        p->h_gseg = p->h_res + 64;
+        p->res_pool_cap = pool->n_out;
+    }
 
     // theta -> payload in the pinned staging buffers (the graph's first nodes copy them to the device)
     refresh_payload(p, thetas);
@@ -767,7 +785,7 @@ extern "C" int fh_program_evaluate(fh_program *p, uint64_t basis_index, const do
         for (int q = 0; q < p->n_params; ++q) grads[q] = 0.0;
         for (int s = 0; s < p->n_segments; ++s) grads[p->seg_param[s]] += p->seg_scale[s] * p->h_gseg[s];
     }
-    if (pool && pool_count > 0) memcpy(pool_out, pool->h_out, sizeof(double) * pool_count);
+    if (pool && pool_count > 0) memcpy(pool_out, p->h_res + 64 + p->res_segs + pool_first, sizeof(double) * pool_count);
     return FH_OK;
 }
 
