@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""BASELINE.json configs 1-4 end to end through the drop-in drivers (wall clock on one B200).
+   python tools/run_configs.py [--json out.json]
+cfg1 ADAPT 2x2 (the reference's own CPU-runnable case), cfg2 HVA 2x3, cfg3 ADAPT 3x3 (first epochs), cfg4 iQCC 3x3
+(Lanczos ground state + first epoch).  Energies are checked against the drivers' own ED reference, not an oracle."""
+import contextlib, io, json, os, sys, tempfile, time
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [R, os.path.join(R, "quantum-simulation-of-fermi-hubbard-model_b200")]
+import numpy as np
+import torch
+
+out = {}
+os.chdir(tempfile.mkdtemp(prefix="fhsim_cfg_"))
+
+
+def quiet(fn):
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        t0 = time.perf_counter()
+        res = fn()
+        dt = time.perf_counter() - t0
+    return res, dt
+
+
+# ---- cfg1: ADAPT-VQE 2x2, U=4, (2,2): run to 6 epochs ---------------------------------------------------------
+from models.adapt_vqe import ADAPT
+vqe, t_init = quiet(lambda: ADAPT(n_epoch=6, threshold1=1e-2, threshold2=1e-2, x_dimension=2, y_dimension=2, n_electrons=4,
+                                  n_spin_up=2, n_spin_down=2, tunneling=1, coulomb=4, verbose=False))
+_, t_run = quiet(vqe.run)
+out["cfg1_adapt_2x2"] = {"init_s": t_init, "run_s": t_run, "epochs": len(vqe.results["epoch loss"]),
+                         "optimizer_iterations": len(vqe.results["iteration loss"]),
+                         "ms_per_iteration": 1e3 * t_run / max(1, len(vqe.results["iteration loss"])),
+                         "final_energy": vqe.results["epoch loss"][-1], "ed_energy": float(vqe.ground_state_energy),
+                         "final_fidelity": vqe.results["fidelity"][-1], "n_params": vqe.results["n_params"][-1]}
+print("cfg1", out["cfg1_adapt_2x2"])
+
+# ---- cfg2: HVA 2x3, reps=4, energy + gradients, 100 Adam epochs ------------------------------------------------
+from models.hva import HVA
+hva, t_init = quiet(lambda: HVA(n_epoch=100, reps=4, lr=1e-2, threshold=1e-2, x_dimension=2, y_dimension=3, n_electrons=6,
+                                n_spin_up=3, n_spin_down=3, tunneling=1, coulomb=4, verbose=False))
+rng = np.random.default_rng(20260)
+with torch.no_grad():
+    for k in ("theta_U", "theta_h", "theta_v"):
+        hva.params[k].copy_(torch.from_numpy(rng.uniform(-0.3, 0.3, hva.params[k].numel()).astype(np.float32)))
+_, t_run = quiet(hva.run)
+out["cfg2_hva_2x3"] = {"init_s": t_init, "run_s": t_run, "epochs": len(hva.results["loss"]),
+                       "ms_per_epoch": 1e3 * t_run / len(hva.results["loss"]), "first_loss": hva.results["loss"][0],
+                       "last_loss": hva.results["loss"][-1], "ed_energy": float(hva.ground_state_energy)}
+print("cfg2", out["cfg2_hva_2x3"])
+
+# ---- cfg3: ADAPT-VQE 3x3, U=6, (5,4): two epochs (52 + next batch of operators) ---------------------------------
+from models.adapt_vqe_for_3x3 import ADAPT as ADAPT33
+a33, t_init = quiet(lambda: ADAPT33(n_epoch=2, threshold1=1e-2, threshold2=5e-2, x_dimension=3, y_dimension=3,
+                                    n_electrons=9, n_spin_up=5, n_spin_down=4, tunneling=1, coulomb=6, verbose=False))
+_, t_sel = quiet(a33.select_operator)
+_, t_run = quiet(a33.run)
+out["cfg3_adapt_3x3"] = {"init_s_incl_lanczos_k4": t_init, "first_screening_s": t_sel, "run_s": t_run,
+                         "epochs": len(a33.results["epoch loss"]),
+                         "optimizer_iterations": len(a33.results["iteration loss"]),
+                         "ms_per_iteration": 1e3 * t_run / max(1, len(a33.results["iteration loss"])),
+                         "first_loss": a33.results["iteration loss"][0], "final_energy": a33.results["epoch loss"][-1],
+                         "ed_energy": float(a33.ground_state_energy), "final_fidelity": a33.results["fidelity"][-1],
+                         "n_params": a33.results["n_params"]}
+print("cfg3", out["cfg3_adapt_3x3"])
+
+# ---- cfg4: iQCC 3x3: full-space Lanczos + one epoch --------------------------------------------------------------
+from fhsim.symbolic import fermi_hubbard
+from models.iqcc_hubbard import IQCC
+iq, t_init = quiet(lambda: IQCC(fermi_hubbard(3, 3, 1.0, 6.0), n_epoch=1, lr=1e-2, threshold=5e-2, verbose=False))
+n_terms0 = len(iq.currentHamiltonian.terms)
+_, t_run = quiet(iq.run)
+out["cfg4_iqcc_3x3"] = {"init_s_incl_full_space_lanczos": t_init, "run_s": t_run, "ed_energy": float(iq.ground_state_energy),
+                        "iterations": len(iq.loss_history["iteration"]), "epoch_energy": iq.loss_history["epoch"],
+                        "h_terms_before": n_terms0, "h_terms_after_dressing": len(iq.currentHamiltonian.terms), "Ng": iq.Ng}
+print("cfg4", out["cfg4_iqcc_3x3"])
+
+if len(sys.argv) > 2 and sys.argv[1] == "--json":
+    json.dump(out, open(os.path.join(R, sys.argv[2]), "w"), indent=1)
