@@ -104,7 +104,9 @@ struct __align__(16) TileRec {          // 144 bytes = 9 x 16 B; k_tile reads it
     unsigned lowmask[4];
     // word 3: nterms (diag); seg = index of this op among the tile's parametrised ops in execution order of this
     // direction, or -1 (used by the fused adjoint sweep, which runs the dagger records)
-    int nterms, seg, pad[2];
+    int nterms, seg;
+    unsigned zeta_local;                // in-tile bits of zeta in tile-local coordinates (sign without an index load)
+    int pad;
     // words 4..7
     double m[8];
     // word 8: normalised generator element of a rotation op (gradient of the adjoint sweep)

@@ -342,17 +342,25 @@ __global__ void __launch_bounds__(512, 2) k_tile(double2 *__restrict__ psi, cons
                     const double2 *mp = reinterpret_cast<const double2 *>(rec[sidx].m);
                     const double2 ma = mp[0], mb = mp[1], mc = mp[2], md = mp[3];
                     const unsigned npairs = L >> q1.z;
+                    // warp-uniform per op: sign of the out-of-tile bits, slot-space image of the x-mask (the slot map
+                    // is XOR-linear), in-tile part of zeta in local coordinates
+                    const unsigned sbase = (unsigned)__popc(base & q0.z);
+                    const unsigned zloc = rp[3].z;
+                    const unsigned xs = tile_slot(q0.w);
+                    const int nlfix = (int)q1.z;
                     for (unsigned k = threadIdx.x; k < npairs; k += blockDim.x) {
                         unsigned il = k;
                         il = ((il & ~q2.x) << 1) | (il & q2.x);
                         il = ((il & ~q2.y) << 1) | (il & q2.y);
-                        il = ((il & ~q2.z) << 1) | (il & q2.z);
-                        il = ((il & ~q2.w) << 1) | (il & q2.w);
+                        if (nlfix > 2) {
+                            il = ((il & ~q2.z) << 1) | (il & q2.z);
+                            il = ((il & ~q2.w) << 1) | (il & q2.w);
+                        }
                         il |= q1.x;
-                        const unsigned jl = tile_slot(il ^ q0.w);
+                        const double sg = ((sbase + (unsigned)__popc(il & zloc)) & 1u) ? -1.0 : 1.0;
                         il = tile_slot(il);
+                        const unsigned jl = il ^ xs;
                         double2 a = buf[il], b = buf[jl];
-                        const double sg = (__popc(gidx[il] & q0.z) & 1) ? -1.0 : 1.0;
                         if (type == 3) {
                             const double s01 = sg * mb.x, s10 = sg * mc.x;
                             const double2 ra = make_double2(ma.x * a.x + s01 * b.x, ma.x * a.y + s01 * b.y);

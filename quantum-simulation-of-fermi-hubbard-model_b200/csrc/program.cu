@@ -326,6 +326,8 @@ static void build_tile_records(fh_program *p) {
                         }
                     r.nlfix = nl;
                     r.lfixval = lv;
+                    for (int b = 0; b < t.nbits; ++b)
+                        if (op.zeta >> t.bits[b] & 1ull) r.zeta_local |= 1u << b;
                     (dir ? p->pair_rec_dag : p->pair_rec_fwd)[sub.index] = (int)recs.size();
                 } else {
                     const DiagOp &d = p->diagops[sub.index];
