@@ -264,6 +264,9 @@ void launch_diag_adjoint(cudaStream_t s, int sm, double2 *psi, double2 *lam, con
                          double *d_partials, int max_blocks, int *blocks_used);
 void launch_tile(cudaStream_t s, double2 *psi, const TileLaunch &tl, const TileRec *d_recs, const TileTerm *d_terms,
                  int n);
+// nl consecutive tile runs in one cooperative launch (grid barriers between runs); returns 0 if unavailable
+int launch_tile_multi(cudaStream_t s, int sm, double2 *psi, const TileLaunch *d_tls, int nl, int max_bits, int min_bits,
+                      const TileRec *d_recs, const TileTerm *d_terms, int n);
 // fused adjoint step of a whole tile run (dagger records): gradient partials of every parametrised op into
 // gpart[(seg_base + rec.seg) * FH_GRAD_BLOCKS + block], then the inverse op on psi AND lam
 void launch_tile_adjoint(cudaStream_t s, double2 *psi, double2 *lam, const TileLaunch &tl, const TileRec *d_recs,

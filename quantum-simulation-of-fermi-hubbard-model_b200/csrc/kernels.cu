@@ -11,6 +11,8 @@
 //   k_apply_table             K2: out = H in fused with <in|H|in>
 //   k_pool / k_pool_finalize  K3: batched pool gradients 2 Im <lambda|G_k|psi>
 //   k_inner, k_axpby, ...     K4: Lanczos vector kernels
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 #define FULL 0xffffffffu
@@ -264,10 +266,9 @@ __device__ __forceinline__ unsigned tile_slot(unsigned l) {
     return l ^ ((l >> 3) & 7u) ^ ((l >> 6) & 7u) ^ ((l >> 9) & 7u) ^ ((l >> 12) & 7u);
 }
 
-__global__ void __launch_bounds__(512, 2) k_tile(double2 *__restrict__ psi, const TileLaunch tl,
-                                              const TileRec *__restrict__ recs, const TileTerm *__restrict__ terms,
-                                              int n) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ void tile_run(double2 *__restrict__ psi, const TileLaunch &tl,
+                                         const TileRec *__restrict__ recs, const TileTerm *__restrict__ terms, int n,
+                                         unsigned char *smem_raw) {
     __shared__ TileRec rec[TILE_MAX_SUB];
     __shared__ TileTerm tterm[TILE_MAX_TERMS];
     __shared__ unsigned slo[64], shi[128];      // scatter tables: local index bits -> global bit positions
@@ -429,6 +430,30 @@ __global__ void __launch_bounds__(512, 2) k_tile(double2 *__restrict__ psi, cons
             psi[gidx[sl]] = buf[sl];
         }
         __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(512, 2) k_tile(double2 *__restrict__ psi, const TileLaunch tl,
+                                                 const TileRec *__restrict__ recs, const TileTerm *__restrict__ terms,
+                                                 int n) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    tile_run(psi, tl, recs, terms, n, smem_raw);
+}
+
+// Several consecutive tile runs in ONE cooperative launch: a grid-wide barrier replaces the kernel boundary between
+// runs (the 18-qubit regime is launch-latency bound: 13 runs for the forward pass of the benchmark circuit).
+__global__ void __launch_bounds__(512, 2) k_tile_multi(double2 *__restrict__ psi, const TileLaunch *__restrict__ tls,
+                                                       int nl, const TileRec *__restrict__ recs,
+                                                       const TileTerm *__restrict__ terms, int n) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ TileLaunch tl;
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    for (int l = 0; l < nl; ++l) {
+        if (threadIdx.x < sizeof(TileLaunch) / 4)
+            reinterpret_cast<unsigned *>(&tl)[threadIdx.x] = reinterpret_cast<const unsigned *>(tls + l)[threadIdx.x];
+        __syncthreads();
+        tile_run(psi, tl, recs, terms, n, smem_raw);
+        if (l + 1 < nl) grid.sync();
     }
 }
 
@@ -1371,6 +1396,38 @@ void launch_tile(cudaStream_t s, double2 *psi, const TileLaunch &tl, const TileR
     if (threads < 64) threads = 64;
     ++g_fh_launch_count;
     k_tile<<<grid, threads, smem, s>>>(psi, tl, d_recs, d_terms, n);
+}
+
+static int g_tile_multi_blocks_per_sm = -1;
+
+// returns 0 when the cooperative launch cannot be used (caller falls back to one launch per run)
+int launch_tile_multi(cudaStream_t s, int sm, double2 *psi, const TileLaunch *d_tls, int nl, int max_bits, int min_bits,
+                      const TileRec *d_recs, const TileTerm *d_terms, int n) {
+    const size_t smem = ((size_t)1 << max_bits) * (sizeof(double2) + sizeof(unsigned int));
+    int threads = max_bits >= 1 ? (1 << (max_bits - 1)) : 1;
+    if (threads > 512) threads = 512;
+    if (threads < 64) threads = 64;
+    if (g_tile_multi_blocks_per_sm < 0) {
+        cudaFuncSetAttribute(k_tile_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_tile_multi, 512, ((size_t)1 << 12) * 20) != cudaSuccess) nb = 0;
+        g_tile_multi_blocks_per_sm = nb;
+    }
+    int per_sm = g_tile_multi_blocks_per_sm;
+    if (max_bits > 12) per_sm = per_sm > 1 ? 1 : per_sm;
+    if (per_sm <= 0) return 0;
+    const u64 ntiles = 1ull << (n - min_bits);
+    u64 grid = (u64)sm * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    void *args[] = {(void *)&psi, (void *)&d_tls, (void *)&nl, (void *)&d_recs, (void *)&d_terms, (void *)&n};
+    ++g_fh_launch_count;
+    if (cudaLaunchCooperativeKernel((const void *)k_tile_multi, dim3((unsigned)grid), dim3(threads), args, smem, s) !=
+        cudaSuccess) {
+        cudaGetLastError();
+        --g_fh_launch_count;
+        return 0;
+    }
+    return 1;
 }
 
 static bool g_tile_adj_attr_set = false;

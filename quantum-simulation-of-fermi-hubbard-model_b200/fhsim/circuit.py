@@ -13,6 +13,7 @@ the result to ``libfhsim`` through the C-ABI.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -426,6 +427,8 @@ class DeviceProgram:
         n = self.n
         if tile_bits is None:
             tile_bits = max(1, min(12, n - 7)) if n > 8 else n
+            if os.environ.get("FHSIM_TILE_BITS"):            # tuning knob (tools/, profiles/)
+                tile_bits = int(os.environ["FHSIM_TILE_BITS"])
         tile_bits = min(tile_bits, n, 13)
         if low_bits is None:
             low_bits = 1 if n <= 20 else 2
