@@ -123,7 +123,8 @@ int fh_program_create(fh_ctx *ctx, int n_qubits, int n_params, fh_program **out)
 int fh_program_destroy(fh_program *prog);
 int fh_program_add_pair(fh_program *prog, uint64_t x, uint64_t fixmask, uint64_t fixval, uint64_t zeta,
                         int kind, int param, double scale, double bhat_re, double bhat_im, const double m[8]);
-/* diagonal op; param < 0: fixed angles coef[m]; else angle[m] = theta[param] * coef[m] */
+/* diagonal op; param < 0: fixed angles coef[m]; else angle[m] = theta[param] * coef[m].  z[m] == 0 is a plain phase
+ * exp(-i angle[m]) (it appears when a sharded state folds the rank bits of a Z string into a sign) */
 int fh_program_add_diag(fh_program *prog, int n_terms, const uint64_t *z, const double *coef, int param);
 /* ops added between begin/end are fused into ONE shared-memory tile kernel over the given bit positions
  * (ascending; every pair op inside must have its x-mask within those bits) */
