@@ -625,7 +625,7 @@ static void build_pool_passes(fh_pool *pool) {
         for (int e = 0; e < n_entries; ++e)
             if (popcnt(pool->entries[e].x) <= T) todo.push_back(e);
     std::vector<char> covered(n_entries, 0);
-    const int min_pass = 10;
+    const int min_pass = 24;      // measured: a pass costs about as much as 20-25 entries on k_pool32 (profiles/r01_s6_ncu_full_24q.md)
     while ((int)todo.size() >= min_pass) {
         u64 bits = 0;
         while (popcnt(bits) < T) {
