@@ -32,7 +32,7 @@ from __future__ import annotations
 import numpy as np
 
 from .circuit import DiagOpSpec, Marker, PairOpSpec
-from .tables import DiagPiece, GeneratorPlan, PauliTable, popcount
+from .tables import DiagPiece, PauliTable, popcount
 
 
 # ---------------------------------------------------------------------------------------------

@@ -7,7 +7,7 @@ from hypothesis import given, settings, strategies as st
 from emulate import apply_op, run_circuit, run_items
 from fhsim.circuit import Circuit, absorb_phases, schedule
 from fhsim.sharded import QubitLayout, dagger_ops, lower_diag, lower_pair, plan_circuit, swap_steps
-from fhsim.tables import GeneratorPlan, PauliTable, strings_commute
+from fhsim.tables import PauliTable, strings_commute
 from oracle import pauli, statevector as sv
 
 N = 6

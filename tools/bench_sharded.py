@@ -133,7 +133,7 @@ def main():
 
     check = None
     if args.check_single and rank == 0 and n <= 28:
-        from fhsim.backend import Context, DevicePool, DeviceTable
+        from fhsim.backend import DevicePool, DeviceTable
         ctx = engine.ctx
         c1 = Circuit(n, len(picks))
         for j, k in enumerate(picks):
