@@ -782,6 +782,27 @@ __global__ void __launch_bounds__(256) k_apply_table4(const TabGroup *__restrict
             // all R outputs see the same x-bit pattern unless the mask contains bit 8..10: a pattern no class has a
             // weight for (half of all cases for a hopping group) skips the class loop and the gathers
             if (rpat == 0u && !((g1.w >> pat0) & 1u)) continue;
+            if (REAL && rpat == 0u && g0.w == 1u) {
+                // one class, one shared table entry (every hopping group): the R weights are +-v, so only the sign
+                // bits are formed and applied to the gathered amplitudes -- no weight array, no liveness tests
+                const uint4 cl = Cl[g0.z];
+                unsigned sb;
+                if (sizeof(IDX) == 4) sb = __popc((unsigned)j0 & cl.x);
+                else sb = __popcll((u64)j0 & ((u64)cl.x | ((u64)cl.y << 32)));
+                const unsigned zr = cl.x >> 8;
+                const double v = V[cl.z + pat0].x;
+                double2 vv[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) vv[r] = in[j0 ^ ((IDX)r << 8)];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int f = (int)((sb + __popc(zr & (unsigned)r)) << 31);
+                    const double w = __hiloint2double(__double2hiint(v) ^ f, __double2loint(v));
+                    ar[r] += w * vv[r].x;
+                    ai[r] += w * vv[r].y;
+                }
+                continue;
+            }
             double wr[R], wi[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) wr[r] = wi[r] = 0.0;
