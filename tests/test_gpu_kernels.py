@@ -289,6 +289,44 @@ def test_program_evaluate_energy_grads_pool(ctx, lat, u, up, dn, fuse, separable
     assert abs(res2["expvals"][0] - e2) < E_TOL and np.abs(res2["grads"] - g2).max() < G_TOL
 
 
+def test_adjoint_gradient_vs_finite_difference_22_qubits(ctx):
+    """The n >= 20/22 branches inside fh_program_evaluate (K2 with 8 outputs per thread + diagonal factor tables,
+    standalone diagonal kernel through phase tables, fused adjoint tiles on 12-bit tiles) against central differences
+    of the same program's energy, plus norm and energy consistency with the immediate-mode K2."""
+    from operators.tools import get_interacting_term
+    nx, ny, u, n = 11, 1, 4.0, 22
+    h_op = fermi_hubbard(nx, ny, 1.0, u)
+    h_tab = PauliTable.from_operator(h_op, n)
+    coulomb = GeneratorPlan(jordan_wigner(get_interacting_term(h_op)), n)
+    circ = Circuit(n, 4)
+    for q in range(0, n, 3):
+        circ.ry(0.2 + 0.05 * q, q)
+    circ.generator(coulomb, param=0)
+    for a, b, p in ((0, 2, 1), (7, 9, 2), (12, 20, 1), (1, 3, 3), (15, 17, 2)):
+        circ.fermionic_single_excitation(0.3, a, b)
+        circ.pauli_rotation((1 << (n - 1 - a)) | (1 << (n - 1 - b)), 0, 0.5, param=p)
+    circ.generator(coulomb, param=3)
+    prog = circ.compile(ctx)
+    dtab = DeviceTable(ctx, h_tab)
+    thetas = np.array([0.31, -0.22, 0.57, 0.13])
+    basis = sum(1 << (n - 1 - q) for q in (0, 1, 4, 5, 8, 9, 12, 13, 16, 17, 20))
+    out = State(ctx, n)
+    res = prog.evaluate(basis, thetas, [dtab], grads=True, state_out=out)
+    assert abs(out.norm2() - 1.0) < 1e-12
+    assert abs(dtab.expval(out) - res["expvals"][0]) < 1e-10
+    hstep = 1e-5
+    for j in range(4):
+        tp, tm = thetas.copy(), thetas.copy()
+        tp[j] += hstep
+        tm[j] -= hstep
+        fd = (prog.evaluate(basis, tp, [dtab])["expvals"][0] - prog.evaluate(basis, tm, [dtab])["expvals"][0]) / (2 * hstep)
+        assert abs(res["grads"][j] - fd) < 2e-8, (j, res["grads"][j], fd)
+    unfused = circ.compile(ctx, fuse=False)
+    res2 = unfused.evaluate(basis, thetas, [dtab], grads=True)
+    assert abs(res2["expvals"][0] - res["expvals"][0]) < 1e-10
+    assert np.abs(res2["grads"] - res["grads"]).max() < 1e-9
+
+
 def test_known_answers_3x3_first_screening(ctx):
     """E_HF = -5/3 and exactly 52 operators at |g| = 4/3 through the CUDA path."""
     n, h_tab, pool_ops, dec, diag, _, _ = lattice(3, 3, 6.0)
