@@ -112,24 +112,56 @@ class ADAPT(HubbardProblem):
         return float(np.abs(overlaps[0]) ** 2)
 
     # -- checkpoints ----------------------------------------------------------------------------
+    def _pool_index_of(self, gate):
+        """Index of a selected gate in the pool (identity first, then by generator: unpickled gates are copies)."""
+        for i, g in enumerate(self.gateOperatorPool):
+            if g is gate:
+                return i
+        gen = gate.keywords['generator'] if hasattr(gate, 'keywords') else None
+        for i, g in enumerate(self.gateOperatorPool):
+            if gen is not None and g.keywords['generator'] == gen:
+                return i
+        raise ValueError('selected gate is not in the operator pool')
+
     def save_model(self):
+        """Reference layout (pickle of the ParameterDict + gate closures, adapt_vqe.py:269-280) plus a portable twin
+        ``<model>.npz`` (pool indices of the selected operators, parameters, results as JSON): the pickles embed
+        torch / operator classes and do not travel between installations."""
+        import json
         ensure_parent(self.model_filepath)
         ensure_parent(self.result_filepath)
         with open(self.model_filepath, 'wb') as file:
             pickle.dump({'params': self.params, 'circuit': self.selected_gates}, file)
         with open(self.result_filepath, 'wb') as file:
             pickle.dump(self.results, file)
+        indices = [self._pool_index_of(g) for g in self.selected_gates]
+        portable = {k: v for k, v in self.results.items() if k != 'selected operators'}
+        np.savez(self.model_filepath + '.npz', selected_indices=np.asarray(indices, dtype=np.int64),
+                 t=self.params['t'].detach().cpu().numpy(), results_json=np.asarray(json.dumps(portable)))
 
     def load_model(self):
-        for path in (self.model_filepath, self.result_filepath):
-            if not os.path.exists(path):
-                raise ValueError('Please check if the file ' + path + 'exists!')
-        with open(self.model_filepath, 'rb') as file:
-            state_dict = pickle.load(file)
-        self.params = state_dict['params'].to(self.device)
-        self.selected_gates = state_dict['circuit']
-        with open(self.result_filepath, 'rb') as file:
-            self.results = pickle.load(file)
+        """Pickles if both exist (reference behaviour, adapt_vqe.py:282-295), else the portable ``.npz`` twin."""
+        import json
+        if os.path.exists(self.model_filepath) and os.path.exists(self.result_filepath):
+            with open(self.model_filepath, 'rb') as file:
+                state_dict = pickle.load(file)
+            self.params = state_dict['params'].to(self.device)
+            self.selected_gates = state_dict['circuit']
+            with open(self.result_filepath, 'rb') as file:
+                self.results = pickle.load(file)
+            return
+        twin = self.model_filepath + '.npz'
+        if not os.path.exists(twin):
+            raise ValueError('Please check if the file ' + self.model_filepath + 'exists!')
+        data = np.load(twin)
+        indices = [int(i) for i in data['selected_indices']]
+        self.selected_gates = [self.gateOperatorPool[i] for i in indices]
+        self.params = nn.ParameterDict({
+            'e': nn.Parameter(torch.zeros(len(self.gateOperatorPool)), requires_grad=True),
+            't': nn.Parameter(torch.from_numpy(np.asarray(data['t'], dtype=np.float32)), requires_grad=True),
+        }).to(self.device)
+        self.results = json.loads(str(data['results_json']))
+        self.results['selected operators'] = [self.fermionOperatorPool[i] for i in indices]
 
     # -- circuit --------------------------------------------------------------------------------
     def build_circuit(self) -> Circuit:

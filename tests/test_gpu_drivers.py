@@ -79,6 +79,16 @@ def test_adapt_2x2_first_epochs_match_oracle():
                   n_spin_up=2, n_spin_down=2, tunneling=1, coulomb=u, verbose=False, load_model=True)
     assert torch.equal(again.params['t'], vqe.params['t']) and len(again.selected_gates) == len(vqe.selected_gates)
     assert abs(again.circuit(mode='train')[0].item() - e_or) < 1e-10
+    # portable twin: remove the pickles, resume from <model>.npz
+    os.remove(vqe.model_filepath)
+    os.remove(vqe.result_filepath)
+    twin = ADAPT(n_epoch=2, threshold1=1e-2, threshold2=5e-2, x_dimension=nx, y_dimension=ny, n_electrons=4,
+                 n_spin_up=2, n_spin_down=2, tunneling=1, coulomb=u, verbose=False, load_model=True)
+    assert torch.equal(twin.params['t'], vqe.params['t'])
+    assert [twin._pool_index_of(g) for g in twin.selected_gates] == sel
+    assert twin.results['epoch loss'] == vqe.results['epoch loss']
+    assert twin.results['selected operators'] == vqe.results['selected operators']
+    assert abs(twin.circuit(mode='train')[0].item() - e_or) < 1e-10
 
 
 def test_adapt_2x3_selection_sequence():
