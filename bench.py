@@ -387,8 +387,7 @@ def run_gpu_arm(args, rank, world, local_rank):
 
     value = world * n_pool * args.steps / (total_ms * 1e-3)
     e2e_value = world * n_pool * args.steps / e2e_total
-    h2d = 160 * len(wl["circ"].ops)            # op payload staged from pinned host memory each step (upper bound)
-    d2h = 8 * (n_pool + 4)
+    h2d, d2h = prog.payload_bytes()            # pinned op-payload arena in, scalars + pool gradients out (per step)
     line = {
         "metric": METRIC, "value": value, "unit": "gradients/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,

@@ -150,6 +150,9 @@ int fh_program_evaluate(fh_program *prog, uint64_t basis_index, const double *th
                         int n_overlaps, fh_state *const *targets, double *overlaps,
                         fh_state *state_out);
 
+/* measurement: bytes one fh_program_evaluate call copies host->device (the theta-dependent op payload, one pinned
+ * arena) and at most device->host (scalars + gradient segments + pool outputs) */
+int fh_program_payload_bytes(const fh_program *prog, size_t *h2d_bytes, size_t *d2h_bytes);
 /* measurement: device time (CUDA events bracketing the graph launch on the context's stream) and number of
  * kernel launches of the most recent fh_program_evaluate call */
 int fh_program_last_stats(const fh_program *prog, double *elapsed_ms, int *kernel_launches);

@@ -860,6 +860,13 @@ extern "C" int fh_program_evaluate(fh_program *p, uint64_t basis_index, const do
     return FH_OK;
 }
 
+extern "C" int fh_program_payload_bytes(const fh_program *p, size_t *h2d_bytes, size_t *d2h_bytes) {
+    FH_REQUIRE(p && p->finalized, "fh_program_payload_bytes: program missing or not finalized");
+    if (h2d_bytes) *h2d_bytes = p->arena_bytes;
+    if (d2h_bytes) *d2h_bytes = sizeof(double) * (64 + (size_t)p->res_segs + (size_t)p->res_pool_cap);
+    return FH_OK;
+}
+
 extern "C" int fh_program_last_stats(const fh_program *p, double *elapsed_ms, int *kernel_launches) {
     FH_REQUIRE(p, "fh_program_last_stats: program is NULL");
     if (elapsed_ms) *elapsed_ms = p->last_ms;

@@ -498,6 +498,12 @@ class DeviceProgram:
         _cabi.check(_cabi.lib().fh_program_last_stats(self._h, _cabi.C.byref(ms), _cabi.C.byref(nl)))
         return ms.value, nl.value
 
+    def payload_bytes(self):
+        """(host->device, device->host) bytes of one ``evaluate`` call."""
+        a, b = _cabi.C.c_size_t(), _cabi.C.c_size_t()
+        _cabi.check(_cabi.lib().fh_program_payload_bytes(self._h, _cabi.C.byref(a), _cabi.C.byref(b)))
+        return a.value, b.value
+
     def time_items(self, state, first=0, count=None, dagger=False, reps=20):
         """Average device milliseconds of items [first, first+count) launched back to back (measurement)."""
         if count is None:
