@@ -613,6 +613,8 @@ class CudaEngine:
         self.ctx = Context(device, stream=_cabi.C.c_void_p(self.stream.cuda_stream))
         self._spare = None
         self._programs = {}             # compiled local segments, keyed by the planner
+        self._tables = {}               # uploaded per-layout observable tables
+        self._pools = {}                # uploaded per-layout screening pools
         self.a2a_ms = 0.0
         self._host_staged = dist is not None and dist.get_backend() == "gloo"
 
@@ -699,26 +701,32 @@ class CudaEngine:
     def apply_table(self, local_tab, h_in, h_out, accumulate):
         from .backend import DeviceTable
         C = self._cabi.C
-        tab = DeviceTable(self.ctx, local_tab)
-        try:
-            re, im = C.c_double(), C.c_double()
-            fn = self._cabi.lib().fh_apply_table_accumulate if (accumulate and h_out is not None) \
-                else self._cabi.lib().fh_apply_table
-            self._cabi.check(fn(tab._h, h_in[0].st._h, h_out[0].st._h if h_out is not None else None,
-                                C.byref(re), C.byref(im)))
-            return complex(re.value, im.value)
-        finally:
-            tab.close()
+        # per-layout tables recur every evaluation: keep the uploaded ones (small) instead of rebuilding them
+        key = (local_tab.x.tobytes(), local_tab.z.tobytes(), local_tab.coeff.tobytes())
+        tab = self._tables.get(key)
+        if tab is None:
+            if len(self._tables) >= 16:
+                self._tables.pop(next(iter(self._tables))).close()
+            tab = self._tables[key] = DeviceTable(self.ctx, local_tab)
+        re, im = C.c_double(), C.c_double()
+        fn = self._cabi.lib().fh_apply_table_accumulate if (accumulate and h_out is not None) \
+            else self._cabi.lib().fh_apply_table
+        self._cabi.check(fn(tab._h, h_in[0].st._h, h_out[0].st._h if h_out is not None else None,
+                            C.byref(re), C.byref(im)))
+        return complex(re.value, im.value)
 
     def pool_partial(self, local_entries, h_psi, h_lam, n_out):
         from .backend import DevicePool
         if not local_entries:
             return np.zeros(n_out)
-        pool = DevicePool.from_entries(self.ctx, self.n_local, local_entries, n_out)
-        try:
-            return pool.gradients(h_psi[0].st, h_lam[0].st).copy()
-        finally:
-            pool.close()
+        # the x-mask cover of a per-layout pool costs host time (greedy over ~10^3 entries): cache the uploaded pools
+        key = (n_out, tuple(local_entries))
+        pool = self._pools.get(key)
+        if pool is None:
+            if len(self._pools) >= 8:
+                self._pools.pop(next(iter(self._pools))).close()
+            pool = self._pools[key] = DevicePool.from_entries(self.ctx, self.n_local, local_entries, n_out)
+        return pool.gradients(h_psi[0].st, h_lam[0].st).copy()
 
     def inner(self, ha, hb):
         return ha[0].st.inner(hb[0].st)
