@@ -289,6 +289,57 @@ def test_program_evaluate_energy_grads_pool(ctx, lat, u, up, dn, fuse, separable
     assert abs(res2["expvals"][0] - e2) < E_TOL and np.abs(res2["grads"] - g2).max() < G_TOL
 
 
+@pytest.mark.parametrize("tile_bits", [3, 4, 7, 11, 12, 13])
+def test_tile_runs_random_gate_circuits(ctx, tile_bits):
+    """k_tile on random gate sequences (1-qubit rotations, CNOT, Givens, fermionic Givens, RZ, Pauli rotations with
+    Z tails, X) clustered on wire triples: every tile size, forward and dagger, against the numpy interpreter of
+    the op semantics and against the unfused k_pair / k_diag path."""
+    import emulate
+    n, n_params = 14, 6
+    rng = np.random.default_rng(1000 + tile_bits)
+    th = rng.uniform(-1.0, 1.0, n_params)
+    circ = Circuit(n, n_params)
+    for _ in range(14):
+        w = [int(v) for v in rng.choice(n, size=3, replace=False)]
+        for _ in range(int(rng.integers(1, 6))):
+            kind = int(rng.integers(0, 8))
+            a, b, c = (w[int(i)] for i in rng.permutation(3))
+            ang = float(rng.uniform(-2.0, 2.0))
+            if kind == 0:
+                circ.ry(0.0, a, param=int(rng.integers(n_params)))
+            elif kind == 1:
+                circ.rx(ang, a)
+            elif kind == 2:
+                circ.cnot(a, b)
+            elif kind == 3:
+                circ.single_excitation(ang, a, b)
+            elif kind == 4:
+                circ.fermionic_single_excitation(ang, a, b)
+            elif kind == 5:
+                circ.rz(ang, a)
+            elif kind == 6:
+                # Pauli string with X/Y letters on the triple and a Z tail elsewhere
+                x = circ._bit(a) | circ._bit(b) | (circ._bit(c) if rng.integers(2) else 0)
+                z = int(rng.integers(1 << n))
+                circ.pauli_rotation(x, z, 0.5, param=int(rng.integers(n_params)))
+            else:
+                circ.pauli_x(a)
+    psi0 = rand_state(n, 77 + tile_bits)
+    want = emulate.run_circuit(circ, psi0.copy(), th)
+    fused = circ.compile(ctx, tile_bits=tile_bits, low_bits=0)
+    assert fused.n_tiles > 0
+    st = State.from_numpy(ctx, psi0)
+    fused.run(st, th)
+    got = st.numpy()
+    assert np.abs(got - want).max() < AMP_TOL
+    plain = circ.compile(ctx, fuse=False)
+    st2 = State.from_numpy(ctx, psi0)
+    plain.run(st2, th)
+    assert np.abs(st2.numpy() - got).max() < AMP_TOL
+    fused.run(st, th, dagger=True)
+    assert np.abs(st.numpy() - psi0).max() < AMP_TOL
+
+
 def test_adjoint_gradient_vs_finite_difference_22_qubits(ctx):
     """The n >= 20/22 branches inside fh_program_evaluate (K2 with 8 outputs per thread + diagonal factor tables,
     standalone diagonal kernel through phase tables, fused adjoint tiles on 12-bit tiles) against central differences
