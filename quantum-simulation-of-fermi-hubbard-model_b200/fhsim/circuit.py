@@ -360,23 +360,62 @@ def absorb_phases(ops):
     return out
 
 
+def _noncommuting_bitsets(ops):
+    """For every op the set (Python int, bit j) of ops j it does NOT commute with, by the string-level rule of
+    ``_ops_commute``: some string of one anticommutes with some string of the other.  One vectorised sweep per op
+    over all strings of the circuit instead of a Python double loop per op pair (the scheduler asks O(ops x tiles)
+    such questions; 3x3 with 204 generators: 0.14 s -> ~0.02 s per compile)."""
+    m = len(ops)
+    starts, xs, zs = [], [], []
+    for op in ops:
+        starts.append(len(xs))
+        for (x, z) in op.strings:
+            xs.append(x)
+            zs.append(z)
+    if not xs:
+        return [0] * m
+    X, Z = np.array(xs, dtype=np.uint64), np.array(zs, dtype=np.uint64)
+    starts_a = np.array(starts, dtype=np.intp)
+    counts = np.diff(np.append(starts_a, len(xs)))
+    nonempty = counts > 0
+    # reduceat needs strictly valid segment starts: run it over the ops that own strings only
+    seg = starts_a[nonempty]
+    out = []
+    for i, op in enumerate(ops):
+        if not op.strings:
+            out.append(0)
+            continue
+        anti = np.zeros(len(xs), dtype=bool)
+        for (x, z) in op.strings:
+            anti |= ((np.bitwise_count(X & np.uint64(z)) + np.bitwise_count(Z & np.uint64(x))) & 1).astype(bool)
+        per_op = np.zeros(m, dtype=bool)
+        per_op[nonempty] = np.logical_or.reduceat(anti, seg)
+        out.append(int.from_bytes(np.packbits(per_op, bitorder="little").tobytes(), "little"))
+    return out
+
+
 def schedule(ops, n, tile_bits, low_bits, lookahead=512):
     """Greedy in-order packing of commuting-compatible ops into tiles.
 
     Returns a list of launch items: ('tile', [bit positions], [ops]) or ('op', op).  An op may jump
     ahead of skipped ops only if it commutes with every one of them (string-level check).
     """
+    ops = list(ops)
+    noncommuting = _noncommuting_bitsets(ops)
     items = []
-    remaining = list(ops)
+    remaining = list(range(len(ops)))
     base_bits = (1 << low_bits) - 1
     while remaining:
         bits = base_bits
         chosen, skipped = [], []
+        skipped_set = 0
         scanned = n_terms = 0
-        for op in remaining:
+        for i in remaining:
+            op = ops[i]
             scanned += 1
-            if skipped and any(not _ops_commute(op, s) for s in skipped):
-                skipped.append(op)
+            if noncommuting[i] & skipped_set:
+                skipped.append(i)
+                skipped_set |= 1 << i
             else:
                 need = bits | op.tile_bits
                 nt = len(op.z) if isinstance(op, DiagOpSpec) else 0
@@ -385,21 +424,23 @@ def schedule(ops, n, tile_bits, low_bits, lookahead=512):
                         and n_terms + nt <= MAX_TILE_TERMS):
                     bits = need
                     n_terms += nt
-                    chosen.append(op)
+                    chosen.append(i)
                 else:
-                    skipped.append(op)
+                    skipped.append(i)
+                    skipped_set |= 1 << i
             if len(skipped) >= lookahead:
                 break
         rest = skipped + remaining[scanned:]
         if not chosen:                                   # cannot happen (first op always fits) but stay safe
-            items.append(("op", remaining[0]))
+            items.append(("op", ops[remaining[0]]))
             remaining = remaining[1:]
             continue
-        alone = sum(_op_bytes(o, n) + _LAUNCH_BYTES for o in chosen)
+        chosen_ops = [ops[i] for i in chosen]
+        alone = sum(_op_bytes(o, n) + _LAUNCH_BYTES for o in chosen_ops)
         fused = 32.0 * 2 ** n + _LAUNCH_BYTES
         if len(chosen) == 1 or fused >= alone:
             # keep program order: only the leading run of chosen ops is emitted unfused
-            items.extend(("op", o) for o in chosen)
+            items.extend(("op", o) for o in chosen_ops)
         else:
             # pad the tile with the lowest free bits so global accesses stay wide
             b = 0
@@ -407,7 +448,7 @@ def schedule(ops, n, tile_bits, low_bits, lookahead=512):
                 if not bits >> b & 1:
                     bits |= 1 << b
                 b += 1
-            items.append(("tile", [p for p in range(n) if bits >> p & 1], chosen))
+            items.append(("tile", [p for p in range(n) if bits >> p & 1], chosen_ops))
         remaining = rest
     return items
 
