@@ -67,6 +67,8 @@ extern "C" int fh_ctx_destroy(fh_ctx *ctx) {
     cudaFree(ctx->d_result);
     cudaFreeHost(ctx->h_result);
     if (ctx->d_flush) cudaFree(ctx->d_flush);
+    for (auto &blk : ctx->scratch_cache) cudaFree(blk.second);
+    ctx->scratch_cache.clear();
     if (ctx->d_diag) cudaFree(ctx->d_diag);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
@@ -74,6 +76,42 @@ extern "C" int fh_ctx_destroy(fh_ctx *ctx) {
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return FH_OK;
+}
+
+int fh_ctx_scratch_get(fh_ctx *ctx, size_t bytes, void **out) {
+    for (size_t k = 0; k < ctx->scratch_cache.size(); ++k)
+        if (ctx->scratch_cache[k].first == bytes) {
+            *out = ctx->scratch_cache[k].second;
+            ctx->scratch_cached_bytes -= bytes;
+            ctx->scratch_cache.erase(ctx->scratch_cache.begin() + (long)k);
+            return FH_OK;
+        }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess && !ctx->scratch_cache.empty()) {
+        // out of memory with blocks of other sizes parked in the cache: release them and retry once
+        cudaGetLastError();
+        for (auto &blk : ctx->scratch_cache) cudaFree(blk.second);
+        ctx->scratch_cache.clear();
+        ctx->scratch_cached_bytes = 0;
+        e = cudaMalloc(out, bytes);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fh_set_error("scratch allocation of %llu bytes failed: %s", (unsigned long long)bytes, cudaGetErrorString(e));
+        return FH_ECUDA;
+    }
+    return FH_OK;
+}
+
+void fh_ctx_scratch_put(fh_ctx *ctx, size_t bytes, void *ptr) {
+    if (!ptr) return;
+    if (ctx->scratch_cache.size() < FH_SCRATCH_CACHE_MAX_BLOCKS &&
+        ctx->scratch_cached_bytes + bytes <= FH_SCRATCH_CACHE_MAX_BYTES) {
+        ctx->scratch_cache.emplace_back(bytes, ptr);
+        ctx->scratch_cached_bytes += bytes;
+    } else {
+        cudaFree(ptr);
+    }
 }
 
 extern "C" int fh_ctx_sync(fh_ctx *ctx) {

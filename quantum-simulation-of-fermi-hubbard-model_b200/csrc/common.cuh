@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/fhsim.h"
@@ -199,7 +200,16 @@ struct fh_ctx {
     void *d_flush = nullptr;
     size_t flush_bytes = 0;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    // state-sized scratch buffers handed back by destroyed programs (fh_ctx_scratch_get / _put): cudaFree of a
+    // multi-MiB block costs 4-5 ms and a driver compiles a new program every ADAPT epoch
+    std::vector<std::pair<size_t, void *>> scratch_cache;
+    size_t scratch_cached_bytes = 0;
 };
+
+#define FH_SCRATCH_CACHE_MAX_BYTES ((size_t)1 << 30)      // blocks above 1 GiB in total are freed, not cached
+#define FH_SCRATCH_CACHE_MAX_BLOCKS 12
+int fh_ctx_scratch_get(fh_ctx *ctx, size_t bytes, void **out);      // exact-size reuse, else cudaMalloc
+void fh_ctx_scratch_put(fh_ctx *ctx, size_t bytes, void *ptr);      // caller has synchronised the stream
 
 #define FH_MAX_PARTIALS 4096
 

@@ -6,6 +6,11 @@ R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [R, os.path.join(R, "quantum-simulation-of-fermi-hubbard-model_b200")]
 which = sys.argv[1] if len(sys.argv) > 1 else "2x2"
 os.chdir(tempfile.mkdtemp(prefix="fhsim_prof_"))
+import torch
+_w = torch.nn.Parameter(torch.zeros(2))          # pay torch's lazy optimizer imports (~2.5 s) outside the profile
+_o = torch.optim.Adam([_w], lr=1e-3)
+_w.sum().backward()
+_o.step()
 buf = io.StringIO()
 with contextlib.redirect_stdout(buf):
     if which == "2x2":
@@ -25,5 +30,6 @@ with contextlib.redirect_stdout(buf):
 its = len(vqe.results["iteration loss"])
 print(f"{which}: {its} optimiser iterations in {dt:.3f} s = {1e3 * dt / its:.3f} ms per iteration (under cProfile)")
 s = io.StringIO()
-pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(45)
-print(s.getvalue()[:9000])
+pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(40)
+pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(30)
+print(s.getvalue()[:20000])

@@ -12,6 +12,14 @@ import torch
 out = {}
 os.chdir(tempfile.mkdtemp(prefix="fhsim_cfg_"))
 
+# torch imports torch._dynamo / sympy / triton lazily on the first optimizer step (~2.5 s, once per process):
+# pay that here so the per-iteration figures below are the drivers' own cost
+_w = torch.nn.Parameter(torch.zeros(2))
+_o = torch.optim.Adam([_w], lr=1e-3)
+_w.sum().backward()
+_o.step()
+del _w, _o
+
 
 def quiet(fn):
     buf = io.StringIO()
