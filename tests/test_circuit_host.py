@@ -134,6 +134,35 @@ def test_scheduler_preserves_the_unitary(tile_bits, low_bits):
     assert np.abs(run_items(items, psi, th, n) - want).max() < 1e-12
 
 
+def test_noncommuting_bitsets_equal_the_pairwise_string_rule():
+    """The scheduler's vectorised commutation table answers exactly what the pairwise string-level rule answers,
+    including ops without strings (commute with everything) and circuits with no strings at all."""
+    from fhsim.circuit import DiagOpSpec, PairOpSpec, _noncommuting_bitsets, _ops_commute, absorb_phases
+    nx, ny, n = 2, 3, 12
+    pool = hubbard_interaction_pool_simplified(nx, ny)
+    rng = np.random.default_rng(5)
+    c = Circuit(n, 20)
+    for p, k in enumerate(rng.choice(len(pool), size=20, replace=False)):
+        c.generator(GeneratorPlan(jordan_wigner(pool[k]), n), param=p)
+    for w in range(n):
+        c.ry(0.3, w)
+        c.rz(0.2, w)
+    for w in range(n - 1):
+        c.cnot(w, w + 1)
+    c.generator(GeneratorPlan(jordan_wigner(get_interacting_term(fermi_hubbard(nx, ny, 1.0, 4.0))), n), angle=0.3)
+    c.basis_change_separable(nx, ny)
+    ops = absorb_phases(c.ops)
+    ops.insert(7, PairOpSpec(1, 1, 0, 0))                 # an op that declares no strings
+    ops.append(DiagOpSpec([3], [0.1]))
+    sets = _noncommuting_bitsets(ops)
+    assert len(sets) == len(ops)
+    for i, a in enumerate(ops):
+        for j, b in enumerate(ops):
+            assert bool(sets[i] >> j & 1) == (not _ops_commute(a, b)), (i, j)
+    assert _noncommuting_bitsets([PairOpSpec(1, 1, 0, 0), DiagOpSpec([1], [0.5])]) == [0, 0]
+    assert _noncommuting_bitsets([]) == []
+
+
 @pytest.mark.parametrize("lat", [(2, 2), (3, 1), (2, 3), (3, 2), (3, 3)])
 def test_separable_basis_change_equals_reference_network(lat):
     """W compiled from the tensor structure of the FT matrix (36 fermionic Givens at 3x3) is the
