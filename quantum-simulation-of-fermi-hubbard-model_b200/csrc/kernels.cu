@@ -266,6 +266,40 @@ __device__ __forceinline__ unsigned tile_slot(unsigned l) {
     return l ^ ((l >> 3) & 7u) ^ ((l >> 6) & 7u) ^ ((l >> 9) & 7u) ^ ((l >> 12) & 7u);
 }
 
+// Tile geometry helpers.  TileLaunch arrives as a kernel argument (constant bank); indexing its bits[] with a run-time
+// subscript makes the compiler copy the struct to local memory and every access becomes a dependent LDL (measured
+// with clock64 at 18 qubits: 850 cycles for the two masks, 1 450 for one deposit_zeros, 840 for the scatter tables of
+// a ~10 000-cycle launch).  All loops below are fully unrolled with compile-time subscripts, so bits[] stays in the
+// constant bank.
+#define TILE_BITS_CAP 16
+__device__ __forceinline__ unsigned tile_scatter(const TileLaunch &tl, int T, unsigned v, int lo, int hi) {
+    unsigned g = 0;             // sum over local bits b in [lo, hi) of ((v >> (b - lo)) & 1) << bits[b]
+#pragma unroll
+    for (int b = 0; b < TILE_BITS_CAP; ++b)
+        if (b >= lo && b < hi && b < T) g |= ((v >> (b - lo)) & 1u) << tl.bits[b];
+    return g;
+}
+
+__device__ __forceinline__ unsigned tile_mask(const TileLaunch &tl, int T, int lo, int hi) {
+    unsigned m = 0;
+#pragma unroll
+    for (int b = 0; b < TILE_BITS_CAP; ++b)
+        if (b >= lo && b < hi && b < T) m |= 1u << tl.bits[b];
+    return m;
+}
+
+// deposit_zeros(v, tl.bits, T) with compile-time subscripts
+__device__ __forceinline__ u64 tile_base(const TileLaunch &tl, int T, u64 v) {
+#pragma unroll
+    for (int k = 0; k < TILE_BITS_CAP; ++k)
+        if (k < T) {
+            const unsigned p = tl.bits[k];
+            const u64 low = v & ((1ull << p) - 1ull);
+            v = ((v >> p) << (p + 1)) | low;
+        }
+    return v;
+}
+
 __device__ __forceinline__ void tile_run(double2 *__restrict__ psi, const TileLaunch &tl,
                                          const TileRec *__restrict__ recs, const TileTerm *__restrict__ terms, int n,
                                          unsigned char *smem_raw) {
@@ -275,15 +309,36 @@ __device__ __forceinline__ void tile_run(double2 *__restrict__ psi, const TileLa
     __shared__ double2 ph[192];                 // diagonal ops: phase factor tables over local bits 0..5 / 6..12
     const int T = tl.nbits, nsub = tl.nsub;
     unsigned lomask_g = 0, himask_g = 0;        // global masks of the tile's local bits 0..5 / 6..
-    for (int b = 0; b < T; ++b) {
-        if (b < 6) lomask_g |= 1u << tl.bits[b];
-        else himask_g |= 1u << tl.bits[b];
-    }
+    lomask_g = tile_mask(tl, T, 0, 6);
+    himask_g = tile_mask(tl, T, 6, TILE_BITS_CAP);
     const unsigned L = 1u << T;
     double2 *buf = reinterpret_cast<double2 *>(smem_raw);
     unsigned int *gidx = reinterpret_cast<unsigned int *>(buf + L);
 
-    // ---- prologue: one coalesced copy of the launch's records (issued first, consumed after the tile load) ----
+    // ---- prologue ----
+    // The first batch of the CTA's first tile is addressed straight from tl.bits (no shared-memory table yet) and its
+    // four 128-bit loads are issued BEFORE the record copy and the table construction, so the two global-memory
+    // latencies of a launch (op records, tile) overlap instead of adding up and one barrier covers both.  Measured
+    // with clock64 at 18 qubits: prologue 2 100-2 500 + tile load 2 900 cycles before, see DESIGN 7.
+    const u64 ntiles = 1ull << (n - T);
+    const bool have_tile = (u64)blockIdx.x < ntiles;
+    unsigned gg0[4];
+    double2 vv0[4];
+    if (have_tile) {
+        const unsigned base0 = (unsigned)tile_base(tl, T, (u64)blockIdx.x);
+        // scatter of this thread's batch-0 local index
+        const unsigned gt = tile_scatter(tl, T, threadIdx.x, 0, TILE_BITS_CAP);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned l = threadIdx.x + u * blockDim.x;
+            if (l < L) {
+                // blockDim is a power of two > threadIdx.x: the bits of u * blockDim are disjoint from the thread's
+                const unsigned gu = tile_scatter(tl, T, u * blockDim.x, 0, TILE_BITS_CAP);
+                gg0[u] = base0 | gt | gu;
+                vv0[u] = psi[gg0[u]];
+            }
+        }
+    }
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(recs + tl.first_rec);
         uint4 *dst = reinterpret_cast<uint4 *>(rec);
@@ -294,23 +349,27 @@ __device__ __forceinline__ void tile_run(double2 *__restrict__ psi, const TileLa
         const int tchunks = tl.nterms * (int)(sizeof(TileTerm) / 16);
         for (int c = threadIdx.x; c < tchunks; c += blockDim.x) tdst[c] = __ldg(tsrc + c);
     }
-    for (unsigned v = threadIdx.x; v < 64u; v += blockDim.x) {
-        unsigned g = 0;
-        for (int b = 0; b < 6 && b < T; ++b) g |= ((v >> b) & 1u) << tl.bits[b];
-        slo[v] = g;
-    }
-    for (unsigned v = threadIdx.x; v < 128u; v += blockDim.x) {
-        unsigned g = 0;
-        for (int b = 6; b < T; ++b) g |= ((v >> (b - 6)) & 1u) << tl.bits[b];
-        shi[v] = g;
+    for (unsigned v = threadIdx.x; v < 64u; v += blockDim.x) slo[v] = tile_scatter(tl, T, v, 0, 6);
+    for (unsigned v = threadIdx.x; v < 128u; v += blockDim.x) shi[v] = tile_scatter(tl, T, v, 6, TILE_BITS_CAP);
+    if (have_tile) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned l = threadIdx.x + u * blockDim.x;
+            if (l < L) {
+                const unsigned sl = tile_slot(l);
+                gidx[sl] = gg0[u];
+                buf[sl] = vv0[u];
+            }
+        }
     }
     __syncthreads();
 
-    const u64 ntiles = 1ull << (n - T);
+    bool first = true;
     for (u64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const unsigned base = (unsigned)deposit_zeros(t, tl.bits, T);
+        const unsigned base = (unsigned)tile_base(tl, T, t);
         // four independent 128-bit loads in flight per thread before anything is written to shared memory
-        for (unsigned l0 = threadIdx.x; l0 < L; l0 += 4 * blockDim.x) {
+        // (batch 0 of the first tile is already in place)
+        for (unsigned l0 = threadIdx.x + (first ? 4u * blockDim.x : 0u); l0 < L; l0 += 4 * blockDim.x) {
             unsigned gg[4];
             double2 vv[4];
 #pragma unroll
@@ -331,7 +390,8 @@ __device__ __forceinline__ void tile_run(double2 *__restrict__ psi, const TileLa
                 }
             }
         }
-        __syncthreads();
+        if (!first || L > 4u * blockDim.x) __syncthreads();     // CTA-uniform condition
+        first = false;
         int sidx = 0;
         while (sidx < nsub) {
             const uint4 *rp = reinterpret_cast<const uint4 *>(&rec[sidx]);
@@ -482,10 +542,8 @@ __global__ void __launch_bounds__(512, 1) k_tile_adjoint(double2 *__restrict__ p
     unsigned int *gidx = reinterpret_cast<unsigned int *>(bufl + L);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     unsigned lomask_g = 0, himask_g = 0;
-    for (int b = 0; b < T; ++b) {
-        if (b < 6) lomask_g |= 1u << tl.bits[b];
-        else himask_g |= 1u << tl.bits[b];
-    }
+    lomask_g = tile_mask(tl, T, 0, 6);
+    himask_g = tile_mask(tl, T, 6, TILE_BITS_CAP);
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(recs + tl.first_rec);
         uint4 *dst = reinterpret_cast<uint4 *>(rec);
@@ -496,22 +554,14 @@ __global__ void __launch_bounds__(512, 1) k_tile_adjoint(double2 *__restrict__ p
         const int tchunks = tl.nterms * (int)(sizeof(TileTerm) / 16);
         for (int c = threadIdx.x; c < tchunks; c += blockDim.x) tdst[c] = __ldg(tsrc + c);
     }
-    for (unsigned v = threadIdx.x; v < 64u; v += blockDim.x) {
-        unsigned g = 0;
-        for (int b = 0; b < 6 && b < T; ++b) g |= ((v >> b) & 1u) << tl.bits[b];
-        slo[v] = g;
-    }
-    for (unsigned v = threadIdx.x; v < 128u; v += blockDim.x) {
-        unsigned g = 0;
-        for (int b = 6; b < T; ++b) g |= ((v >> (b - 6)) & 1u) << tl.bits[b];
-        shi[v] = g;
-    }
+    for (unsigned v = threadIdx.x; v < 64u; v += blockDim.x) slo[v] = tile_scatter(tl, T, v, 0, 6);
+    for (unsigned v = threadIdx.x; v < 128u; v += blockDim.x) shi[v] = tile_scatter(tl, T, v, 6, TILE_BITS_CAP);
     for (int o = threadIdx.x; o < TILE_MAX_SUB; o += blockDim.x) cacc[o] = 0.0;
     __syncthreads();
 
     const u64 ntiles = 1ull << (n - T);
     for (u64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const unsigned base = (unsigned)deposit_zeros(t, tl.bits, T);
+        const unsigned base = (unsigned)tile_base(tl, T, t);
         for (unsigned l = threadIdx.x; l < L; l += blockDim.x) {
             const unsigned g = base | slo[l & 63u] | shi[l >> 6];
             const unsigned sl = tile_slot(l);
