@@ -19,6 +19,7 @@
 
 // number of kernel launches issued through the wrappers below (measurement; read via fh_program_last_stats)
 long long g_fh_launch_count = 0;
+thread_local int g_fh_tile_pdl_scope = 0;     // > 0 while fh_program_evaluate enqueues its kernels (see launch_tile)
 
 // ----------------------------------------------------------------------------------------------
 // small device helpers
@@ -300,6 +301,10 @@ __device__ __forceinline__ u64 tile_base(const TileLaunch &tl, int T, u64 v) {
     return v;
 }
 
+// PDL = launched with programmatic stream serialization (launch_tile): the op records and the scatter tables are set up
+// while the previous kernel of the stream / graph is still draining, and only then griddepcontrol.wait orders the tile
+// loads after that kernel's writes.  Without PDL the first tile batch is issued before the record copy instead.
+template <bool PDL>
 __device__ __forceinline__ void tile_run(double2 *__restrict__ psi, const TileLaunch &tl,
                                          const TileRec *__restrict__ recs, const TileTerm *__restrict__ terms, int n,
                                          unsigned char *smem_raw) {
@@ -321,9 +326,10 @@ __device__ __forceinline__ void tile_run(double2 *__restrict__ psi, const TileLa
     // latencies of a launch (op records, tile) overlap instead of adding up and one barrier covers both.  Measured
     // with clock64 at 18 qubits: prologue 2 100-2 500 + tile load 2 900 cycles before, see DESIGN 7.
     const u64 ntiles = 1ull << (n - T);
-    const bool have_tile = (u64)blockIdx.x < ntiles;
+    const bool have_tile = !PDL && (u64)blockIdx.x < ntiles;
     unsigned gg0[4];
     double2 vv0[4];
+    if (PDL) asm volatile("griddepcontrol.launch_dependents;");     // the next launch may start its own prologue
     if (have_tile) {
         const unsigned base0 = (unsigned)tile_base(tl, T, (u64)blockIdx.x);
         // scatter of this thread's batch-0 local index
@@ -365,6 +371,10 @@ __device__ __forceinline__ void tile_run(double2 *__restrict__ psi, const TileLa
     __syncthreads();
 
     bool first = true;
+    if (PDL) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");          // the previous kernel's amplitudes are complete
+        first = false;                                                // nothing was pre-loaded
+    }
     for (u64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const unsigned base = (unsigned)tile_base(tl, T, t);
         // four independent 128-bit loads in flight per thread before anything is written to shared memory
@@ -493,11 +503,12 @@ __device__ __forceinline__ void tile_run(double2 *__restrict__ psi, const TileLa
     }
 }
 
+template <bool PDL>
 __global__ void __launch_bounds__(512, 2) k_tile(double2 *__restrict__ psi, const TileLaunch tl,
                                                  const TileRec *__restrict__ recs, const TileTerm *__restrict__ terms,
                                                  int n) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    tile_run(psi, tl, recs, terms, n, smem_raw);
+    tile_run<PDL>(psi, tl, recs, terms, n, smem_raw);
 }
 
 // Several consecutive tile runs in ONE cooperative launch: a grid-wide barrier replaces the kernel boundary between
@@ -512,7 +523,7 @@ __global__ void __launch_bounds__(512, 2) k_tile_multi(double2 *__restrict__ psi
         if (threadIdx.x < sizeof(TileLaunch) / 4)
             reinterpret_cast<unsigned *>(&tl)[threadIdx.x] = reinterpret_cast<const unsigned *>(tls + l)[threadIdx.x];
         __syncthreads();
-        tile_run(psi, tl, recs, terms, n, smem_raw);
+        tile_run<false>(psi, tl, recs, terms, n, smem_raw);
         if (l + 1 < nl) grid.sync();
     }
 }
@@ -1456,7 +1467,8 @@ void launch_tile(cudaStream_t s, double2 *psi, const TileLaunch &tl, const TileR
     const int nbits = tl.nbits;
     const size_t smem = ((size_t)1 << nbits) * (sizeof(double2) + sizeof(unsigned int));
     if (!g_tile_attr_set) {
-        cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
+        cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
+        cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
         g_tile_attr_set = true;
     }
     u64 ntiles = 1ull << (n - nbits);
@@ -1466,7 +1478,28 @@ void launch_tile(cudaStream_t s, double2 *psi, const TileLaunch &tl, const TileR
     if (threads > 512) threads = 512;
     if (threads < 64) threads = 64;
     ++g_fh_launch_count;
-    k_tile<<<grid, threads, smem, s>>>(psi, tl, d_recs, d_terms, n);
+    // Programmatic dependent launch: the launch may begin while the previous kernel on the stream is finishing;
+    // k_tile<true> sets up its records and tables and then waits (griddepcontrol.wait) before it touches the state.
+    // Captured into the evaluation graph as a programmatic edge (18-qubit screening step 0.217 -> 0.206 ms).  On by
+    // default inside fh_program_evaluate; FHSIM_PDL=1 turns it on for every tile launch, FHSIM_NO_PDL=1 off.
+    static const bool pdl_all = getenv("FHSIM_PDL") != nullptr, pdl_off = getenv("FHSIM_NO_PDL") != nullptr;
+    const bool pdl = !pdl_off && (pdl_all || g_fh_tile_pdl_scope > 0);
+    if (pdl) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3((unsigned)threads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, k_tile<true>, psi, tl, d_recs, d_terms, n);
+    } else {
+        k_tile<false><<<grid, threads, smem, s>>>(psi, tl, d_recs, d_terms, n);
+    }
 }
 
 static int g_tile_multi_blocks_per_sm = -1;

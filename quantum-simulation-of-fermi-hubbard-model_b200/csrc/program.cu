@@ -85,6 +85,7 @@ struct fh_program {
 };
 
 extern long long g_fh_launch_count;
+extern thread_local int g_fh_tile_pdl_scope;      // kernels.cu: tile launches inside evaluate use PDL
 
 static inline int popcnt(u64 v) { return __builtin_popcountll(v); }
 
@@ -817,7 +818,10 @@ extern "C" int fh_program_evaluate(fh_program *p, uint64_t basis_index, const do
     if (no_graph) {
         const long long before = g_fh_launch_count;
         FH_CUDA(cudaEventRecord(p->ev0, ctx->stream));
-        FH_TRY(enqueue_evaluation(p, key, tables, pool, targets, state_out));
+        ++g_fh_tile_pdl_scope;
+        const int rc = enqueue_evaluation(p, key, tables, pool, targets, state_out);
+        --g_fh_tile_pdl_scope;
+        FH_TRY(rc);
         FH_CUDA(cudaEventRecord(p->ev1, ctx->stream));
         p->last_launches = (int)(g_fh_launch_count - before);
     } else {
@@ -825,7 +829,9 @@ extern "C" int fh_program_evaluate(fh_program *p, uint64_t basis_index, const do
             drop_graph(p);
             const long long before = g_fh_launch_count;
             FH_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            ++g_fh_tile_pdl_scope;
             const int rc = enqueue_evaluation(p, key, tables, pool, targets, state_out);
+            --g_fh_tile_pdl_scope;
             cudaGraph_t g = nullptr;
             const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
             if (rc != FH_OK) {
