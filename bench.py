@@ -41,6 +41,9 @@ L2_FLUSH_BYTES = 256 << 20
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_pool launch of this workload (ncu --set full,
 # profiles/r01_s2_ncu_full_18q.md rows "k_pool"): psi and lambda (8 MiB) are read from HBM once, everything else hits L2
 K3_DRAM_BYTES_PER_LAUNCH = 8431360
+# the same for one k_tile launch of this workload (profiles/r01_s6_ncu_full_18q.md, dram_rd 6.59 MB + dram_wr ~0: ncu
+# replays every kernel with a cold cache; inside the step the 4 MiB state comes from L2)
+K_TILE_DRAM_BYTES_PER_LAUNCH = 6590000
 
 
 def measured_peak_gbs():
@@ -348,6 +351,31 @@ def run_gpu_arm(args, rank, world, local_rank):
     alg_bytes = 4.0 * (1 << n) * n_pool              # 4*2^n B per gradient
     achieved = alg_bytes / k3 / 1e9
 
+    # ---- the kernel that dominates the step by time: k_tile (15 of the 19 launches, ~73 % of the step in the ncu
+    # launch list profiles/r01_s8_launches.csv).  Timed alone: the 13 forward runs on one state and the 2 W-dagger runs
+    # of the lambda branch, launched back to back (warm L2, as inside the step), CUDA events on the library's stream.
+    tile = None
+    try:
+        if prog.n_tiles == prog.n_items:
+            n_dag = prog.n_items - marker
+            t_fwd = statistics.median(prog.time_items(phi, 0, prog.n_items, False, 20) for _ in range(5))
+            t_dag = statistics.median(prog.time_items(lam, marker, n_dag, True, 20) for _ in range(5))
+            n_tile_launches = prog.n_items + n_dag
+            tile_s = (t_fwd + t_dag) * 1e-3
+            tile_alg = 32.0 * (1 << n) * n_tile_launches          # one read + one write of the state per launch
+            tile = {"bound": "hbm", "kernel": "k_tile (fused runs of rotations in shared-memory tiles)",
+                    "achieved": tile_alg / tile_s / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": tile_alg / tile_s / 1e9 / peak, "traffic": K_TILE_DRAM_BYTES_PER_LAUNCH,
+                    "peak_source": peak_src, "kernel_ms": 1e3 * tile_s / n_tile_launches,
+                    "launches_per_step": n_tile_launches, "share_of_step": 1e3 * tile_s / (total_ms / args.steps),
+                    "note": "18-qubit state (4 MiB) is L2-resident and the launches are latency-bound (128 CTAs, one "
+                            "dependent chain per fused op): effective GB/s vs HBM peak; algorithmic bytes = 32*2^n per "
+                            "launch; traffic = ncu dram bytes of one launch under cold-cache replay; the HBM-bound "
+                            "figure for this kernel is hbm_regime.tile_W"}
+    except Exception as exc:                                       # never lose the bench line over a side measurement
+        print(f"k_tile roofline measurement failed: {exc}", file=sys.stderr)
+        tile = None
+
     # ---- the same kernels where the state no longer fits L2 (3x4 lattice, 24 qubits, 256 MiB): true HBM rooflines ----
     hbm = None
     if world == 1 and not args.no_hbm_regime:
@@ -385,6 +413,13 @@ def run_gpu_arm(args, rank, world, local_rank):
                           f"(oracle/literal.py, torch CPU, {passes} gate passes/step; ansatz prefix untimed); "
                           f"max |g_cpu - g_gpu| on the sample = {err:.2e}")}
 
+    roofline_k3 = {"bound": "hbm", "kernel": "k_pool (K3 pool screening) + k_pool_finalize",
+                   "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                   "traffic": K3_DRAM_BYTES_PER_LAUNCH, "peak_source": peak_src, "kernel_ms": k3 * 1e3,
+                   "share_of_step": k3 * 1e3 / (total_ms / args.steps),
+                   "note": "the kernel that produces the metric's unit (one launch = 324 gradients); 18-qubit working "
+                           "set (8 MiB) is L2-resident: effective GB/s vs HBM peak; algorithmic bytes = 4*2^n per "
+                           "gradient x 324"}
     value = world * n_pool * args.steps / (total_ms * 1e-3)
     e2e_value = world * n_pool * args.steps / e2e_total
     h2d, d2h = prog.payload_bytes()            # pinned op-payload arena in, scalars + pool gradients out (per step)
@@ -401,11 +436,8 @@ def run_gpu_arm(args, rank, world, local_rank):
         "launches_per_step": launches,
         "h_evals_per_s": world * len(h_ms) / (sum(h_ms) * 1e-3),
         "h_eval_ms": statistics.median(h_ms), "h_eval_launches": h_launches,
-        "roofline": {"bound": "hbm", "kernel": "k_pool (K3 pool screening) + k_pool_finalize",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": K3_DRAM_BYTES_PER_LAUNCH, "peak_source": peak_src, "kernel_ms": k3 * 1e3,
-                     "note": "18-qubit working set (8 MiB) is L2-resident: effective GB/s vs HBM peak; "
-                             "algorithmic bytes = 4*2^n per gradient x 324"},
+        "roofline": tile if tile is not None else roofline_k3,
+        "roofline_k3": roofline_k3,
         "hbm_regime": hbm,
         "cpu_baseline": cpu,
         "pool_sharded": pool_sharded,
