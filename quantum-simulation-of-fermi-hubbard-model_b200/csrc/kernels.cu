@@ -267,6 +267,23 @@ __device__ __forceinline__ unsigned tile_slot(unsigned l) {
     return l ^ ((l >> 3) & 7u) ^ ((l >> 6) & 7u) ^ ((l >> 9) & 7u) ^ ((l >> 12) & 7u);
 }
 
+// Optional in-kernel timeline (make TIMELINE=1 -> -DFH_TILE_TIMELINE; tools/probe_timeline.py): thread 0 of CTA 0
+// stamps clock64() at the phase boundaries of tile_run into g_fh_tile_timeline, read back by fh_debug_tile_timeline.
+// Slots: 0 entry, 1 prologue done (records, tables[, first batch] + barrier), 2 tile in shared memory, 4+k start of op k
+// (k < 40), 3 ops done, 63 tile stored.  Compiled out by default (the macro expands to nothing).
+#ifdef FH_TILE_TIMELINE
+__device__ long long g_fh_tile_timeline[64];
+#define FH_TLMARK(k)                                                              \
+    do {                                                                          \
+        if (blockIdx.x == 0 && threadIdx.x == 0) g_fh_tile_timeline[k] = clock64(); \
+    } while (0)
+extern "C" int fh_debug_tile_timeline(long long *out64) {
+    return (int)cudaMemcpyFromSymbol(out64, g_fh_tile_timeline, sizeof(long long) * 64);
+}
+#else
+#define FH_TLMARK(k) do { } while (0)
+#endif
+
 // Tile geometry helpers.  TileLaunch arrives as a kernel argument (constant bank); indexing its bits[] with a run-time
 // subscript makes the compiler copy the struct to local memory and every access becomes a dependent LDL (measured
 // with clock64 at 18 qubits: 850 cycles for the two masks, 1 450 for one deposit_zeros, 840 for the scatter tables of
@@ -312,6 +329,7 @@ __device__ __forceinline__ void tile_run(double2 *__restrict__ psi, const TileLa
     __shared__ TileTerm tterm[TILE_MAX_TERMS];
     __shared__ unsigned slo[64], shi[128];      // scatter tables: local index bits -> global bit positions
     __shared__ double2 ph[192];                 // diagonal ops: phase factor tables over local bits 0..5 / 6..12
+    FH_TLMARK(0);
     const int T = tl.nbits, nsub = tl.nsub;
     unsigned lomask_g = 0, himask_g = 0;        // global masks of the tile's local bits 0..5 / 6..
     lomask_g = tile_mask(tl, T, 0, 6);
@@ -370,6 +388,7 @@ __device__ __forceinline__ void tile_run(double2 *__restrict__ psi, const TileLa
     }
     __syncthreads();
 
+    FH_TLMARK(1);
     bool first = true;
     if (PDL) {
         asm volatile("griddepcontrol.wait;" ::: "memory");          // the previous kernel's amplitudes are complete
@@ -402,8 +421,10 @@ __device__ __forceinline__ void tile_run(double2 *__restrict__ psi, const TileLa
         }
         if (!first || L > 4u * blockDim.x) __syncthreads();     // CTA-uniform condition
         first = false;
+        FH_TLMARK(2);
         int sidx = 0;
         while (sidx < nsub) {
+            if (sidx < 40) FH_TLMARK(4 + sidx);
             const uint4 *rp = reinterpret_cast<const uint4 *>(&rec[sidx]);
             const uint4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
             // q0 = {fixmask_out, fixval_out, zeta, xlocal}; q1 = {lfixval, type, nlfix, term_off}; q2 = lowmask[4]
@@ -495,11 +516,13 @@ __device__ __forceinline__ void tile_run(double2 *__restrict__ psi, const TileLa
             }
             __syncthreads();
         }
+        FH_TLMARK(3);
         for (unsigned l = threadIdx.x; l < L; l += blockDim.x) {
             const unsigned sl = tile_slot(l);
             psi[gidx[sl]] = buf[sl];
         }
         __syncthreads();
+        FH_TLMARK(63);
     }
 }
 

@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""In-kernel phase timeline of the fused tile kernel (k_tile) for every launch item of the bench circuit.
+
+Builds a SEPARATE library with -DFH_TILE_TIMELINE (csrc/build_timeline/libfhsim_timeline.so; the shipped
+fhsim/lib/libfhsim.so has the instrumentation compiled out), loads it in place of the shipped one and prints, per launch item, the
+clock64() deltas thread 0 of CTA 0 stamped at the phase boundaries of tile_run (cycles at the SM clock):
+
+    python tools/probe_timeline.py            # needs a GPU; the build step also works without one
+
+Round-1 result at 18 qubits (T = 11, 512 threads, 1.965 GHz): prologue 2 100-2 500, tile load 2 900, ~700 per fermionic
+double excitation, 900-1 000 per Givens of W, store 1 300 -- see DESIGN.md 7.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(R, "quantum-simulation-of-fermi-hubbard-model_b200")
+CSRC = os.path.join(PKG, "csrc")
+OUT = os.path.join(CSRC, "build_timeline", "libfhsim_timeline.so")
+
+
+def build():
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    srcs = ["kernels.cu", "api.cu", "program.cu", "lanczos.cu"]
+    cmd = ["nvcc", "-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
+           "-DFH_TILE_TIMELINE", "-shared", "-cudart", "static", "-o", OUT] + [os.path.join(CSRC, f) for f in srcs]
+    subprocess.check_call(cmd)
+
+
+def main():
+    if not os.path.exists(OUT) or "--rebuild" in sys.argv:
+        build()
+    if "--build-only" in sys.argv:
+        return
+    sys.path[:0] = [R, PKG]
+    from fhsim import _cabi
+    _cabi.LIB_PATH = OUT                      # load the instrumented build instead of the shipped library
+    import bench
+    from fhsim.backend import Context, State
+    ctx = Context(0)
+    wl = bench.build_gpu_workload(ctx)
+    prog, n = wl["prog"], bench.N_QUBITS
+    st = State(ctx, n)
+    st.set_basis(wl["basis"])
+    lib = _cabi.lib()
+    buf = (C.c_longlong * 64)()
+    for item in range(prog.n_items):
+        for _ in range(3):
+            prog.run(st, wl["thetas"], item, 1)
+        ctx.sync()
+        if lib.fh_debug_tile_timeline(buf) != 0:
+            raise RuntimeError("fh_debug_tile_timeline failed")
+        t = list(buf)
+        nops = sum(1 for k in range(4, 44) if t[2] <= t[k] <= t[3])
+        marks = [t[4 + k] for k in range(nops)] + [t[3]]
+        per_op = [marks[k + 1] - marks[k] for k in range(nops)]
+        print(f"item {item:2d}: prologue {t[1] - t[0]:6d}  load {t[2] - t[1]:6d}  ops({nops}) {t[3] - t[2]:6d} {per_op}  "
+              f"store {t[63] - t[3]:6d}  total {t[63] - t[0]:6d} cycles", flush=True)
+
+
+if __name__ == "__main__":
+    main()
