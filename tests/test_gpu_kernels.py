@@ -394,6 +394,40 @@ def test_known_answers_3x3_first_screening(ctx):
     assert (g > 1e-9).sum() == 52 and np.allclose(g[g > 1e-9], 4.0 / 3.0, atol=G_TOL)
 
 
+def test_evaluate_graph_equals_item_by_item_run_18_qubits(ctx):
+    """fh_program_evaluate launches its tile kernels with programmatic dependent launch (the next kernel's prologue
+    overlaps the previous kernel's tail, griddepcontrol.wait before the first state access); fh_program_run launches
+    the same items one by one without it.  Same circuit, same parameters: the final states must agree to rounding
+    (a missing dependency would show up as O(1) differences), and replays of the graph must be bit-identical."""
+    n, h_tab, pool_ops, _, _, _, _ = lattice(3, 3, 6.0)
+    plans = [GeneratorPlan(g, n) for g in pool_ops]
+    rng = np.random.default_rng(2718)
+    picks = [int(k) for k in rng.choice(len(plans), size=40, replace=False)]
+    th = rng.uniform(-0.3, 0.3, len(picks))
+    circ = Circuit(n, len(picks))
+    for p, k in enumerate(picks):
+        circ.generator(plans[k], param=p)
+    circ.basis_change_separable(3, 3)
+    prog = circ.compile(ctx)
+    assert prog.n_tiles >= 8
+    occ = [0, 2, 4, 6, 12, 1, 3, 5, 7]
+    basis = sum(1 << (n - 1 - q) for q in occ)
+    dtab = DeviceTable(ctx, h_tab)
+    out = State(ctx, n)
+    res = prog.evaluate(basis, th, [dtab], state_out=out)
+    via_graph = out.numpy().copy()
+    st = State(ctx, n)
+    st.set_basis(basis)
+    prog.run(st, th)
+    via_run = st.numpy()
+    assert abs(np.vdot(via_run, via_run).real - 1.0) < 1e-12
+    assert np.abs(via_graph - via_run).max() < 1e-14
+    for _ in range(5):
+        again = prog.evaluate(basis, th, [dtab], state_out=out)
+        assert again["expvals"][0] == res["expvals"][0]
+        assert np.array_equal(out.numpy(), via_graph)
+
+
 def test_lanczos_vs_sector_ed(ctx):
     for (nx, ny, u, up, dn) in [(2, 2, 4.0, 2, 2), (2, 3, 4.0, 3, 3)]:
         n, h_tab, _, _, _, o_h, _ = lattice(nx, ny, u)
