@@ -142,7 +142,9 @@ int fh_program_run(fh_program *prog, fh_state *st, const double *thetas, int n_t
  *   if pool != NULL: pool_out[k] = 2 Im <lambda_s| G_k |psi_s> with psi_s the state after ops[0:pool_pos)
  *     and lambda_s the back-propagated H psi  (replaces select_operator, adapt_vqe.py:297-310);
  *   if n_overlaps > 0: overlaps[2v], [2v+1] = <targets[v]|psi>  (fidelity, adapt_vqe.py:404-408);
- *   if state_out != NULL it receives psi. */
+ *   if state_out != NULL it receives psi.
+ * The fused tile kernels of the graph are launched with programmatic stream serialization (their set-up overlaps the
+ * previous kernel's tail; FHSIM_NO_PDL=1 disables it); results are bit-identical run to run. */
 int fh_program_evaluate(fh_program *prog, uint64_t basis_index, const double *thetas, int n_thetas,
                         int n_tables, fh_table *const *tables, double *expvals,
                         double *grads,
