@@ -126,13 +126,10 @@ class LiteralSimulator:
         for x, z, coeff in terms:
             col = idx ^ int(x)
             k = bin(int(x) & int(z)).count("1") & 3
-            par = torch.zeros_like(idx)
-            zz = col & int(z)
-            while True:
-                par ^= zz & 1
-                zz = zz >> 1
-                if not bool(zz.any()):
-                    break
+            par = col & int(z)                  # parity of the set bits: XOR-fold (vectorised, 6 passes)
+            for sh in (32, 16, 8, 4, 2, 1):
+                par = par ^ (par >> sh)
+            par = par & 1
             data = (1 - 2 * par).to(CD) * complex([1, 1j, -1, -1j][k])
             val = torch.sum(torch.conj(flat) * data * flat[col])
             total = total + (complex(coeff) * val).real
@@ -170,17 +167,19 @@ def adapt_eval_circuit(n, occupied, selected, t_params, pool, e_params, diagonal
 
 
 def screen_by_backprop(n, occupied, selected, thetas, pool, diagonal, decomposition, h_terms,
-                       chunk=None):
-    """|d<H>/d e_k| at e=0 for every pool element by append-and-backprop, float32 result as the
-    reference returns it (adapt_vqe.py:306-310).  ``chunk`` evaluates the pool in slices of that
+                       chunk=None, dtype=torch.float32):
+    """d<H>/d e_k at e=0 for every pool element by append-and-backprop, float32 parameters and result as
+    the reference has them (adapt_vqe.py:306-310; ``dtype=torch.float64`` keeps the parameters in double so the
+    result can be compared with the closed form at 1e-12).  ``chunk`` evaluates the pool in slices of that
     many operators (identical arithmetic per operator, bounded autograd memory)."""
-    t = torch.tensor(np.asarray(thetas, dtype=np.float32), dtype=torch.float32)
-    grads = np.zeros(len(pool), dtype=np.float32)
+    np_dtype = np.float32 if dtype == torch.float32 else np.float64
+    t = torch.tensor(np.asarray(thetas, dtype=np_dtype), dtype=dtype)
+    grads = np.zeros(len(pool), dtype=np_dtype)
     passes = 0
     step = len(pool) if not chunk else chunk
     for lo in range(0, len(pool), step):
         sub = pool[lo:lo + step]
-        e = torch.zeros(len(sub), dtype=torch.float32, requires_grad=True)
+        e = torch.zeros(len(sub), dtype=dtype, requires_grad=True)
         loss, sim = adapt_eval_circuit(n, occupied, selected, t, sub, e, diagonal, decomposition, h_terms)
         loss.backward()
         grads[lo:lo + step] = e.grad.numpy()

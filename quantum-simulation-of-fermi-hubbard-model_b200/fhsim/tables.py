@@ -51,10 +51,24 @@ class PauliTable:
 
     def __init__(self, n_qubits, x, z, coeff):
         self.n_qubits = int(n_qubits)
-        self.x = np.ascontiguousarray(x, dtype=np.uint64)
-        self.z = np.ascontiguousarray(z, dtype=np.uint64)
-        self.coeff = np.ascontiguousarray(coeff, dtype=np.complex128)
-        self.k = np.array([popcount(int(a) & int(b)) & 3 for a, b in zip(self.x, self.z)], dtype=np.uint8)
+        x = np.ascontiguousarray(x, dtype=np.uint64).reshape(-1)
+        z = np.ascontiguousarray(z, dtype=np.uint64).reshape(-1)
+        coeff = np.ascontiguousarray(coeff, dtype=np.complex128).reshape(-1)
+        if not (len(x) == len(z) == len(coeff)):
+            raise ValueError("PauliTable: x, z and coeff must have the same length")
+        # canonical form: one entry per string.  Duplicate (x, z) are merged (coefficients added, first-seen order),
+        # exactly what accumulating into a QubitOperator's ``terms`` dict does, so every method (as_dict, dressed,
+        # the device upload) sees the same operator.
+        if len(x) > 1:
+            keys = np.stack([x, z], axis=1)
+            uniq, first, inv = np.unique(keys, axis=0, return_index=True, return_inverse=True)
+            if len(uniq) != len(x):
+                summed = np.zeros(len(uniq), dtype=np.complex128)
+                np.add.at(summed, inv.reshape(-1), coeff)
+                order = np.argsort(first, kind="stable")
+                x, z, coeff = uniq[order, 0].copy(), uniq[order, 1].copy(), summed[order]
+        self.x, self.z, self.coeff = x, z, coeff
+        self.k = (np.bitwise_count(self.x & self.z) & 3).astype(np.uint8)
 
     @classmethod
     def from_operator(cls, op, n_qubits, compress=True):

@@ -2,7 +2,7 @@
 norm preservation, U(theta) U(-theta) = 1, Hermiticity <phi|H psi> = conj <psi|H phi>, commutation of the 8 strings of
 every pool operator, gradient = central finite difference, scheduler / lowering invariants on random circuits."""
 import numpy as np
-from hypothesis import given, settings, strategies as st
+from hypothesis import example, given, settings, strategies as st
 
 from emulate import apply_op, run_circuit, run_items
 from fhsim.circuit import Circuit, absorb_phases, schedule
@@ -180,6 +180,7 @@ def test_swap_steps_is_a_permutation_with_the_requested_rank_bits(seed):
 
 @settings(max_examples=30, deadline=None)
 @given(seed=st.integers(0, 10 ** 6), tau=angles)
+@example(seed=267, tau=0.0)        # draws the string (x=18, z=0) twice: duplicates must be merged, not dropped
 def test_dressing_preserves_the_spectrum(seed, tau):
     """exp(i tau P/2) H exp(-i tau P/2) is a similarity transform: <psi'|H'|psi'> with psi' = exp(i tau P/2) psi
     equals <psi|H|psi>."""
@@ -196,3 +197,13 @@ def test_dressing_preserves_the_spectrum(seed, tau):
     psi_rot = sv.pauli_rotation(psi, -tau, xp, zp, n)       # exp(+i tau P / 2) psi
     e1 = sv.expval(psi_rot, dressed.as_dict(), n).real
     assert abs(e0 - e1) < 1e-11
+
+
+def test_pauli_table_merges_duplicate_strings():
+    """One entry per string: duplicates are summed in first-seen order, so as_dict / dressed / upload agree."""
+    t = PauliTable(5, [18, 3, 18, 7], [0, 1, 0, 2], [0.5, 1.0, 0.25, -2.0])
+    assert [int(v) for v in t.x] == [18, 3, 7] and [int(v) for v in t.z] == [0, 1, 2]
+    assert np.allclose(t.coeff, [0.75, 1.0, -2.0])
+    assert t.as_dict() == {(18, 0): 0.75, (3, 1): 1.0, (7, 2): -2.0}
+    same = t.dressed(1, 0, 0.0)
+    assert same.as_dict() == t.as_dict()
