@@ -180,3 +180,28 @@ def energy_of(n, occupied, generators, thetas, h_table, diagonal, decomposition)
     psi = adapt_state(n, occupied, generators, thetas)
     phi = basis_change(psi, diagonal, decomposition, n)
     return expval(phi, h_table, n).real
+
+
+def trotter_circuit_gradient(psi0, layers, thetas, h_table, n):
+    """E = <psi|H|psi> and dE/dtheta_p for psi = prod_l Trotterize(theta_{p_l}, G_l) psi0, layers = [(p_l, table_l)]
+    applied first to last; several layers may share one parameter (HVA: reference hva.py:283-298 applies one theta per
+    layer of bonds, one theta_U per Coulomb layer).  Exact derivative of the LITERAL Trotter product
+    prod_m exp(-i theta c_m P_m) (adapt_vqe.py:87-98), string by string -- no commutation assumption:
+        d/dtheta exp(-i theta c P) = -i c P exp(-i theta c P)   =>   dE/dtheta += 2 c Im <lambda_m| P_m |psi_m>
+    with psi_m, lambda_m the state and H|psi_final> pulled back to just after string m."""
+    thetas = np.asarray(thetas, dtype=np.float64)
+    psi = psi0.copy()
+    for p, table in layers:
+        psi = trotterize(psi, thetas[p], table, n)
+    lam = apply_table(psi, h_table, n)
+    energy = np.vdot(psi, lam).real
+    grads = np.zeros(len(thetas))
+    for p, table in reversed(layers):
+        for (x, z), c in reversed(list(table.items())):
+            if x == 0 and z == 0:
+                continue
+            cr = complex(c).real
+            grads[p] += 2.0 * cr * np.vdot(lam, apply_pauli(psi, x, z, n)).imag
+            psi = pauli_rotation(psi, -2.0 * thetas[p] * cr, x, z, n)
+            lam = pauli_rotation(lam, -2.0 * thetas[p] * cr, x, z, n)
+    return energy, grads

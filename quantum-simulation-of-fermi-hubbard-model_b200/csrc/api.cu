@@ -23,6 +23,11 @@ extern "C" int fh_version(void) { return 100; }
 
 static inline int popcnt(u64 v) { return __builtin_popcountll(v); }
 
+u64 fh_next_uid() {
+    static u64 next = 1;
+    return __atomic_fetch_add(&next, 1, __ATOMIC_RELAXED);
+}
+
 // ----------------------------------------------------------------------------------------------
 // context
 // ----------------------------------------------------------------------------------------------
@@ -49,6 +54,7 @@ extern "C" int fh_ctx_create(int device, void *stream, fh_ctx **out) {
     cudaDeviceProp prop;
     FH_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
+    FH_TRY(fh_kernels_init_device());
     FH_CUDA(cudaMalloc(&ctx->d_partials, sizeof(double) * 2 * FH_MAX_PARTIALS));
     FH_CUDA(cudaMalloc(&ctx->d_result, sizeof(double) * 64));
     FH_CUDA(cudaMalloc(&ctx->d_diag, fh_diag_scratch_bytes()));
@@ -183,9 +189,9 @@ extern "C" int fh_state_create(fh_ctx *ctx, int n_qubits, fh_state **out) {
     st->owned = true;
     cudaError_t e = cudaMalloc(&st->d, st->dim * sizeof(double2));
     if (e != cudaSuccess) {
-        delete st;
         fh_set_error("fh_state_create: cudaMalloc of %llu bytes failed: %s", st->dim * 16ull, cudaGetErrorString(e));
         cudaGetLastError();
+        delete st;
         return FH_ENOMEM;
     }
     launch_set_basis(ctx->stream, st->d, st->dim, 0);

@@ -213,15 +213,21 @@ void fh_ctx_scratch_put(fh_ctx *ctx, size_t bytes, void *ptr);      // caller ha
 
 #define FH_MAX_PARTIALS 4096
 
+// Every handle carries a process-wide unique id (never reused): cached CUDA graphs key on (address, uid), so a handle
+// that was freed and re-allocated at the same host address is never mistaken for the one a graph was captured with.
+u64 fh_next_uid();
+
 struct fh_state {
     fh_ctx *ctx;
     int n;
     u64 dim;
     double2 *d;
     bool owned;
+    u64 uid = fh_next_uid();
 };
 
 struct fh_table {
+    u64 uid = fh_next_uid();
     fh_ctx *ctx;
     int n;
     int n_terms, n_groups;
@@ -237,6 +243,7 @@ struct fh_table {
 };
 
 struct fh_pool {
+    u64 uid = fh_next_uid();
     fh_ctx *ctx;
     int n;
     int n_entries, n_out;
@@ -312,3 +319,6 @@ void launch_sector_random(cudaStream_t s, int sm, double2 *v, int n, int n_up, i
 void launch_caxpy(cudaStream_t s, int sm, double2 *y, double ar, double ai, const double2 *x, u64 dim);      // y += (ar + i ai) x
 
 int fh_alloc_check(void *p, const char *what);
+// opt every kernel that needs more than 48 KB of dynamic shared memory in on the CURRENT device (the attribute is
+// per device; called from fh_ctx_create)
+int fh_kernels_init_device();

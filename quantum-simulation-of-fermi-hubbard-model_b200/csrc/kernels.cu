@@ -1483,17 +1483,10 @@ void launch_diag_adjoint(cudaStream_t s, int sm, double2 *psi, double2 *lam, con
     *blocks_used = grid;
 }
 
-static bool g_tile_attr_set = false;
-
 void launch_tile(cudaStream_t s, double2 *psi, const TileLaunch &tl, const TileRec *d_recs, const TileTerm *d_terms,
                  int n) {
     const int nbits = tl.nbits;
     const size_t smem = ((size_t)1 << nbits) * (sizeof(double2) + sizeof(unsigned int));
-    if (!g_tile_attr_set) {
-        cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
-        cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
-        g_tile_attr_set = true;
-    }
     u64 ntiles = 1ull << (n - nbits);
     const int grid = (int)(ntiles > 148ull * 16 ? 148ull * 16 : ntiles);
     // one thread per index pair of the tile (at most 512, at least two warps)
@@ -1525,7 +1518,7 @@ void launch_tile(cudaStream_t s, double2 *psi, const TileLaunch &tl, const TileR
     }
 }
 
-static int g_tile_multi_blocks_per_sm = -1;
+static int g_tile_multi_blocks_per_sm = -1;      // occupancy query result (same for every B200 of the box)
 
 // returns 0 when the cooperative launch cannot be used (caller falls back to one launch per run)
 int launch_tile_multi(cudaStream_t s, int sm, double2 *psi, const TileLaunch *d_tls, int nl, int max_bits, int min_bits,
@@ -1535,7 +1528,6 @@ int launch_tile_multi(cudaStream_t s, int sm, double2 *psi, const TileLaunch *d_
     if (threads > 512) threads = 512;
     if (threads < 64) threads = 64;
     if (g_tile_multi_blocks_per_sm < 0) {
-        cudaFuncSetAttribute(k_tile_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_tile_multi, 512, ((size_t)1 << 12) * 20) != cudaSuccess) nb = 0;
         g_tile_multi_blocks_per_sm = nb;
@@ -1557,16 +1549,10 @@ int launch_tile_multi(cudaStream_t s, int sm, double2 *psi, const TileLaunch *d_
     return 1;
 }
 
-static bool g_tile_adj_attr_set = false;
-
 void launch_tile_adjoint(cudaStream_t s, double2 *psi, double2 *lam, const TileLaunch &tl, const TileRec *d_recs,
                          const TileTerm *d_terms, int n, double *d_gpart, int seg_base) {
     const int nbits = tl.nbits;
     const size_t smem = ((size_t)1 << nbits) * (2 * sizeof(double2) + sizeof(unsigned int));
-    if (!g_tile_adj_attr_set) {
-        cudaFuncSetAttribute(k_tile_adjoint, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        g_tile_adj_attr_set = true;
-    }
     const u64 ntiles = 1ull << (n - nbits);
     const int grid = (int)(ntiles > (u64)FH_GRAD_BLOCKS ? (u64)FH_GRAD_BLOCKS : ntiles);
     int threads = nbits >= 1 ? (1 << (nbits - 1)) : 1;
@@ -1646,16 +1632,10 @@ void launch_pool(cudaStream_t s, const PoolEntry *entries, int first_entry, int 
     }
 }
 
-static bool g_pool_tile_attr_set = false;
-
 void launch_pool_tiles(cudaStream_t s, const PoolPass *d_passes, int npasses, const PoolTileRec *d_recs, int tile_bits,
                        int grid_x, int chunks, int n, const double2 *psi, const double2 *lam, double *d_partials, int e0,
                        int e1) {
     if (npasses <= 0) return;
-    if (!g_pool_tile_attr_set) {
-        cudaFuncSetAttribute(k_pool_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
-        g_pool_tile_attr_set = true;
-    }
     const size_t smem = ((size_t)1 << tile_bits) * 2 * sizeof(double2);
     int threads = 1 << (tile_bits > 3 ? tile_bits - 3 : 0);
     if (threads > 512) threads = 512;
@@ -1727,4 +1707,16 @@ void launch_scale(cudaStream_t s, int sm, double2 *y, double a, u64 dim) {
 }
 void launch_sector_random(cudaStream_t s, int sm, double2 *v, int n, int n_up, int n_dn, u64 seed) {
     ++g_fh_launch_count; k_sector_random<<<vec_grid(1ull << n, sm), 256, 0, s>>>(v, n, n_up, n_dn, seed);
+}
+
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: one process may drive several GPUs
+// (fhsim.backend.default_context(device)), so every context sets it for its own device.
+int fh_kernels_init_device() {
+    FH_CUDA(cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+    FH_CUDA(cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+    FH_CUDA(cudaFuncSetAttribute(k_tile_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+    FH_CUDA(cudaFuncSetAttribute(k_tile_adjoint, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    FH_CUDA(cudaFuncSetAttribute(k_pool_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024));
+    return FH_OK;
 }

@@ -29,6 +29,9 @@ struct EvalKey {
     const void *pool;
     int pool_pos, pool_first, pool_count;
     const void *state_out;
+    // unique ids of the same handles: a freed handle whose address is reused by a new one gets a new id, so the graph
+    // (which bakes in the device pointers behind the handles) is re-captured instead of replayed on freed memory
+    u64 table_uid[FH_MAX_RESULT_TABLES], target_uid[FH_MAX_OVERLAPS], pool_uid, state_out_uid;
     bool operator==(const EvalKey &o) const { return memcmp(this, &o, sizeof(EvalKey)) == 0; }
 };
 
@@ -802,9 +805,17 @@ extern "C" int fh_program_evaluate(fh_program *p, uint64_t basis_index, const do
     key.n_tables = n_tables;
     key.n_overlaps = n_overlaps;
     key.want_grads = grads != nullptr;
-    for (int t = 0; t < n_tables; ++t) key.tables[t] = tables[t];
-    for (int v = 0; v < n_overlaps; ++v) key.targets[v] = targets[v];
+    for (int t = 0; t < n_tables; ++t) {
+        key.tables[t] = tables[t];
+        key.table_uid[t] = tables[t]->uid;
+    }
+    for (int v = 0; v < n_overlaps; ++v) {
+        key.targets[v] = targets[v];
+        key.target_uid[v] = targets[v]->uid;
+    }
     key.pool = pool;
+    key.pool_uid = pool ? pool->uid : 0;
+    key.state_out_uid = state_out ? state_out->uid : 0;
     key.pool_pos = pool ? pool_pos : 0;
     key.pool_first = pool ? pool_first : 0;
     key.pool_count = pool ? pool_count : 0;

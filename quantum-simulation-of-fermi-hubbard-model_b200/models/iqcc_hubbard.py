@@ -136,6 +136,7 @@ class IQCC:
         loss = self.get_circuit(tau, DIS_gates)
         loss.backward()
         grads = np.abs(tau.grad.detach().cpu().numpy())
+        self.last_screening = (list(DIS_strings), grads.copy())      # every candidate with its |gradient| (float32)
         prog, pool = self._screen_objects
         prog.close()
         pool.close()
