@@ -118,7 +118,8 @@ struct __align__(16) TileTerm {         // 48 bytes
     u64 z;
     double angle, c, s;
     double coef;                        // d(angle)/d(theta) (0 for fixed terms)
-    double pad;
+    unsigned zlocal;                    // in-tile bits of z in tile-local coordinates (sign without a global index)
+    unsigned pad;
 };
 
 struct TileOp {                         // host bookkeeping of one tile run

@@ -294,7 +294,8 @@ static void set_tile_term(TileTerm &tt, const DiagTerm &t, bool dagger) {
     tt.c = t.c;
     tt.s = dagger ? -t.s : t.s;
     tt.coef = t.coef;
-    tt.pad = 0.0;
+    tt.zlocal = 0;
+    tt.pad = 0;
 }
 
 static void build_tile_records(fh_program *p) {
@@ -350,6 +351,8 @@ static void build_tile_records(fh_program *p) {
                     for (int m = 0; m < d.count; ++m) {
                         TileTerm tt;
                         set_tile_term(tt, p->dterms[d.first + m], dir != 0);
+                        for (int b = 0; b < t.nbits; ++b)
+                            if (tt.z >> t.bits[b] & 1ull) tt.zlocal |= 1u << b;
                         (dir ? p->dterm_tt_dag : p->dterm_tt_fwd)[d.first + m] = (int)tts.size();
                         tts.push_back(tt);
                     }
@@ -488,8 +491,11 @@ static void refresh_payload(fh_program *p, const double *thetas) {
             t.c = cos(t.angle);
             t.s = sin(t.angle);
             if (p->dterm_tt_fwd[m] >= 0) {
-                set_tile_term(p->h_tterms_fwd[p->dterm_tt_fwd[m]], t, false);
-                set_tile_term(p->h_tterms_dag[p->dterm_tt_dag[m]], t, true);
+                TileTerm &f = p->h_tterms_fwd[p->dterm_tt_fwd[m]], &g = p->h_tterms_dag[p->dterm_tt_dag[m]];
+                const unsigned zl = f.zlocal;         // geometry: fixed at finalize
+                set_tile_term(f, t, false);
+                set_tile_term(g, t, true);
+                f.zlocal = g.zlocal = zl;
             }
         }
     }

@@ -1,0 +1,498 @@
+// K1, fused tile runs with TMA tile movement (sm_100a).
+//
+// A tile = all 2^T amplitudes that differ only in T chosen index bits.  The gather "every amplitude whose other bits
+// equal this tile's" is done by the Tensor Memory Accelerator instead of by per-thread address arithmetic: the state
+// is described to cuTensorMapEncodeTiled as a tensor of doubles whose dim 0 is the WHOLE flat state (stride 8 B) and
+// whose higher dims are the runs of consecutive tile bits, each with stride 16 B << (first bit of the run) -- the
+// strides deliberately overlap dim 0.  One cp.async.bulk.tensor.5d with box = (low run, run, run, run, run) and dim-0
+// coordinate = 2 * (tile base index) then lands the tile in shared memory in tile-local index order; tile bits that do
+// not fit the 5 dims are iterated (2^extra boxes per tile, issued by the lanes of warp 0).  The same map stores the
+// tile back (cp.async.bulk.tensor ... bulk_group).  Verified on B200 by tools/probes/probe_tma.cu (profiles/r02_*).
+//
+// Shared-memory layout: with dim 0 = exactly 8 amplitudes (128 B) the map uses CU_TENSOR_MAP_SWIZZLE_128B, i.e. local
+// index l lives in 16-byte slot l ^ ((l >> 3) & 7): the strided pair accesses of the op loop spread over the eight
+// 16-byte bank groups.  Tiles whose lowest run is shorter than 3 bits use the linear layout.
+//
+// Persistent CTAs: when there are more tiles than resident CTAs every CTA owns two tile buffers and the load of tile
+// i+1 (and the store of tile i-1) overlap the op loop of tile i (mbarrier complete_tx for loads, bulk groups for
+// stores).  Op loop: the index/sign decode of op k+1 is computed before the barrier that ends op k, so the dependent
+// chain per op is LDS -> FP64 -> STS -> barrier.
+#include <cuda.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "devmath.cuh"
+
+extern long long g_fh_launch_count;
+extern thread_local int g_fh_tile_pdl_scope;
+
+void launch_tile_ldg(cudaStream_t s, double2 *psi, const TileLaunch &tl, const TileRec *d_recs, const TileTerm *d_terms,
+                     int n);
+
+// ----------------------------------------------------------------------------------------------
+// host: tensor maps
+// ----------------------------------------------------------------------------------------------
+struct TmaPlan {
+    int map_bits;              // tile-local bits [0, map_bits) are covered by one box
+    int n_extra;               // remaining local bits: 2^n_extra boxes per tile
+    int swizzle;               // 1: CU_TENSOR_MAP_SWIZZLE_128B layout
+    int pad;
+    unsigned char extra[8];    // global positions of the extra bits (ascending)
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return q == cudaDriverEntryPointSuccess ? reinterpret_cast<EncodeTiledFn>(p) : nullptr;
+    }();
+    return fn;
+}
+
+struct TmaEntry {
+    CUtensorMap map;
+    TmaPlan plan;
+    bool ok;
+};
+
+struct TmaKey {
+    const void *ptr;
+    int n, T;
+    unsigned char bits[16];
+    bool operator<(const TmaKey &o) const { return memcmp(this, &o, sizeof(TmaKey)) < 0; }
+};
+
+// dims of the box for a tile bit set: (first global bit, number of bits) per dim, dim 0 first
+static void plan_dims(const unsigned char *bits, int T, bool want_swizzle, std::vector<std::pair<int, int>> &dims,
+                      TmaPlan &plan) {
+    std::vector<std::pair<int, int>> runs;
+    for (int b = 0; b < T; ++b) {
+        if (!runs.empty() && runs.back().first + runs.back().second == bits[b]) runs.back().second++;
+        else runs.push_back({bits[b], 1});
+    }
+    dims.clear();
+    const int r0 = runs[0].second;
+    const bool swz = want_swizzle && r0 >= 3;
+    int first = swz ? 3 : (r0 < 7 ? r0 : 7);          // dim 0 box <= 256 doubles
+    dims.push_back({0, first});
+    for (int done = first; done < r0;) {
+        const int take = r0 - done > 8 ? 8 : r0 - done;
+        dims.push_back({done, take});
+        done += take;
+    }
+    for (size_t k = 1; k < runs.size(); ++k)
+        for (int done = 0; done < runs[k].second;) {
+            const int take = runs[k].second - done > 8 ? 8 : runs[k].second - done;
+            dims.push_back({runs[k].first + done, take});
+            done += take;
+        }
+    if (dims.size() > 5) dims.resize(5);
+    int covered = 0;
+    for (auto &d : dims) covered += d.second;
+    memset(&plan, 0, sizeof(plan));
+    plan.map_bits = covered;
+    plan.n_extra = T - covered;
+    plan.swizzle = swz ? 1 : 0;
+    for (int b = covered; b < T; ++b) plan.extra[b - covered] = bits[b];
+}
+
+static std::mutex g_tma_mutex;
+static std::map<TmaKey, TmaEntry> g_tma_cache;
+
+// tensor map + box plan for (state buffer, tile bit set); nullptr when the TMA path does not apply
+static const TmaEntry *tma_entry(const double2 *psi, int n, const TileLaunch &tl) {
+    const int T = tl.nbits;
+    if (n > 30 || T < 3 || T > FH_MAX_TILE_BITS || tl.bits[0] != 0) return nullptr;       // dim-0 coordinate is an int32 count of doubles
+    TmaKey key;
+    memset(&key, 0, sizeof(key));
+    key.ptr = psi;
+    key.n = n;
+    key.T = T;
+    memcpy(key.bits, tl.bits, 16);
+    std::lock_guard<std::mutex> lock(g_tma_mutex);
+    auto it = g_tma_cache.find(key);
+    if (it != g_tma_cache.end()) return it->second.ok ? &it->second : nullptr;
+    TmaEntry e;
+    memset(&e, 0, sizeof(e));
+    e.ok = false;
+    EncodeTiledFn enc = encode_fn();
+    if (enc) {
+        std::vector<std::pair<int, int>> dims;
+        plan_dims(tl.bits, T, true, dims, e.plan);
+        // every box must start on a 1024-byte boundary of the tile buffer for the 128-byte swizzle, and the bulk copy
+        // of 2^n_extra boxes should stay a handful of instructions
+        if (e.plan.swizzle && e.plan.map_bits < 6) plan_dims(tl.bits, T, false, dims, e.plan);
+        if (e.plan.n_extra <= 6) {
+            cuuint64_t gdim[5], gstride[4];
+            cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+            gdim[0] = 2ull << n;
+            box[0] = 2u << dims[0].second;
+            for (int k = 1; k < 5; ++k) {
+                if (k < (int)dims.size()) {
+                    gdim[k] = 1ull << dims[k].second;
+                    box[k] = 1u << dims[k].second;
+                    gstride[k - 1] = 16ull << dims[k].first;
+                } else {
+                    gdim[k] = 1;
+                    box[k] = 1;
+                    gstride[k - 1] = 16ull << n;
+                }
+            }
+            const CUresult r = enc(&e.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, const_cast<double2 *>(psi), gdim, gstride, box,
+                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   e.plan.swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            e.ok = (r == CUDA_SUCCESS);
+        }
+    }
+    if (g_tma_cache.size() > 4096) g_tma_cache.clear();
+    auto ins = g_tma_cache.emplace(key, e);
+    return ins.first->second.ok ? &ins.first->second : nullptr;
+}
+
+// ----------------------------------------------------------------------------------------------
+// device: TMA / mbarrier primitives
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_%=;\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(unsigned dst, const CUtensorMap *map, unsigned bar, int c0) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %4, %4, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(0)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap *map, unsigned src, int c0) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %3, %3, %3}], [%1];" ::"l"(map), "r"(src),
+                 "r"(c0), "r"(0)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <bool SWZ>
+__device__ __forceinline__ unsigned tslot(unsigned l) {
+    return SWZ ? (l ^ ((l >> 3) & 7u)) : l;
+}
+
+// dim-0 coordinate (in doubles) of box q of the tile with base index `base`
+__device__ __forceinline__ int box_coord(const TmaPlan &plan, unsigned base, unsigned q) {
+    unsigned g = base;
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        if (e < plan.n_extra) g |= ((q >> e) & 1u) << plan.extra[e];
+    return (int)(g << 1);
+}
+
+// all lanes of warp 0 call these; lane q moves box q, q + 32, ...
+__device__ __forceinline__ void warp_load_tile(const CUtensorMap *map, const TmaPlan &plan, unsigned base, unsigned dst,
+                                               unsigned bar, unsigned tile_bytes, int lane) {
+    if (lane == 0) mbar_expect_tx(bar, tile_bytes);
+    __syncwarp();
+    const unsigned nbox = 1u << plan.n_extra, box_bytes = 16u << plan.map_bits;
+    for (unsigned q = lane; q < nbox; q += 32) tma_load_5d(dst + q * box_bytes, map, bar, box_coord(plan, base, q));
+}
+__device__ __forceinline__ void warp_store_tile(const CUtensorMap *map, const TmaPlan &plan, unsigned base, unsigned src,
+                                                int lane) {
+    const unsigned nbox = 1u << plan.n_extra, box_bytes = 16u << plan.map_bits;
+    for (unsigned q = lane; q < nbox; q += 32) tma_store_5d(map, src + q * box_bytes, box_coord(plan, base, q));
+    bulk_commit();
+}
+
+__device__ __forceinline__ double flip_sign(double v, unsigned sbit) {
+    return __hiloint2double(__double2hiint(v) ^ (int)sbit, __double2loint(v));
+}
+
+// decoded position of this thread's pair for one op (computed one op ahead of its use)
+struct PairPrep {
+    unsigned si, sj;     // shared-memory slots of the pair
+    unsigned sbit;       // sign of the off-diagonal elements as an IEEE sign bit
+    unsigned active;     // this thread has a pair of this op in this tile
+};
+
+template <bool SWZ>
+__device__ __forceinline__ PairPrep prep_pair(const TileRec *rec, unsigned base, unsigned k, int T) {
+    const uint4 *rp = reinterpret_cast<const uint4 *>(rec);
+    const uint4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
+    // q0 = {fixmask_out, fixval_out, zeta, xlocal}; q1 = {lfixval, type, nlfix, term_off}; q2 = lowmask[4]
+    const unsigned zloc = rp[3].z;
+    PairPrep p;
+    const unsigned npairs = (1u << T) >> q1.z;
+    p.active = (q1.y != 2u) && ((base & q0.x) == q0.y) && (k < npairs);
+    unsigned il = k;
+    il = ((il & ~q2.x) << 1) | (il & q2.x);
+    il = ((il & ~q2.y) << 1) | (il & q2.y);
+    il = ((il & ~q2.z) << 1) | (il & q2.z);
+    il = ((il & ~q2.w) << 1) | (il & q2.w);
+    il |= q1.x;
+    p.sbit = ((unsigned)(__popc(base & q0.z) + __popc(il & zloc)) & 1u) << 31;
+    p.si = tslot<SWZ>(il);
+    p.sj = p.si ^ tslot<SWZ>(q0.w);           // the slot map is XOR-linear
+    return p;
+}
+
+__device__ __forceinline__ void apply_pair(double2 *buf, const TileRec *rec, const PairPrep &p) {
+    const double2 *mp = reinterpret_cast<const double2 *>(rec->m);
+    const int type = rec->type;
+    double2 a = buf[p.si], b = buf[p.sj];
+    if (type == 3) {            // real matrix (Givens)
+        const double m00 = mp[0].x, m01 = flip_sign(mp[1].x, p.sbit), m10 = flip_sign(mp[2].x, p.sbit), m11 = mp[3].x;
+        const double2 ra = make_double2(m00 * a.x + m01 * b.x, m00 * a.y + m01 * b.y);
+        const double2 rb = make_double2(m10 * a.x + m11 * b.x, m10 * a.y + m11 * b.y);
+        a = ra;
+        b = rb;
+    } else if (type == 6) {     // real diagonal, complex off-diagonal (every rotation exp(-i a G))
+        const double m00 = mp[0].x, m11 = mp[3].x;
+        const double2 mb = make_double2(flip_sign(mp[1].x, p.sbit), flip_sign(mp[1].y, p.sbit));
+        const double2 mc = make_double2(flip_sign(mp[2].x, p.sbit), flip_sign(mp[2].y, p.sbit));
+        const double2 ra = make_double2(m00 * a.x + (mb.x * b.x - mb.y * b.y), m00 * a.y + (mb.x * b.y + mb.y * b.x));
+        const double2 rb = make_double2(m11 * b.x + (mc.x * a.x - mc.y * a.y), m11 * b.y + (mc.x * a.y + mc.y * a.x));
+        a = ra;
+        b = rb;
+    } else {
+        const double2 ma = mp[0], md = mp[3];
+        const double2 mb = make_double2(flip_sign(mp[1].x, p.sbit), flip_sign(mp[1].y, p.sbit));
+        const double2 mc = make_double2(flip_sign(mp[2].x, p.sbit), flip_sign(mp[2].y, p.sbit));
+        const double2 ra = cadd(cmul(ma, a), cmul(mb, b));
+        const double2 rb = cadd(cmul(mc, a), cmul(md, b));
+        a = ra;
+        b = rb;
+    }
+    buf[p.si] = a;
+    buf[p.sj] = b;
+}
+
+// diagonal op on one tile: exp(-i sum_m angle_m sgn_m(index)).  Terms whose in-tile z bits sit entirely in local bits
+// 0..5 (or entirely in 6..) are folded into two phase tables built once per (op, tile); terms straddling both halves
+// are evaluated per amplitude from the tile-local z-mask (no global index needed).
+template <bool SWZ>
+__device__ __forceinline__ void apply_diag(double2 *buf, double2 *ph, const TileRec *rec, const TileTerm *tterm,
+                                           const TileLaunch &tl, int T, unsigned base, unsigned lomask_g, unsigned himask_g) {
+    const TileTerm *dt = tterm + rec->term_off;
+    const int cnt = rec->nterms;
+    const unsigned L = 1u << T;
+    for (unsigned v = threadIdx.x; v < 192u; v += blockDim.x) {
+        const bool lo = v < 64u;
+        const unsigned gl = base | (lo ? tile_scatter(tl, T, v, 0, 6) : tile_scatter(tl, T, v - 64u, 6, TILE_BITS_CAP));
+        double tot = 0.0;
+        for (int m = 0; m < cnt; ++m) {
+            const unsigned z = (unsigned)dt[m].z;
+            const bool in_lo = (z & himask_g) == 0u;
+            const bool in_hi = (z & lomask_g) == 0u && !in_lo;
+            if (lo ? in_lo : in_hi) tot += ((__popc(gl & z) & 1) ? -1.0 : 1.0) * dt[m].angle;
+        }
+        double sn, cs;
+        sincos(tot, &sn, &cs);
+        ph[v] = make_double2(cs, -sn);
+    }
+    __syncthreads();
+    for (unsigned l = threadIdx.x; l < L; l += blockDim.x) {
+        double2 f = cmul(ph[l & 63u], ph[64u + (l >> 6)]);
+        for (int m = 0; m < cnt; ++m) {
+            const unsigned z = (unsigned)dt[m].z;
+            if ((z & himask_g) != 0u && (z & lomask_g) != 0u) {
+                const unsigned par = (unsigned)(__popc(base & z) + __popc(l & dt[m].zlocal)) & 1u;
+                f = cmul(f, make_double2(dt[m].c, par ? dt[m].s : -dt[m].s));
+            }
+        }
+        const unsigned sl = tslot<SWZ>(l);
+        buf[sl] = cmul(f, buf[sl]);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// forward / dagger run on one state
+// ----------------------------------------------------------------------------------------------
+template <bool PDL, bool SWZ>
+__global__ void __launch_bounds__(512, 2)
+    k_tile_tma(const __grid_constant__ CUtensorMap map, const TileLaunch tl, const TmaPlan plan,
+               const TileRec *__restrict__ recs, const TileTerm *__restrict__ terms, int n, int stages) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long full_bar[2];
+    const int T = tl.nbits, nsub = tl.nsub;
+    const unsigned L = 1u << T, tile_bytes = L * 16u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // carve: [tile buffers, 1024-byte aligned][records][terms][phase tables]
+    const unsigned raw = smem_u32(smem_raw);
+    const unsigned pad = ((raw + 1023u) & ~1023u) - raw;
+    unsigned char *tiles = smem_raw + pad;
+    TileRec *rec = reinterpret_cast<TileRec *>(tiles + (size_t)stages * tile_bytes);
+    TileTerm *tterm = reinterpret_cast<TileTerm *>(rec + nsub);
+    double2 *ph = reinterpret_cast<double2 *>(tterm + tl.nterms);
+    const unsigned lomask_g = tile_mask(tl, T, 0, 6), himask_g = tile_mask(tl, T, 6, TILE_BITS_CAP);
+
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&full_bar[0]), 1);
+        mbar_init(smem_u32(&full_bar[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (PDL) asm volatile("griddepcontrol.launch_dependents;");
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(recs + tl.first_rec);
+        uint4 *dst = reinterpret_cast<uint4 *>(rec);
+        const int chunks = nsub * (int)(sizeof(TileRec) / 16);
+        for (int c = threadIdx.x; c < chunks; c += blockDim.x) dst[c] = __ldg(src + c);
+        const uint4 *tsrc = reinterpret_cast<const uint4 *>(terms + tl.first_term);
+        uint4 *tdst = reinterpret_cast<uint4 *>(tterm);
+        const int tchunks = tl.nterms * (int)(sizeof(TileTerm) / 16);
+        for (int c = threadIdx.x; c < tchunks; c += blockDim.x) tdst[c] = __ldg(tsrc + c);
+    }
+    __syncthreads();
+    if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");     // the previous kernel's amplitudes are complete
+
+    const unsigned ntiles = 1u << (n - T);
+    const unsigned tiles_u32 = smem_u32(tiles);
+    if (warp == 0 && blockIdx.x < ntiles)
+        warp_load_tile(&map, plan, (unsigned)tile_base(tl, T, blockIdx.x), tiles_u32, smem_u32(&full_bar[0]), tile_bytes, lane);
+
+    unsigned it = 0;
+    for (unsigned t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const unsigned st = stages == 2 ? (it & 1u) : 0u;
+        const unsigned parity = stages == 2 ? ((it >> 1) & 1u) : (it & 1u);
+        if (stages == 2 && warp == 0 && t + gridDim.x < ntiles) {
+            bulk_wait_read0();          // the store of tile it-1 has finished reading buffer st^1
+            warp_load_tile(&map, plan, (unsigned)tile_base(tl, T, t + gridDim.x), tiles_u32 + (st ^ 1u) * tile_bytes,
+                           smem_u32(&full_bar[st ^ 1u]), tile_bytes, lane);
+        }
+        const unsigned base = (unsigned)tile_base(tl, T, t);
+        double2 *buf = reinterpret_cast<double2 *>(tiles + (size_t)st * tile_bytes);
+        PairPrep cur = prep_pair<SWZ>(&rec[0], base, threadIdx.x, T);
+        mbar_wait(smem_u32(&full_bar[st]), parity);
+
+        for (int sidx = 0; sidx < nsub; ++sidx) {
+            const TileRec *r = &rec[sidx];
+            const int type = r->type;
+            PairPrep nxt;
+            nxt.active = 0u;
+            if (type != 2) {
+                if (cur.active) apply_pair(buf, r, cur);
+                if (sidx + 1 < nsub) nxt = prep_pair<SWZ>(&rec[sidx + 1], base, threadIdx.x, T);
+                // ops with more pairs than threads (pattern pins a single bit): the remaining pairs of this thread
+                const unsigned npairs = L >> (unsigned)r->nlfix;
+                for (unsigned k = threadIdx.x + blockDim.x; k < npairs; k += blockDim.x) {
+                    const PairPrep more = prep_pair<SWZ>(r, base, k, T);
+                    if (more.active) apply_pair(buf, r, more);
+                }
+            } else {
+                apply_diag<SWZ>(buf, ph, r, tterm, tl, T, base, lomask_g, himask_g);
+                if (sidx + 1 < nsub) nxt = prep_pair<SWZ>(&rec[sidx + 1], base, threadIdx.x, T);
+            }
+            cur = nxt;
+            if (sidx + 1 < nsub) __syncthreads();
+        }
+        fence_async_smem();             // generic-proxy writes of the op loop -> visible to the bulk store
+        __syncthreads();
+        if (warp == 0) {
+            warp_store_tile(&map, plan, base, tiles_u32 + st * tile_bytes, lane);
+            if (stages == 1 && t + gridDim.x < ntiles) {
+                bulk_wait_read0();
+                warp_load_tile(&map, plan, (unsigned)tile_base(tl, T, t + gridDim.x), tiles_u32, smem_u32(&full_bar[0]),
+                               tile_bytes, lane);
+            }
+        }
+    }
+    if (warp == 0) bulk_wait0();        // every store of this CTA is complete before it exits
+}
+
+// ----------------------------------------------------------------------------------------------
+// launch
+// ----------------------------------------------------------------------------------------------
+static size_t tile_tma_smem(const TileLaunch &tl, int stages) {
+    return 1024 + (size_t)stages * (16ull << tl.nbits) + (size_t)tl.nsub * sizeof(TileRec) + (size_t)tl.nterms * sizeof(TileTerm) +
+           192 * sizeof(double2) + 64;
+}
+
+void launch_tile(cudaStream_t s, double2 *psi, const TileLaunch &tl, const TileRec *d_recs, const TileTerm *d_terms, int n) {
+    const bool force_ldg = getenv("FHSIM_TILE_LDG") != nullptr;      // read per call: tests flip it at run time
+    const TmaEntry *e = force_ldg ? nullptr : tma_entry(psi, n, tl);
+    if (!e) {
+        launch_tile_ldg(s, psi, tl, d_recs, d_terms, n);
+        return;
+    }
+    const int nbits = tl.nbits;
+    const unsigned long long ntiles = 1ull << (n - nbits);
+    int dev = 0, sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+    // one tile per CTA while the tiles fit the machine in one wave of <= 2 CTAs per SM; otherwise persistent CTAs with
+    // two tile buffers each (load of the next tile and store of the previous one overlap the op loop)
+    int stages = 1;
+    unsigned long long grid = ntiles;
+    const size_t smem1 = tile_tma_smem(tl, 1), smem2 = tile_tma_smem(tl, 2);
+    const size_t sm_budget = 220 * 1024;
+    if (ntiles > (unsigned long long)sm * 2) {
+        if (smem2 <= sm_budget) {
+            stages = 2;
+            int per_sm = (int)(sm_budget / smem2);
+            if (per_sm > 2) per_sm = 2;
+            grid = (unsigned long long)sm * per_sm;
+        } else {
+            grid = (unsigned long long)sm;
+        }
+        if (grid > ntiles) grid = ntiles;
+    }
+    const size_t smem = stages == 2 ? smem2 : smem1;
+    int threads = nbits >= 1 ? (1 << (nbits - 1)) : 1;
+    if (threads > 512) threads = 512;
+    if (threads < 64) threads = 64;
+    static const bool pdl_all = getenv("FHSIM_PDL") != nullptr, pdl_off = getenv("FHSIM_NO_PDL") != nullptr;
+    const bool pdl = !pdl_off && (pdl_all || g_fh_tile_pdl_scope > 0);
+    ++g_fh_launch_count;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    if (pdl) {
+        if (e->plan.swizzle) cudaLaunchKernelEx(&cfg, k_tile_tma<true, true>, e->map, tl, e->plan, d_recs, d_terms, n, stages);
+        else cudaLaunchKernelEx(&cfg, k_tile_tma<true, false>, e->map, tl, e->plan, d_recs, d_terms, n, stages);
+    } else {
+        if (e->plan.swizzle) cudaLaunchKernelEx(&cfg, k_tile_tma<false, true>, e->map, tl, e->plan, d_recs, d_terms, n, stages);
+        else cudaLaunchKernelEx(&cfg, k_tile_tma<false, false>, e->map, tl, e->plan, d_recs, d_terms, n, stages);
+    }
+}
+
+int fh_tile_tma_init_device() {
+    const int bytes = 224 * 1024;
+    FH_CUDA(cudaFuncSetAttribute(k_tile_tma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    FH_CUDA(cudaFuncSetAttribute(k_tile_tma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    FH_CUDA(cudaFuncSetAttribute(k_tile_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    FH_CUDA(cudaFuncSetAttribute(k_tile_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return FH_OK;
+}

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from fhsim.backend import Context, DevicePool, DeviceTable, State, lanczos
-from fhsim.circuit import Circuit
+from fhsim.circuit import Circuit, DiagOpSpec
 from fhsim.symbolic import QubitOperator, fermi_hubbard, givens_decomposition_square, jordan_wigner
 from fhsim.tables import GeneratorPlan, PauliTable, pack_term
 from operators.fourier import fourier_transform_matrix
@@ -460,3 +460,88 @@ def test_error_paths(ctx):
     tab = PauliTable(3, [1], [0], [1.0])
     with pytest.raises(ValueError):
         DeviceTable(ctx, tab).apply(st)              # qubit-count mismatch
+
+
+def _random_clustered_circuit(n, n_params, seed, groups=14):
+    rng = np.random.default_rng(seed)
+    circ = Circuit(n, n_params)
+    for _ in range(groups):
+        w = [int(v) for v in rng.choice(n, size=3, replace=False)]
+        for _ in range(int(rng.integers(1, 6))):
+            kind = int(rng.integers(0, 8))
+            a, b, c = (w[int(i)] for i in rng.permutation(3))
+            ang = float(rng.uniform(-2.0, 2.0))
+            if kind == 0:
+                circ.ry(0.0, a, param=int(rng.integers(n_params)))
+            elif kind == 1:
+                circ.rx(ang, a)
+            elif kind == 2:
+                circ.cnot(a, b)
+            elif kind == 3:
+                circ.single_excitation(ang, a, b)
+            elif kind == 4:
+                circ.fermionic_single_excitation(ang, a, b)
+            elif kind == 5:
+                circ.rz(ang, a)
+            elif kind == 6:
+                x = circ._bit(a) | circ._bit(b) | (circ._bit(c) if rng.integers(2) else 0)
+                z = int(rng.integers(1 << n))
+                circ.pauli_rotation(x, z, 0.5, param=int(rng.integers(n_params)))
+            else:
+                circ.pauli_x(a)
+    return circ
+
+
+@pytest.mark.parametrize("n,tile_bits,low_bits", [(14, 8, 1), (14, 10, 3), (16, 11, 2), (18, 11, 1), (18, 12, 4),
+                                                   (20, 13, 3), (22, 11, 3), (22, 12, 1)])
+def test_tile_tma_path_equals_register_staged_path_and_interpreter(ctx, n, tile_bits, low_bits, monkeypatch):
+    """k_tile_tma (TMA tile gather / scatter, hardware 128-byte swizzle, one or two tile buffers per CTA) against the
+    register-staged k_tile (FHSIM_TILE_LDG=1) on the same compiled program, forward and dagger, and against the numpy
+    interpreter of the op semantics where that finishes in seconds.  n = 22 runs persistent CTAs (2 048 / 1 024 tiles)."""
+    import emulate
+    n_params = 6
+    th = np.random.default_rng(5 + n).uniform(-1.0, 1.0, n_params)
+    circ = _random_clustered_circuit(n, n_params, 4000 + 31 * n + tile_bits, groups=18)
+    psi0 = rand_state(n, 300 + n)
+    prog = circ.compile(ctx, tile_bits=tile_bits, low_bits=low_bits)
+    assert prog.n_tiles > 0
+    monkeypatch.delenv("FHSIM_TILE_LDG", raising=False)
+    st = State.from_numpy(ctx, psi0)
+    prog.run(st, th)
+    got = st.numpy()
+    monkeypatch.setenv("FHSIM_TILE_LDG", "1")
+    st2 = State.from_numpy(ctx, psi0)
+    prog.run(st2, th)
+    ref = st2.numpy()
+    monkeypatch.delenv("FHSIM_TILE_LDG", raising=False)
+    assert np.abs(got - ref).max() < 1e-13
+    assert abs(np.vdot(got, got).real - 1.0) < 1e-12
+    if n <= 18:
+        want = emulate.run_circuit(circ, psi0.copy(), th)
+        assert np.abs(got - want).max() < AMP_TOL
+    prog.run(st, th, dagger=True)
+    assert np.abs(st.numpy() - psi0).max() < AMP_TOL
+
+
+def test_tile_tma_coulomb_layers_with_straddling_terms(ctx):
+    """Diagonal ops inside TMA tiles: ZZ terms whose two bits sit in different halves of the tile (evaluated from the
+    tile-local z-mask) and terms with bits outside the tile, interleaved with hopping rotations -- vs the interpreter."""
+    import emulate
+    n = 16
+    rng = np.random.default_rng(99)
+    circ = Circuit(n, 3)
+    for rep in range(3):
+        zs = [int((1 << int(a)) | (1 << int(b))) for a, b in (rng.choice(n, size=2, replace=False) for _ in range(20))]
+        zs += [1 << int(q) for q in rng.choice(n, size=6, replace=False)]
+        circ.ops.append(DiagOpSpec(zs, [float(v) for v in rng.uniform(-1, 1, len(zs))], rep, [(0, z) for z in zs]))
+        for _ in range(4):
+            a, b = (int(v) for v in rng.choice(n, size=2, replace=False))
+            circ.fermionic_single_excitation(float(rng.uniform(-2, 2)), a, b)
+    th = rng.uniform(-1, 1, 3)
+    psi0 = rand_state(n, 5)
+    want = emulate.run_circuit(circ, psi0.copy(), th)
+    for tb, lb in ((10, 3), (12, 1), (9, 4)):
+        prog = circ.compile(ctx, tile_bits=tb, low_bits=lb)
+        st = State.from_numpy(ctx, psi0)
+        prog.run(st, th)
+        assert np.abs(st.numpy() - want).max() < AMP_TOL

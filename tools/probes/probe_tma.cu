@@ -190,8 +190,8 @@ int main() {
         {"A: runs [0-2],[5],[9-10],[14] no swizzle", {{0, 3}, {5, 1}, {9, 2}, {14, 1}}, CU_TENSOR_MAP_SWIZZLE_NONE, 0, (1u << 3) | (1u << 12)},
         {"B: same, SWIZZLE_128B (inner = 128 B)", {{0, 3}, {5, 1}, {9, 2}, {14, 1}}, CU_TENSOR_MAP_SWIZZLE_128B, 0, (1u << 3) | (1u << 12)},
         {"C: runs [0-4],[7-8],[12] SWIZZLE_128B, run0 split 3+2", {{0, 5}, {7, 2}, {12, 1}}, CU_TENSOR_MAP_SWIZZLE_128B, 3, (1u << 5) | (1u << 17)},
-        {"D: runs [0-1],[4],[6],[9-10] SWIZZLE_128B (inner = 64 B)", {{0, 2}, {4, 1}, {6, 1}, {9, 2}}, CU_TENSOR_MAP_SWIZZLE_128B, 0, (1u << 2) | (1u << 16)},
-        {"E: runs [0],[3],[5],[7],[9] SWIZZLE_128B (inner = 32 B)", {{0, 1}, {3, 1}, {5, 1}, {7, 1}, {9, 1}}, CU_TENSOR_MAP_SWIZZLE_128B, 0, (1u << 1)},
+        {"D: runs [0-1],[4],[6],[9-10] no swizzle (inner = 32 B rows)", {{0, 2}, {4, 1}, {6, 1}, {9, 2}}, CU_TENSOR_MAP_SWIZZLE_NONE, 0, (1u << 2) | (1u << 16)},
+        {"E: runs [0],[3],[5],[7],[9] no swizzle (inner = 32 B)", {{0, 1}, {3, 1}, {5, 1}, {7, 1}, {9, 1}}, CU_TENSOR_MAP_SWIZZLE_NONE, 0, (1u << 1)},
         {"F: runs [0-3],[5],[7],[9],[11] no swizzle (W-like)", {{0, 4}, {5, 1}, {7, 1}, {9, 1}, {11, 1}}, CU_TENSOR_MAP_SWIZZLE_NONE, 0, (1u << 13) | (1u << 4)},
     };
     for (auto &c : cases) {
