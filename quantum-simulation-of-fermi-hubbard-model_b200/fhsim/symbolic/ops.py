@@ -52,6 +52,22 @@ class SymbolicOperator:
     def _format_factor(factor) -> str:
         raise NotImplementedError
 
+    # -- pickling -----------------------------------------------------------
+    # OpenFermion operators pickle as cls.__new__(cls) + the instance dict {'terms': {...}}; this class has __slots__,
+    # whose default state is (None, {'terms': ...}).  Accept both so checkpoints written by the reference load
+    # (fhsim/checkpoint.py maps the class paths).
+    def __getstate__(self):
+        return {"terms": self.terms}
+
+    def __setstate__(self, state):
+        if isinstance(state, tuple) and len(state) == 2:
+            merged = {}
+            for part in state:
+                if part:
+                    merged.update(part)
+            state = merged
+        self.terms = dict(state["terms"])
+
     # -- construction -------------------------------------------------------
     def __init__(self, term=None, coefficient=1.0):
         if not isinstance(coefficient, _COEFF_TYPES):

@@ -14,6 +14,8 @@ from __future__ import annotations
 
 import os
 import pickle
+
+from fhsim import checkpoint
 import time
 from functools import partial
 
@@ -144,11 +146,11 @@ class ADAPT(HubbardProblem):
         import json
         if os.path.exists(self.model_filepath) and os.path.exists(self.result_filepath):
             with open(self.model_filepath, 'rb') as file:
-                state_dict = pickle.load(file)
+                state_dict = checkpoint.load(file)
             self.params = state_dict['params'].to(self.device)
             self.selected_gates = state_dict['circuit']
             with open(self.result_filepath, 'rb') as file:
-                self.results = pickle.load(file)
+                self.results = checkpoint.load(file)
             return
         twin = self.model_filepath + '.npz'
         if not os.path.exists(twin):

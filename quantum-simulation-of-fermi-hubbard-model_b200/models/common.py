@@ -11,6 +11,8 @@ from __future__ import annotations
 import os
 import pickle
 
+from fhsim import checkpoint
+
 import numpy as np
 import torch
 
@@ -231,7 +233,7 @@ class HubbardProblem:
         path = self.wf_filepath
         if os.path.exists(path):
             with open(path, 'rb') as file:
-                cached = pickle.load(file)
+                cached = checkpoint.load(file)
             return cached['energy'], cached['wave function']
         energy, wf = solver(sparse_operator=get_sparse_operator(self.fermionHamiltonian, self.n_qubits),
                             particle_number=self.n_electrons, spin_up=self.n_spin_up, spin_down=self.n_spin_down)

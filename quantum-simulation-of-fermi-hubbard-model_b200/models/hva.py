@@ -10,6 +10,8 @@ from __future__ import annotations
 import os
 import pickle
 
+from fhsim import checkpoint
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -100,9 +102,9 @@ class HVA(HubbardProblem):
             if not os.path.exists(path):
                 raise ValueError('Please check if the file ' + path + 'exists!')
         with open(self.model_filepath, 'rb') as file:
-            self.params = pickle.load(file)['params'].to(self.device)
+            self.params = checkpoint.load(file)['params'].to(self.device)
         with open(self.result_filepath, 'rb') as file:
-            self.results = pickle.load(file)
+            self.results = checkpoint.load(file)
 
     # flat parameter layout handed to the backend: [theta_U | theta_h | theta_v]
     def build_circuit(self) -> Circuit:

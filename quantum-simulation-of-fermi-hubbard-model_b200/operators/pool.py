@@ -5,6 +5,8 @@ Only ``hubbard_interaction_pool_simplified`` (reference :220-255) is used by any
 other generators of the reference file are kept as symbolic helpers with the same
 signatures.
 """
+from functools import reduce
+
 from fhsim.symbolic import FermionOperator, hermitian_conjugated, normal_ordered
 
 
@@ -137,3 +139,84 @@ def general_operator_pool(Nx, Ny):
                         push(normal_ordered(FermionOperator(f'{k1}^ {k2}^ {k3} {k4}', 1j)
                                             - FermionOperator(f'{k3}^ {k4}^ {k1} {k2}', 1j)))
     return pool
+
+
+def spin_complemented_pool(n_electrons, n_orbitals, generalized=True, faithful=True):
+    """Spin-complemented singles A_pq = tau_{p up,q up} + tau_{p dn,q dn} and doubles A1 (same-spin), A2 (opposite-spin)
+    (reference :48-131); no driver calls it.
+
+    ``faithful=True`` reproduces the reference's output exactly, including its stale-variable slip: inside the doubles
+    loop the reference re-assigns ``s_up/s_down`` where ``p_up/p_down`` was meant (reference :111-113), so every double
+    excitation is built with the ``p`` left over from the singles loop (the last orbital).  ``faithful=False`` uses the
+    loop's own ``p``."""
+    n_occ = n_electrons // 2
+    end = n_orbitals if generalized else n_occ
+    pool = []
+    p_left_over = None
+    for q in range(end):
+        for p in range(q + 1 if generalized else n_occ, n_orbitals):
+            p_left_over = p
+            up = FermionOperator(f'{2 * p}^ {2 * q}') - FermionOperator(f'{2 * q}^ {2 * p}')
+            down = FermionOperator(f'{2 * p + 1}^ {2 * q + 1}') - FermionOperator(f'{2 * q + 1}^ {2 * p + 1}')
+            op = normal_ordered(up + down)
+            if op.many_body_order() > 0:
+                pool.append(op)
+    for s_ in range(end):
+        for r in range(s_, end):
+            for q in range(r + 1 if generalized else n_occ, n_orbitals):
+                for p in range(q, n_orbitals):
+                    pp = p_left_over if faithful else p
+                    if pp is None:
+                        raise NameError("p_up is not defined (the reference fails the same way when no single excitation exists)")
+                    pu, pd, qu, qd, ru, rd, su, sd = 2 * pp, 2 * pp + 1, 2 * q, 2 * q + 1, 2 * r, 2 * r + 1, 2 * s_, 2 * s_ + 1
+                    same = FermionOperator(f'{pu}^ {qu}^ {ru} {su}')
+                    same += FermionOperator(f'{pd}^ {qd}^ {rd} {sd}')
+                    same -= hermitian_conjugated(same)
+                    same = normal_ordered(same)
+                    mixed = FermionOperator(f'{pu}^ {qd}^ {ru} {sd}')
+                    mixed += FermionOperator(f'{pd}^ {qu}^ {rd} {su}')
+                    mixed -= hermitian_conjugated(mixed)
+                    mixed = normal_ordered(mixed)
+                    if same.many_body_order() > 0:
+                        pool.append(same)
+                    if mixed.many_body_order() > 0:
+                        pool.append(mixed)
+    return pool
+
+
+def hubbard_interation_pool_modified(Nx, Ny):
+    """Five momentum channels (ZS, ZS2, W, BCS, BCS2) restricted to nearest-neighbour transfers q, each returned as ONE
+    summed FermionOperator (reference :257-340, name spelled as there); no driver calls it.  Q_N = (Nx//2, Ny//2)."""
+    to_index, to_xy = _index_maps(Nx)
+    names = ('ZS channel', 'ZS2 channel', 'W channel', 'BCS channel', 'BCS2 channel')
+    members = {name: [] for name in names}
+    seen = {name: set() for name in names}
+    hx, hy = Nx // 2, Ny // 2
+
+    def push(name, i1, i2, i3, i4):
+        op = normal_ordered(FermionOperator(f'{i1}^ {i2}^ {i3} {i4}'))
+        key = _canonical_key(op) if op.terms else frozenset()
+        if key not in seen[name]:
+            seen[name].add(key)
+            members[name].append(op)
+
+    for spin in (0, 1):
+        o = spin ^ 1
+        for k1 in range(Nx * Ny):
+            kx1, ky1 = to_xy(k1)
+            for k2 in range(Nx * Ny):
+                kx2, ky2 = to_xy(k2)
+                for qx, qy in ((1, 0), (0, 1), (-1, 0), (0, -1)):
+                    plus = to_index((kx1 + qx) % Nx, (ky1 + qy) % Ny, spin)
+                    minus = to_index((kx2 - qx) % Nx, (ky2 - qy) % Ny, o)
+                    push('ZS channel', plus, minus, to_index(kx2, ky2, o), to_index(kx1, ky1, spin))
+                    push('ZS2 channel', plus, minus, to_index(kx1, ky1, o), to_index(kx2, ky2, spin))
+                    push('W channel', to_index(kx1, ky1, spin), to_index(kx2, ky2, o),
+                         to_index((kx2 + hx + qx) % Nx, (ky2 + hy + qy) % Ny, o),
+                         to_index((kx1 - hx - qx) % Nx, (ky1 - hy - qy) % Ny, spin))
+                    push('BCS channel', to_index(kx1, ky1, spin), to_index((-kx1 + qx) % Nx, (-ky1 + qy) % Ny, o),
+                         to_index((-kx2 + qx) % Nx, (-ky2 + qy) % Ny, o), to_index(kx2, ky2, spin))
+                    push('BCS2 channel', to_index(kx1, ky1, spin),
+                         to_index((-kx1 + hx + qx) % Nx, (-ky1 + hy + qy) % Ny, o),
+                         to_index((-kx2 + hx + qx) % Nx, (-ky2 + hy + qy) % Ny, o), to_index(kx2, ky2, spin))
+    return {name: reduce(lambda a, b: a + b, members[name]) for name in names}

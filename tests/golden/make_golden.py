@@ -131,6 +131,19 @@ def main():
         json.dump(golden, f, separators=(",", ":"))
     print("wrote", os.path.join(HERE, "reference_host_tables.json"))
 
+    # pools no driver uses (operators/pool.py:48-131, 257-340): signatures kept, outputs pinned all the same
+    unused = {"_generator": "tests/golden/make_golden.py",
+              "spin_complemented_pool": {}, "hubbard_interation_pool_modified": {}}
+    for (n_el, n_orb, gen) in [(4, 4, True), (4, 4, False), (2, 3, True)]:
+        ops = ref_pool.spin_complemented_pool(n_el, n_orb, gen)
+        unused["spin_complemented_pool"][f"{n_el},{n_orb},{int(gen)}"] = [_fermion_terms(op) for op in ops]
+    for (nx, ny) in [(2, 2), (2, 3)]:
+        ch = ref_pool.hubbard_interation_pool_modified(nx, ny)
+        unused["hubbard_interation_pool_modified"][f"{nx}x{ny}"] = {k: _fermion_terms(v) for k, v in ch.items()}
+    with open(os.path.join(HERE, "reference_unused_pools.json"), "w") as f:
+        json.dump(unused, f, separators=(",", ":"))
+    print("wrote", os.path.join(HERE, "reference_unused_pools.json"))
+
 
 if __name__ == "__main__":
     main()

@@ -113,3 +113,31 @@ def test_hva_layers(nx, ny, u):
     for op, want in zip(vset, g["hva_vertical"]):
         _same_terms(_terms(op), want)
     assert all(isinstance(op, FermionOperator) for op in hset + vset)
+
+
+# pools no driver uses (reference operators/pool.py:48-131, 257-340): signatures kept, outputs pinned by the reference's
+# own loops all the same (tests/golden/reference_unused_pools.json)
+with open(os.path.join(HERE, "golden", "reference_unused_pools.json")) as _f:
+    UNUSED = json.load(_f)
+
+
+@pytest.mark.parametrize("key", sorted(UNUSED["spin_complemented_pool"]))
+def test_spin_complemented_pool_matches_reference_including_its_stale_variable(key):
+    from operators.pool import spin_complemented_pool
+    n_el, n_orb, gen = (int(v) for v in key.split(","))
+    mine = spin_complemented_pool(n_el, n_orb, bool(gen))
+    gold = UNUSED["spin_complemented_pool"][key]
+    assert len(mine) == len(gold)
+    for op, want in zip(mine, gold):
+        _same_terms(_terms(op), want)
+
+
+@pytest.mark.parametrize("key", sorted(UNUSED["hubbard_interation_pool_modified"]))
+def test_hubbard_interation_pool_modified_matches_reference(key):
+    from operators.pool import hubbard_interation_pool_modified
+    nx, ny = (int(v) for v in key.split("x"))
+    mine = hubbard_interation_pool_modified(nx, ny)
+    gold = UNUSED["hubbard_interation_pool_modified"][key]
+    assert list(mine) == list(gold)
+    for name in gold:
+        _same_terms(_terms(mine[name]), gold[name], tol=1e-12)

@@ -486,3 +486,35 @@ def test_state_mode_twice_with_different_parameters_does_not_replay_a_stale_grap
         state = vqe.circuit(mode='state').numpy()
         phi = sv.basis_change(sv.adapt_state(n, occ, [pool[k] for k in sel], th.astype(np.float64)), diag, layers, n)
         assert np.abs(state - phi).max() < 1e-11
+
+
+def test_adapt_resumes_from_a_reference_written_checkpoint():
+    """load_model=True on pickles whose class paths are the reference environment's (openfermion.*, __main__.
+    Trotterize_generator): the shipped 3x3 configuration of the reference resumes this way (adapt_vqe_for_3x3.py:482)."""
+    import pickle
+    from models.adapt_vqe import ADAPT
+    from refpickle import dumps_like_reference
+    kw = dict(n_epoch=1, threshold1=1e-2, threshold2=5e-2, x_dimension=2, y_dimension=2, n_electrons=4, n_spin_up=2,
+              n_spin_down=2, tunneling=1, coulomb=4.0, verbose=False)
+    vqe = ADAPT(**kw)
+    vqe.run()
+    e_ref = vqe.circuit(mode='train')[0].item()
+    with open(vqe.model_filepath, 'rb') as f:
+        model = pickle.load(f)
+    with open(vqe.result_filepath, 'rb') as f:
+        results = pickle.load(f)
+    with open(vqe.model_filepath, 'wb') as f:
+        f.write(dumps_like_reference(model))
+    with open(vqe.result_filepath, 'wb') as f:
+        f.write(dumps_like_reference(results))
+    os.remove(vqe.model_filepath + '.npz')
+    with pytest.raises((ModuleNotFoundError, AttributeError)):
+        with open(vqe.model_filepath, 'rb') as f:
+            pickle.load(f)
+    again = ADAPT(**kw, load_model=True)
+    assert torch.equal(again.params['t'], vqe.params['t'])
+    assert again.results['selected operators'] == vqe.results['selected operators']
+    assert abs(again.circuit(mode='train')[0].item() - e_ref) < 1e-12
+    again.n_epoch = 2
+    again.run()                                                     # resumes at epoch 2 (reference adapt_vqe.py:379)
+    assert len(again.results['epoch loss']) == 2
