@@ -189,26 +189,83 @@ def cpu_reference_sample(n_ops, picks=None, thetas=None):
     return one_step, torch.get_num_threads()
 
 
+def reference_chunk_ops():
+    """Pool operators per timed chunk of the reference-faithful CPU path: 32 ("3x3 screening is run in
+    pool chunks of 32 ops"; ~19 GB of autograd-saved statevectors), fewer only if the host cannot hold that."""
+    if os.environ.get("FH_BENCH_REF_OPS"):               # contract tests on small hosts
+        return max(1, int(os.environ["FH_BENCH_REF_OPS"]))
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available / 2 ** 30
+    except Exception:
+        avail = 64.0
+    return 32 if avail >= 40 else (16 if avail >= 24 else 8)
+
+
+def run_cpu_closed_form(args):
+    """'CPU-closed-form' of BASELINE.md 3: the SAME algorithm the GPU path runs (g_k = 2 Im <lambda|G_k|psi>,
+    lambda = W^dagger H W psi) on the host cores -- oracle/cpu_closed_form.c (plain C + OpenMP) executing the same
+    host-compiled op list as the CUDA program -- for the whole 324-operator screening step, on 1 thread and on all cores.
+    It separates the algorithmic gain (closed form vs append-and-backprop) from the kernel/hardware gain.  No torch, no
+    CUDA in this process."""
+    from fhsim.circuit import Circuit, Marker
+    from oracle import cpu_closed_form as cf
+    n = N_QUBITS
+    h_tab, plans, dec, diag, basis = build_tables()
+    cores = os.cpu_count() or 1
+    # first-epoch picks at the HF state, exactly as the GPU arm selects them
+    c0 = Circuit(n, 0)
+    c0.marker("ansatz_end")
+    c0.basis_change_separable(NX, NY)
+    _, g0 = cf.screening(n, basis, [], c0.ops[1:], [], h_tab, plans, threads=cores)
+    picks = [k for k in range(len(plans)) if abs(g0[k]) > 1e-9]
+    assert len(picks) == 52, len(picks)
+    thetas = np.random.default_rng(1234).uniform(-0.1, 0.1, len(picks))
+    circ = Circuit(n, len(picks))
+    for j, k in enumerate(picks):
+        circ.generator(plans[k], param=j)
+    circ.marker("ansatz_end")
+    circ.basis_change_separable(NX, NY)
+    cut = next(i for i, op in enumerate(circ.ops) if isinstance(op, Marker))
+    ansatz, w_ops = circ.ops[:cut], circ.ops[cut + 1:]
+    out = {"cores": cores}
+    for label, threads in (("1thread", 1), ("allcores", cores)):
+        cf.screening(n, basis, ansatz, w_ops, thetas, h_tab, plans, threads)            # warm-up
+        reps, t0 = 0, time.perf_counter()
+        while reps < 3 or (time.perf_counter() - t0 < 3.0 and reps < 200):
+            energy, grads = cf.screening(n, basis, ansatz, w_ops, thetas, h_tab, plans, threads)
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        out[label] = {"value": len(plans) / dt, "unit": "gradients/s", "ms_per_screening": 1e3 * dt, "threads": threads,
+                      "reps": reps}
+    out["energy"] = float(energy)
+    out["checksum"] = float(np.abs(grads).sum())
+    out["sample"] = ("whole 324-operator screening of the bench workload (52 ansatz rotations, W, H, W^dagger, 324 pair-form "
+                     "reductions) by oracle/cpu_closed_form.c: gcc -O3 -fopenmp, complex128, same op list as the CUDA program")
+    print(json.dumps({"impl": "cpu-closed-form", **out}))
+
+
 # ---------------------------------------------------------------------------------------------
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    n_ops = 4
+    n_ops = reference_chunk_ops()
     one_step, cores = cpu_reference_sample(n_ops)
     budget_s = 150.0
     times = []
-    t_first, _, passes = one_step()                       # warm-up / calibration
+    t_first, _, passes = one_step()                       # warm-up / calibration (untimed)
     steps = max(1, min(args.steps, int(budget_s / max(t_first, 1e-3))))
-    warm = max(0, min(args.warmup, 1))
-    for _ in range(warm):
-        one_step()
+    warm = 1
     for _ in range(steps):
         dt, _, _ = one_step()
         times.append(dt)
     total = sum(times)
     value = n_ops * len(times) / total
-    sample = (f"{n_ops} of 324 pool operators appended to the 52-operator ansatz state (prefix prepared untimed), "
-              f"W + per-term <H> + autograd backward timed; {passes} gate passes per step")
+    sample = (f"one chunk of {n_ops} of the 324 pool operators appended to the 52-operator ansatz state and back-propagated "
+              f"(reference algorithm, adapt_vqe.py:297-310, in pool chunks as BASELINE.md 3 specifies); W, the 100-term <H> and "
+              f"their backward are inside the timed region and amortised over the {n_ops} operators of the chunk; the ansatz "
+              f"prefix is prepared untimed (the reference would re-run it per chunk); {passes} gate passes per step; "
+              f"steps bounded to ~{int(budget_s)} s of CPU work")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "gradients/s", "n_gpus": args.gpus,
         "steps": len(times), "steps_requested": args.steps, "warmup": warm, "ms_per_step": 1e3 * total / len(times),
@@ -398,20 +455,31 @@ def run_gpu_arm(args, rank, world, local_rank):
 
     # ---- CPU baseline (bounded sample of the same workload) ----
     cpu = None
+    cpu_closed = None
     if not args.no_cpu_baseline and world == 1:          # rank 0 at N=1 only
-        n_ops = 4
+        n_ops = reference_chunk_ops()
+        warm_step, cores = cpu_reference_sample(2, wl["picks"], thetas)
+        warm_step()                                       # thread pool / allocator warm-up on a 2-operator chunk
         one_step, cores = cpu_reference_sample(n_ops, wl["picks"], thetas)
-        one_step()
-        ts, grads_cpu, passes = [], None, 0
-        for _ in range(3):
-            dt, grads_cpu, passes = one_step()
-            ts.append(dt)
-        cpu_val = n_ops / statistics.median(ts)
+        dt, grads_cpu, passes = one_step()
+        cpu_val = n_ops / dt
+        # float32 parameters and gradients, as the reference has them: agreement is bounded by float32 rounding here; the
+        # 1e-12 agreement of this path with the closed form in float64 is tests/test_oracle_literal.py
         err = float(np.abs(np.abs(grads_cpu) - np.abs(res["pool"][:n_ops]).astype(np.float32)).max())
         cpu = {"value": cpu_val, "unit": "gradients/s", "cores": cores, "kind": "port",
-               "sample": (f"{n_ops} of 324 pool operators by the reference's append-and-backprop algorithm "
-                          f"(oracle/literal.py, torch CPU, {passes} gate passes/step; ansatz prefix untimed); "
-                          f"max |g_cpu - g_gpu| on the sample = {err:.2e}")}
+               "sample": (f"one chunk of {n_ops} of the 324 pool operators by the reference's append-and-backprop algorithm "
+                          f"(oracle/literal.py, torch CPU, {passes} gate passes, {dt:.1f} s; W + <H> + backward amortised over "
+                          f"the chunk, ansatz prefix untimed); max |g_cpu - g_gpu| on the chunk = {err:.2e} (float32 gradients)")}
+        try:                                              # fair algorithm-for-algorithm CPU number, in a fresh process
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "cpu-closed-form"], capture_output=True,
+                                 text=True, timeout=600)
+            cpu_closed = json.loads(out.stdout.strip().splitlines()[-1])
+            cpu_closed.pop("impl", None)
+            ref_sum = float(np.abs(res["pool"]).sum())
+            cpu_closed["abs_sum_error_vs_gpu"] = abs(cpu_closed.pop("checksum") - ref_sum)
+            cpu_closed["energy_error_vs_gpu"] = abs(cpu_closed.pop("energy") - float(res["expvals"][0]))
+        except Exception as exc:
+            print(f"closed-form CPU leg failed: {exc}", file=sys.stderr)
 
     roofline_k3 = {"bound": "hbm", "kernel": "k_pool (K3 pool screening) + k_pool_finalize",
                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -440,6 +508,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         "roofline_k3": roofline_k3,
         "hbm_regime": hbm,
         "cpu_baseline": cpu,
+        "cpu_closed_form": cpu_closed,
         "pool_sharded": pool_sharded,
         "clocks": clocks,
         "energy": float(res["expvals"][0]),
@@ -455,7 +524,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="fhsim", choices=["fhsim", "reference"])
+    ap.add_argument("--impl", default="fhsim", choices=["fhsim", "reference", "cpu-closed-form"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hbm-regime", action="store_true")
     args = ap.parse_args()
@@ -464,6 +533,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
+        return
+    if args.impl == "cpu-closed-form":
+        if rank == 0:
+            run_cpu_closed_form(args)
         return
     if world == 1 and args.gpus > 1:
         print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks"}))

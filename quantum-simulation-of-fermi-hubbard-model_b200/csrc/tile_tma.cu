@@ -105,7 +105,7 @@ static void plan_dims(const unsigned char *bits, int T, bool want_swizzle, std::
     plan.map_bits = covered;
     plan.n_extra = T - covered;
     plan.swizzle = swz ? 1 : 0;
-    for (int b = covered; b < T; ++b) plan.extra[b - covered] = bits[b];
+    for (int b = covered; b < T && b - covered < 8; ++b) plan.extra[b - covered] = bits[b];
 }
 
 static std::mutex g_tma_mutex;
@@ -330,6 +330,22 @@ __device__ __forceinline__ void apply_diag(double2 *buf, double2 *ph, const Tile
     }
 }
 
+// Optional in-kernel timeline (make TIMELINE=1 / tools/probe_timeline.py): thread 0 of CTA 0 stamps clock64() at the phase
+// boundaries.  Slots: 0 entry, 1 prologue done, 2 first tile landed, 4+k start of op k (k < 40), 3 ops done, 62 store
+// issued, 63 stores complete.  Compiled out by default.
+#ifdef FH_TILE_TIMELINE
+__device__ long long g_fh_tma_timeline[64];
+#define TMA_TLMARK(k)                                                              \
+    do {                                                                           \
+        if (blockIdx.x == 0 && threadIdx.x == 0) g_fh_tma_timeline[k] = clock64(); \
+    } while (0)
+extern "C" int fh_debug_tile_tma_timeline(long long *out64) {
+    return (int)cudaMemcpyFromSymbol(out64, g_fh_tma_timeline, sizeof(long long) * 64);
+}
+#else
+#define TMA_TLMARK(k) do { } while (0)
+#endif
+
 // ----------------------------------------------------------------------------------------------
 // forward / dagger run on one state
 // ----------------------------------------------------------------------------------------------
@@ -350,6 +366,7 @@ __global__ void __launch_bounds__(512, 2)
     TileTerm *tterm = reinterpret_cast<TileTerm *>(rec + nsub);
     double2 *ph = reinterpret_cast<double2 *>(tterm + tl.nterms);
     const unsigned lomask_g = tile_mask(tl, T, 0, 6), himask_g = tile_mask(tl, T, 6, TILE_BITS_CAP);
+    TMA_TLMARK(0);
 
     if (threadIdx.x == 0) {
         mbar_init(smem_u32(&full_bar[0]), 1);
@@ -369,6 +386,7 @@ __global__ void __launch_bounds__(512, 2)
     }
     __syncthreads();
     if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");     // the previous kernel's amplitudes are complete
+    TMA_TLMARK(1);
 
     const unsigned ntiles = 1u << (n - T);
     const unsigned tiles_u32 = smem_u32(tiles);
@@ -388,8 +406,10 @@ __global__ void __launch_bounds__(512, 2)
         double2 *buf = reinterpret_cast<double2 *>(tiles + (size_t)st * tile_bytes);
         PairPrep cur = prep_pair<SWZ>(&rec[0], base, threadIdx.x, T);
         mbar_wait(smem_u32(&full_bar[st]), parity);
+        TMA_TLMARK(2);
 
         for (int sidx = 0; sidx < nsub; ++sidx) {
+            if (sidx < 40) TMA_TLMARK(4 + sidx);
             const TileRec *r = &rec[sidx];
             const int type = r->type;
             PairPrep nxt;
@@ -410,10 +430,12 @@ __global__ void __launch_bounds__(512, 2)
             cur = nxt;
             if (sidx + 1 < nsub) __syncthreads();
         }
+        TMA_TLMARK(3);
         fence_async_smem();             // generic-proxy writes of the op loop -> visible to the bulk store
         __syncthreads();
         if (warp == 0) {
             warp_store_tile(&map, plan, base, tiles_u32 + st * tile_bytes, lane);
+            TMA_TLMARK(62);
             if (stages == 1 && t + gridDim.x < ntiles) {
                 bulk_wait_read0();
                 warp_load_tile(&map, plan, (unsigned)tile_base(tl, T, t + gridDim.x), tiles_u32, smem_u32(&full_bar[0]),
@@ -422,6 +444,7 @@ __global__ void __launch_bounds__(512, 2)
         }
     }
     if (warp == 0) bulk_wait0();        // every store of this CTA is complete before it exits
+    TMA_TLMARK(63);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -9,7 +9,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_contract_json():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+                         capture_output=True, text=True, timeout=600, cwd=ROOT,
+                         env={**os.environ, "FH_BENCH_REF_OPS": "2"})       # 2-operator chunk: seconds, not 19 GB
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -32,3 +33,13 @@ def test_bench_without_gpu_fails_loudly():
                           "--no-hbm-regime"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode != 0
     assert not [l for l in out.stdout.splitlines() if l.startswith('{"metric"')]
+
+
+def test_cpu_closed_form_leg_prints_both_thread_counts():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "cpu-closed-form"], capture_output=True,
+                         text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["impl"] == "cpu-closed-form" and d["1thread"]["threads"] == 1 and d["allcores"]["threads"] == d["cores"]
+    assert d["1thread"]["value"] > 0 and d["allcores"]["value"] > 0
+    assert abs(d["energy"] - 0.1938641953852845) < 1e-10          # the bench workload's energy (GPU, oracle)

@@ -23,7 +23,7 @@ OUT = os.path.join(CSRC, "build_timeline", "libfhsim_timeline.so")
 
 def build():
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    srcs = ["kernels.cu", "api.cu", "program.cu", "lanczos.cu"]
+    srcs = ["kernels.cu", "tile_tma.cu", "api.cu", "program.cu", "lanczos.cu"]
     cmd = ["nvcc", "-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
            "-DFH_TILE_TIMELINE", "-shared", "-cudart", "static", "-o", OUT] + [os.path.join(CSRC, f) for f in srcs]
     subprocess.check_call(cmd)
@@ -50,14 +50,18 @@ def main():
         for _ in range(3):
             prog.run(st, wl["thetas"], item, 1)
         ctx.sync()
-        if lib.fh_debug_tile_timeline(buf) != 0:
-            raise RuntimeError("fh_debug_tile_timeline failed")
+        tma = not os.environ.get("FHSIM_TILE_LDG")
+        fn = lib.fh_debug_tile_tma_timeline if tma else lib.fh_debug_tile_timeline
+        if fn(buf) != 0:
+            raise RuntimeError("timeline read-back failed")
         t = list(buf)
         nops = sum(1 for k in range(4, 44) if t[2] <= t[k] <= t[3])
         marks = [t[4 + k] for k in range(nops)] + [t[3]]
         per_op = [marks[k + 1] - marks[k] for k in range(nops)]
+        tail = f"store issue {t[62] - t[3]:6d}  store done {t[63] - t[62]:6d}" if tma else f"store {t[63] - t[3]:6d}"
         print(f"item {item:2d}: prologue {t[1] - t[0]:6d}  load {t[2] - t[1]:6d}  ops({nops}) {t[3] - t[2]:6d} {per_op}  "
-              f"store {t[63] - t[3]:6d}  total {t[63] - t[0]:6d} cycles", flush=True)
+              f"{tail}  total {t[63] - t[0]:6d} cycles   [{1e3 * prog.time_items(st, item, 1, False, 20):.2f} us/launch back to back]",
+              flush=True)
 
 
 if __name__ == "__main__":
