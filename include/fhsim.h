@@ -169,6 +169,16 @@ int fh_program_time_items(fh_program *prog, fh_state *st, int first, int count, 
  * evecs (may be NULL) receives k device states. */
 int fh_lanczos(const fh_table *tab, int n_up, int n_dn, int k, double tol, int max_iter, uint64_t seed,
                double *evals, fh_state *const *evecs, int *iterations);
+/* The same eigenproblem on SECTOR-COMPRESSED vectors (one amplitude per (N_up, N_dn) state, rank = rank_up * D_dn +
+ * rank_dn), iteration scalars kept on the device: what linalg/exact_diagonalization.py:26-51 does when it restricts the
+ * sparse matrix to the sector before calling eigsh.  3x3: 15 876 amplitudes per vector instead of 2^18; 4x4: 165 636 900
+ * (2.65 GB) instead of 64 GiB, so the 32-qubit ground state of models/adapt_vqe.py:221-247 fits one GPU.  The table must
+ * conserve both particle numbers (FH_EINVAL otherwise); fh_lanczos takes this path by itself whenever it applies.
+ * evecs (may be NULL): k full 2^n device states (amplitudes outside the sector are zero).
+ * compressed_out (may be NULL): host buffer of k * dim_sector complex128 values in rank order.
+ * stats (may be NULL): double[4] = sector dimension, seconds in the iteration loops, matvecs, host synchronisations. */
+int fh_lanczos_sector(const fh_table *tab, int n_up, int n_dn, int k, double tol, int max_iter, uint64_t seed,
+                      double *evals, fh_state *const *evecs, double *compressed_out, int *iterations, double *stats);
 
 #ifdef __cplusplus
 }

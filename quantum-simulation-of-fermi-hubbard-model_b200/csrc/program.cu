@@ -13,6 +13,21 @@ int fh_enqueue_apply_table(const fh_table *tab, const double2 *in, double2 *out,
 int fh_enqueue_pool(const fh_pool *pool, const double2 *psi, const double2 *lam, int first, int count,
                     double *d_out_override);
 
+// tile_tma.cu: several consecutive tile runs in one cooperative launch
+struct ChainRunHost {
+    TileLaunch tl;
+    int second_store;
+    int init_basis;
+};
+int plan_tile_chain(int sm, double2 *psi, double2 *psi2, const ChainRunHost *hruns, int nruns, int n, void *h_runs,
+                    void *h_maps, int map_base, int *grid_out, size_t *smem_out, int *rec_cap_out, int *term_cap_out,
+                    int *tbits_out);
+int launch_tile_chain(cudaStream_t s, const void *d_runs, int nruns, const void *d_maps, const TileRec *d_recs,
+                      const TileTerm *d_terms, int n, unsigned *d_sync, unsigned long long basis, int grid, size_t smem,
+                      int rec_cap, int term_cap, int tbits);
+size_t fh_chain_run_bytes();
+size_t fh_chain_map_bytes();
+
 #define FH_MAX_RESULT_TABLES 8
 #define FH_MAX_OVERLAPS 8
 
@@ -60,6 +75,13 @@ struct fh_program {
     // at the head of the captured graph); the typed pointers are views into them
     unsigned char *h_arena = nullptr, *d_arena = nullptr;
     size_t arena_bytes = 0;
+    // chain descriptors (ChainRun records + tensor maps) behind the payload in the same arenas: region 0 belongs to the
+    // captured evaluation graph (uploaded by the graph's first copy node), region 1 to immediate-mode runs
+    size_t chain_off[2] = {0, 0}, chain_maps_off[2] = {0, 0};
+    int chain_cap_runs = 0, chain_cap_maps = 0;
+    int chain_used_runs[2] = {0, 0}, chain_used_maps[2] = {0, 0};
+    int chain_region = 1;                 // region the next chain is planned into
+    unsigned *d_sync = nullptr;           // [2 * chain_cap_runs] run-boundary counters of the chains
     // static launch descriptors of every tile run (forward order / reverse order of the dagger runs): the argument
     // arrays of the cooperative multi-run kernel
     TileLaunch *d_tl_fwd = nullptr, *d_tl_dag_rev = nullptr;
@@ -132,6 +154,7 @@ extern "C" int fh_program_destroy(fh_program *p) {
     fh_ctx_scratch_put(p->ctx, state_bytes, p->d_psi);
     fh_ctx_scratch_put(p->ctx, state_bytes, p->d_lam);
     fh_ctx_scratch_put(p->ctx, state_bytes, p->d_chk);
+    cudaFree(p->d_sync);
     cudaFree(p->d_gpart);
     cudaFree(p->d_gfirst);
     cudaFree(p->d_res);
@@ -404,7 +427,19 @@ extern "C" int fh_program_finalize(fh_program *p) {
             off[k] = total;
             total += align(sz[k]);
         }
-        p->arena_bytes = total;
+        p->arena_bytes = total;           // theta-dependent payload; the chain regions follow
+        p->chain_cap_runs = 2 * (int)p->tiles.size() + 2;
+        p->chain_cap_maps = p->chain_cap_runs + 4;
+        if (!p->tiles.empty()) {
+            for (int reg = 0; reg < 2; ++reg) {
+                p->chain_off[reg] = total;
+                total += align(fh_chain_run_bytes() * (size_t)p->chain_cap_runs);
+                p->chain_maps_off[reg] = total;
+                total += align(fh_chain_map_bytes() * (size_t)p->chain_cap_maps);
+            }
+            FH_CUDA(cudaMalloc(&p->d_sync, sizeof(unsigned) * 2 * (size_t)p->chain_cap_runs));
+            FH_CUDA(cudaMemsetAsync(p->d_sync, 0, sizeof(unsigned) * 2 * (size_t)p->chain_cap_runs, ctx->stream));
+        }
         if (total) {
             FH_CUDA(cudaMalloc(&p->d_arena, total));
             FH_CUDA(cudaMallocHost(&p->h_arena, total));
@@ -428,7 +463,8 @@ extern "C" int fh_program_finalize(fh_program *p) {
         if (sz[3]) memcpy(p->h_recs_dag, p->recs_dag.data(), sz[3]);
         if (sz[4]) memcpy(p->h_tterms_fwd, p->tterms_fwd.data(), sz[4]);
         if (sz[5]) memcpy(p->h_tterms_dag, p->tterms_dag.data(), sz[5]);
-        if (total) FH_CUDA(cudaMemcpyAsync(p->d_arena, p->h_arena, total, cudaMemcpyHostToDevice, ctx->stream));
+        if (p->arena_bytes)
+            FH_CUDA(cudaMemcpyAsync(p->d_arena, p->h_arena, p->arena_bytes, cudaMemcpyHostToDevice, ctx->stream));
     }
     if (!p->tiles.empty()) {
         const size_t nt = p->tiles.size();
@@ -502,9 +538,15 @@ static void refresh_payload(fh_program *p, const double *thetas) {
 }
 
 // copy the pinned payload to the device (these become the first nodes of the captured graph)
-static int enqueue_payload_upload(fh_program *p) {
-    if (p->arena_bytes)
-        FH_CUDA(cudaMemcpyAsync(p->d_arena, p->h_arena, p->arena_bytes, cudaMemcpyHostToDevice, p->ctx->stream));
+static int enqueue_payload_upload(fh_program *p, bool with_graph_chains = false) {
+    size_t bytes = p->arena_bytes;
+    if (with_graph_chains && p->chain_cap_runs > 0 && !p->tiles.empty()) {
+        // region 0 sits right behind the payload: one copy node moves both.  The host side of the region is filled
+        // while the evaluation is being captured (nothing executes before the graph is launched).
+        bytes = p->chain_maps_off[0] + fh_chain_map_bytes() * (size_t)p->chain_cap_maps;
+        FH_CUDA(cudaMemsetAsync(p->d_sync, 0, sizeof(unsigned) * (size_t)p->chain_cap_runs, p->ctx->stream));
+    }
+    if (bytes) FH_CUDA(cudaMemcpyAsync(p->d_arena, p->h_arena, bytes, cudaMemcpyHostToDevice, p->ctx->stream));
     return FH_OK;
 }
 
@@ -548,47 +590,104 @@ static void apply_item(fh_program *p, const Item &it, double2 *st, int dagger) {
     }
 }
 
-// Apply items [lo, hi) in execution order of the direction.  Consecutive tile runs go into ONE cooperative launch
-// (grid barriers instead of kernel boundaries) when the state is small enough for launch latency to matter.
-static void apply_range(fh_program *p, int lo, int hi, double2 *st, int dagger) {
-    // measured on the 18-qubit benchmark step: 19 -> 7 launches, same time (kernel boundaries inside a CUDA graph cost
-    // about as much as a grid barrier plus the per-run prologue), so this stays opt-in
-    static const char *env = getenv("FHSIM_PERSISTENT");
-    const bool enabled = env ? atoi(env) != 0 : false;
+// One cooperative launch for the consecutive tile items [k0, k0 + run) (positions in travel order) of the range, or 0.
+static int try_chain(fh_program *p, int lo, int hi, int k0, int run, double2 *st, int dagger, double2 *chk, int chk_pos,
+                     bool init_basis, u64 basis) {
     fh_ctx *ctx = p->ctx;
+    const int reg = p->chain_region;
+    if (p->tiles.empty() || p->chain_used_runs[reg] + run > p->chain_cap_runs) return 0;
+    std::vector<ChainRunHost> hr((size_t)run);
+    int n_second = 0;
+    for (int r = 0; r < run; ++r) {
+        const int idx = dagger ? hi - 1 - (k0 + r) : lo + k0 + r;
+        const TileOp &t = p->tiles[p->items[idx].index];
+        hr[r].tl.nbits = t.nbits;
+        hr[r].tl.nsub = t.nsub;
+        hr[r].tl.first_rec = dagger ? t.first_rec_dag : t.first_rec_fwd;
+        hr[r].tl.first_term = dagger ? t.first_term_dag : t.first_term_fwd;
+        hr[r].tl.nterms = t.nterms;
+        memcpy(hr[r].tl.bits, t.bits, 16);
+        hr[r].second_store = (!dagger && chk && idx + 1 == chk_pos) ? 1 : 0;
+        hr[r].init_basis = (init_basis && r == 0) ? 1 : 0;
+        n_second += hr[r].second_store;
+    }
+    if (p->chain_used_maps[reg] + run + n_second > p->chain_cap_maps) return 0;
+    unsigned char *h_runs = p->h_arena + p->chain_off[reg] + fh_chain_run_bytes() * (size_t)p->chain_used_runs[reg];
+    unsigned char *h_maps = p->h_arena + p->chain_maps_off[reg];
+    int grid = 0, rec_cap = 0, term_cap = 0, tbits = 0;
+    size_t smem = 0;
+    const int nmaps = plan_tile_chain(ctx->sm_count, st, chk, hr.data(), run, p->n, h_runs,
+                                      h_maps + fh_chain_map_bytes() * (size_t)p->chain_used_maps[reg], p->chain_used_maps[reg],
+                                      &grid, &smem, &rec_cap, &term_cap, &tbits);
+    if (nmaps < 0) return 0;
+    const unsigned char *d_runs = p->d_arena + p->chain_off[reg] + fh_chain_run_bytes() * (size_t)p->chain_used_runs[reg];
+    const unsigned char *d_maps = p->d_arena + p->chain_maps_off[reg];
+    unsigned *d_sync = p->d_sync + (size_t)reg * p->chain_cap_runs + p->chain_used_runs[reg];
+    if (reg == 1) {
+        // immediate mode: descriptors and counters travel right before the launch
+        cudaMemcpyAsync(const_cast<unsigned char *>(d_runs), h_runs, fh_chain_run_bytes() * (size_t)run, cudaMemcpyHostToDevice,
+                        ctx->stream);
+        const size_t mo = fh_chain_map_bytes() * (size_t)p->chain_used_maps[reg];
+        cudaMemcpyAsync(const_cast<unsigned char *>(d_maps) + mo, h_maps + mo, fh_chain_map_bytes() * (size_t)nmaps,
+                        cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemsetAsync(d_sync, 0, sizeof(unsigned) * (size_t)run, ctx->stream);
+    }
+    if (!launch_tile_chain(ctx->stream, d_runs, run, d_maps, dagger ? p->d_recs_dag : p->d_recs_fwd,
+                           dagger ? p->d_tterms_dag : p->d_tterms_fwd, p->n, d_sync, basis, grid, smem, rec_cap, term_cap,
+                           tbits))
+        return 0;
+    p->chain_used_runs[reg] += run;
+    p->chain_used_maps[reg] += nmaps;
+    return 1;
+}
+
+// Apply items [lo, hi) in execution order of the direction.  Consecutive tile runs go into ONE cooperative launch
+// (k_tile_chain) when every tile of every run can be resident at once (18-20 qubits); otherwise one launch per item.
+// Optional extras of the forward direction: `basis` (>= 0: the state is |basis> before the first item; a chain that starts
+// the range synthesises it, else a set-basis launch) and `chk` (copy of the state after item chk_pos - 1, fused into
+// the chain as a second tile store, else a device-to-device copy).
+static int apply_range(fh_program *p, int lo, int hi, double2 *st, int dagger, double2 *chk = nullptr, int chk_pos = -1,
+                       long long basis = -1) {
+    fh_ctx *ctx = p->ctx;
+    const size_t bytes = sizeof(double2) << p->n;
     const int count = hi - lo;
+    bool basis_pending = basis >= 0;
+    auto settle_basis = [&]() {
+        if (basis_pending) launch_set_basis(ctx->stream, st, 1ull << p->n, (u64)basis);
+        basis_pending = false;
+    };
+    if (chk && chk_pos == lo && !dagger) {
+        settle_basis();
+        FH_CUDA(cudaMemcpyAsync(chk, st, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     int k = 0;
     while (k < count) {
         const int idx = dagger ? hi - 1 - k : lo + k;
         const Item &it = p->items[idx];
-        int run = 1;
-        if (enabled && it.type == 3) {
-            // extend over following tile items whose tile indices are consecutive in the direction of travel
-            while (k + run < count) {
-                const Item &nx = p->items[dagger ? hi - 1 - (k + run) : lo + k + run];
-                if (nx.type != 3 || nx.index != it.index + (dagger ? -run : run)) break;
-                ++run;
-            }
-        }
-        if (run >= 2) {
-            int max_bits = 0, min_bits = 64;
+        if (it.type == 3) {
+            int run = 1;
+            while (k + run < count && p->items[dagger ? hi - 1 - (k + run) : lo + k + run].type == 3) ++run;
+            bool has_chk = false;
             for (int r = 0; r < run; ++r) {
-                const int nb = p->tiles[it.index + (dagger ? -r : r)].nbits;
-                max_bits = nb > max_bits ? nb : max_bits;
-                min_bits = nb < min_bits ? nb : min_bits;
+                const int j = dagger ? hi - 1 - (k + r) : lo + k + r;
+                has_chk = has_chk || (!dagger && chk && j + 1 == chk_pos);
             }
-            const size_t nt = p->tiles.size();
-            const TileLaunch *d_tls = dagger ? p->d_tl_dag_rev + (nt - 1 - (size_t)it.index) : p->d_tl_fwd + it.index;
-            if (launch_tile_multi(ctx->stream, ctx->sm_count, st, d_tls, run, max_bits, min_bits,
-                                  dagger ? p->d_recs_dag : p->d_recs_fwd, dagger ? p->d_tterms_dag : p->d_tterms_fwd,
-                                  p->n)) {
+            const bool use_basis = basis_pending && k == 0;
+            if ((run >= 2 || has_chk || use_basis) &&
+                try_chain(p, lo, hi, k, run, st, dagger, chk, chk_pos, use_basis, basis >= 0 ? (u64)basis : 0ull)) {
+                if (use_basis) basis_pending = false;
                 k += run;
                 continue;
             }
         }
+        settle_basis();
         apply_item(p, it, st, dagger);
+        if (!dagger && chk && idx + 1 == chk_pos && chk_pos != lo)
+            FH_CUDA(cudaMemcpyAsync(chk, st, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
         ++k;
     }
+    settle_basis();
+    return FH_OK;
 }
 
 extern "C" int fh_program_run(fh_program *p, fh_state *st, const double *thetas, int n_thetas, int first, int count,
@@ -598,7 +697,9 @@ extern "C" int fh_program_run(fh_program *p, fh_state *st, const double *thetas,
     FH_REQUIRE(st->n == p->n, "fh_program_run: state has %d qubits, program %d", st->n, p->n);
     FH_REQUIRE(first >= 0 && count >= 0 && first + count <= (int)p->items.size(), "fh_program_run: op range out of bounds");
     FH_TRY(upload_payload(p, thetas, n_thetas));
-    apply_range(p, first, first + count, st->d, dagger);
+    p->chain_region = 1;
+    p->chain_used_runs[1] = p->chain_used_maps[1] = 0;
+    FH_TRY(apply_range(p, first, first + count, st->d, dagger));
     FH_CUDA(cudaGetLastError());
     FH_CUDA(cudaStreamSynchronize(p->ctx->stream));   // pinned payload may be rewritten by the next call
     return FH_OK;
@@ -683,7 +784,7 @@ static void adjoint_item(fh_program *p, const Item &it, double2 *psi, double2 *l
 // Enqueue one whole evaluation on the stream (this is what gets captured into the CUDA graph).
 // Result buffer h_res (doubles): [0, 2T) expvals re/im, [2T, 2T+2V) overlaps re/im.
 static int enqueue_evaluation(fh_program *p, const EvalKey &k, fh_table *const *tables, const fh_pool *pool,
-                              fh_state *const *targets, fh_state *state_out) {
+                              fh_state *const *targets, fh_state *state_out, bool capturing) {
     fh_ctx *ctx = p->ctx;
     const int n_items = (int)p->items.size();
     const size_t bytes = sizeof(double2) << p->n;
@@ -701,16 +802,17 @@ static int enqueue_evaluation(fh_program *p, const EvalKey &k, fh_table *const *
     if (want_grads) chk_pos = last_param + 1;
     if (want_pool && k.pool_pos > chk_pos) chk_pos = k.pool_pos;
 
-    FH_TRY(enqueue_payload_upload(p));
-    launch_set_basis(ctx->stream, p->d_psi, 1ull << p->n, k.basis);
+    FH_TRY(enqueue_payload_upload(p, capturing));
+    p->chain_region = capturing ? 0 : 1;
+    p->chain_used_runs[p->chain_region] = p->chain_used_maps[p->chain_region] = 0;
     double2 *psi = p->d_psi;
-    if (need_adjoint && chk_pos < n_items) {
-        apply_range(p, 0, chk_pos, psi, 0);
-        FH_CUDA(cudaMemcpyAsync(p->d_chk, psi, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
-        apply_range(p, chk_pos, n_items, psi, 0);
-    } else {
-        apply_range(p, 0, n_items, psi, 0);
-    }
+    // forward pass; the checkpoint of psi after items[0:chk_pos) (the fixed suffix is only unwound on lambda) and the
+    // initial basis state ride along in the tile chains where they can
+    if (need_adjoint && chk_pos < n_items)
+        FH_TRY(apply_range(p, 0, n_items, psi, 0, p->d_chk, chk_pos, (long long)k.basis));
+    else
+        FH_TRY(apply_range(p, 0, n_items, psi, 0, nullptr, -1, (long long)k.basis));
+    (void)bytes;
     for (int t = 0; t < k.n_tables; ++t) {
         const fh_table *tab = tables[t];
         double2 *h_out = (t == 0 && need_adjoint) ? p->d_lam : nullptr;
@@ -732,7 +834,7 @@ static int enqueue_evaluation(fh_program *p, const EvalKey &k, fh_table *const *
         double2 *lam = p->d_lam;
         if (want_grads && p->n_param_ops > 0)
             FH_CUDA(cudaMemsetAsync(p->d_gpart, 0, sizeof(double) * (size_t)p->n_param_ops * FH_GRAD_BLOCKS, ctx->stream));
-        apply_range(p, chk_pos, n_items, lam, 1);
+        FH_TRY(apply_range(p, chk_pos, n_items, lam, 1));
         if (chk_pos < n_items) psi = p->d_chk;
         int stop = want_grads ? first_param : n_items;      // lowest item the sweep must undo
         if (want_pool && k.pool_pos < stop) stop = k.pool_pos;
@@ -836,7 +938,7 @@ extern "C" int fh_program_evaluate(fh_program *p, uint64_t basis_index, const do
         const long long before = g_fh_launch_count;
         FH_CUDA(cudaEventRecord(p->ev0, ctx->stream));
         ++g_fh_tile_pdl_scope;
-        const int rc = enqueue_evaluation(p, key, tables, pool, targets, state_out);
+        const int rc = enqueue_evaluation(p, key, tables, pool, targets, state_out, false);
         --g_fh_tile_pdl_scope;
         FH_TRY(rc);
         FH_CUDA(cudaEventRecord(p->ev1, ctx->stream));
@@ -847,7 +949,7 @@ extern "C" int fh_program_evaluate(fh_program *p, uint64_t basis_index, const do
             const long long before = g_fh_launch_count;
             FH_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
             ++g_fh_tile_pdl_scope;
-            const int rc = enqueue_evaluation(p, key, tables, pool, targets, state_out);
+            const int rc = enqueue_evaluation(p, key, tables, pool, targets, state_out, true);
             --g_fh_tile_pdl_scope;
             cudaGraph_t g = nullptr;
             const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);

@@ -346,6 +346,37 @@ extern "C" int fh_debug_tile_tma_timeline(long long *out64) {
 #define TMA_TLMARK(k) do { } while (0)
 #endif
 
+// The op loop of one tile: every op of the run in order, one CTA barrier between ops.  `cur` is the decoded pair of
+// op 0 for this thread (prepared by the caller while the tile was still in flight).
+template <bool SWZ>
+__device__ __forceinline__ void tile_ops(double2 *buf, double2 *ph, const TileRec *rec, const TileTerm *tterm,
+                                         const TileLaunch &tl, int T, int nsub, unsigned base, PairPrep cur,
+                                         unsigned lomask_g, unsigned himask_g) {
+    const unsigned L = 1u << T;
+    for (int sidx = 0; sidx < nsub; ++sidx) {
+        if (sidx < 40) TMA_TLMARK(4 + sidx);
+        const TileRec *r = &rec[sidx];
+        const int type = r->type;
+        PairPrep nxt;
+        nxt.active = 0u;
+        if (type != 2) {
+            if (cur.active) apply_pair(buf, r, cur);
+            if (sidx + 1 < nsub) nxt = prep_pair<SWZ>(&rec[sidx + 1], base, threadIdx.x, T);
+            // ops with more pairs than threads (pattern pins a single bit): the remaining pairs of this thread
+            const unsigned npairs = L >> (unsigned)r->nlfix;
+            for (unsigned k = threadIdx.x + blockDim.x; k < npairs; k += blockDim.x) {
+                const PairPrep more = prep_pair<SWZ>(r, base, k, T);
+                if (more.active) apply_pair(buf, r, more);
+            }
+        } else {
+            apply_diag<SWZ>(buf, ph, r, tterm, tl, T, base, lomask_g, himask_g);
+            if (sidx + 1 < nsub) nxt = prep_pair<SWZ>(&rec[sidx + 1], base, threadIdx.x, T);
+        }
+        cur = nxt;
+        if (sidx + 1 < nsub) __syncthreads();
+    }
+}
+
 // ----------------------------------------------------------------------------------------------
 // forward / dagger run on one state
 // ----------------------------------------------------------------------------------------------
@@ -408,28 +439,7 @@ __global__ void __launch_bounds__(512, 2)
         mbar_wait(smem_u32(&full_bar[st]), parity);
         TMA_TLMARK(2);
 
-        for (int sidx = 0; sidx < nsub; ++sidx) {
-            if (sidx < 40) TMA_TLMARK(4 + sidx);
-            const TileRec *r = &rec[sidx];
-            const int type = r->type;
-            PairPrep nxt;
-            nxt.active = 0u;
-            if (type != 2) {
-                if (cur.active) apply_pair(buf, r, cur);
-                if (sidx + 1 < nsub) nxt = prep_pair<SWZ>(&rec[sidx + 1], base, threadIdx.x, T);
-                // ops with more pairs than threads (pattern pins a single bit): the remaining pairs of this thread
-                const unsigned npairs = L >> (unsigned)r->nlfix;
-                for (unsigned k = threadIdx.x + blockDim.x; k < npairs; k += blockDim.x) {
-                    const PairPrep more = prep_pair<SWZ>(r, base, k, T);
-                    if (more.active) apply_pair(buf, r, more);
-                }
-            } else {
-                apply_diag<SWZ>(buf, ph, r, tterm, tl, T, base, lomask_g, himask_g);
-                if (sidx + 1 < nsub) nxt = prep_pair<SWZ>(&rec[sidx + 1], base, threadIdx.x, T);
-            }
-            cur = nxt;
-            if (sidx + 1 < nsub) __syncthreads();
-        }
+        tile_ops<SWZ>(buf, ph, rec, tterm, tl, T, nsub, base, cur, lomask_g, himask_g);
         TMA_TLMARK(3);
         fence_async_smem();             // generic-proxy writes of the op loop -> visible to the bulk store
         __syncthreads();
@@ -445,6 +455,145 @@ __global__ void __launch_bounds__(512, 2)
     }
     if (warp == 0) bulk_wait0();        // every store of this CTA is complete before it exits
     TMA_TLMARK(63);
+}
+
+// ----------------------------------------------------------------------------------------------
+// chain: several consecutive tile runs of one state in ONE cooperative launch
+// ----------------------------------------------------------------------------------------------
+// At 18-20 qubits the whole state is a few MiB and a tile run is a few microseconds, so a kernel boundary per run
+// (drain, launch, prologue, descriptor fetch, cold op records) costs more than the run itself.  k_tile_chain keeps one
+// CTA per tile resident for the whole sequence of runs: per run it waits until every tile of the previous run has been
+// stored (one counter per run boundary in global memory, release/acquire at gpu scope; all CTAs are co-resident because
+// the launch is cooperative), pulls its tile with TMA, applies the ops, stores it with TMA.  The descriptors of run r+1
+// (geometry, tensor maps, op records) are prefetched into the alternate shared-memory buffers while run r computes.
+// Extras: the first run of a forward pass can synthesise the basis state instead of loading it (no set-basis kernel),
+// and any run can store its tile to a second buffer as well (the psi checkpoint of the adjoint sweep).
+struct __align__(16) ChainRun {
+    TileLaunch tl;
+    TmaPlan plan;
+    int map_index;       // tensor map of the state for this run's tile bits
+    int map2_index;      // second store target, or -1
+    int init_basis;      // 1: the tile is |basis> restricted to it (nothing is loaded)
+    int ntiles;
+    int pad[3];
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned *p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+template <typename T>
+__device__ __forceinline__ void smem_copy16(T *dst, const T *src, int count) {     // count objects, sizeof(T) % 16 == 0
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    const int chunks = count * (int)(sizeof(T) / 16);
+    for (int c = threadIdx.x; c < chunks; c += blockDim.x) d4[c] = __ldg(s4 + c);
+}
+
+__global__ void __launch_bounds__(512, 2)
+    k_tile_chain(const ChainRun *__restrict__ runs, int nruns, const CUtensorMap *__restrict__ maps,
+                 const TileRec *__restrict__ recs, const TileTerm *__restrict__ terms, int n, unsigned *__restrict__ sync,
+                 unsigned long long basis, int rec_cap, int term_cap, int tile_bits_max) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long full_bar;
+    __shared__ ChainRun srun[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned raw = smem_u32(smem_raw);
+    const unsigned pad = ((raw + 1023u) & ~1023u) - raw;
+    unsigned char *tile = smem_raw + pad;
+    unsigned char *after = tile + (16u << tile_bits_max);
+    TileRec *rec_base = reinterpret_cast<TileRec *>(after);                 // two buffers of rec_cap records
+    TileTerm *term_base = reinterpret_cast<TileTerm *>(rec_base + 2 * rec_cap);      // two buffers of term_cap terms
+    double2 *ph = reinterpret_cast<double2 *>(term_base + 2 * term_cap);
+    double2 *buf = reinterpret_cast<double2 *>(tile);
+    const unsigned tile_u32 = smem_u32(tile), bar = smem_u32(&full_bar);
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    smem_copy16(&srun[0], runs, 1);
+    __syncthreads();
+    smem_copy16(rec_base, recs + srun[0].tl.first_rec, srun[0].tl.nsub);
+    smem_copy16(term_base, terms + srun[0].tl.first_term, srun[0].tl.nterms);
+    __syncthreads();
+
+    unsigned uses = 0;
+    int prev_active = 0;                    // CTAs that stored a tile in the previous run
+    for (int r = 0; r < nruns; ++r) {
+        const ChainRun &R = srun[r & 1];
+        const TileLaunch &tl = R.tl;
+        const int T = tl.nbits, nsub = tl.nsub;
+        const unsigned L = 1u << T, tile_bytes = L * 16u;
+        const bool active = blockIdx.x < (unsigned)R.ntiles;
+        const unsigned base = (unsigned)tile_base(tl, T, blockIdx.x);
+        const CUtensorMap *map = maps + R.map_index;
+        if (active && warp == 0 && !R.init_basis) {
+            if (r > 0) {
+                if (lane == 0) {
+                    const unsigned want = (unsigned)prev_active;
+                    while (ld_acquire_gpu(sync + (r - 1)) < want) { }
+                    fence_async_all();          // the other CTAs' tile stores -> visible to this CTA's bulk loads
+                }
+                __syncwarp();
+            }
+            warp_load_tile(map, R.plan, base, tile_u32, bar, tile_bytes, lane);
+        }
+        // prefetch the next run's geometry and op records into the alternate buffers
+        if (r + 1 < nruns) smem_copy16(&srun[(r + 1) & 1], runs + r + 1, 1);
+        if (active) {
+            const TileRec *rec = rec_base + (r & 1) * rec_cap;
+            const TileTerm *tterm = term_base + (r & 1) * term_cap;
+            const unsigned lomask_g = tile_mask(tl, T, 0, 6), himask_g = tile_mask(tl, T, 6, TILE_BITS_CAP);
+            const bool swz = R.plan.swizzle != 0;
+            PairPrep cur = swz ? prep_pair<true>(&rec[0], base, threadIdx.x, T) : prep_pair<false>(&rec[0], base, threadIdx.x, T);
+            if (R.init_basis) {
+                // |basis> restricted to this tile: zeros, and 1 at the tile-local index of the basis state if it is here
+                const unsigned tmask = lomask_g | himask_g;
+                for (unsigned l = threadIdx.x; l < L; l += blockDim.x) buf[l] = make_double2(0.0, 0.0);
+                __syncthreads();
+                if (threadIdx.x == 0 && ((unsigned)basis & ~tmask) == base) {
+                    unsigned l = 0;
+#pragma unroll
+                    for (int b = 0; b < TILE_BITS_CAP; ++b)
+                        if (b < T) l |= (((unsigned)basis >> tl.bits[b]) & 1u) << b;
+                    buf[swz ? tslot<true>(l) : l] = make_double2(1.0, 0.0);
+                }
+                __syncthreads();
+            } else {
+                mbar_wait(bar, uses & 1u);
+                ++uses;
+            }
+            if (swz) tile_ops<true>(buf, ph, rec, tterm, tl, T, nsub, base, cur, lomask_g, himask_g);
+            else tile_ops<false>(buf, ph, rec, tterm, tl, T, nsub, base, cur, lomask_g, himask_g);
+            fence_async_smem();
+        }
+        __syncthreads();                    // ops done (all threads); srun[(r+1)&1] is visible
+        if (r + 1 < nruns) {
+            const ChainRun &N = srun[(r + 1) & 1];
+            smem_copy16(rec_base + ((r + 1) & 1) * rec_cap, recs + N.tl.first_rec, N.tl.nsub);
+            smem_copy16(term_base + ((r + 1) & 1) * term_cap, terms + N.tl.first_term, N.tl.nterms);
+        }
+        if (active && warp == 0) {
+            warp_store_tile(map, R.plan, base, tile_u32, lane);
+            if (R.map2_index >= 0) warp_store_tile(maps + R.map2_index, R.plan, base, tile_u32, lane);
+            bulk_wait0();                   // this lane's stores are complete (global writes performed)
+            fence_async_all();
+            __syncwarp();
+            if (lane == 0 && r + 1 < nruns) {
+                __threadfence();
+                red_release_gpu_add(sync + r, 1u);
+            }
+        }
+        prev_active = min((int)gridDim.x, R.ntiles);
+        __syncthreads();                    // tile buffer free for the next load; next records visible
+    }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -517,5 +666,95 @@ int fh_tile_tma_init_device() {
     FH_CUDA(cudaFuncSetAttribute(k_tile_tma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     FH_CUDA(cudaFuncSetAttribute(k_tile_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     FH_CUDA(cudaFuncSetAttribute(k_tile_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    FH_CUDA(cudaFuncSetAttribute(k_tile_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     return FH_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// chain launch (host)
+// ----------------------------------------------------------------------------------------------
+struct ChainRunHost {
+    TileLaunch tl;
+    int second_store;     // 1: also store this run's tile to `psi2`
+    int init_basis;
+};
+
+static int g_chain_blocks_per_sm[2] = {-1, -1};
+
+// Plans one cooperative launch for `nruns` consecutive tile runs on `psi`.  Writes the ChainRun records and the tensor
+// maps into host staging memory (`h_runs`, `h_maps`: the caller copies them to `d_runs`, `d_maps` on the stream BEFORE
+// the launch -- inside a captured graph that copy is one more memcpy node).  Returns the number of maps used, or -1
+// when the chain does not apply (TMA path unavailable, or more tiles than co-resident CTAs).
+int plan_tile_chain(int sm, double2 *psi, double2 *psi2, const ChainRunHost *hruns, int nruns, int n, void *h_runs_v,
+                    void *h_maps_v, int map_base, int *grid_out, size_t *smem_out, int *rec_cap_out, int *term_cap_out,
+                    int *tbits_out) {
+    ChainRun *h_runs = reinterpret_cast<ChainRun *>(h_runs_v);
+    CUtensorMap *h_maps = reinterpret_cast<CUtensorMap *>(h_maps_v);
+    if (getenv("FHSIM_TILE_LDG") || getenv("FHSIM_NO_CHAIN")) return -1;
+    int nmaps = 0, grid = 0, rec_cap = 1, term_cap = 1, tbits = 0;
+    for (int r = 0; r < nruns; ++r) {
+        const TileLaunch &tl = hruns[r].tl;
+        const TmaEntry *e = tma_entry(psi, n, tl);
+        if (!e) return -1;
+        ChainRun cr;
+        memset(&cr, 0, sizeof(cr));
+        cr.tl = tl;
+        cr.plan = e->plan;
+        cr.map_index = map_base + nmaps;
+        h_maps[nmaps++] = e->map;
+        cr.map2_index = -1;
+        if (hruns[r].second_store) {
+            const TmaEntry *e2 = tma_entry(psi2, n, tl);
+            if (!e2) return -1;
+            cr.map2_index = map_base + nmaps;
+            h_maps[nmaps++] = e2->map;
+        }
+        cr.init_basis = hruns[r].init_basis;
+        cr.ntiles = 1 << (n - tl.nbits);
+        if (n - tl.nbits > 12) return -1;
+        h_runs[r] = cr;
+        grid = cr.ntiles > grid ? cr.ntiles : grid;
+        rec_cap = tl.nsub > rec_cap ? tl.nsub : rec_cap;
+        term_cap = tl.nterms > term_cap ? tl.nterms : term_cap;
+        tbits = tl.nbits > tbits ? tl.nbits : tbits;
+    }
+    const size_t smem = 1024 + (16ull << tbits) + 2 * (size_t)rec_cap * sizeof(TileRec) + 2 * (size_t)term_cap * sizeof(TileTerm) +
+                        192 * sizeof(double2) + 64;
+    if (smem > 220 * 1024) return -1;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_chain, 512, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    if ((long long)per_sm * sm < grid) return -1;
+    *grid_out = grid;
+    *smem_out = smem;
+    *rec_cap_out = rec_cap;
+    *term_cap_out = term_cap;
+    *tbits_out = tbits;
+    return nmaps;
+}
+
+size_t fh_chain_run_bytes() { return sizeof(ChainRun); }
+size_t fh_chain_map_bytes() { return sizeof(CUtensorMap); }
+
+int launch_tile_chain(cudaStream_t s, const void *d_runs, int nruns, const void *d_maps, const TileRec *d_recs,
+                      const TileTerm *d_terms, int n, unsigned *d_sync, unsigned long long basis, int grid, size_t smem,
+                      int rec_cap, int term_cap, int tbits) {
+    const ChainRun *runs = reinterpret_cast<const ChainRun *>(d_runs);
+    const CUtensorMap *maps = reinterpret_cast<const CUtensorMap *>(d_maps);
+    int threads = tbits >= 1 ? (1 << (tbits - 1)) : 1;
+    if (threads > 512) threads = 512;
+    if (threads < 64) threads = 64;
+    void *args[] = {(void *)&runs, (void *)&nruns, (void *)&maps, (void *)&d_recs, (void *)&d_terms, (void *)&n,
+                    (void *)&d_sync, (void *)&basis, (void *)&rec_cap, (void *)&term_cap, (void *)&tbits};
+    ++g_fh_launch_count;
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_tile_chain, dim3((unsigned)grid), dim3((unsigned)threads),
+                                                      args, smem, s);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        --g_fh_launch_count;
+        return 0;
+    }
+    return 1;
 }

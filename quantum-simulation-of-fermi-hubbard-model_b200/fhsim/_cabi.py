@@ -66,6 +66,8 @@ SIGNATURES = {
     "fh_program_last_stats": [_vp, _f64p, C.POINTER(C.c_int)],
     "fh_program_time_items": [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _f64p],
     "fh_lanczos": [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint64, _f64p, _vpp, C.POINTER(C.c_int)],
+    "fh_lanczos_sector": [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint64, _f64p, _vpp, _f64p,
+                          C.POINTER(C.c_int), _f64p],
 }
 _SPECIAL = {"fh_version": ([], C.c_int), "fh_last_error": ([], C.c_char_p)}
 

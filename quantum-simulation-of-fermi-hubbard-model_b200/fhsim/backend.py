@@ -252,3 +252,41 @@ def lanczos(table: DeviceTable, k=1, n_up=-1, n_dn=-1, tol=1e-10, max_iter=1000,
     _cabi.check(_cabi.lib().fh_lanczos(table._h, int(n_up), int(n_dn), int(k), float(tol), int(max_iter), int(seed),
                                        evals.ctypes.data_as(_cabi._f64p), arr, C.byref(iters)))
     return evals, vecs, iters.value
+
+
+def lanczos_sector(table: DeviceTable, n_up, n_dn, k=1, tol=1e-10, max_iter=1000, seed=7, want_vectors=False,
+                   want_compressed=False):
+    """k lowest eigenpairs in the (n_up, n_dn) sector on SECTOR-COMPRESSED vectors (``fh_lanczos_sector``): the route
+    for lattices whose full state does not fit one GPU (4x4: 2.65 GB per vector instead of 64 GiB).
+    Returns (evals, full-space States or [], compressed eigenvectors [k, dim_sector] or None, info dict)."""
+    from math import comb
+    ctx = table.ctx
+    half = table.n // 2
+    dim = comb(half, int(n_up)) * comb(half, int(n_dn))
+    evals = np.zeros(k)
+    vecs = [State(ctx, table.n) for _ in range(k)] if want_vectors else []
+    arr = (C.c_void_p * max(k, 1))(*[v._h for v in vecs]) if want_vectors else None
+    comp = np.zeros((k, dim), dtype=np.complex128) if want_compressed else None
+    iters = C.c_int()
+    stats = np.zeros(4)
+    _cabi.check(_cabi.lib().fh_lanczos_sector(
+        table._h, int(n_up), int(n_dn), int(k), float(tol), int(max_iter), int(seed), evals.ctypes.data_as(_cabi._f64p), arr,
+        comp.ctypes.data_as(_cabi._f64p) if want_compressed else None, C.byref(iters), stats.ctypes.data_as(_cabi._f64p)))
+    info = {"sector_dim": int(stats[0]), "loop_seconds": float(stats[1]), "matvecs": int(stats[2]), "host_syncs": int(stats[3]),
+            "iterations": iters.value}
+    return evals, vecs, comp, info
+
+
+def sector_indices(n, n_up, n_dn):
+    """Full 2^n index of every compressed amplitude in rank order (rank = rank_up * D_dn + rank_dn; up = even wires)."""
+    from itertools import combinations
+    half = n // 2
+
+    def patterns(count, shift):
+        out = []
+        for pat in range(1 << half):
+            if bin(pat).count("1") == count:
+                out.append(sum(1 << (2 * b + shift) for b in range(half) if pat >> b & 1))
+        return np.array(out, dtype=np.uint64)
+    up, dn = patterns(n_up, 1), patterns(n_dn, 0)
+    return (up[:, None] | dn[None, :]).reshape(-1)

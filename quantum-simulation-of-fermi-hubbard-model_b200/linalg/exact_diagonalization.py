@@ -14,7 +14,7 @@ import itertools
 
 import numpy as np
 
-from fhsim.backend import DeviceTable, default_context, lanczos
+from fhsim.backend import DeviceTable, default_context, lanczos, lanczos_sector, sector_indices
 from fhsim.symbolic import FermionOperator, QubitOperator, count_qubits, jordan_wigner
 from fhsim.tables import PauliTable
 
@@ -91,8 +91,44 @@ def _lowest(sparse_operator, particle_number, spin_up, spin_down, k, tol, seed):
 
 def jw_get_ground_state(sparse_operator, particle_number, spin_up, spin_down, tol=1e-11, seed=7):
     """-> (E0, ground state as a length-2^n complex vector)."""
-    evals, vecs = _lowest(sparse_operator, particle_number, spin_up, spin_down, 1, tol, seed)
+    handle = _as_handle(sparse_operator)
+    if handle.n_qubits > 30:
+        raise MemoryError(f"a {handle.n_qubits}-qubit state vector does not fit one device / the host as a dense array; "
+                          "use jw_get_ground_state_compressed (sector-compressed eigenvector)")
+    evals, vecs = _lowest(handle, particle_number, spin_up, spin_down, 1, tol, seed)
     return float(evals[0]), vecs[0]
+
+
+class SectorVector:
+    """Eigenvector stored on its (N_up, N_dn) sector only: ``amplitudes[r]`` belongs to the flat index ``indices()[r]``
+    (wire 0 = MSB).  4x4: 165 636 900 amplitudes (2.65 GB) instead of 2^32 (64 GiB)."""
+
+    def __init__(self, n_qubits, spin_up, spin_down, amplitudes):
+        self.n_qubits, self.spin_up, self.spin_down = n_qubits, spin_up, spin_down
+        self.amplitudes = amplitudes
+
+    def indices(self):
+        return sector_indices(self.n_qubits, self.spin_up, self.spin_down)
+
+    def to_dense(self):
+        if self.n_qubits > 30:
+            raise MemoryError("dense form of a >30-qubit state requested")
+        out = np.zeros(1 << self.n_qubits, dtype=np.complex128)
+        out[self.indices().astype(np.int64)] = self.amplitudes
+        return out
+
+
+def jw_get_ground_state_compressed(sparse_operator, particle_number, spin_up, spin_down, tol=1e-10, seed=7, max_iter=2000,
+                                   want_vector=True):
+    """-> (E0, SectorVector, info): the ground state of the sector by Lanczos on sector-compressed vectors
+    (``fh_lanczos_sector``).  The route for the 4x4 lattice (32 qubits) of reference adapt_vqe.py:221-247."""
+    handle = _as_handle(sparse_operator)
+    if spin_up + spin_down != particle_number:
+        raise ValueError('spin up plus spin down must equal to n_electrons!')
+    evals, _, comp, info = lanczos_sector(handle.device_table(), spin_up, spin_down, k=1, tol=tol, max_iter=max_iter, seed=seed,
+                                          want_compressed=want_vector)
+    vec = SectorVector(handle.n_qubits, spin_up, spin_down, comp[0]) if want_vector else None
+    return float(evals[0]), vec, info
 
 
 def jw_get_ground_state_for_3x3(sparse_operator, particle_number, spin_up, spin_down, tol=1e-11, seed=7):

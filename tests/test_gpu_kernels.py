@@ -5,7 +5,7 @@ Tolerances: amplitudes 1e-12 abs, energies 1e-10 abs, gradients 1e-9 abs (BASELI
 import numpy as np
 import pytest
 
-from fhsim.backend import Context, DevicePool, DeviceTable, State, lanczos
+from fhsim.backend import Context, DevicePool, DeviceTable, State, lanczos, lanczos_sector, sector_indices
 from fhsim.circuit import Circuit, DiagOpSpec
 from fhsim.symbolic import QubitOperator, fermi_hubbard, givens_decomposition_square, jordan_wigner
 from fhsim.tables import GeneratorPlan, PauliTable, pack_term
@@ -545,3 +545,130 @@ def test_tile_tma_coulomb_layers_with_straddling_terms(ctx):
         st = State.from_numpy(ctx, psi0)
         prog.run(st, th)
         assert np.abs(st.numpy() - want).max() < AMP_TOL
+
+
+@pytest.mark.parametrize("n,tile_bits", [(14, 9), (18, 11), (20, 12)])
+def test_tile_chain_equals_one_launch_per_run(ctx, n, tile_bits, monkeypatch):
+    """k_tile_chain (all tile runs of a range in one cooperative launch, run-boundary counters instead of kernel
+    boundaries) vs one k_tile_tma launch per run (FHSIM_NO_CHAIN=1) vs the interpreter, forward and dagger."""
+    import emulate
+    n_params = 6
+    th = np.random.default_rng(50 + n).uniform(-1.0, 1.0, n_params)
+    circ = _random_clustered_circuit(n, n_params, 9000 + n, groups=24)
+    psi0 = rand_state(n, 900 + n)
+    prog = circ.compile(ctx, tile_bits=tile_bits, low_bits=3)
+    assert prog.n_tiles >= 3
+    monkeypatch.delenv("FHSIM_NO_CHAIN", raising=False)
+    st = State.from_numpy(ctx, psi0)
+    prog.run(st, th)
+    got = st.numpy()
+    monkeypatch.setenv("FHSIM_NO_CHAIN", "1")
+    st2 = State.from_numpy(ctx, psi0)
+    prog.run(st2, th)
+    ref = st2.numpy()
+    monkeypatch.delenv("FHSIM_NO_CHAIN", raising=False)
+    assert np.array_equal(got, ref)                      # same kernels' arithmetic, only the launch structure differs
+    if n <= 18:
+        assert np.abs(got - emulate.run_circuit(circ, psi0.copy(), th)).max() < AMP_TOL
+    prog.run(st, th, dagger=True)
+    assert np.abs(st.numpy() - psi0).max() < AMP_TOL
+    for _ in range(3):                                   # counters are reset per launch: repeated runs stay exact
+        prog.run(st, th)
+        prog.run(st, th, dagger=True)
+    assert np.abs(st.numpy() - psi0).max() < 1e-11
+
+
+def test_evaluate_with_chains_basis_synthesis_and_checkpoint_store(ctx, monkeypatch):
+    """fh_program_evaluate at 3x3: the captured graph with chains (first run synthesises |HF>, the run before the pool
+    position stores psi to the checkpoint as well) vs a graph captured with FHSIM_NO_CHAIN=1 (set-basis kernel, one
+    launch per run, device-to-device checkpoint copy): energies, gradients, pool gradients, overlaps and state_out."""
+    n, h_tab, pool_ops, dec, diag, o_h, o_pool = lattice(3, 3, 6.0)
+    plans = [GeneratorPlan(g, n) for g in pool_ops]
+    picks = [3, 17, 40, 77, 120, 200, 250, 300]
+    th = np.random.default_rng(4).uniform(-0.3, 0.3, len(picks))
+    occ = [0, 2, 4, 6, 12, 1, 3, 5, 7]
+    basis = sum(1 << (n - 1 - q) for q in occ)
+    dtab = DeviceTable(ctx, h_tab)
+    dpool = DevicePool(ctx, plans, n)
+    target = State.from_numpy(ctx, rand_state(n, 11))
+
+    def build():
+        circ = Circuit(n, len(picks))
+        for j, k in enumerate(picks):
+            circ.generator(plans[k], param=j)
+        circ.marker("ansatz_end")
+        circ.basis_change_separable(3, 3)
+        return circ.compile(ctx)
+
+    results = []
+    for no_chain in (False, True):
+        if no_chain:
+            monkeypatch.setenv("FHSIM_NO_CHAIN", "1")
+        else:
+            monkeypatch.delenv("FHSIM_NO_CHAIN", raising=False)
+        prog = build()
+        out = State(ctx, n)
+        r1 = prog.evaluate(basis, th, [dtab], grads=True, pool=dpool, pool_pos=prog.markers["ansatz_end"], targets=[target],
+                           state_out=out)
+        r2 = prog.evaluate(basis, th, [dtab], pool=dpool, pool_pos=prog.markers["ansatz_end"])       # screening-only graph
+        r3 = prog.evaluate(basis, th, [dtab])                                                        # energy-only graph
+        r1b = prog.evaluate(basis, th, [dtab], grads=True, pool=dpool, pool_pos=prog.markers["ansatz_end"], targets=[target],
+                            state_out=out)                                                           # re-captured, replayed
+        assert np.array_equal(r1["pool"], r1b["pool"]) and np.array_equal(r1["grads"], r1b["grads"])
+        results.append((r1, r2, r3, out.numpy(), prog.last_stats()[1]))
+    monkeypatch.delenv("FHSIM_NO_CHAIN", raising=False)
+    (a1, a2, a3, sa, la), (b1, b2, b3, sb, lb) = results
+    assert la < lb                                        # fewer launches with chains
+    assert np.array_equal(sa, sb)
+    for a, b in ((a1, b1), (a2, b2), (a3, b3)):
+        assert np.array_equal(a["expvals"], b["expvals"])
+        if a["pool"] is not None:
+            assert np.array_equal(a["pool"], b["pool"])
+        if a["grads"] is not None:
+            assert np.array_equal(a["grads"], b["grads"])
+    assert np.array_equal(a1["overlaps"], b1["overlaps"])
+    # and against the oracle
+    psi = sv.adapt_state(n, occ, [o_pool[k] for k in picks], th)
+    g_or, e_or, _ = sv.pool_gradients(psi, o_h, o_pool, diag, dec, n)
+    assert abs(a1["expvals"][0] - e_or) < E_TOL and np.abs(a1["pool"] - g_or).max() < G_TOL
+
+
+@pytest.mark.parametrize("lat,u,up,dn,k", [((2, 2), 4.0, 2, 2, 3), ((2, 3), 4.0, 3, 3, 2), ((3, 3), 6.0, 5, 4, 4), ((2, 4), 2.0, 4, 4, 1)])
+def test_sector_compressed_lanczos_vs_sector_ed(ctx, lat, u, up, dn, k):
+    """fh_lanczos_sector (compressed vectors, device-resident iteration) vs scipy on the sector matrix: energies 1e-9,
+    eigenvectors span the oracle's eigenspaces, compressed and scattered vectors agree, nothing leaves the sector."""
+    n, h_tab, _, _, _, o_h, _ = lattice(*lat, u)
+    tab = DeviceTable(ctx, h_tab)
+    evals, vecs, comp, info = lanczos_sector(tab, up, dn, k=k, tol=1e-11, max_iter=3000, seed=7, want_vectors=True,
+                                              want_compressed=True)
+    want, wvecs, idx = ed.ground_state(o_h, n, up + dn, up, dn, k=max(k + 2, 6))
+    assert np.abs(evals - want[:k]).max() < 1e-9
+    assert info["sector_dim"] == len(idx) and info["matvecs"] >= info["iterations"] - 8 * k
+    sidx = sector_indices(n, up, dn)
+    assert sorted(int(v) for v in sidx) == sorted(int(v) for v in idx)
+    level = [w for w, e in zip(wvecs, want) if abs(e - want[0]) < 1e-7]      # the oracle's (possibly degenerate) ground level
+    for e in range(k):
+        full = vecs[e].numpy()
+        assert abs(np.linalg.norm(full) - 1.0) < 1e-10
+        outside = np.ones(1 << n, bool)
+        outside[idx] = False
+        assert np.abs(full[outside]).max() == 0.0
+        assert np.abs(full[sidx.astype(np.int64)] - comp[e]).max() == 0.0
+        resid = sv.apply_table(full, o_h, n) - evals[e] * full
+        assert np.linalg.norm(resid) < 1e-7
+        if abs(evals[e] - want[0]) < 1e-7:
+            proj = sum(abs(np.vdot(w, full)) ** 2 for w in level)
+            assert abs(proj - 1.0) < 1e-7
+    gram = np.array([[np.vdot(a.numpy(), b.numpy()) for b in vecs] for a in vecs])
+    assert np.abs(gram - np.eye(k)).max() < 1e-9
+    # fh_lanczos takes the compressed route by itself for sector requests and gives the same energies
+    ev2, v2, it2 = lanczos(tab, k=k, n_up=up, n_dn=dn, tol=1e-11, max_iter=3000, seed=7)
+    assert np.abs(ev2 - evals).max() < 1e-12
+
+
+def test_sector_lanczos_rejects_tables_that_leave_the_sector(ctx):
+    n = 8
+    op = QubitOperator("X0 X1", 0.5) + QubitOperator("Z0 Z3", 0.25)         # X0 X1 creates / destroys an up-down pair
+    tab = DeviceTable(ctx, PauliTable.from_operator(op, n))
+    with pytest.raises(ValueError, match="conserve"):
+        lanczos_sector(tab, 2, 2)
