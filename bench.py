@@ -152,6 +152,46 @@ def build_gpu_workload(ctx):
                 plans=plans, dec=dec, diag=diag, h_tab=h_tab)
 
 
+def build_lattice_workload(ctx, nx, ny, u, n_ops):
+    """The screening workload on an arbitrary lattice (as tools/bench_sharded.py builds it): k-space HF basis state, the
+    first ``n_ops`` operators of the HF screening with theta_j = 0.05 (-1)^j, separable W, full pool."""
+    from fhsim.backend import DevicePool, DeviceTable
+    from fhsim.circuit import Circuit
+    from fhsim.symbolic import fermi_hubbard, jordan_wigner
+    from fhsim.tables import GeneratorPlan, PauliTable
+    from operators.pool import hubbard_interaction_pool_simplified
+    ns, n = nx * ny, 2 * nx * ny
+
+    def f(k, length):
+        if length == 1:
+            return 0.0
+        c = np.cos(2 * np.pi * k / length)
+        return c if length == 2 else 2 * c
+    eps = [round(-(f(s % nx, nx) + f(s // nx, ny)), 12) for s in range(ns)]
+    n_up = (ns + 1) // 2
+    n_dn = ns - n_up
+    order = sorted(range(ns), key=lambda s: eps[s])
+    occ = [2 * s for s in order[:n_up]] + [2 * s + 1 for s in order[:n_dn]]
+    basis = sum(1 << (n - 1 - q) for q in occ)
+    dtab = DeviceTable(ctx, PauliTable.from_operator(fermi_hubbard(nx, ny, 1.0, u), n))
+    plans = [GeneratorPlan(jordan_wigner(g), n) for g in hubbard_interaction_pool_simplified(nx, ny)]
+    dpool = DevicePool(ctx, plans, n)
+    c0 = Circuit(n, 0)
+    c0.marker("ansatz_end")
+    c0.basis_change_separable(nx, ny)
+    p0 = c0.compile(ctx)
+    g0 = p0.evaluate(basis, [], [dtab], pool=dpool, pool_pos=0)["pool"]
+    p0.close()
+    picks = [k for k in range(len(plans)) if abs(g0[k]) > 1e-9][:n_ops]
+    thetas = np.array([0.05 * (-1) ** j for j in range(len(picks))])
+    circ = Circuit(n, len(picks))
+    for j, k in enumerate(picks):
+        circ.generator(plans[k], param=j)
+    circ.marker("ansatz_end")
+    circ.basis_change_separable(nx, ny)
+    return dict(prog=circ.compile(ctx), dtab=dtab, dpool=dpool, basis=basis, thetas=thetas, picks=picks, plans=plans)
+
+
 def cpu_reference_sample(n_ops, picks=None, thetas=None):
     """Reference CPU path (oracle/literal.py: gate-by-gate torch + autograd) on a bounded sample:
     screening of the first ``n_ops`` pool operators appended to the ansatz state.  The ansatz prefix
@@ -338,28 +378,58 @@ def run_gpu_arm(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_total = float(t.item())
 
-    # ---- pool-sharded screening of ONE state across the ranks: psi/lambda recomputed on every
-    # rank, the 324 operators split 324/world per rank, <= 41 doubles all-gathered.  Reported next to the replica
-    # numbers; it is a latency (not throughput) mode at 18 qubits because K3 is ~12 % of the step.
+    # ---- the two paths that really shard across GPUs; every rank takes part ----
+    # (1) Pool-sharded screening of ONE state.  At 18 qubits it is withdrawn: K3 is ~17 % of a 0.2 ms step, so splitting
+    #     the pool cannot pay for a collective (round 1 measured 0.46-0.60 ms vs 0.23 ms on one GPU) -- 18-qubit
+    #     screenings are replicas only.  It is measured where K3 dominates the step: the 3x4 lattice (24 qubits, 792
+    #     operators, state 256 MiB), one screening on one GPU vs the same screening with the pool split over the ranks.
+    # (2) cfg 5: the 4x4 lattice (32 qubits, 64 GiB state) sharded by its top index bits, global<->local qubit swaps
+    #     through fh_comm (NCCL all-to-all pipelined against the local bit permutation).
     pool_sharded = None
+    sharded_4x4 = None
     if dist is not None:
         from fhsim.parallel import screen_pool_sharded
         dev = torch.device("cuda", local_rank)
-        for _ in range(3):
-            full = screen_pool_sharded(prog, basis, thetas, [dtab], dpool, marker, dist, dev)
-        assert np.abs(full["pool"] - res["pool"]).max() < 1e-12
-        barrier()
-        t0 = time.perf_counter()
-        n_ps = min(args.steps, 200)
-        for _ in range(n_ps):
-            screen_pool_sharded(prog, basis, thetas, [dtab], dpool, marker, dist, dev)
-        barrier()
-        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        pool_sharded = {"ms_per_screening": 1e3 * float(t.item()) / n_ps, "ops_per_rank": -(-n_pool // world),
-                        "collective": "all_gather of <= %d doubles per rank (NCCL)" % -(-n_pool // world),
-                        "note": "one 324-operator screening split across ranks; wall clock, L2 not flushed"}
-        step()      # restore the full-pool graph
+        try:
+            wl24 = build_lattice_workload(ctx, 3, 4, 4.0, 16)
+            p24, m24 = wl24["prog"], wl24["prog"].markers["ansatz_end"]
+            one = p24.evaluate(wl24["basis"], wl24["thetas"], [wl24["dtab"]], pool=wl24["dpool"], pool_pos=m24)
+            full = screen_pool_sharded(p24, wl24["basis"], wl24["thetas"], [wl24["dtab"]], wl24["dpool"], m24, dist, dev)
+            parity = float(np.abs(full["pool"] - one["pool"]).max())
+            times = {}
+            for label in ("single_gpu", "pool_sharded"):
+                ts = []
+                for _ in range(5):
+                    barrier()
+                    t0 = time.perf_counter()
+                    if label == "single_gpu":
+                        p24.evaluate(wl24["basis"], wl24["thetas"], [wl24["dtab"]], pool=wl24["dpool"], pool_pos=m24)
+                    else:
+                        screen_pool_sharded(p24, wl24["basis"], wl24["thetas"], [wl24["dtab"]], wl24["dpool"], m24, dist, dev)
+                    ctx.sync()
+                    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ts.append(float(t.item()))
+                times[label] = 1e3 * statistics.median(ts[1:])
+            n24 = wl24["dpool"].n_out
+            pool_sharded = {"workload": "3x4 Hubbard, 24 qubits, 16-operator ansatz, 792-operator pool, one screening",
+                            "single_gpu_ms": times["single_gpu"], "pool_sharded_ms": times["pool_sharded"],
+                            "speedup": times["single_gpu"] / times["pool_sharded"], "ops_per_rank": -(-n24 // world),
+                            "max_abs_diff_vs_single_gpu": parity,
+                            "collective": "all_gather of <= %d doubles per rank (NCCL); psi / lambda recomputed per rank" % -(-n24 // world),
+                            "at_18_qubits": "withdrawn: replicas only (K3 is ~17 % of the step; see DESIGN 6)"}
+            for o in (wl24["prog"], wl24["dpool"], wl24["dtab"]):
+                o.close()
+        except Exception as exc:
+            print(f"pool-sharded measurement failed: {exc!r}", file=sys.stderr)
+        if not args.no_sharded:
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                from bench_sharded import run_sharded
+                sharded_4x4 = run_sharded("4x4", 4.0, 16, 1, dist, local_rank, False, True, measured_peak_gbs()[0])
+            except Exception as exc:
+                print(f"sharded 4x4 measurement failed: {exc!r}", file=sys.stderr)
+            torch.cuda.set_device(local_rank)
 
     if rank != 0:
         if dist is not None:
@@ -510,6 +580,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         "cpu_baseline": cpu,
         "cpu_closed_form": cpu_closed,
         "pool_sharded": pool_sharded,
+        "sharded_4x4": sharded_4x4,
         "clocks": clocks,
         "energy": float(res["expvals"][0]),
     }
@@ -527,6 +598,7 @@ def main():
     ap.add_argument("--impl", default="fhsim", choices=["fhsim", "reference", "cpu-closed-form"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hbm-regime", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the sharded 4x4 (32-qubit) block of multi-GPU runs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

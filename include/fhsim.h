@@ -180,6 +180,27 @@ int fh_lanczos(const fh_table *tab, int n_up, int n_dn, int k, double tol, int m
 int fh_lanczos_sector(const fh_table *tab, int n_up, int n_dn, int k, double tol, int max_iter, uint64_t seed,
                       double *evals, fh_state *const *evecs, double *compressed_out, int *iterations, double *stats);
 
+/* ---- multi-GPU: communicator for the sharded-state path (BASELINE cfg 5) -------------------
+ * The reference is single-process / single-device (models/adapt_vqe.py:156 hard-codes cuda:0), so these entry points
+ * have no reference counterpart; they carry the global<->local qubit swap of a state sharded by its top index bits.
+ * One process per GPU.  Rank 0 creates the id, the launcher distributes the 128 bytes (any channel: file, socket,
+ * torch.distributed broadcast), every rank calls fh_comm_init.  NCCL (NVLink 5 / NVSwitch) is loaded at run time. */
+typedef struct fh_comm fh_comm;
+int fh_comm_unique_id(unsigned char *out128);
+int fh_comm_init(fh_ctx *ctx, const unsigned char *id128, int rank, int world, fh_comm **out);
+int fh_comm_destroy(fh_comm *comm);
+int fh_comm_info(const fh_comm *comm, int *rank, int *world, double *last_exchange_ms);
+/* Global<->local qubit swap of a slab: optional local bit permutation (n_pairs disjoint transpositions a[k]<->b[k] of
+ * index bits, staged in `scratch`) followed by the all-to-all of the world equal chunks: dst chunk p <- chunk `rank` of
+ * rank p.  Chunk k+1 is permuted on the compute stream while chunk k is on the wire (communication stream).  Enqueues
+ * only; later work on the context's stream is ordered after the exchange.  src, scratch, dst: distinct slabs. */
+int fh_comm_swap_exchange(fh_comm *comm, const fh_state *src, fh_state *scratch, fh_state *dst, int n_pairs,
+                          const int32_t *a, const int32_t *b);
+int fh_comm_last_exchange_ms(fh_comm *comm, double *ms);
+int fh_comm_all_reduce_sum(fh_comm *comm, double *values, int count);       /* host in/out, count <= 4096 */
+int fh_comm_all_gather(fh_comm *comm, const double *in, int count, double *out);   /* host; out[world * count] */
+int fh_comm_barrier(fh_comm *comm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,7 @@ struct TileLaunch {
     int nsub;                           // records in this run
     int first_rec;                      // offset into the record array of the chosen direction
     int first_term, nterms;             // range in the tile-term array of the chosen direction
+    int ptab_first, ptab_words;         // range in the pair-table array of the chosen direction (16-bit entries)
     unsigned char bits[16];             // ascending global bit positions of the tile
 };
 
@@ -99,15 +100,15 @@ struct __align__(16) TileRec {          // 144 bytes = 9 x 16 B; k_tile reads it
     // word 1
     unsigned lfixval;                   // pattern bits inside the tile, in tile-local coordinates
     int type;                           // 1 pair (complex matrix), 3 pair (real matrix), 6 pair (real diagonal), 2 diag
-    int nlfix, term_off;
+    int nlfix, term_off;                // term_off: diag ops: first term; pair ops: first word of the op in the run's pair table
     // word 2: bit-insertion masks (1<<p)-1 of the (at most 4) pattern bits inside the tile, ascending;
     // unused slots hold 0xffffffff (insertion is then a no-op)
     unsigned lowmask[4];
     // word 3: nterms (diag); seg = index of this op among the tile's parametrised ops in execution order of this
     // direction, or -1 (used by the fused adjoint sweep, which runs the dagger records)
-    int nterms, seg;
+    int nterms, seg;                    // nterms: diag ops: term count; pair ops: slot image of the x-mask (TMA layout)
     unsigned zeta_local;                // in-tile bits of zeta in tile-local coordinates (sign without an index load)
-    int pad;
+    int reps;                           // pair ops: pair-table entries per thread = ceil(pairs in a tile / threads per CTA)
     // words 4..7
     double m[8];
     // word 8: normalised generator element of a rotation op (gradient of the adjoint sweep)
@@ -130,6 +131,7 @@ struct TileOp {                         // host bookkeeping of one tile run
     int first_rec_fwd, first_rec_dag;   // offsets into the two record arrays
     int first_term_fwd, first_term_dag, nterms;
     int n_param_subs;                   // parametrised ops inside this tile
+    int first_ptab_fwd, first_ptab_dag, ptab_words;
 };
 
 struct TabTerm {
@@ -281,7 +283,11 @@ size_t fh_diag_scratch_bytes();
 void launch_diag_adjoint(cudaStream_t s, int sm, double2 *psi, double2 *lam, const DiagTerm *d_terms, int nterms, int n,
                          double *d_partials, int max_blocks, int *blocks_used);
 void launch_tile(cudaStream_t s, double2 *psi, const TileLaunch &tl, const TileRec *d_recs, const TileTerm *d_terms,
-                 int n);
+                 const unsigned short *d_ptab, int n);
+// geometry the TMA tile kernels will use for a tile bit set: -1 TMA path not applicable, 0 linear shared-memory layout,
+// 1 hardware 128-byte swizzle (slot = l ^ ((l >> 3) & 7)); threads per CTA of the tile kernels
+int fh_tile_tma_layout(const unsigned char *bits, int nbits, int n);
+int fh_tile_threads(int nbits);
 // nl consecutive tile runs in one cooperative launch (grid barriers between runs); returns 0 if unavailable
 int launch_tile_multi(cudaStream_t s, int sm, double2 *psi, const TileLaunch *d_tls, int nl, int max_bits, int min_bits,
                       const TileRec *d_recs, const TileTerm *d_terms, int n);

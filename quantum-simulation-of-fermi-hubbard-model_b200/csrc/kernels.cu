@@ -1212,6 +1212,38 @@ __global__ void __launch_bounds__(256) k_swap_bits(const double2 *__restrict__ s
     }
 }
 
+// the same permutation restricted to the destination range [first, first + count): one chunk of a pipelined exchange
+__global__ void __launch_bounds__(256) k_swap_bits_range(const double2 *__restrict__ src, double2 *__restrict__ dst, u64 first,
+                                                         u64 count, const SwapPairs sp) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
+        const u64 i = first + t;
+        u64 j = i;
+#pragma unroll 1
+        for (int k = 0; k < sp.n; ++k) {
+            const u64 q = ((j >> sp.a[k]) ^ (j >> sp.b[k])) & 1ull;
+            j ^= (q << sp.a[k]) | (q << sp.b[k]);
+        }
+        dst[i] = src[j];
+    }
+}
+
+void launch_swap_bits_range(cudaStream_t s, int sm, const double2 *src, double2 *dst, int n, int npairs, const int *a,
+                            const int *b, u64 first, u64 count) {
+    SwapPairs sp;
+    sp.n = npairs;
+    for (int k = 0; k < npairs; ++k) {
+        sp.a[k] = (unsigned char)a[k];
+        sp.b[k] = (unsigned char)b[k];
+    }
+    (void)n;
+    u64 blocks = (count + 255) / 256;
+    if (blocks > (u64)sm * 32) blocks = (u64)sm * 32;
+    if (blocks < 1) blocks = 1;
+    ++g_fh_launch_count;
+    k_swap_bits_range<<<(int)blocks, 256, 0, s>>>(src, dst, first, count, sp);
+}
+
 void launch_swap_bits(cudaStream_t s, int sm, const double2 *src, double2 *dst, int n, int npairs, const int *a,
                       const int *b) {
     SwapPairs sp;

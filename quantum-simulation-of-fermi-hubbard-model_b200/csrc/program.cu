@@ -21,10 +21,10 @@ struct ChainRunHost {
 };
 int plan_tile_chain(int sm, double2 *psi, double2 *psi2, const ChainRunHost *hruns, int nruns, int n, void *h_runs,
                     void *h_maps, int map_base, int *grid_out, size_t *smem_out, int *rec_cap_out, int *term_cap_out,
-                    int *tbits_out);
+                    int *tab_cap_out, int *tbits_out);
 int launch_tile_chain(cudaStream_t s, const void *d_runs, int nruns, const void *d_maps, const TileRec *d_recs,
-                      const TileTerm *d_terms, int n, unsigned *d_sync, unsigned long long basis, int grid, size_t smem,
-                      int rec_cap, int term_cap, int tbits);
+                      const TileTerm *d_terms, const unsigned short *d_ptab, int n, unsigned *d_sync, unsigned long long basis,
+                      int grid, size_t smem, int rec_cap, int term_cap, int tab_cap, int tbits);
 size_t fh_chain_run_bytes();
 size_t fh_chain_map_bytes();
 
@@ -69,6 +69,9 @@ struct fh_program {
     std::vector<TileTerm> tterms_fwd, tterms_dag;
     std::vector<int> pair_rec_fwd, pair_rec_dag;       // pair index -> record index (or -1)
     std::vector<int> dterm_tt_fwd, dterm_tt_dag;       // diag term index -> tile-term index (or -1)
+    // static per-thread pair tables of the TMA tile kernels (theta-independent: uploaded once at finalize)
+    std::vector<unsigned short> ptab_fwd, ptab_dag;
+    unsigned short *d_ptab_fwd = nullptr, *d_ptab_dag = nullptr;
     TileRec *d_recs_fwd = nullptr, *d_recs_dag = nullptr, *h_recs_fwd = nullptr, *h_recs_dag = nullptr;
     TileTerm *d_tterms_fwd = nullptr, *d_tterms_dag = nullptr, *h_tterms_fwd = nullptr, *h_tterms_dag = nullptr;
     // the theta-dependent payload above lives in ONE pinned arena mirrored by ONE device arena (a single copy node
@@ -155,6 +158,8 @@ extern "C" int fh_program_destroy(fh_program *p) {
     fh_ctx_scratch_put(p->ctx, state_bytes, p->d_lam);
     fh_ctx_scratch_put(p->ctx, state_bytes, p->d_chk);
     cudaFree(p->d_sync);
+    cudaFree(p->d_ptab_fwd);
+    cudaFree(p->d_ptab_dag);
     cudaFree(p->d_gpart);
     cudaFree(p->d_gfirst);
     cudaFree(p->d_res);
@@ -329,9 +334,13 @@ static void build_tile_records(fh_program *p) {
     for (auto &t : p->tiles) {
         unsigned tilemask = 0;
         for (int b = 0; b < t.nbits; ++b) tilemask |= 1u << t.bits[b];
+        const int layout = fh_tile_tma_layout(t.bits, t.nbits, p->n), threads = fh_tile_threads(t.nbits);
         for (int dir = 0; dir < 2; ++dir) {
             std::vector<TileRec> &recs = dir ? p->recs_dag : p->recs_fwd;
             std::vector<TileTerm> &tts = dir ? p->tterms_dag : p->tterms_fwd;
+            std::vector<unsigned short> &ptab = dir ? p->ptab_dag : p->ptab_fwd;
+            const size_t tab_start = ptab.size();
+            (dir ? t.first_ptab_dag : t.first_ptab_fwd) = (int)tab_start;
             (dir ? t.first_rec_dag : t.first_rec_fwd) = (int)recs.size();
             (dir ? t.first_term_dag : t.first_term_fwd) = (int)tts.size();
             int term_off = 0, seg = 0;
@@ -365,6 +374,27 @@ static void build_tile_records(fh_program *p) {
                     for (int b = 0; b < t.nbits; ++b)
                         if (op.zeta >> t.bits[b] & 1ull) r.zeta_local |= 1u << b;
                     (dir ? p->pair_rec_dag : p->pair_rec_fwd)[sub.index] = (int)recs.size();
+                    if (layout >= 0) {
+                        // per-thread pair table: 16-bit entry [rep * threads + tid] = slot of the pattern side | in-tile sign
+                        // parity << 13 | valid << 14 for pair number rep * threads + tid of this op; partner slot = slot ^ xs
+                        auto slot = [&](unsigned l) { return layout ? (l ^ ((l >> 3) & 7u)) : l; };
+                        const unsigned npairs = (1u << t.nbits) >> nl;
+                        const unsigned reps = (npairs + (unsigned)threads - 1u) / (unsigned)threads;
+                        r.term_off = (int)(ptab.size() - tab_start);
+                        r.reps = (int)reps;
+                        r.nterms = (int)slot(sub.xlocal);
+                        for (unsigned k = 0; k < reps * (unsigned)threads; ++k) {
+                            unsigned short word = 0;
+                            if (k < npairs) {
+                                unsigned il = k;
+                                for (int q = 0; q < 4; ++q) il = ((il & ~r.lowmask[q]) << 1) | (il & r.lowmask[q]);
+                                il |= lv;
+                                const unsigned par = (unsigned)__builtin_popcount(il & r.zeta_local) & 1u;
+                                word = (unsigned short)(slot(il) | (par << 13) | (1u << 14));
+                            }
+                            ptab.push_back(word);
+                        }
+                    }
                 } else {
                     const DiagOp &d = p->diagops[sub.index];
                     r.type = 2;
@@ -385,6 +415,7 @@ static void build_tile_records(fh_program *p) {
             }
             t.nterms = term_off;
             t.n_param_subs = seg;
+            t.ptab_words = (int)(ptab.size() - tab_start);
         }
     }
 }
@@ -397,6 +428,8 @@ static TileLaunch make_tile_launch(const TileOp &t, int dagger) {
     tl.first_rec = dagger ? t.first_rec_dag : t.first_rec_fwd;
     tl.first_term = dagger ? t.first_term_dag : t.first_term_fwd;
     tl.nterms = t.nterms;
+    tl.ptab_first = dagger ? t.first_ptab_dag : t.first_ptab_fwd;
+    tl.ptab_words = t.ptab_words;
     memcpy(tl.bits, t.bits, 16);
     return tl;
 }
@@ -466,6 +499,8 @@ extern "C" int fh_program_finalize(fh_program *p) {
         if (p->arena_bytes)
             FH_CUDA(cudaMemcpyAsync(p->d_arena, p->h_arena, p->arena_bytes, cudaMemcpyHostToDevice, ctx->stream));
     }
+    FH_TRY(upload_vec(&p->d_ptab_fwd, p->ptab_fwd, ctx->stream));
+    FH_TRY(upload_vec(&p->d_ptab_dag, p->ptab_dag, ctx->stream));
     if (!p->tiles.empty()) {
         const size_t nt = p->tiles.size();
         std::vector<TileLaunch> fwd(nt), dag_rev(nt);
@@ -578,15 +613,9 @@ static void apply_item(fh_program *p, const Item &it, double2 *st, int dagger) {
         launch_diag(ctx->stream, ctx->sm_count, st, p->d_dterms + d.first, d.count, p->n, dagger, ctx->d_diag);
     } else {
         const TileOp &t = p->tiles[it.index];
-        TileLaunch tl;
-        tl.nbits = t.nbits;
-        tl.nsub = t.nsub;
-        tl.first_rec = dagger ? t.first_rec_dag : t.first_rec_fwd;
-        tl.first_term = dagger ? t.first_term_dag : t.first_term_fwd;
-        tl.nterms = t.nterms;
-        memcpy(tl.bits, t.bits, 16);
+        const TileLaunch tl = make_tile_launch(t, dagger);
         launch_tile(ctx->stream, st, tl, dagger ? p->d_recs_dag : p->d_recs_fwd,
-                    dagger ? p->d_tterms_dag : p->d_tterms_fwd, p->n);
+                    dagger ? p->d_tterms_dag : p->d_tterms_fwd, dagger ? p->d_ptab_dag : p->d_ptab_fwd, p->n);
     }
 }
 
@@ -601,12 +630,7 @@ static int try_chain(fh_program *p, int lo, int hi, int k0, int run, double2 *st
     for (int r = 0; r < run; ++r) {
         const int idx = dagger ? hi - 1 - (k0 + r) : lo + k0 + r;
         const TileOp &t = p->tiles[p->items[idx].index];
-        hr[r].tl.nbits = t.nbits;
-        hr[r].tl.nsub = t.nsub;
-        hr[r].tl.first_rec = dagger ? t.first_rec_dag : t.first_rec_fwd;
-        hr[r].tl.first_term = dagger ? t.first_term_dag : t.first_term_fwd;
-        hr[r].tl.nterms = t.nterms;
-        memcpy(hr[r].tl.bits, t.bits, 16);
+        hr[r].tl = make_tile_launch(t, dagger);
         hr[r].second_store = (!dagger && chk && idx + 1 == chk_pos) ? 1 : 0;
         hr[r].init_basis = (init_basis && r == 0) ? 1 : 0;
         n_second += hr[r].second_store;
@@ -614,11 +638,11 @@ static int try_chain(fh_program *p, int lo, int hi, int k0, int run, double2 *st
     if (p->chain_used_maps[reg] + run + n_second > p->chain_cap_maps) return 0;
     unsigned char *h_runs = p->h_arena + p->chain_off[reg] + fh_chain_run_bytes() * (size_t)p->chain_used_runs[reg];
     unsigned char *h_maps = p->h_arena + p->chain_maps_off[reg];
-    int grid = 0, rec_cap = 0, term_cap = 0, tbits = 0;
+    int grid = 0, rec_cap = 0, term_cap = 0, tab_cap = 0, tbits = 0;
     size_t smem = 0;
     const int nmaps = plan_tile_chain(ctx->sm_count, st, chk, hr.data(), run, p->n, h_runs,
                                       h_maps + fh_chain_map_bytes() * (size_t)p->chain_used_maps[reg], p->chain_used_maps[reg],
-                                      &grid, &smem, &rec_cap, &term_cap, &tbits);
+                                      &grid, &smem, &rec_cap, &term_cap, &tab_cap, &tbits);
     if (nmaps < 0) return 0;
     const unsigned char *d_runs = p->d_arena + p->chain_off[reg] + fh_chain_run_bytes() * (size_t)p->chain_used_runs[reg];
     const unsigned char *d_maps = p->d_arena + p->chain_maps_off[reg];
@@ -633,8 +657,8 @@ static int try_chain(fh_program *p, int lo, int hi, int k0, int run, double2 *st
         cudaMemsetAsync(d_sync, 0, sizeof(unsigned) * (size_t)run, ctx->stream);
     }
     if (!launch_tile_chain(ctx->stream, d_runs, run, d_maps, dagger ? p->d_recs_dag : p->d_recs_fwd,
-                           dagger ? p->d_tterms_dag : p->d_tterms_fwd, p->n, d_sync, basis, grid, smem, rec_cap, term_cap,
-                           tbits))
+                           dagger ? p->d_tterms_dag : p->d_tterms_fwd, dagger ? p->d_ptab_dag : p->d_ptab_fwd, p->n, d_sync,
+                           basis, grid, smem, rec_cap, term_cap, tab_cap, tbits))
         return 0;
     p->chain_used_runs[reg] += run;
     p->chain_used_maps[reg] += nmaps;
@@ -752,13 +776,7 @@ static void adjoint_item(fh_program *p, const Item &it, double2 *psi, double2 *l
     static const bool unfused = getenv("FHSIM_UNFUSED_ADJOINT") != nullptr;
     if (!unfused && t.nbits <= FH_TILE_ADJOINT_MAX_BITS) {
         // one launch: gradient partials of every parametrised op of the run + the inverse run on psi and lam
-        TileLaunch tl;
-        tl.nbits = t.nbits;
-        tl.nsub = t.nsub;
-        tl.first_rec = t.first_rec_dag;
-        tl.first_term = t.first_term_dag;
-        tl.nterms = t.nterms;
-        memcpy(tl.bits, t.bits, 16);
+        const TileLaunch tl = make_tile_launch(t, 1);
         launch_tile_adjoint(p->ctx->stream, psi, lam, tl, p->d_recs_dag, p->d_tterms_dag, p->n, p->d_gpart, p->n_segments);
         for (int s = t.first_sub + t.nsub - 1; s >= t.first_sub; --s) {
             const TileSub &sub = p->subs[s];

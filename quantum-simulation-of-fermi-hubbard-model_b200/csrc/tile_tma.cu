@@ -233,63 +233,62 @@ __device__ __forceinline__ double flip_sign(double v, unsigned sbit) {
     return __hiloint2double(__double2hiint(v) ^ (int)sbit, __double2loint(v));
 }
 
-// decoded position of this thread's pair for one op (computed one op ahead of its use)
-struct PairPrep {
-    unsigned si, sj;     // shared-memory slots of the pair
-    unsigned sbit;       // sign of the off-diagonal elements as an IEEE sign bit
-    unsigned active;     // this thread has a pair of this op in this tile
+// Pair ops are driven by a per-thread table built on the host once per program (program.cu: build_tile_records): 16-bit
+// entry [rep * threads + tid] of an op = slot of the pattern side | in-tile sign parity << 13 | valid << 14; the partner
+// slot is entry ^ xs with xs = slot image of the op's x-mask (the slot map is XOR-linear).  The table of a run arrives in
+// shared memory by bulk copy next to the op records, so the op loop does no index arithmetic at all:
+// LDS entry -> LDS amplitudes -> FP64 -> STS.
+struct OpHdr {
+    unsigned fixmask_out, fixval_out, zeta;   // pattern / sign bits outside the tile (uniform per tile)
+    unsigned xs;                              // slot image of the x-mask
+    int type, reps, off;                      // record type, table entries per thread, first table entry (or first term)
+    double2 m0, m1, m2, m3;                   // 2x2 block
 };
 
-template <bool SWZ>
-__device__ __forceinline__ PairPrep prep_pair(const TileRec *rec, unsigned base, unsigned k, int T) {
+__device__ __forceinline__ void load_hdr(const TileRec *rec, OpHdr &h) {
     const uint4 *rp = reinterpret_cast<const uint4 *>(rec);
-    const uint4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
-    // q0 = {fixmask_out, fixval_out, zeta, xlocal}; q1 = {lfixval, type, nlfix, term_off}; q2 = lowmask[4]
-    const unsigned zloc = rp[3].z;
-    PairPrep p;
-    const unsigned npairs = (1u << T) >> q1.z;
-    p.active = (q1.y != 2u) && ((base & q0.x) == q0.y) && (k < npairs);
-    unsigned il = k;
-    il = ((il & ~q2.x) << 1) | (il & q2.x);
-    il = ((il & ~q2.y) << 1) | (il & q2.y);
-    il = ((il & ~q2.z) << 1) | (il & q2.z);
-    il = ((il & ~q2.w) << 1) | (il & q2.w);
-    il |= q1.x;
-    p.sbit = ((unsigned)(__popc(base & q0.z) + __popc(il & zloc)) & 1u) << 31;
-    p.si = tslot<SWZ>(il);
-    p.sj = p.si ^ tslot<SWZ>(q0.w);           // the slot map is XOR-linear
-    return p;
+    const uint4 q0 = rp[0], q1 = rp[1], q3 = rp[3];
+    h.fixmask_out = q0.x;
+    h.fixval_out = q0.y;
+    h.zeta = q0.z;
+    h.type = (int)q1.y;
+    h.off = (int)q1.w;
+    h.reps = (int)q3.w;
+    h.xs = q3.x;
+    const double2 *mp = reinterpret_cast<const double2 *>(rec->m);
+    h.m0 = mp[0];
+    h.m1 = mp[1];
+    h.m2 = mp[2];
+    h.m3 = mp[3];
 }
 
-__device__ __forceinline__ void apply_pair(double2 *buf, const TileRec *rec, const PairPrep &p) {
-    const double2 *mp = reinterpret_cast<const double2 *>(rec->m);
-    const int type = rec->type;
-    double2 a = buf[p.si], b = buf[p.sj];
-    if (type == 3) {            // real matrix (Givens)
-        const double m00 = mp[0].x, m01 = flip_sign(mp[1].x, p.sbit), m10 = flip_sign(mp[2].x, p.sbit), m11 = mp[3].x;
-        const double2 ra = make_double2(m00 * a.x + m01 * b.x, m00 * a.y + m01 * b.y);
-        const double2 rb = make_double2(m10 * a.x + m11 * b.x, m10 * a.y + m11 * b.y);
+__device__ __forceinline__ void apply_pair_entry(double2 *buf, const OpHdr &h, unsigned e, unsigned sb) {
+    const unsigned si = e & 0x1fffu, sj = si ^ h.xs;
+    const unsigned sbit = (((e >> 13) ^ sb) & 1u) << 31;
+    double2 a = buf[si], b = buf[sj];
+    if (h.type == 3) {            // real matrix (Givens)
+        const double m01 = flip_sign(h.m1.x, sbit), m10 = flip_sign(h.m2.x, sbit);
+        const double2 ra = make_double2(h.m0.x * a.x + m01 * b.x, h.m0.x * a.y + m01 * b.y);
+        const double2 rb = make_double2(m10 * a.x + h.m3.x * b.x, m10 * a.y + h.m3.x * b.y);
         a = ra;
         b = rb;
-    } else if (type == 6) {     // real diagonal, complex off-diagonal (every rotation exp(-i a G))
-        const double m00 = mp[0].x, m11 = mp[3].x;
-        const double2 mb = make_double2(flip_sign(mp[1].x, p.sbit), flip_sign(mp[1].y, p.sbit));
-        const double2 mc = make_double2(flip_sign(mp[2].x, p.sbit), flip_sign(mp[2].y, p.sbit));
-        const double2 ra = make_double2(m00 * a.x + (mb.x * b.x - mb.y * b.y), m00 * a.y + (mb.x * b.y + mb.y * b.x));
-        const double2 rb = make_double2(m11 * b.x + (mc.x * a.x - mc.y * a.y), m11 * b.y + (mc.x * a.y + mc.y * a.x));
+    } else if (h.type == 6) {     // real diagonal, complex off-diagonal (every rotation exp(-i a G))
+        const double2 mb = make_double2(flip_sign(h.m1.x, sbit), flip_sign(h.m1.y, sbit));
+        const double2 mc = make_double2(flip_sign(h.m2.x, sbit), flip_sign(h.m2.y, sbit));
+        const double2 ra = make_double2(h.m0.x * a.x + (mb.x * b.x - mb.y * b.y), h.m0.x * a.y + (mb.x * b.y + mb.y * b.x));
+        const double2 rb = make_double2(h.m3.x * b.x + (mc.x * a.x - mc.y * a.y), h.m3.x * b.y + (mc.x * a.y + mc.y * a.x));
         a = ra;
         b = rb;
     } else {
-        const double2 ma = mp[0], md = mp[3];
-        const double2 mb = make_double2(flip_sign(mp[1].x, p.sbit), flip_sign(mp[1].y, p.sbit));
-        const double2 mc = make_double2(flip_sign(mp[2].x, p.sbit), flip_sign(mp[2].y, p.sbit));
-        const double2 ra = cadd(cmul(ma, a), cmul(mb, b));
-        const double2 rb = cadd(cmul(mc, a), cmul(md, b));
+        const double2 mb = make_double2(flip_sign(h.m1.x, sbit), flip_sign(h.m1.y, sbit));
+        const double2 mc = make_double2(flip_sign(h.m2.x, sbit), flip_sign(h.m2.y, sbit));
+        const double2 ra = cadd(cmul(h.m0, a), cmul(mb, b));
+        const double2 rb = cadd(cmul(mc, a), cmul(h.m3, b));
         a = ra;
         b = rb;
     }
-    buf[p.si] = a;
-    buf[p.sj] = b;
+    buf[si] = a;
+    buf[sj] = b;
 }
 
 // diagonal op on one tile: exp(-i sum_m angle_m sgn_m(index)).  Terms whose in-tile z bits sit entirely in local bits
@@ -346,76 +345,95 @@ extern "C" int fh_debug_tile_tma_timeline(long long *out64) {
 #define TMA_TLMARK(k) do { } while (0)
 #endif
 
-// The op loop of one tile: every op of the run in order, one CTA barrier between ops.  `cur` is the decoded pair of
-// op 0 for this thread (prepared by the caller while the tile was still in flight).
+// The op loop of one tile: every op of the run in order, one CTA barrier between ops.  Header, matrix and table entry
+// of op k+1 are fetched (LDS) before the barrier that ends op k, so the dependent chain per op is
+// barrier -> LDS amplitudes -> FP64 -> STS.
 template <bool SWZ>
 __device__ __forceinline__ void tile_ops(double2 *buf, double2 *ph, const TileRec *rec, const TileTerm *tterm,
-                                         const TileLaunch &tl, int T, int nsub, unsigned base, PairPrep cur,
+                                         const unsigned short *ptab, const TileLaunch &tl, int T, int nsub, unsigned base,
                                          unsigned lomask_g, unsigned himask_g) {
-    const unsigned L = 1u << T;
+    OpHdr h;
+    load_hdr(&rec[0], h);
+    unsigned e = h.type != 2 ? ptab[h.off + threadIdx.x] : 0u;
     for (int sidx = 0; sidx < nsub; ++sidx) {
         if (sidx < 40) TMA_TLMARK(4 + sidx);
-        const TileRec *r = &rec[sidx];
-        const int type = r->type;
-        PairPrep nxt;
-        nxt.active = 0u;
-        if (type != 2) {
-            if (cur.active) apply_pair(buf, r, cur);
-            if (sidx + 1 < nsub) nxt = prep_pair<SWZ>(&rec[sidx + 1], base, threadIdx.x, T);
-            // ops with more pairs than threads (pattern pins a single bit): the remaining pairs of this thread
-            const unsigned npairs = L >> (unsigned)r->nlfix;
-            for (unsigned k = threadIdx.x + blockDim.x; k < npairs; k += blockDim.x) {
-                const PairPrep more = prep_pair<SWZ>(r, base, k, T);
-                if (more.active) apply_pair(buf, r, more);
+        if (h.type != 2) {
+            if ((base & h.fixmask_out) == h.fixval_out) {
+                const unsigned sb = (unsigned)__popc(base & h.zeta);
+                if (e >> 14) apply_pair_entry(buf, h, e, sb);
+                for (int rep = 1; rep < h.reps; ++rep) {        // ops with more pairs in a tile than threads in the CTA
+                    const unsigned e2 = ptab[h.off + rep * (int)blockDim.x + (int)threadIdx.x];
+                    if (e2 >> 14) apply_pair_entry(buf, h, e2, sb);
+                }
             }
         } else {
-            apply_diag<SWZ>(buf, ph, r, tterm, tl, T, base, lomask_g, himask_g);
-            if (sidx + 1 < nsub) nxt = prep_pair<SWZ>(&rec[sidx + 1], base, threadIdx.x, T);
+            apply_diag<SWZ>(buf, ph, &rec[sidx], tterm, tl, T, base, lomask_g, himask_g);
         }
-        cur = nxt;
-        if (sidx + 1 < nsub) __syncthreads();
+        if (sidx + 1 < nsub) {
+            load_hdr(&rec[sidx + 1], h);
+            e = h.type != 2 ? ptab[h.off + threadIdx.x] : 0u;
+            __syncthreads();
+        }
     }
 }
 
 // ----------------------------------------------------------------------------------------------
 // forward / dagger run on one state
 // ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// op records, diagonal terms and pair table of one run -> shared memory by three bulk copies signalling `bar`
+__device__ __forceinline__ void fetch_run_descriptors(const TileLaunch &tl, const TileRec *recs, const TileTerm *terms,
+                                                      const unsigned short *ptab, TileRec *s_rec, TileTerm *s_term, unsigned short *s_tab,
+                                                      unsigned bar) {
+    const unsigned rb = (unsigned)tl.nsub * (unsigned)sizeof(TileRec), tb = (unsigned)tl.nterms * (unsigned)sizeof(TileTerm),
+                   pb = (unsigned)tl.ptab_words * 2u;
+    mbar_expect_tx(bar, rb + tb + pb);
+    bulk_g2s(smem_u32(s_rec), recs + tl.first_rec, rb, bar);
+    if (tb) bulk_g2s(smem_u32(s_term), terms + tl.first_term, tb, bar);
+    if (pb) bulk_g2s(smem_u32(s_tab), ptab + tl.ptab_first, pb, bar);
+}
+
 template <bool PDL, bool SWZ>
 __global__ void __launch_bounds__(512, 2)
     k_tile_tma(const __grid_constant__ CUtensorMap map, const TileLaunch tl, const TmaPlan plan,
-               const TileRec *__restrict__ recs, const TileTerm *__restrict__ terms, int n, int stages) {
+               const TileRec *__restrict__ recs, const TileTerm *__restrict__ terms, const unsigned short *__restrict__ ptab, int n,
+               int stages) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long full_bar[2];
+    __shared__ __align__(8) unsigned long long full_bar[2], desc_bar;
     const int T = tl.nbits, nsub = tl.nsub;
     const unsigned L = 1u << T, tile_bytes = L * 16u;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // carve: [tile buffers, 1024-byte aligned][records][terms][phase tables]
+    // carve: [tile buffers, 1024-byte aligned][records][terms][pair table][phase tables]
     const unsigned raw = smem_u32(smem_raw);
     const unsigned pad = ((raw + 1023u) & ~1023u) - raw;
     unsigned char *tiles = smem_raw + pad;
     TileRec *rec = reinterpret_cast<TileRec *>(tiles + (size_t)stages * tile_bytes);
     TileTerm *tterm = reinterpret_cast<TileTerm *>(rec + nsub);
-    double2 *ph = reinterpret_cast<double2 *>(tterm + tl.nterms);
+    unsigned short *stab = reinterpret_cast<unsigned short *>(tterm + tl.nterms);
+    double2 *ph = reinterpret_cast<double2 *>(stab + tl.ptab_words);
     const unsigned lomask_g = tile_mask(tl, T, 0, 6), himask_g = tile_mask(tl, T, 6, TILE_BITS_CAP);
     TMA_TLMARK(0);
 
     if (threadIdx.x == 0) {
         mbar_init(smem_u32(&full_bar[0]), 1);
         mbar_init(smem_u32(&full_bar[1]), 1);
+        mbar_init(smem_u32(&desc_bar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        prefetch_tensormap(&map);
+        // records / terms / table were written before the previous kernel started (payload copy at the head of the
+        // graph, static table): they may be fetched while that kernel is still running
+        fetch_run_descriptors(tl, recs, terms, ptab, rec, tterm, stab, smem_u32(&desc_bar));
     }
     if (PDL) asm volatile("griddepcontrol.launch_dependents;");
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(recs + tl.first_rec);
-        uint4 *dst = reinterpret_cast<uint4 *>(rec);
-        const int chunks = nsub * (int)(sizeof(TileRec) / 16);
-        for (int c = threadIdx.x; c < chunks; c += blockDim.x) dst[c] = __ldg(src + c);
-        const uint4 *tsrc = reinterpret_cast<const uint4 *>(terms + tl.first_term);
-        uint4 *tdst = reinterpret_cast<uint4 *>(tterm);
-        const int tchunks = tl.nterms * (int)(sizeof(TileTerm) / 16);
-        for (int c = threadIdx.x; c < tchunks; c += blockDim.x) tdst[c] = __ldg(tsrc + c);
-    }
-    __syncthreads();
+    __syncthreads();                                                // barrier objects are initialised
     if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");     // the previous kernel's amplitudes are complete
     TMA_TLMARK(1);
 
@@ -423,6 +441,7 @@ __global__ void __launch_bounds__(512, 2)
     const unsigned tiles_u32 = smem_u32(tiles);
     if (warp == 0 && blockIdx.x < ntiles)
         warp_load_tile(&map, plan, (unsigned)tile_base(tl, T, blockIdx.x), tiles_u32, smem_u32(&full_bar[0]), tile_bytes, lane);
+    mbar_wait(smem_u32(&desc_bar), 0);
 
     unsigned it = 0;
     for (unsigned t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
@@ -435,11 +454,9 @@ __global__ void __launch_bounds__(512, 2)
         }
         const unsigned base = (unsigned)tile_base(tl, T, t);
         double2 *buf = reinterpret_cast<double2 *>(tiles + (size_t)st * tile_bytes);
-        PairPrep cur = prep_pair<SWZ>(&rec[0], base, threadIdx.x, T);
         mbar_wait(smem_u32(&full_bar[st]), parity);
         TMA_TLMARK(2);
-
-        tile_ops<SWZ>(buf, ph, rec, tterm, tl, T, nsub, base, cur, lomask_g, himask_g);
+        tile_ops<SWZ>(buf, ph, rec, tterm, stab, tl, T, nsub, base, lomask_g, himask_g);
         TMA_TLMARK(3);
         fence_async_smem();             // generic-proxy writes of the op loop -> visible to the bulk store
         __syncthreads();
@@ -453,7 +470,8 @@ __global__ void __launch_bounds__(512, 2)
             }
         }
     }
-    if (warp == 0) bulk_wait0();        // every store of this CTA is complete before it exits
+    // shared memory must outlive the bulk stores' reads; their global writes are complete at grid end like any store
+    if (warp == 0) bulk_wait_read0();
     TMA_TLMARK(63);
 }
 
@@ -496,44 +514,61 @@ __device__ __forceinline__ void smem_copy16(T *dst, const T *src, int count) {  
     for (int c = threadIdx.x; c < chunks; c += blockDim.x) d4[c] = __ldg(s4 + c);
 }
 
+#define FH_CHAIN_MAX_RUNS 48
+
 __global__ void __launch_bounds__(512, 2)
     k_tile_chain(const ChainRun *__restrict__ runs, int nruns, const CUtensorMap *__restrict__ maps,
-                 const TileRec *__restrict__ recs, const TileTerm *__restrict__ terms, int n, unsigned *__restrict__ sync,
-                 unsigned long long basis, int rec_cap, int term_cap, int tile_bits_max) {
+                 const TileRec *__restrict__ recs, const TileTerm *__restrict__ terms, const unsigned short *__restrict__ ptab, int n,
+                 unsigned *__restrict__ sync, unsigned long long basis, int rec_cap, int term_cap, int tab_cap,
+                 int tile_bits_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long full_bar;
-    __shared__ ChainRun srun[2];
+    __shared__ __align__(8) unsigned long long full_bar, desc_bar[2];
+    __shared__ ChainRun srun[FH_CHAIN_MAX_RUNS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned raw = smem_u32(smem_raw);
     const unsigned pad = ((raw + 1023u) & ~1023u) - raw;
     unsigned char *tile = smem_raw + pad;
     unsigned char *after = tile + (16u << tile_bits_max);
-    TileRec *rec_base = reinterpret_cast<TileRec *>(after);                 // two buffers of rec_cap records
+    TileRec *rec_base = reinterpret_cast<TileRec *>(after);                          // two buffers of rec_cap records
     TileTerm *term_base = reinterpret_cast<TileTerm *>(rec_base + 2 * rec_cap);      // two buffers of term_cap terms
-    double2 *ph = reinterpret_cast<double2 *>(term_base + 2 * term_cap);
+    unsigned short *tab_base = reinterpret_cast<unsigned short *>(term_base + 2 * term_cap);     // two buffers of tab_cap entries
+    double2 *ph = reinterpret_cast<double2 *>(tab_base + 2 * tab_cap);
     double2 *buf = reinterpret_cast<double2 *>(tile);
     const unsigned tile_u32 = smem_u32(tile), bar = smem_u32(&full_bar);
 
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
+        mbar_init(smem_u32(&desc_bar[0]), 1);
+        mbar_init(smem_u32(&desc_bar[1]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    smem_copy16(&srun[0], runs, 1);
+    smem_copy16(srun, runs, nruns);
     __syncthreads();
-    smem_copy16(rec_base, recs + srun[0].tl.first_rec, srun[0].tl.nsub);
-    smem_copy16(term_base, terms + srun[0].tl.first_term, srun[0].tl.nterms);
-    __syncthreads();
+    if (threadIdx.x == 0) {
+        fetch_run_descriptors(srun[0].tl, recs, terms, ptab, rec_base, term_base, tab_base, smem_u32(&desc_bar[0]));
+        prefetch_tensormap(maps + srun[0].map_index);
+    }
 
     unsigned uses = 0;
     int prev_active = 0;                    // CTAs that stored a tile in the previous run
     for (int r = 0; r < nruns; ++r) {
-        const ChainRun &R = srun[r & 1];
+        const ChainRun &R = srun[r];
         const TileLaunch &tl = R.tl;
         const int T = tl.nbits, nsub = tl.nsub;
         const unsigned L = 1u << T, tile_bytes = L * 16u;
         const bool active = blockIdx.x < (unsigned)R.ntiles;
         const unsigned base = (unsigned)tile_base(tl, T, blockIdx.x);
         const CUtensorMap *map = maps + R.map_index;
+        const int pb = r & 1;
+        if (threadIdx.x == 0 && r + 1 < nruns) {
+            // descriptors of the next run into the other buffers (their last readers finished before the barrier that
+            // ended run r-1), tensor maps of the next run towards the TMA unit
+            const ChainRun &N = srun[r + 1];
+            fetch_run_descriptors(N.tl, recs, terms, ptab, rec_base + (pb ^ 1) * rec_cap, term_base + (pb ^ 1) * term_cap,
+                                  tab_base + (pb ^ 1) * tab_cap, smem_u32(&desc_bar[pb ^ 1]));
+            prefetch_tensormap(maps + N.map_index);
+            if (N.map2_index >= 0) prefetch_tensormap(maps + N.map2_index);
+        }
         if (active && warp == 0 && !R.init_basis) {
             if (r > 0) {
                 if (lane == 0) {
@@ -545,14 +580,13 @@ __global__ void __launch_bounds__(512, 2)
             }
             warp_load_tile(map, R.plan, base, tile_u32, bar, tile_bytes, lane);
         }
-        // prefetch the next run's geometry and op records into the alternate buffers
-        if (r + 1 < nruns) smem_copy16(&srun[(r + 1) & 1], runs + r + 1, 1);
+        mbar_wait(smem_u32(&desc_bar[pb]), (unsigned)(r >> 1) & 1u);
         if (active) {
-            const TileRec *rec = rec_base + (r & 1) * rec_cap;
-            const TileTerm *tterm = term_base + (r & 1) * term_cap;
+            const TileRec *rec = rec_base + pb * rec_cap;
+            const TileTerm *tterm = term_base + pb * term_cap;
+            const unsigned short *stab = tab_base + pb * tab_cap;
             const unsigned lomask_g = tile_mask(tl, T, 0, 6), himask_g = tile_mask(tl, T, 6, TILE_BITS_CAP);
             const bool swz = R.plan.swizzle != 0;
-            PairPrep cur = swz ? prep_pair<true>(&rec[0], base, threadIdx.x, T) : prep_pair<false>(&rec[0], base, threadIdx.x, T);
             if (R.init_basis) {
                 // |basis> restricted to this tile: zeros, and 1 at the tile-local index of the basis state if it is here
                 const unsigned tmask = lomask_g | himask_g;
@@ -570,29 +604,28 @@ __global__ void __launch_bounds__(512, 2)
                 mbar_wait(bar, uses & 1u);
                 ++uses;
             }
-            if (swz) tile_ops<true>(buf, ph, rec, tterm, tl, T, nsub, base, cur, lomask_g, himask_g);
-            else tile_ops<false>(buf, ph, rec, tterm, tl, T, nsub, base, cur, lomask_g, himask_g);
+            if (swz) tile_ops<true>(buf, ph, rec, tterm, stab, tl, T, nsub, base, lomask_g, himask_g);
+            else tile_ops<false>(buf, ph, rec, tterm, stab, tl, T, nsub, base, lomask_g, himask_g);
             fence_async_smem();
         }
-        __syncthreads();                    // ops done (all threads); srun[(r+1)&1] is visible
-        if (r + 1 < nruns) {
-            const ChainRun &N = srun[(r + 1) & 1];
-            smem_copy16(rec_base + ((r + 1) & 1) * rec_cap, recs + N.tl.first_rec, N.tl.nsub);
-            smem_copy16(term_base + ((r + 1) & 1) * term_cap, terms + N.tl.first_term, N.tl.nterms);
-        }
+        __syncthreads();                    // ops done (all threads)
         if (active && warp == 0) {
             warp_store_tile(map, R.plan, base, tile_u32, lane);
             if (R.map2_index >= 0) warp_store_tile(maps + R.map2_index, R.plan, base, tile_u32, lane);
-            bulk_wait0();                   // this lane's stores are complete (global writes performed)
-            fence_async_all();
-            __syncwarp();
-            if (lane == 0 && r + 1 < nruns) {
-                __threadfence();
-                red_release_gpu_add(sync + r, 1u);
+            if (r + 1 < nruns) {
+                bulk_wait0();               // this lane's stores are complete (global writes performed)
+                fence_async_all();
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence();
+                    red_release_gpu_add(sync + r, 1u);
+                }
+            } else {
+                bulk_wait_read0();
             }
         }
         prev_active = min((int)gridDim.x, R.ntiles);
-        __syncthreads();                    // tile buffer free for the next load; next records visible
+        __syncthreads();                    // tile buffer free for the next load
     }
 }
 
@@ -601,13 +634,32 @@ __global__ void __launch_bounds__(512, 2)
 // ----------------------------------------------------------------------------------------------
 static size_t tile_tma_smem(const TileLaunch &tl, int stages) {
     return 1024 + (size_t)stages * (16ull << tl.nbits) + (size_t)tl.nsub * sizeof(TileRec) + (size_t)tl.nterms * sizeof(TileTerm) +
-           192 * sizeof(double2) + 64;
+           (size_t)tl.ptab_words * 2 + 192 * sizeof(double2) + 64;
 }
 
-void launch_tile(cudaStream_t s, double2 *psi, const TileLaunch &tl, const TileRec *d_recs, const TileTerm *d_terms, int n) {
+int fh_tile_threads(int nbits) {
+    int threads = nbits >= 1 ? (1 << (nbits - 1)) : 1;
+    if (threads > 512) threads = 512;
+    if (threads < 64) threads = 64;
+    return threads;
+}
+
+// -1: the TMA kernels do not take this tile (launch_tile falls back to the register-staged kernel); else the layout
+int fh_tile_tma_layout(const unsigned char *bits, int T, int n) {
+    if (n > 30 || T < 3 || T > FH_MAX_TILE_BITS || bits[0] != 0) return -1;
+    std::vector<std::pair<int, int>> dims;
+    TmaPlan plan;
+    plan_dims(bits, T, true, dims, plan);
+    if (plan.swizzle && plan.map_bits < 6) plan_dims(bits, T, false, dims, plan);
+    if (plan.n_extra > 6) return -1;
+    return plan.swizzle;
+}
+
+void launch_tile(cudaStream_t s, double2 *psi, const TileLaunch &tl, const TileRec *d_recs, const TileTerm *d_terms,
+                 const unsigned short *d_ptab, int n) {
     const bool force_ldg = getenv("FHSIM_TILE_LDG") != nullptr;      // read per call: tests flip it at run time
     const TmaEntry *e = force_ldg ? nullptr : tma_entry(psi, n, tl);
-    if (!e) {
+    if (!e || !d_ptab) {
         launch_tile_ldg(s, psi, tl, d_recs, d_terms, n);
         return;
     }
@@ -621,22 +673,27 @@ void launch_tile(cudaStream_t s, double2 *psi, const TileLaunch &tl, const TileR
     int stages = 1;
     unsigned long long grid = ntiles;
     const size_t smem1 = tile_tma_smem(tl, 1), smem2 = tile_tma_smem(tl, 2);
-    const size_t sm_budget = 220 * 1024;
+    const size_t sm_budget = 224 * 1024;
+    if (smem1 > sm_budget) {
+        launch_tile_ldg(s, psi, tl, d_recs, d_terms, n);
+        return;
+    }
     if (ntiles > (unsigned long long)sm * 2) {
-        if (smem2 <= sm_budget) {
+        // more tiles than one wave: persistent CTAs.  Two CTAs per SM with one buffer each (the sibling's op loop hides
+        // this CTA's tile traffic, twice the warps for the barrier-separated ops) if they fit, else one CTA per SM with
+        // two buffers (load of tile i+1 / store of tile i-1 under the op loop of tile i), else one buffer
+        if (2 * smem1 <= sm_budget) {
+            grid = (unsigned long long)sm * 2;
+        } else if (smem2 <= sm_budget) {
             stages = 2;
-            int per_sm = (int)(sm_budget / smem2);
-            if (per_sm > 2) per_sm = 2;
-            grid = (unsigned long long)sm * per_sm;
+            grid = (unsigned long long)sm;
         } else {
             grid = (unsigned long long)sm;
         }
         if (grid > ntiles) grid = ntiles;
     }
     const size_t smem = stages == 2 ? smem2 : smem1;
-    int threads = nbits >= 1 ? (1 << (nbits - 1)) : 1;
-    if (threads > 512) threads = 512;
-    if (threads < 64) threads = 64;
+    const int threads = fh_tile_threads(nbits);
     static const bool pdl_all = getenv("FHSIM_PDL") != nullptr, pdl_off = getenv("FHSIM_NO_PDL") != nullptr;
     const bool pdl = !pdl_off && (pdl_all || g_fh_tile_pdl_scope > 0);
     ++g_fh_launch_count;
@@ -652,11 +709,11 @@ void launch_tile(cudaStream_t s, double2 *psi, const TileLaunch &tl, const TileR
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     if (pdl) {
-        if (e->plan.swizzle) cudaLaunchKernelEx(&cfg, k_tile_tma<true, true>, e->map, tl, e->plan, d_recs, d_terms, n, stages);
-        else cudaLaunchKernelEx(&cfg, k_tile_tma<true, false>, e->map, tl, e->plan, d_recs, d_terms, n, stages);
+        if (e->plan.swizzle) cudaLaunchKernelEx(&cfg, k_tile_tma<true, true>, e->map, tl, e->plan, d_recs, d_terms, d_ptab, n, stages);
+        else cudaLaunchKernelEx(&cfg, k_tile_tma<true, false>, e->map, tl, e->plan, d_recs, d_terms, d_ptab, n, stages);
     } else {
-        if (e->plan.swizzle) cudaLaunchKernelEx(&cfg, k_tile_tma<false, true>, e->map, tl, e->plan, d_recs, d_terms, n, stages);
-        else cudaLaunchKernelEx(&cfg, k_tile_tma<false, false>, e->map, tl, e->plan, d_recs, d_terms, n, stages);
+        if (e->plan.swizzle) cudaLaunchKernelEx(&cfg, k_tile_tma<false, true>, e->map, tl, e->plan, d_recs, d_terms, d_ptab, n, stages);
+        else cudaLaunchKernelEx(&cfg, k_tile_tma<false, false>, e->map, tl, e->plan, d_recs, d_terms, d_ptab, n, stages);
     }
 }
 
@@ -679,19 +736,18 @@ struct ChainRunHost {
     int init_basis;
 };
 
-static int g_chain_blocks_per_sm[2] = {-1, -1};
-
 // Plans one cooperative launch for `nruns` consecutive tile runs on `psi`.  Writes the ChainRun records and the tensor
 // maps into host staging memory (`h_runs`, `h_maps`: the caller copies them to `d_runs`, `d_maps` on the stream BEFORE
 // the launch -- inside a captured graph that copy is one more memcpy node).  Returns the number of maps used, or -1
 // when the chain does not apply (TMA path unavailable, or more tiles than co-resident CTAs).
 int plan_tile_chain(int sm, double2 *psi, double2 *psi2, const ChainRunHost *hruns, int nruns, int n, void *h_runs_v,
                     void *h_maps_v, int map_base, int *grid_out, size_t *smem_out, int *rec_cap_out, int *term_cap_out,
-                    int *tbits_out) {
+                    int *tab_cap_out, int *tbits_out) {
     ChainRun *h_runs = reinterpret_cast<ChainRun *>(h_runs_v);
     CUtensorMap *h_maps = reinterpret_cast<CUtensorMap *>(h_maps_v);
     if (getenv("FHSIM_TILE_LDG") || getenv("FHSIM_NO_CHAIN")) return -1;
-    int nmaps = 0, grid = 0, rec_cap = 1, term_cap = 1, tbits = 0;
+    int nmaps = 0, grid = 0, rec_cap = 1, term_cap = 1, tab_cap = 8, tbits = 0;
+    if (nruns > FH_CHAIN_MAX_RUNS) return -1;
     for (int r = 0; r < nruns; ++r) {
         const TileLaunch &tl = hruns[r].tl;
         const TmaEntry *e = tma_entry(psi, n, tl);
@@ -716,11 +772,12 @@ int plan_tile_chain(int sm, double2 *psi, double2 *psi2, const ChainRunHost *hru
         grid = cr.ntiles > grid ? cr.ntiles : grid;
         rec_cap = tl.nsub > rec_cap ? tl.nsub : rec_cap;
         term_cap = tl.nterms > term_cap ? tl.nterms : term_cap;
+        tab_cap = tl.ptab_words > tab_cap ? tl.ptab_words : tab_cap;
         tbits = tl.nbits > tbits ? tl.nbits : tbits;
     }
     const size_t smem = 1024 + (16ull << tbits) + 2 * (size_t)rec_cap * sizeof(TileRec) + 2 * (size_t)term_cap * sizeof(TileTerm) +
-                        192 * sizeof(double2) + 64;
-    if (smem > 220 * 1024) return -1;
+                        2 * (size_t)tab_cap * 2 + 192 * sizeof(double2) + 64;
+    if (smem > 200 * 1024) return -1;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_chain, 512, smem) != cudaSuccess) {
         cudaGetLastError();
@@ -731,6 +788,7 @@ int plan_tile_chain(int sm, double2 *psi, double2 *psi2, const ChainRunHost *hru
     *smem_out = smem;
     *rec_cap_out = rec_cap;
     *term_cap_out = term_cap;
+    *tab_cap_out = tab_cap;
     *tbits_out = tbits;
     return nmaps;
 }
@@ -739,15 +797,14 @@ size_t fh_chain_run_bytes() { return sizeof(ChainRun); }
 size_t fh_chain_map_bytes() { return sizeof(CUtensorMap); }
 
 int launch_tile_chain(cudaStream_t s, const void *d_runs, int nruns, const void *d_maps, const TileRec *d_recs,
-                      const TileTerm *d_terms, int n, unsigned *d_sync, unsigned long long basis, int grid, size_t smem,
-                      int rec_cap, int term_cap, int tbits) {
+                      const TileTerm *d_terms, const unsigned short *d_ptab, int n, unsigned *d_sync, unsigned long long basis,
+                      int grid, size_t smem, int rec_cap, int term_cap, int tab_cap, int tbits) {
     const ChainRun *runs = reinterpret_cast<const ChainRun *>(d_runs);
     const CUtensorMap *maps = reinterpret_cast<const CUtensorMap *>(d_maps);
-    int threads = tbits >= 1 ? (1 << (tbits - 1)) : 1;
-    if (threads > 512) threads = 512;
-    if (threads < 64) threads = 64;
-    void *args[] = {(void *)&runs, (void *)&nruns, (void *)&maps, (void *)&d_recs, (void *)&d_terms, (void *)&n,
-                    (void *)&d_sync, (void *)&basis, (void *)&rec_cap, (void *)&term_cap, (void *)&tbits};
+    const int threads = fh_tile_threads(tbits);
+    void *args[] = {(void *)&runs, (void *)&nruns, (void *)&maps, (void *)&d_recs, (void *)&d_terms, (void *)&d_ptab,
+                    (void *)&n, (void *)&d_sync, (void *)&basis, (void *)&rec_cap, (void *)&term_cap, (void *)&tab_cap,
+                    (void *)&tbits};
     ++g_fh_launch_count;
     const cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_tile_chain, dim3((unsigned)grid), dim3((unsigned)threads),
                                                       args, smem, s);

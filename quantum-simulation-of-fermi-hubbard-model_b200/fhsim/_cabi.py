@@ -66,6 +66,15 @@ SIGNATURES = {
     "fh_program_last_stats": [_vp, _f64p, C.POINTER(C.c_int)],
     "fh_program_time_items": [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _f64p],
     "fh_lanczos": [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint64, _f64p, _vpp, C.POINTER(C.c_int)],
+    "fh_comm_unique_id": [C.POINTER(C.c_ubyte)],
+    "fh_comm_init": [_vp, C.POINTER(C.c_ubyte), C.c_int, C.c_int, _vpp],
+    "fh_comm_destroy": [_vp],
+    "fh_comm_info": [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), _f64p],
+    "fh_comm_swap_exchange": [_vp, _vp, _vp, _vp, C.c_int, _i32p, _i32p],
+    "fh_comm_last_exchange_ms": [_vp, _f64p],
+    "fh_comm_all_reduce_sum": [_vp, _f64p, C.c_int],
+    "fh_comm_all_gather": [_vp, _f64p, C.c_int, _f64p],
+    "fh_comm_barrier": [_vp],
     "fh_lanczos_sector": [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint64, _f64p, _vpp, _f64p,
                           C.POINTER(C.c_int), _f64p],
 }

@@ -368,15 +368,25 @@ class ShardedSimulator:
         self.engine.copy(dst.h, src.h)
         dst.layout = src.layout.copy()
 
+    def _swap_exchange(self, h, pairs):
+        """Local bit transpositions ``pairs`` then the all-to-all of the top-local chunks.  Engines that own a
+        communicator (CudaEngine with fh_comm) run both as ONE pipelined exchange: the permutation of chunk k+1
+        overlaps chunk k on the wire."""
+        fused = getattr(self.engine, "swap_exchange", None)
+        if fused is not None:
+            fused(h, pairs)
+            return
+        if pairs:
+            self.engine.swap_bits(h, pairs)
+        self.engine.all_to_all(h)
+
     def relayout(self, states, new_globals):
         """Make ``new_globals`` the rank bits of every state in ``states`` (all must share one layout)."""
         lay = states[0].layout
         assert all(s.layout == lay for s in states)
         pairs, new_lay = swap_steps(lay, new_globals)
         for s in states:
-            if pairs:
-                self.engine.swap_bits(s.h, pairs)
-            self.engine.all_to_all(s.h)
+            self._swap_exchange(s.h, pairs)
             s.layout = new_lay.copy()
             self.swap_count += 1
 
@@ -430,9 +440,7 @@ class ShardedSimulator:
         for step in steps:
             if step[0] == "swap":
                 _, pairs, _, new_lay = step
-                if pairs:
-                    self.engine.swap_bits(st.h, pairs)
-                self.engine.all_to_all(st.h)
+                self._swap_exchange(st.h, pairs)
                 st.layout = new_lay.copy()
                 self.swap_count += 1
                 continue
@@ -616,7 +624,25 @@ class CudaEngine:
         self._tables = {}               # uploaded per-layout observable tables
         self._pools = {}                # uploaded per-layout screening pools
         self.a2a_ms = 0.0
+        self.time_exchanges = True      # False: exchanges are enqueued without a host synchronisation (a2a_ms not updated)
         self._host_staged = dist is not None and dist.get_backend() == "gloo"
+        # communicator behind the C-ABI (fh_comm_*: NCCL resolved inside libfhsim, exchange pipelined against the local
+        # bit permutation on a side stream).  torch.distributed only distributes the 128-byte id.  FHSIM_COMM=torch
+        # keeps the round-1 path (all_to_all_single).
+        self._comm = None
+        self._spare2 = None
+        import os
+        if dist is not None and self.world > 1 and not self._host_staged and os.environ.get("FHSIM_COMM", "fhsim") != "torch":
+            C = _cabi.C
+            buf = (C.c_ubyte * 128)()
+            if self.rank == 0:
+                _cabi.check(_cabi.lib().fh_comm_unique_id(buf))
+            t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=self.device)
+            dist.broadcast(t, 0)
+            idb = (C.c_ubyte * 128)(*t.cpu().tolist())
+            h = _cabi._vp()
+            _cabi.check(_cabi.lib().fh_comm_init(self.ctx._h, idb, self.rank, self.world, C.byref(h)))
+            self._comm = h
 
     # slabs are torch tensors wrapped (borrowed) as fh_state handles
     class _Slab:
@@ -678,8 +704,44 @@ class CudaEngine:
         self._cabi.check(self._cabi.lib().fh_state_swap_bits(spare.st._h, h[0].st._h, len(pairs), ap, bp))
         self._spare, h[0] = h[0], spare
 
+    def swap_exchange(self, h, pairs):
+        """Fused local permutation + all-to-all (see ShardedSimulator._swap_exchange)."""
+        if self._comm is None:
+            if pairs:
+                self.swap_bits(h, pairs)
+            self.all_to_all(h)
+            return
+        L, C = self._cabi.lib(), self._cabi.C
+        spare = self._spare_slab()
+        aa, ap = self._cabi.i32_array([p[0] for p in pairs])
+        ba, bp = self._cabi.i32_array([p[1] for p in pairs])
+        third = None
+        if pairs:
+            if self._spare2 is None:
+                free, _ = self.torch.cuda.mem_get_info(self.device)
+                if free > 2.0 * (16 << self.n_local):           # a third slab fits comfortably: pipelined exchange
+                    self._spare2 = self._alloc()
+            third = self._spare2
+        if pairs and third is None:
+            # not enough memory for a third slab (32-GiB slabs at N = 2): permute first, then exchange back into h
+            self._cabi.check(L.fh_state_swap_bits(spare.st._h, h[0].st._h, len(pairs), ap, bp))
+            self._cabi.check(L.fh_comm_swap_exchange(self._comm, spare.st._h, None, h[0].st._h, 0, None, None))
+        elif pairs:
+            self._cabi.check(L.fh_comm_swap_exchange(self._comm, h[0].st._h, spare.st._h, third.st._h, len(pairs), ap, bp))
+            self._spare2, h[0] = h[0], third
+        else:
+            self._cabi.check(L.fh_comm_swap_exchange(self._comm, h[0].st._h, None, spare.st._h, 0, None, None))
+            self._spare, h[0] = h[0], spare
+        if self.time_exchanges:
+            ms = C.c_double()
+            self._cabi.check(L.fh_comm_last_exchange_ms(self._comm, C.byref(ms)))
+            self.a2a_ms += ms.value
+
     def all_to_all(self, h):
         if self.world == 1:
+            return
+        if self._comm is not None:
+            self.swap_exchange(h, [])
             return
         torch = self.torch
         spare = self._spare_slab()
@@ -731,12 +793,35 @@ class CudaEngine:
     def inner(self, ha, hb):
         return ha[0].st.inner(hb[0].st)
 
+    def close(self):
+        """Release cached device objects, the spare slabs and the communicator."""
+        for cache in (self._programs, self._tables, self._pools):
+            for obj in list(cache.values()):
+                try:
+                    obj.close()
+                except Exception:
+                    pass
+            cache.clear()
+        for name in ("_spare", "_spare2"):
+            slab = getattr(self, name)
+            if slab is not None:
+                slab.st.close()
+                setattr(self, name, None)
+        if self._comm is not None:
+            self.sync()
+            self._cabi.lib().fh_comm_destroy(self._comm)
+            self._comm = None
+
     def sync(self):
         self.stream.synchronize()
 
     def all_reduce(self, arr):
         if self.world == 1:
             return np.asarray(arr, dtype=np.float64)
+        if self._comm is not None and np.size(arr) <= 4096:
+            v = np.ascontiguousarray(arr, dtype=np.float64).copy()
+            self._cabi.check(self._cabi.lib().fh_comm_all_reduce_sum(self._comm, v.ctypes.data_as(self._cabi._f64p), int(v.size)))
+            return v
         t = self.torch.as_tensor(np.asarray(arr, dtype=np.float64), device="cpu" if self._host_staged else self.device)
         self.dist.all_reduce(t)
         return t.cpu().numpy()

@@ -36,25 +36,15 @@ def eps_k(nx, ny, t=1.0):
     return [round(-t * (f(s % nx, nx) + f(s // nx, ny)), 12) for s in range(nx * ny)]
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--lattice", default="4x4")
-    ap.add_argument("--u", type=float, default=4.0)
-    ap.add_argument("--n-ops", type=int, default=16)
-    ap.add_argument("--steps", type=int, default=2)
-    ap.add_argument("--check-single", action="store_true")
-    ap.add_argument("--json", default=None)
-    args = ap.parse_args()
+def run_sharded(lattice="4x4", u=4.0, n_ops=16, steps=2, dist=None, local_rank=0, check_single=False, profile=True,
+                peak_gbs=None):
+    """The sharded-state screening benchmark on an initialised process group (or a single GPU when ``dist`` is None).
+    Every rank calls it; rank 0 gets the result dict, the others None."""
     import torch
-    import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    d = dist
+    rank = d.get_rank() if d is not None else 0
+    world = d.get_world_size() if d is not None else 1
     torch.cuda.set_device(local_rank)
-    d = None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        d = dist
 
     from fhsim.circuit import Circuit
     from fhsim.sharded import CudaEngine, ShardedSimulator
@@ -62,11 +52,11 @@ def main():
     from fhsim.tables import GeneratorPlan, PauliTable
     from operators.pool import hubbard_interaction_pool_simplified
 
-    nx, ny = map(int, args.lattice.split("x"))
+    nx, ny = map(int, lattice.split("x"))
     ns, n = nx * ny, 2 * nx * ny
     g = world.bit_length() - 1
     t0 = time.time()
-    h_tab = PauliTable.from_operator(fermi_hubbard(nx, ny, 1.0, args.u), n)
+    h_tab = PauliTable.from_operator(fermi_hubbard(nx, ny, 1.0, u), n)
     plans = [GeneratorPlan(jordan_wigner(op), n) for op in hubbard_interaction_pool_simplified(nx, ny)]
     n_up = (ns + 1) // 2
     n_dn = ns - n_up
@@ -74,7 +64,7 @@ def main():
     order = sorted(range(ns), key=lambda s: eps[s])                  # stable: ties by ascending orbital index
     occ = [2 * s for s in order[:n_up]] + [2 * s + 1 for s in order[:n_dn]]
     basis = sum(1 << (n - 1 - q) for q in occ)
-    e_hf = sum(eps[s] for s in order[:n_up]) + sum(eps[s] for s in order[:n_dn]) + args.u * n_up * n_dn / ns
+    e_hf = sum(eps[s] for s in order[:n_up]) + sum(eps[s] for s in order[:n_dn]) + u * n_up * n_dn / ns
     w = Circuit(n, 0)
     w.basis_change_separable(nx, ny)
     host_s = time.time() - t0
@@ -87,7 +77,7 @@ def main():
         if d is None:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        d.all_reduce(t, op=dist.ReduceOp.MAX)
+        d.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         return float(t.item())
 
     # ---- first screening at the HF state: analytic known answers + operator picks -------------------------
@@ -96,18 +86,19 @@ def main():
     t0 = time.time()
     e0, g0 = sim.adapt_screening(basis, empty.ops, w.ops, h_tab, plans)
     first_s = sync_max(time.time() - t0)
-    gmax = 2.0 * args.u / ns
+    gmax = 2.0 * u / ns
     spectrum_ok = bool(np.all((np.abs(g0) < 1e-9) | (np.abs(np.abs(g0) - gmax) < 1e-9)))
-    picks = [k for k in range(len(plans)) if abs(g0[k]) > 1e-9][:args.n_ops]
+    picks = [k for k in range(len(plans)) if abs(g0[k]) > 1e-9][:n_ops]
     thetas = np.array([0.05 * (-1) ** j for j in range(len(picks))])
     ans = Circuit(n, len(picks))
     for j, k in enumerate(picks):
         ans.generator(plans[k], param=j)
 
-    # ---- timed evaluations -----------------------------------------------------------------------------
+    # ---- timed evaluations: exchanges are enqueued without host synchronisation -------------------------------
     res = []
-    for step in range(args.steps + 1):                     # first one is the warm-up (program compilation)
+    for step in range(steps + 1):                          # first one is the warm-up (program compilation)
         engine.a2a_ms = 0.0
+        engine.time_exchanges = False
         s0, p0 = sim.swap_count, dict(sim.pass_count)
         if d is not None:
             d.barrier()
@@ -118,21 +109,23 @@ def main():
         t0 = time.time()
         e2, g2 = sim.adapt_screening(basis, ans.ops, w.ops, h_tab, plans, thetas, len(picks))
         t_full = sync_max(time.time() - t0)
-        res.append(dict(energy_s=t_energy, screening_s=t_full, a2a_ms=sync_max(engine.a2a_ms),
-                        swaps=sim.swap_count - s0, table_passes=sim.pass_count["table"] - p0["table"],
-                        pool_passes=sim.pass_count["pool"] - p0["pool"]))
+        res.append(dict(energy_s=t_energy, screening_s=t_full, swaps=sim.swap_count - s0,
+                        table_passes=sim.pass_count["table"] - p0["table"], pool_passes=sim.pass_count["pool"] - p0["pool"]))
     timed = res[1:]
     best = min(timed, key=lambda r: r["screening_s"])
-    # one more evaluation with a synchronisation after every phase: where the time goes (not a bench number)
-    sim.profiling = True
-    engine.a2a_ms = 0.0
-    sim.adapt_screening(basis, ans.ops, w.ops, h_tab, plans, thetas, len(picks))
-    phases = {k: round(sync_max(v), 5) for k, v in sim.profile.items()}
-    phases["a2a_ms_inside"] = round(sync_max(engine.a2a_ms), 3)
-    sim.profiling = False
+    phases = None
+    if profile:
+        # one more evaluation with a synchronisation after every phase and after every exchange: where the time goes
+        sim.profiling = True
+        engine.time_exchanges = True
+        engine.a2a_ms = 0.0
+        sim.adapt_screening(basis, ans.ops, w.ops, h_tab, plans, thetas, len(picks))
+        phases = {k: round(sync_max(v), 5) for k, v in sim.profile.items()}
+        phases["a2a_ms_inside"] = round(sync_max(engine.a2a_ms), 3)
+        sim.profiling = False
 
     check = None
-    if args.check_single and rank == 0 and n <= 28:
+    if check_single and rank == 0 and n <= 28:
         from fhsim.backend import DevicePool, DeviceTable
         ctx = engine.ctx
         c1 = Circuit(n, len(picks))
@@ -147,12 +140,15 @@ def main():
                  "energy_diff": float(abs(one["expvals"][0] - e2.real))}
         prog.close()
 
+    out = None
     if rank == 0:
         n_pool = len(plans)
         alg_bytes = 4.0 * (1 << n) * n_pool
         out = {
-            "lattice": args.lattice, "n_qubits": n, "n_gpus": world, "slab_GiB": 16.0 * (1 << (n - g)) / 2 ** 30,
+            "lattice": lattice, "n_qubits": n, "n_gpus": world, "slab_GiB": 16.0 * (1 << (n - g)) / 2 ** 30,
             "pool": n_pool, "ansatz_ops": len(picks), "host_compile_s": round(host_s, 2),
+            "communicator": "fh_comm (NCCL inside libfhsim, pipelined swap exchange)" if engine._comm is not None
+                            else ("torch.distributed all_to_all_single" if world > 1 else "none"),
             "hf_screening": {"E": e0.real, "E_analytic": e_hf, "abs_err": abs(e0.real - e_hf),
                              "nonzero": int(np.sum(np.abs(g0) > 1e-9)), "gmax": float(np.abs(g0).max()),
                              "gmax_analytic": gmax, "spectrum_in_{0,2U/N}": spectrum_ok, "seconds_cold": first_s},
@@ -164,6 +160,33 @@ def main():
             "screening_effective_GBps_all_gpus": alg_bytes / best["screening_s"] / 1e9,
             "check_vs_single_gpu": check,
         }
+        if peak_gbs and phases and phases.get("pool_scan"):
+            out["pool_scan_hbm_frac_per_gpu"] = alg_bytes / world / phases["pool_scan"] / 1e9 / peak_gbs
+    engine.close()                       # slabs, cached tables / pools / programs, communicator
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--lattice", default="4x4")
+    ap.add_argument("--u", type=float, default=4.0)
+    ap.add_argument("--n-ops", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--check-single", action="store_true")
+    ap.add_argument("--json", default=None)
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    d = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        d = dist
+    out = run_sharded(args.lattice, args.u, args.n_ops, args.steps, d, local_rank, args.check_single)
+    if out is not None:
         print(json.dumps(out))
         if args.json:
             os.makedirs(os.path.dirname(os.path.abspath(args.json)), exist_ok=True)
