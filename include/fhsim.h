@@ -180,6 +180,19 @@ int fh_lanczos(const fh_table *tab, int n_up, int n_dn, int k, double tol, int m
 int fh_lanczos_sector(const fh_table *tab, int n_up, int n_dn, int k, double tol, int max_iter, uint64_t seed,
                       double *evals, fh_state *const *evecs, double *compressed_out, int *iterations, double *stats);
 
+/* ---- iQCC Hamiltonian dressing on packed Pauli tables (device) --------------------------------------------
+ * replaces the symbolic update of models/iqcc_hubbard.py:184-189,
+ *     H <- H + sin(tau)(-i/2)[H, P] + (1/2)(1 - cos tau)(P H P - H)  =  exp(i tau P/2) H exp(-i tau P/2),
+ * on (x-mask, z-mask, coefficient) arrays resident on the device: XOR of masks, popcount phases, hash merge of the one
+ * possible duplicate per string, ordered compaction.  Bit-identical to the host restatement PauliTable.dressed. */
+typedef struct fh_ptable fh_ptable;
+int fh_ptable_upload(fh_ctx *ctx, int n_qubits, int n_terms, const uint64_t *x, const uint64_t *z, const double *coeff_re,
+                     const double *coeff_im, fh_ptable **out);          /* distinct strings (a canonical table) */
+int fh_ptable_free(fh_ptable *table);
+int fh_ptable_size(const fh_ptable *table, int *n_terms);
+int fh_ptable_download(const fh_ptable *table, uint64_t *x, uint64_t *z, double *coeff_re, double *coeff_im);
+int fh_ptable_dress(fh_ptable *table, uint64_t xp, uint64_t zp, double tau, double tol);   /* P = i^k X^xp Z^zp */
+
 /* ---- multi-GPU: communicator for the sharded-state path (BASELINE cfg 5) -------------------
  * The reference is single-process / single-device (models/adapt_vqe.py:156 hard-codes cuda:0), so these entry points
  * have no reference counterpart; they carry the global<->local qubit swap of a state sharded by its top index bits.

@@ -93,7 +93,7 @@ struct TileLaunch {
 };
 
 // ready-to-execute record of one op inside a tile (built on the host, one array per direction)
-struct __align__(16) TileRec {          // 144 bytes = 9 x 16 B; k_tile reads it as uint4 / double2 words
+struct __align__(16) TileRec {          // 160 bytes = 10 x 16 B; the kernels read it as uint4 / double2 words
     // word 0
     unsigned fixmask_out, fixval_out;   // pattern bits outside the tile: uniform per tile
     unsigned zeta, xlocal;
@@ -113,6 +113,13 @@ struct __align__(16) TileRec {          // 144 bytes = 9 x 16 B; k_tile reads it
     double m[8];
     // word 8: normalised generator element of a rotation op (gradient of the adjoint sweep)
     double bhat[2];
+    // word 9 (TMA tile kernels): register-fused runs.  run_len >= 2 on the FIRST record of a run of Givens-like ops that all
+    // live inside the three tile-local bits run_bits (b0 | b1 << 8 | b2 << 16): the run is applied to 8-amplitude groups
+    // held in registers, one shared-memory round trip and one barrier for the whole run.  sub_i / x3: pattern side and
+    // x-mask of THIS op in the 3-bit coordinates of its run.
+    int run_len;
+    unsigned run_bits;
+    unsigned char sub_i, x3, run_pad[6];
 };
 
 struct __align__(16) TileTerm {         // 48 bytes

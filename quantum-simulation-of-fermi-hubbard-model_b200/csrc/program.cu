@@ -401,14 +401,25 @@ static void build_tile_records(fh_program *p) {
                     r.term_off = term_off;
                     r.nterms = d.count;
                     if (d.param >= 0) r.seg = seg++;
-                    for (int m = 0; m < d.count; ++m) {
-                        TileTerm tt;
-                        set_tile_term(tt, p->dterms[d.first + m], dir != 0);
-                        for (int b = 0; b < t.nbits; ++b)
-                            if (tt.z >> t.bits[b] & 1ull) tt.zlocal |= 1u << b;
-                        (dir ? p->dterm_tt_dag : p->dterm_tt_fwd)[d.first + m] = (int)tts.size();
-                        tts.push_back(tt);
-                    }
+                    // terms whose in-tile z bits straddle the two halves of the tile (local bits 0..5 | 6..) first: the TMA
+                    // kernel evaluates those per amplitude and folds all the others into two phase tables
+                    unsigned lomask = 0, himask = 0;
+                    for (int b = 0; b < t.nbits; ++b) (b < 6 ? lomask : himask) |= 1u << t.bits[b];
+                    int nstr = 0;
+                    for (int pass = 0; pass < 2; ++pass)
+                        for (int m = 0; m < d.count; ++m) {
+                            const u64 z = p->dterms[d.first + m].z;
+                            const bool straddles = (z & lomask) != 0 && (z & himask) != 0;
+                            if (straddles != (pass == 0)) continue;
+                            TileTerm tt;
+                            set_tile_term(tt, p->dterms[d.first + m], dir != 0);
+                            for (int b = 0; b < t.nbits; ++b)
+                                if (tt.z >> t.bits[b] & 1ull) tt.zlocal |= 1u << b;
+                            (dir ? p->dterm_tt_dag : p->dterm_tt_fwd)[d.first + m] = (int)tts.size();
+                            tts.push_back(tt);
+                            nstr += straddles;
+                        }
+                    r.reps = nstr;
                     term_off += d.count;
                 }
                 recs.push_back(r);
@@ -416,6 +427,56 @@ static void build_tile_records(fh_program *p) {
             t.nterms = term_off;
             t.n_param_subs = seg;
             t.ptab_words = (int)(ptab.size() - tab_start);
+            // register-fused runs (TMA kernels): consecutive Givens-like ops (x = two in-tile bits, pattern pins exactly
+            // those two, nothing outside the tile) whose bits stay inside one set of three tile-local bits
+            // Measured (profiles/r02_tile_ab.md): a fused run costs as much as its ops one by one (the op loop is bound by the
+            // instruction stream of each warp, not by the shared-memory round trips), so runs are opt-in: FHSIM_RUNS=1
+            if (layout >= 0 && getenv("FHSIM_RUNS")) {
+                const size_t r0 = recs.size() - (size_t)t.nsub;
+                auto givens_like = [&](const TileRec &r, unsigned &bits2) {
+                    if (r.type == 2 || r.nlfix != 2 || r.fixmask_out != 0u || __builtin_popcount(r.xlocal) != 2) return false;
+                    unsigned pinned = 0;
+                    for (int q = 0; q < 2; ++q) pinned |= r.lowmask[q] + 1u;          // lowmask = (1 << b) - 1
+                    if (pinned != r.xlocal || __builtin_popcount(r.lfixval & r.xlocal) != 1) return false;     // pattern 01 <-> 10
+                    bits2 = r.xlocal;
+                    return true;
+                };
+                size_t i = 0;
+                while (i < (size_t)t.nsub) {
+                    unsigned b2 = 0;
+                    if (!givens_like(recs[r0 + i], b2)) {
+                        ++i;
+                        continue;
+                    }
+                    unsigned B = b2;
+                    size_t j = i + 1;
+                    while (j < (size_t)t.nsub && j - i < 8) {
+                        unsigned c2 = 0;
+                        if (!givens_like(recs[r0 + j], c2) || __builtin_popcount(B | c2) > 3) break;
+                        B |= c2;
+                        ++j;
+                    }
+                    if (j - i >= 2) {
+                        for (int b = 0; b < t.nbits && __builtin_popcount(B) < 3; ++b) B |= 1u << b;     // pad to 3 bits
+                        int pos[3], np = 0;
+                        for (int b = 0; b < t.nbits; ++b)
+                            if (B >> b & 1u) pos[np++] = b;
+                        for (size_t k = i; k < j; ++k) {
+                            TileRec &r = recs[r0 + k];
+                            r.run_len = k == i ? (int)(j - i) : 0;
+                            r.run_bits = (unsigned)pos[0] | ((unsigned)pos[1] << 8) | ((unsigned)pos[2] << 16);
+                            unsigned si = 0, x3 = 0;
+                            for (int q = 0; q < 3; ++q) {
+                                if (r.lfixval >> pos[q] & 1u) si |= 1u << q;
+                                if (r.xlocal >> pos[q] & 1u) x3 |= 1u << q;
+                            }
+                            r.sub_i = (unsigned char)si;
+                            r.x3 = (unsigned char)x3;
+                        }
+                    }
+                    i = j;
+                }
+            }
         }
     }
 }

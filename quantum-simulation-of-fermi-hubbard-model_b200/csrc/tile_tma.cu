@@ -242,6 +242,8 @@ struct OpHdr {
     unsigned fixmask_out, fixval_out, zeta;   // pattern / sign bits outside the tile (uniform per tile)
     unsigned xs;                              // slot image of the x-mask
     int type, reps, off;                      // record type, table entries per thread, first table entry (or first term)
+    int run_len;                              // >= 2: first record of a register-fused run
+    unsigned run_bits;
     double2 m0, m1, m2, m3;                   // 2x2 block
 };
 
@@ -255,6 +257,9 @@ __device__ __forceinline__ void load_hdr(const TileRec *rec, OpHdr &h) {
     h.off = (int)q1.w;
     h.reps = (int)q3.w;
     h.xs = q3.x;
+    const uint2 q9 = *reinterpret_cast<const uint2 *>(&rec->run_len);
+    h.run_len = (int)q9.x;
+    h.run_bits = q9.y;
     const double2 *mp = reinterpret_cast<const double2 *>(rec->m);
     h.m0 = mp[0];
     h.m1 = mp[1];
@@ -262,17 +267,17 @@ __device__ __forceinline__ void load_hdr(const TileRec *rec, OpHdr &h) {
     h.m3 = mp[3];
 }
 
-__device__ __forceinline__ void apply_pair_entry(double2 *buf, const OpHdr &h, unsigned e, unsigned sb) {
-    const unsigned si = e & 0x1fffu, sj = si ^ h.xs;
-    const unsigned sbit = (((e >> 13) ^ sb) & 1u) << 31;
-    double2 a = buf[si], b = buf[sj];
-    if (h.type == 3) {            // real matrix (Givens)
+// 2x2 block on one pair held in registers.  TYPE 3: real matrix (Givens); 6: real diagonal, complex off-diagonal (every
+// rotation exp(-i a G)); anything else: general complex.
+template <int TYPE>
+__device__ __forceinline__ void pair_math(const OpHdr &h, unsigned sbit, double2 &a, double2 &b) {
+    if (TYPE == 3) {
         const double m01 = flip_sign(h.m1.x, sbit), m10 = flip_sign(h.m2.x, sbit);
         const double2 ra = make_double2(h.m0.x * a.x + m01 * b.x, h.m0.x * a.y + m01 * b.y);
         const double2 rb = make_double2(m10 * a.x + h.m3.x * b.x, m10 * a.y + h.m3.x * b.y);
         a = ra;
         b = rb;
-    } else if (h.type == 6) {     // real diagonal, complex off-diagonal (every rotation exp(-i a G))
+    } else if (TYPE == 6) {
         const double2 mb = make_double2(flip_sign(h.m1.x, sbit), flip_sign(h.m1.y, sbit));
         const double2 mc = make_double2(flip_sign(h.m2.x, sbit), flip_sign(h.m2.y, sbit));
         const double2 ra = make_double2(h.m0.x * a.x + (mb.x * b.x - mb.y * b.y), h.m0.x * a.y + (mb.x * b.y + mb.y * b.x));
@@ -287,42 +292,81 @@ __device__ __forceinline__ void apply_pair_entry(double2 *buf, const OpHdr &h, u
         a = ra;
         b = rb;
     }
-    buf[si] = a;
-    buf[sj] = b;
+}
+
+// All pairs of one op that belong to this thread, four at a time: four table entries, then eight independent
+// shared-memory loads in flight, then the arithmetic, then the stores (a CTA is only four warps, so the per-op overhead
+// -- header, barrier -- is paid by four warps and the latency is hidden by the four independent pairs of each thread).
+#define PAIR_UNROLL 4
+// FH_OPLOOP_VARIANT (tools/probe_timeline.py only): 0 full op loop; 1 no arithmetic; 2 no amplitude loads / stores either;
+// 3 no table loads either (header + barrier); 4 barrier only.  Strips the op loop piece by piece to see where the cycles go.
+#ifndef FH_OPLOOP_VARIANT
+#define FH_OPLOOP_VARIANT 0
+#endif
+template <int TYPE>
+__device__ __forceinline__ void pair_block(double2 *buf, const OpHdr &h, const unsigned short *tp, int nthr, unsigned sb) {
+    for (int rep = 0; rep < h.reps; rep += PAIR_UNROLL) {
+        unsigned e[PAIR_UNROLL];
+#pragma unroll
+        for (int u = 0; u < PAIR_UNROLL; ++u) e[u] = (rep + u < h.reps) ? (unsigned)tp[(rep + u) * nthr] : 0u;
+        double2 a[PAIR_UNROLL], b[PAIR_UNROLL];
+#if FH_OPLOOP_VARIANT >= 2
+        if (e[0] == 0xffffffffu) buf[0] = make_double2(0.0, 0.0);          // keep the table loads alive
+        (void)a; (void)b; (void)sb;
+#else
+#pragma unroll
+        for (int u = 0; u < PAIR_UNROLL; ++u)
+            if (e[u] >> 14) {
+                const unsigned si = e[u] & 0x1fffu;
+                a[u] = buf[si];
+                b[u] = buf[si ^ h.xs];
+            }
+#if FH_OPLOOP_VARIANT == 0
+#pragma unroll
+        for (int u = 0; u < PAIR_UNROLL; ++u)
+            if (e[u] >> 14) pair_math<TYPE>(h, (((e[u] >> 13) ^ sb) & 1u) << 31, a[u], b[u]);
+#endif
+#pragma unroll
+        for (int u = 0; u < PAIR_UNROLL; ++u)
+            if (e[u] >> 14) {
+                const unsigned si = e[u] & 0x1fffu;
+                buf[si] = a[u];
+                buf[si ^ h.xs] = b[u];
+            }
+#endif
+    }
 }
 
 // diagonal op on one tile: exp(-i sum_m angle_m sgn_m(index)).  Terms whose in-tile z bits sit entirely in local bits
-// 0..5 (or entirely in 6..) are folded into two phase tables built once per (op, tile); terms straddling both halves
-// are evaluated per amplitude from the tile-local z-mask (no global index needed).
+// 0..5 (or entirely in 6..) are folded into two phase tables built once per (op, tile) as PRODUCTS of the terms' unit
+// phases (cos, sin precomputed on the host: no sincos here); the terms straddling both halves come first in the op's
+// term list (rec->reps of them, sorted by the host) and are evaluated per amplitude from the tile-local z-mask.
 template <bool SWZ>
 __device__ __forceinline__ void apply_diag(double2 *buf, double2 *ph, const TileRec *rec, const TileTerm *tterm,
                                            const TileLaunch &tl, int T, unsigned base, unsigned lomask_g, unsigned himask_g) {
     const TileTerm *dt = tterm + rec->term_off;
-    const int cnt = rec->nterms;
+    const int cnt = rec->nterms, nstr = rec->reps;
     const unsigned L = 1u << T;
     for (unsigned v = threadIdx.x; v < 192u; v += blockDim.x) {
         const bool lo = v < 64u;
         const unsigned gl = base | (lo ? tile_scatter(tl, T, v, 0, 6) : tile_scatter(tl, T, v - 64u, 6, TILE_BITS_CAP));
-        double tot = 0.0;
-        for (int m = 0; m < cnt; ++m) {
+        double2 f = make_double2(1.0, 0.0);
+        for (int m = nstr; m < cnt; ++m) {
             const unsigned z = (unsigned)dt[m].z;
-            const bool in_lo = (z & himask_g) == 0u;
-            const bool in_hi = (z & lomask_g) == 0u && !in_lo;
-            if (lo ? in_lo : in_hi) tot += ((__popc(gl & z) & 1) ? -1.0 : 1.0) * dt[m].angle;
+            const bool in_lo = (z & himask_g) == 0u;          // no bit in the high half (includes terms with no in-tile bit)
+            if (lo == in_lo) {
+                const double sn = (__popc(gl & z) & 1) ? dt[m].s : -dt[m].s;
+                f = cmul(f, make_double2(dt[m].c, sn));
+            }
         }
-        double sn, cs;
-        sincos(tot, &sn, &cs);
-        ph[v] = make_double2(cs, -sn);
+        ph[v] = f;
     }
     __syncthreads();
     for (unsigned l = threadIdx.x; l < L; l += blockDim.x) {
         double2 f = cmul(ph[l & 63u], ph[64u + (l >> 6)]);
-        for (int m = 0; m < cnt; ++m) {
-            const unsigned z = (unsigned)dt[m].z;
-            if ((z & himask_g) != 0u && (z & lomask_g) != 0u) {
-                const unsigned par = (unsigned)(__popc(base & z) + __popc(l & dt[m].zlocal)) & 1u;
-                f = cmul(f, make_double2(dt[m].c, par ? dt[m].s : -dt[m].s));
-            }
+        for (int m = 0; m < nstr; ++m) {
+            const unsigned par = (unsigned)(__popc(base & (unsigned)dt[m].z) + __popc(l & dt[m].zlocal)) & 1u;
+            f = cmul(f, make_double2(dt[m].c, par ? dt[m].s : -dt[m].s));
         }
         const unsigned sl = tslot<SWZ>(l);
         buf[sl] = cmul(f, buf[sl]);
@@ -345,33 +389,95 @@ extern "C" int fh_debug_tile_tma_timeline(long long *out64) {
 #define TMA_TLMARK(k) do { } while (0)
 #endif
 
-// The op loop of one tile: every op of the run in order, one CTA barrier between ops.  Header, matrix and table entry
-// of op k+1 are fetched (LDS) before the barrier that ends op k, so the dependent chain per op is
-// barrier -> LDS amplitudes -> FP64 -> STS.
+// One Givens-like op of a fused run on the 8 amplitudes v[] of a group (sub-index = the group's three run bits): the op
+// rotates the pairs (sub_i, sub_i ^ x3) for both values of the run bit that is not in x3.  The six (x3, sub_i) shapes are
+// spelled out so that v[] is only indexed with compile-time constants (it must stay in registers).
+template <int TYPE>
+__device__ __forceinline__ void run_op(double2 (&v)[8], const OpHdr &h, unsigned shape, unsigned par0, unsigned par1) {
+    const unsigned s0 = (par0 & 1u) << 31, s1 = (par1 & 1u) << 31;
+    switch (shape) {
+        case 0: pair_math<TYPE>(h, s0, v[1], v[2]); pair_math<TYPE>(h, s1, v[5], v[6]); break;   // x3 = 011, pattern 001
+        case 1: pair_math<TYPE>(h, s0, v[2], v[1]); pair_math<TYPE>(h, s1, v[6], v[5]); break;   // x3 = 011, pattern 010
+        case 2: pair_math<TYPE>(h, s0, v[1], v[4]); pair_math<TYPE>(h, s1, v[3], v[6]); break;   // x3 = 101, pattern 001
+        case 3: pair_math<TYPE>(h, s0, v[4], v[1]); pair_math<TYPE>(h, s1, v[6], v[3]); break;   // x3 = 101, pattern 100
+        case 4: pair_math<TYPE>(h, s0, v[2], v[4]); pair_math<TYPE>(h, s1, v[3], v[5]); break;   // x3 = 110, pattern 010
+        default: pair_math<TYPE>(h, s0, v[4], v[2]); pair_math<TYPE>(h, s1, v[5], v[3]); break;  // x3 = 110, pattern 100
+    }
+}
+
+// A run of `m` Givens-like ops inside three tile-local bits, applied to 8-amplitude groups held in registers: one load and
+// one store of the tile and ONE barrier for the whole run (a 3-site Fourier transform of the separable W is one run).
+template <bool SWZ>
+__device__ __forceinline__ void fused_run(double2 *buf, const TileRec *rec, int m, unsigned run_bits, int T, unsigned base) {
+    const unsigned b0 = run_bits & 255u, b1 = (run_bits >> 8) & 255u, b2 = (run_bits >> 16) & 255u;
+    const unsigned m0 = (1u << b0) - 1u, m1 = (1u << b1) - 1u, m2 = (1u << b2) - 1u;
+    const unsigned t0 = tslot<SWZ>(1u << b0), t1 = tslot<SWZ>(1u << b1), t2 = tslot<SWZ>(1u << b2);   // slot map is XOR-linear
+    const unsigned ngroups = (1u << T) >> 3;
+    for (unsigned g = threadIdx.x; g < ngroups; g += blockDim.x) {
+        unsigned gl = g;                                        // group index -> tile-local index with the run bits clear
+        gl = ((gl & ~m0) << 1) | (gl & m0);
+        gl = ((gl & ~m1) << 1) | (gl & m1);
+        gl = ((gl & ~m2) << 1) | (gl & m2);
+        const unsigned s = tslot<SWZ>(gl);
+        double2 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = buf[s ^ ((k & 1) ? t0 : 0u) ^ ((k & 2) ? t1 : 0u) ^ ((k & 4) ? t2 : 0u)];
+        for (int o = 0; o < m; ++o) {
+            OpHdr h;
+            load_hdr(&rec[o], h);
+            const unsigned si = rec[o].sub_i, x3 = rec[o].x3;
+            const unsigned third = 7u & ~x3;                    // the run bit this op does not flip
+            // tile-local index of the two pattern-side amplitudes (third bit 0 / 1) for the sign parity
+            const unsigned l0 = gl | ((si & 1u) << b0) | (((si >> 1) & 1u) << b1) | (((si >> 2) & 1u) << b2);
+            const unsigned l1 = l0 | ((third & 1u) << b0) | (((third >> 1) & 1u) << b1) | (((third >> 2) & 1u) << b2);
+            const unsigned zl = rec[o].zeta_local, pb = (unsigned)__popc(base & h.zeta);
+            const unsigned par0 = pb + (unsigned)__popc(l0 & zl), par1 = pb + (unsigned)__popc(l1 & zl);
+            const unsigned lowbit = x3 & (0u - x3);             // lower x bit of the op
+            const unsigned shape = (x3 == 3u ? 0u : (x3 == 5u ? 2u : 4u)) + ((si & lowbit) ? 0u : 1u);
+            if (h.type == 3) run_op<3>(v, h, shape, par0, par1);
+            else if (h.type == 6) run_op<6>(v, h, shape, par0, par1);
+            else run_op<1>(v, h, shape, par0, par1);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) buf[s ^ ((k & 1) ? t0 : 0u) ^ ((k & 2) ? t1 : 0u) ^ ((k & 4) ? t2 : 0u)] = v[k];
+    }
+}
+
+// The op loop of one tile: every op of the run in order, one CTA barrier between ops.  The header (pattern test, sign
+// mask, 2x2 block) of op k+1 is fetched before the barrier that ends op k.
 template <bool SWZ>
 __device__ __forceinline__ void tile_ops(double2 *buf, double2 *ph, const TileRec *rec, const TileTerm *tterm,
                                          const unsigned short *ptab, const TileLaunch &tl, int T, int nsub, unsigned base,
                                          unsigned lomask_g, unsigned himask_g) {
     OpHdr h;
     load_hdr(&rec[0], h);
-    unsigned e = h.type != 2 ? ptab[h.off + threadIdx.x] : 0u;
-    for (int sidx = 0; sidx < nsub; ++sidx) {
-        if (sidx < 40) TMA_TLMARK(4 + sidx);
+    const int nthr = (int)blockDim.x;
+    int sidx = 0, mark = 0;
+    while (sidx < nsub) {
+        if (mark < 40) TMA_TLMARK(4 + mark);
+        ++mark;
+        int step = 1;
         if (h.type != 2) {
-            if ((base & h.fixmask_out) == h.fixval_out) {
+#if FH_OPLOOP_VARIANT < 3
+            if (h.run_len >= 2) {
+                fused_run<SWZ>(buf, &rec[sidx], h.run_len, h.run_bits, T, base);
+                step = h.run_len;
+            } else if ((base & h.fixmask_out) == h.fixval_out) {
                 const unsigned sb = (unsigned)__popc(base & h.zeta);
-                if (e >> 14) apply_pair_entry(buf, h, e, sb);
-                for (int rep = 1; rep < h.reps; ++rep) {        // ops with more pairs in a tile than threads in the CTA
-                    const unsigned e2 = ptab[h.off + rep * (int)blockDim.x + (int)threadIdx.x];
-                    if (e2 >> 14) apply_pair_entry(buf, h, e2, sb);
-                }
+                const unsigned short *tp = ptab + h.off + threadIdx.x;
+                if (h.type == 3) pair_block<3>(buf, h, tp, nthr, sb);
+                else if (h.type == 6) pair_block<6>(buf, h, tp, nthr, sb);
+                else pair_block<1>(buf, h, tp, nthr, sb);
             }
+#endif
         } else {
             apply_diag<SWZ>(buf, ph, &rec[sidx], tterm, tl, T, base, lomask_g, himask_g);
         }
-        if (sidx + 1 < nsub) {
-            load_hdr(&rec[sidx + 1], h);
-            e = h.type != 2 ? ptab[h.off + threadIdx.x] : 0u;
+        sidx += step;
+        if (sidx < nsub) {
+#if FH_OPLOOP_VARIANT < 4
+            load_hdr(&rec[sidx], h);
+#endif
             __syncthreads();
         }
     }
@@ -402,7 +508,7 @@ __device__ __forceinline__ void fetch_run_descriptors(const TileLaunch &tl, cons
 }
 
 template <bool PDL, bool SWZ>
-__global__ void __launch_bounds__(512, 2)
+__global__ void __launch_bounds__(128, 2)
     k_tile_tma(const __grid_constant__ CUtensorMap map, const TileLaunch tl, const TmaPlan plan,
                const TileRec *__restrict__ recs, const TileTerm *__restrict__ terms, const unsigned short *__restrict__ ptab, int n,
                int stages) {
@@ -516,7 +622,7 @@ __device__ __forceinline__ void smem_copy16(T *dst, const T *src, int count) {  
 
 #define FH_CHAIN_MAX_RUNS 48
 
-__global__ void __launch_bounds__(512, 2)
+__global__ void __launch_bounds__(128, 2)
     k_tile_chain(const ChainRun *__restrict__ runs, int nruns, const CUtensorMap *__restrict__ maps,
                  const TileRec *__restrict__ recs, const TileTerm *__restrict__ terms, const unsigned short *__restrict__ ptab, int n,
                  unsigned *__restrict__ sync, unsigned long long basis, int rec_cap, int term_cap, int tab_cap,
@@ -637,11 +743,12 @@ static size_t tile_tma_smem(const TileLaunch &tl, int stages) {
            (size_t)tl.ptab_words * 2 + 192 * sizeof(double2) + 64;
 }
 
+// Four warps per CTA: every thread owns several independent pairs of an op (latency hidden by instruction-level
+// parallelism), and the per-op overhead (header fetch, barrier) is paid by four warps instead of sixteen.
 int fh_tile_threads(int nbits) {
-    int threads = nbits >= 1 ? (1 << (nbits - 1)) : 1;
-    if (threads > 512) threads = 512;
-    if (threads < 64) threads = 64;
-    return threads;
+    static const int env = getenv("FHSIM_TILE_THREADS") ? atoi(getenv("FHSIM_TILE_THREADS")) : 0;
+    if (env >= 32 && env <= 128 && (env & (env - 1)) == 0) return env;     // the kernels are built for <= 128 threads
+    return nbits >= 8 ? 128 : 64;
 }
 
 // -1: the TMA kernels do not take this tile (launch_tile falls back to the register-staged kernel); else the layout
@@ -679,11 +786,13 @@ void launch_tile(cudaStream_t s, double2 *psi, const TileLaunch &tl, const TileR
         return;
     }
     if (ntiles > (unsigned long long)sm * 2) {
-        // more tiles than one wave: persistent CTAs.  Two CTAs per SM with one buffer each (the sibling's op loop hides
-        // this CTA's tile traffic, twice the warps for the barrier-separated ops) if they fit, else one CTA per SM with
-        // two buffers (load of tile i+1 / store of tile i-1 under the op loop of tile i), else one buffer
-        if (2 * smem1 <= sm_budget) {
-            grid = (unsigned long long)sm * 2;
+        // more tiles than one wave: persistent CTAs.  Several CTAs per SM with one buffer each (the siblings' op loops
+        // hide this CTA's tile traffic) if at least two fit, else one CTA per SM with two buffers (load of tile i+1 /
+        // store of tile i-1 under the op loop of tile i), else one buffer
+        int per_sm = (int)(sm_budget / (smem1 + 1024));
+        if (per_sm > 2) per_sm = 2;                 // registers: two 128-thread CTAs per SM
+        if (per_sm >= 2) {
+            grid = (unsigned long long)sm * per_sm;
         } else if (smem2 <= sm_budget) {
             stages = 2;
             grid = (unsigned long long)sm;
@@ -723,7 +832,7 @@ int fh_tile_tma_init_device() {
     FH_CUDA(cudaFuncSetAttribute(k_tile_tma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     FH_CUDA(cudaFuncSetAttribute(k_tile_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     FH_CUDA(cudaFuncSetAttribute(k_tile_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    FH_CUDA(cudaFuncSetAttribute(k_tile_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    FH_CUDA(cudaFuncSetAttribute(k_tile_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));   // + ~5 KB static
     return FH_OK;
 }
 
@@ -745,7 +854,9 @@ int plan_tile_chain(int sm, double2 *psi, double2 *psi2, const ChainRunHost *hru
                     int *tab_cap_out, int *tbits_out) {
     ChainRun *h_runs = reinterpret_cast<ChainRun *>(h_runs_v);
     CUtensorMap *h_maps = reinterpret_cast<CUtensorMap *>(h_maps_v);
-    if (getenv("FHSIM_TILE_LDG") || getenv("FHSIM_NO_CHAIN")) return -1;
+    // measured at 18 qubits (profiles/r02_*): the chain is not faster than one programmatic-dependent launch per run (the
+    // run-boundary counter costs what the overlapped launch does), so it is opt-in; the tests run both
+    if (getenv("FHSIM_TILE_LDG") || getenv("FHSIM_NO_CHAIN") || !getenv("FHSIM_CHAIN")) return -1;
     int nmaps = 0, grid = 0, rec_cap = 1, term_cap = 1, tab_cap = 8, tbits = 0;
     if (nruns > FH_CHAIN_MAX_RUNS) return -1;
     for (int r = 0; r < nruns; ++r) {
@@ -779,7 +890,7 @@ int plan_tile_chain(int sm, double2 *psi, double2 *psi2, const ChainRunHost *hru
                         2 * (size_t)tab_cap * 2 + 192 * sizeof(double2) + 64;
     if (smem > 200 * 1024) return -1;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_chain, 512, smem) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_chain, fh_tile_threads(tbits), smem) != cudaSuccess) {
         cudaGetLastError();
         return -1;
     }

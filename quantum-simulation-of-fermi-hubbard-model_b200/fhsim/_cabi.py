@@ -66,6 +66,11 @@ SIGNATURES = {
     "fh_program_last_stats": [_vp, _f64p, C.POINTER(C.c_int)],
     "fh_program_time_items": [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _f64p],
     "fh_lanczos": [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint64, _f64p, _vpp, C.POINTER(C.c_int)],
+    "fh_ptable_upload": [_vp, C.c_int, C.c_int, _u64p, _u64p, _f64p, _f64p, _vpp],
+    "fh_ptable_free": [_vp],
+    "fh_ptable_size": [_vp, C.POINTER(C.c_int)],
+    "fh_ptable_download": [_vp, _u64p, _u64p, _f64p, _f64p],
+    "fh_ptable_dress": [_vp, C.c_uint64, C.c_uint64, C.c_double, C.c_double],
     "fh_comm_unique_id": [C.POINTER(C.c_ubyte)],
     "fh_comm_init": [_vp, C.POINTER(C.c_ubyte), C.c_int, C.c_int, _vpp],
     "fh_comm_destroy": [_vp],

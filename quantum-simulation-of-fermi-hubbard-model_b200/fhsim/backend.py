@@ -290,3 +290,47 @@ def sector_indices(n, n_up, n_dn):
         return np.array(out, dtype=np.uint64)
     up, dn = patterns(n_up, 1), patterns(n_dn, 0)
     return (up[:, None] | dn[None, :]).reshape(-1)
+
+
+class DevicePauliTable:
+    """Packed (x, z, coeff) term table resident on the device, for the iQCC dressing update
+    (``fh_ptable_dress``: reference models/iqcc_hubbard.py:184-189 without symbolic operator products)."""
+
+    def __init__(self, ctx: Context, table: PauliTable):
+        self.ctx, self.n = ctx, table.n_qubits
+        self._h = _cabi._vp()
+        xa, xp = _cabi.u64_array(table.x)
+        za, zp = _cabi.u64_array(table.z)
+        ra, rp = _cabi.f64_array(np.real(table.coeff))
+        ia, ip = _cabi.f64_array(np.imag(table.coeff))
+        _cabi.check(_cabi.lib().fh_ptable_upload(ctx._h, self.n, len(xa), xp, zp, rp, ip, C.byref(self._h)))
+
+    def __len__(self):
+        n = C.c_int()
+        _cabi.check(_cabi.lib().fh_ptable_size(self._h, C.byref(n)))
+        return n.value
+
+    def dress(self, xp: int, zp: int, tau: float, tol: float = 1e-12):
+        """In place: exp(i tau P/2) H exp(-i tau P/2) for the Pauli string P = (xp, zp)."""
+        _cabi.check(_cabi.lib().fh_ptable_dress(self._h, int(xp), int(zp), float(tau), float(tol)))
+        return self
+
+    def to_host(self) -> PauliTable:
+        n = len(self)
+        x, z = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+        cr, ci = np.zeros(n), np.zeros(n)
+        if n:
+            _cabi.check(_cabi.lib().fh_ptable_download(self._h, x.ctypes.data_as(_cabi._u64p), z.ctypes.data_as(_cabi._u64p),
+                                                       cr.ctypes.data_as(_cabi._f64p), ci.ctypes.data_as(_cabi._f64p)))
+        return PauliTable(self.n, x, z, cr + 1j * ci)
+
+    def close(self):
+        if self._h:
+            _cabi.lib().fh_ptable_free(self._h)
+            self._h = _cabi._vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

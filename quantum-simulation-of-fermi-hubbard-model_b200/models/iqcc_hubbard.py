@@ -151,19 +151,26 @@ class IQCC:
     def dress_hamiltonian(self, operators, taus):
         """H <- H + sin(tau)(-i/2)[H, P] + (1/2)(1 - cos tau)(P H P - H), last entangler first (reference :184-189).
 
-        Evaluated on the packed (x-mask, z-mask, coefficient) table (``PauliTable.dressed``: anticommuting terms pick
-        up cos/sin copies, duplicates are hash-merged), not by symbolic operator products: the term table grows
-        geometrically with the number of entanglers.  ``currentHamiltonian`` stays a QubitOperator for the callers
+        Evaluated on the packed (x-mask, z-mask, coefficient) table ON THE DEVICE (``fh_ptable_dress``: anticommuting
+        terms pick up cos/sin copies, the one possible duplicate per string is hash-merged; bit-identical to the host
+        restatement ``PauliTable.dressed``), not by symbolic operator products: the term table grows geometrically with
+        the number of entanglers.  ``currentHamiltonian`` stays a QubitOperator for the callers
         that iterate its terms (``partition_hamiltonian``)."""
+        from fhsim.backend import DevicePauliTable
         from fhsim.tables import PauliTable, pack_term
-        table = PauliTable.from_operator(self.currentHamiltonian, self.n_qubits, compress=False)
-        for P_k, tau_k in zip(operators[::-1], taus[::-1]):
-            (term, coeff), = P_k.terms.items()
-            if abs(coeff - 1.0) > 1e-12:
-                raise ValueError('entanglers must be bare Pauli strings')
-            xp, zp = pack_term(term, self.n_qubits)
-            # float32 parameter, promoted exactly: keeps the algebra in double precision
-            table = table.dressed(xp, zp, float(tau_k))
+        host = PauliTable.from_operator(self.currentHamiltonian, self.n_qubits, compress=False)
+        dev = DevicePauliTable(self._ctx, host)              # every entangler is applied on the device: ONE download
+        try:
+            for P_k, tau_k in zip(operators[::-1], taus[::-1]):
+                (term, coeff), = P_k.terms.items()
+                if abs(coeff - 1.0) > 1e-12:
+                    raise ValueError('entanglers must be bare Pauli strings')
+                xp, zp = pack_term(term, self.n_qubits)
+                # float32 parameter, promoted exactly: keeps the algebra in double precision
+                dev.dress(xp, zp, float(tau_k))
+            table = dev.to_host()
+        finally:
+            dev.close()
         self.currentHamiltonian = table.to_operator()
         self.qmlHamiltonian = QubitOperator_to_qmlHamiltonian(self.currentHamiltonian)
 

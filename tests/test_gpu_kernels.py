@@ -558,15 +558,15 @@ def test_tile_chain_equals_one_launch_per_run(ctx, n, tile_bits, monkeypatch):
     psi0 = rand_state(n, 900 + n)
     prog = circ.compile(ctx, tile_bits=tile_bits, low_bits=3)
     assert prog.n_tiles >= 3
-    monkeypatch.delenv("FHSIM_NO_CHAIN", raising=False)
+    monkeypatch.setenv("FHSIM_CHAIN", "1")                 # the chain is opt-in (not faster at 18 qubits)
     st = State.from_numpy(ctx, psi0)
     prog.run(st, th)
     got = st.numpy()
-    monkeypatch.setenv("FHSIM_NO_CHAIN", "1")
+    monkeypatch.delenv("FHSIM_CHAIN", raising=False)
     st2 = State.from_numpy(ctx, psi0)
     prog.run(st2, th)
     ref = st2.numpy()
-    monkeypatch.delenv("FHSIM_NO_CHAIN", raising=False)
+    monkeypatch.setenv("FHSIM_CHAIN", "1")
     assert np.array_equal(got, ref)                      # same kernels' arithmetic, only the launch structure differs
     if n <= 18:
         assert np.abs(got - emulate.run_circuit(circ, psi0.copy(), th)).max() < AMP_TOL
@@ -603,9 +603,9 @@ def test_evaluate_with_chains_basis_synthesis_and_checkpoint_store(ctx, monkeypa
     results = []
     for no_chain in (False, True):
         if no_chain:
-            monkeypatch.setenv("FHSIM_NO_CHAIN", "1")
+            monkeypatch.delenv("FHSIM_CHAIN", raising=False)
         else:
-            monkeypatch.delenv("FHSIM_NO_CHAIN", raising=False)
+            monkeypatch.setenv("FHSIM_CHAIN", "1")
         prog = build()
         out = State(ctx, n)
         r1 = prog.evaluate(basis, th, [dtab], grads=True, pool=dpool, pool_pos=prog.markers["ansatz_end"], targets=[target],
@@ -616,7 +616,7 @@ def test_evaluate_with_chains_basis_synthesis_and_checkpoint_store(ctx, monkeypa
                             state_out=out)                                                           # re-captured, replayed
         assert np.array_equal(r1["pool"], r1b["pool"]) and np.array_equal(r1["grads"], r1b["grads"])
         results.append((r1, r2, r3, out.numpy(), prog.last_stats()[1]))
-    monkeypatch.delenv("FHSIM_NO_CHAIN", raising=False)
+    monkeypatch.delenv("FHSIM_CHAIN", raising=False)
     (a1, a2, a3, sa, la), (b1, b2, b3, sb, lb) = results
     assert la < lb                                        # fewer launches with chains
     assert np.array_equal(sa, sb)
@@ -675,3 +675,66 @@ def test_sector_lanczos_rejects_tables_that_leave_the_sector(ctx):
     tab = DeviceTable(ctx, PauliTable.from_operator(op, n))
     with pytest.raises(ValueError, match="conserve"):
         lanczos_sector(tab, 2, 2)
+
+
+def test_device_dressing_is_bit_identical_to_the_host_restatement(ctx):
+    """fh_ptable_dress vs PauliTable.dressed (reference iqcc_hubbard.py:184-189 on packed tables): same strings in the same
+    order, coefficients bit for bit, over a chain of entanglers that grows the table from 100 to thousands of terms, plus
+    random complex tables (duplicates of generated strings, cancellations, tau = 0)."""
+    from fhsim.backend import DevicePauliTable
+    n = 18
+    host = PauliTable.from_operator(fermi_hubbard(3, 3, 1.0, 6.0), n)
+    dev = DevicePauliTable(ctx, host)
+    rng = np.random.default_rng(12)
+    for step in range(7):
+        xp = int(rng.integers(1, 1 << n))
+        zp = int(rng.integers(0, 1 << n))
+        tau = float(rng.uniform(-2, 2)) if step != 3 else 0.0
+        host = host.dressed(xp, zp, tau)
+        dev.dress(xp, zp, tau)
+        got = dev.to_host()
+        assert len(got) == len(host) == len(dev)
+        assert np.array_equal(got.x, host.x) and np.array_equal(got.z, host.z)
+        assert np.array_equal(got.coeff.real, host.coeff.real) and np.array_equal(got.coeff.imag, host.coeff.imag)
+    assert len(host) > 1000
+    dev.close()
+    # random complex tables on few qubits: generated strings hit existing ones often
+    for seed in range(6):
+        r = np.random.default_rng(100 + seed)
+        m = 7
+        t = PauliTable(m, r.integers(0, 1 << m, 60), r.integers(0, 1 << m, 60), r.normal(size=60) + 1j * r.normal(size=60))
+        d = DevicePauliTable(ctx, t)
+        for _ in range(4):
+            xp, zp, tau = int(r.integers(1, 1 << m)), int(r.integers(0, 1 << m)), float(r.uniform(-3, 3))
+            t = t.dressed(xp, zp, tau)
+            d.dress(xp, zp, tau)
+        g = d.to_host()
+        assert np.array_equal(g.x, t.x) and np.array_equal(g.z, t.z) and np.array_equal(g.coeff, t.coeff)
+        d.close()
+
+
+def test_register_fused_runs_equal_the_op_by_op_tile_kernel(ctx, monkeypatch):
+    """FHSIM_RUNS=1: consecutive Givens-like ops inside three tile-local bits are applied to 8-amplitude groups held in
+    registers (one shared-memory round trip per run).  The separable W of 3x3 (twelve 3-site Fourier transforms) and random
+    Givens circuits, forward and dagger, against the op-by-op records of the same kernels."""
+    n = 18
+    th = []
+    monkeypatch.delenv("FHSIM_RUNS", raising=False)
+    circ = Circuit(n, 0)
+    circ.basis_change_separable(3, 3)
+    rng = np.random.default_rng(3)
+    for _ in range(30):
+        a = int(rng.integers(n - 2))
+        circ.fermionic_single_excitation(float(rng.uniform(-2, 2)), a, a + int(rng.integers(1, 3)))
+    psi0 = rand_state(n, 41)
+    plain = circ.compile(ctx, tile_bits=11, low_bits=3)
+    st = State.from_numpy(ctx, psi0)
+    plain.run(st, th)
+    ref = st.numpy()
+    monkeypatch.setenv("FHSIM_RUNS", "1")
+    fused = circ.compile(ctx, tile_bits=11, low_bits=3)        # the runs are detected when the program is finalised
+    st2 = State.from_numpy(ctx, psi0)
+    fused.run(st2, th)
+    assert np.abs(st2.numpy() - ref).max() < 1e-13
+    fused.run(st2, th, dagger=True)
+    assert np.abs(st2.numpy() - psi0).max() < AMP_TOL

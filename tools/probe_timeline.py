@@ -18,14 +18,15 @@ import sys
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(R, "quantum-simulation-of-fermi-hubbard-model_b200")
 CSRC = os.path.join(PKG, "csrc")
-OUT = os.path.join(CSRC, "build_timeline", "libfhsim_timeline.so")
+VARIANT = os.environ.get("FH_OPLOOP_VARIANT", "0")         # see tile_tma.cu: strips the op loop piece by piece
+OUT = os.path.join(CSRC, "build_timeline", f"libfhsim_timeline_v{VARIANT}.so")
 
 
 def build():
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    srcs = ["kernels.cu", "tile_tma.cu", "api.cu", "program.cu", "lanczos.cu"]
+    srcs = ["kernels.cu", "tile_tma.cu", "api.cu", "program.cu", "lanczos.cu", "comm.cu", "dress.cu"]
     cmd = ["nvcc", "-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
-           "-DFH_TILE_TIMELINE", "-shared", "-cudart", "static", "-o", OUT] + [os.path.join(CSRC, f) for f in srcs]
+           "-DFH_TILE_TIMELINE", f"-DFH_OPLOOP_VARIANT={VARIANT}", "-shared", "-cudart", "static", "-o", OUT] + [os.path.join(CSRC, f) for f in srcs]
     subprocess.check_call(cmd)
 
 
@@ -40,7 +41,9 @@ def main():
     import bench
     from fhsim.backend import Context, State
     ctx = Context(0)
-    wl = bench.build_gpu_workload(ctx)
+    import json
+    picks = json.load(open(os.path.join(R, "tools", "probes", "picks_3x3.json"))) if VARIANT != "0" else None
+    wl = bench.build_gpu_workload(ctx, picks)      # stripped variants cannot screen: operator picks from the oracle
     prog, n = wl["prog"], bench.N_QUBITS
     st = State(ctx, n)
     st.set_basis(wl["basis"])
