@@ -714,7 +714,7 @@ __global__ void __launch_bounds__(256) k_apply_table4(const TabGroup *__restrict
                                                       const double2 *__restrict__ in, double2 *__restrict__ out,
                                                       unsigned nblk, double *__restrict__ partials,
                                                       const double2 *__restrict__ dtab, unsigned *__restrict__ counter,
-                                                      double *__restrict__ result) {
+                                                      double *__restrict__ result, int slow_bits) {
     constexpr int R = 1 << RL;                    // outputs per thread: i0 | (r << 8), r < R
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[8];
@@ -733,7 +733,18 @@ __global__ void __launch_bounds__(256) k_apply_table4(const TabGroup *__restrict
     const uint4 *Cl = dst + ng4;
     const double2 *V = reinterpret_cast<const double2 *>(dst + ng4 + nc4);
     double er = 0.0, ei = 0.0;
-    for (unsigned blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    // Traversal order (states larger than L2): the CTAs that are resident at the same time work on blocks that differ in
+    // the TOP index bits, and the few remaining (slow) bits just above the block advance in Gray-code order.  The window of
+    // amplitudes being read at any moment then spans all high bits -- the partners i ^ x of every group whose x-mask
+    // avoids the slow bits are inside it (L2 hits instead of DRAM gathers) -- and consecutive windows differ in ONE slow
+    // bit, so the partner window of that bit is the one that was just streamed.  slow_bits = 0: linear order.
+    const unsigned fast_mask = slow_bits ? ((nblk >> slow_bits) - 1u) : 0xffffffffu;
+    for (unsigned q = blockIdx.x; q < nblk; q += gridDim.x) {
+        unsigned blk = q;
+        if (slow_bits) {
+            const unsigned hi = q >> (31 - __clz(nblk >> slow_bits));       // q / (nblk >> slow_bits)
+            blk = ((q & fast_mask) << slow_bits) | (hi ^ (hi >> 1));
+        }
         const IDX i0 = ((IDX)blk << (8 + RL)) | (IDX)threadIdx.x;
         double ar[R], ai[R];
 #pragma unroll
@@ -1493,12 +1504,17 @@ void launch_apply_table(cudaStream_t s, int sm, const fh_table *tab, const doubl
         const int rl = tab->n >= 22 ? 3 : 2;          // 8 outputs per thread once there is parallelism to spare
         const unsigned nblk = (unsigned)(dim >> (8 + rl));
         grid = nblk < (unsigned)(sm * 8) ? (int)nblk : sm * 8;
+        // windows of 2^21 amplitudes (32 MiB of input) once the state no longer fits L2
+        int slow_bits = 0;
+        if (tab->n >= 23) slow_bits = tab->n - 21;
+        if (const char *env = getenv("FHSIM_K2_SLOW_BITS")) slow_bits = atoi(env);      // tuning / tests (read per call)
+        if (slow_bits < 0 || (1u << slow_bits) >= nblk) slow_bits = 0;
 #define LAUNCH_TAB4(I, R, M, RLV)                                                                                   \
     do {                                                                                                            \
         ++g_fh_launch_count;                                                                                        \
         k_apply_table4<I, R, M, RLV><<<grid, 256, smem, s>>>(tab->d_groups, ngroups, tab->d_classes, nclasses,      \
                                                              tab->d_vals, nvals, in, out, nblk, d_partials,         \
-                                                             tab->d_diag, tab->ctx->d_counter, d_result);           \
+                                                             tab->d_diag, tab->ctx->d_counter, d_result, slow_bits); \
     } while (0)
 #define LAUNCH_TAB4_M(I, R, RLV)                                                                                    \
     do {                                                                                                            \

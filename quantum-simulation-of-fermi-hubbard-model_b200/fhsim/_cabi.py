@@ -87,6 +87,26 @@ _SPECIAL = {"fh_version": ([], C.c_int), "fh_last_error": ([], C.c_char_p)}
 
 _lib = None
 
+# Interpreter shutdown: module globals and the objects they hold are torn down in no particular order, so a table or a
+# state can outlive the context its native handle points to (fh_*_free dereferences the context -> use after free).  Once
+# the interpreter is exiting, __del__ methods therefore leave the native handles alone; the driver reclaims device memory
+# when the process ends.  Explicit close() calls keep working.
+import atexit as _atexit
+
+_shutting_down = False
+
+
+def _mark_shutdown():
+    global _shutting_down
+    _shutting_down = True
+
+
+_atexit.register(_mark_shutdown)
+
+
+def alive() -> bool:
+    return not _shutting_down
+
 
 class FhsimError(RuntimeError):
     pass

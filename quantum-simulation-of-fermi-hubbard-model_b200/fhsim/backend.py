@@ -48,7 +48,8 @@ class Context:
 
     def __del__(self):
         try:
-            self.close()
+            if _cabi.alive():
+                self.close()
         except Exception:
             pass
 
@@ -132,7 +133,8 @@ class State:
 
     def __del__(self):
         try:
-            self.close()
+            if _cabi.alive():
+                self.close()
         except Exception:
             pass
 
@@ -171,7 +173,8 @@ class DeviceTable:
 
     def __del__(self):
         try:
-            self.close()
+            if _cabi.alive():
+                self.close()
         except Exception:
             pass
 
@@ -237,7 +240,8 @@ class DevicePool:
 
     def __del__(self):
         try:
-            self.close()
+            if _cabi.alive():
+                self.close()
         except Exception:
             pass
 
@@ -331,6 +335,7 @@ class DevicePauliTable:
 
     def __del__(self):
         try:
-            self.close()
+            if _cabi.alive():
+                self.close()
         except Exception:
             pass

@@ -529,7 +529,8 @@ class DeviceProgram:
 
     def __del__(self):
         try:
-            self.close()
+            if _cabi.alive():
+                self.close()
         except Exception:
             pass
 

@@ -738,3 +738,24 @@ def test_register_fused_runs_equal_the_op_by_op_tile_kernel(ctx, monkeypatch):
     assert np.abs(st2.numpy() - ref).max() < 1e-13
     fused.run(st2, th, dagger=True)
     assert np.abs(st2.numpy() - psi0).max() < AMP_TOL
+
+
+def test_apply_table_window_traversal_order_is_a_pure_reordering(ctx, monkeypatch):
+    """K2 above L2 size walks the index space in windows (top bits fast, Gray-coded slow bits, kernels.cu): forced on at 22
+    qubits it must give the same H|psi> bit for bit (every output is computed by the same thread arithmetic) and the same
+    energy to rounding (the per-CTA partial sums collect different blocks)."""
+    n, h_tab, _, _, _, o_h, _ = lattice(3, 3, 6.0)
+    n = 22
+    h22 = PauliTable.from_operator(fermi_hubbard(1, 11, 1.0, 4.0), n)
+    psi = rand_state(n, 77)
+    tab = DeviceTable(ctx, h22)
+    st, out0, out1 = State.from_numpy(ctx, psi), State(ctx, n), State(ctx, n)
+    monkeypatch.setenv("FHSIM_K2_SLOW_BITS", "0")
+    e0 = tab.apply(st, out0)
+    monkeypatch.setenv("FHSIM_K2_SLOW_BITS", "4")
+    e1 = tab.apply(st, out1)
+    monkeypatch.delenv("FHSIM_K2_SLOW_BITS", raising=False)
+    assert np.array_equal(out0.numpy(), out1.numpy())
+    assert abs(e0 - e1) < 1e-11
+    want = sv.apply_table(psi, h22.as_dict(), n)
+    assert np.abs(out1.numpy() - want).max() < AMP_TOL
