@@ -1504,9 +1504,10 @@ void launch_apply_table(cudaStream_t s, int sm, const fh_table *tab, const doubl
         const int rl = tab->n >= 22 ? 3 : 2;          // 8 outputs per thread once there is parallelism to spare
         const unsigned nblk = (unsigned)(dim >> (8 + rl));
         grid = nblk < (unsigned)(sm * 8) ? (int)nblk : sm * 8;
-        // windows of 2^21 amplitudes (32 MiB of input) once the state no longer fits L2
+        // Window traversal (see the kernel): measured on the 3x4 lattice it moves K2 by -4 % (tools/run_k2.py) to +17 %
+        // (bench.py hbm_regime) -- K2 is bound by its instruction stream, not by the DRAM gathers -- so the linear order
+        // stays the default and the windows are opt-in: FHSIM_K2_SLOW_BITS=n-21 gives 32-MiB windows
         int slow_bits = 0;
-        if (tab->n >= 23) slow_bits = tab->n - 21;
         if (const char *env = getenv("FHSIM_K2_SLOW_BITS")) slow_bits = atoi(env);      // tuning / tests (read per call)
         if (slow_bits < 0 || (1u << slow_bits) >= nblk) slow_bits = 0;
 #define LAUNCH_TAB4(I, R, M, RLV)                                                                                   \

@@ -382,6 +382,7 @@ static void build_tile_records(fh_program *p) {
                         const unsigned reps = (npairs + (unsigned)threads - 1u) / (unsigned)threads;
                         r.term_off = (int)(ptab.size() - tab_start);
                         r.reps = (int)reps;
+                        r.run_pad[0] = (npairs == reps * (unsigned)threads) ? 1 : 0;      // table without invalid entries
                         r.nterms = (int)slot(sub.xlocal);
                         for (unsigned k = 0; k < reps * (unsigned)threads; ++k) {
                             unsigned short word = 0;

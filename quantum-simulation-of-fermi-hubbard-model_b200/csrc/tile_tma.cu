@@ -244,6 +244,7 @@ struct OpHdr {
     int type, reps, off;                      // record type, table entries per thread, first table entry (or first term)
     int run_len;                              // >= 2: first record of a register-fused run
     unsigned run_bits;
+    bool full4;                               // no invalid table entry, entries per thread a multiple of 4, type 3 or 6
     double2 m0, m1, m2, m3;                   // 2x2 block
 };
 
@@ -260,6 +261,8 @@ __device__ __forceinline__ void load_hdr(const TileRec *rec, OpHdr &h) {
     const uint2 q9 = *reinterpret_cast<const uint2 *>(&rec->run_len);
     h.run_len = (int)q9.x;
     h.run_bits = q9.y;
+    // pairs of the op in one tile = 2^T >> nlfix = reps * threads exactly  <=>  no invalid entry
+    h.full4 = (h.reps & 3) == 0 && h.reps > 0 && (h.type == 3 || h.type == 6) && rec->run_pad[0] != 0;
     const double2 *mp = reinterpret_cast<const double2 *>(rec->m);
     h.m0 = mp[0];
     h.m1 = mp[1];
@@ -297,18 +300,22 @@ __device__ __forceinline__ void pair_math(const OpHdr &h, unsigned sbit, double2
 // All pairs of one op that belong to this thread, four at a time: four table entries, then eight independent
 // shared-memory loads in flight, then the arithmetic, then the stores (a CTA is only four warps, so the per-op overhead
 // -- header, barrier -- is paid by four warps and the latency is hidden by the four independent pairs of each thread).
-#define PAIR_UNROLL 4
+#ifndef PAIR_UNROLL
+#define PAIR_UNROLL 1
+#endif
 // FH_OPLOOP_VARIANT (tools/probe_timeline.py only): 0 full op loop; 1 no arithmetic; 2 no amplitude loads / stores either;
 // 3 no table loads either (header + barrier); 4 barrier only.  Strips the op loop piece by piece to see where the cycles go.
 #ifndef FH_OPLOOP_VARIANT
 #define FH_OPLOOP_VARIANT 0
 #endif
 template <int TYPE>
-__device__ __forceinline__ void pair_block(double2 *buf, const OpHdr &h, const unsigned short *tp, int nthr, unsigned sb) {
+__device__ __forceinline__ void pair_block(double2 *buf, const OpHdr &h, const unsigned short *tp, int nthr, unsigned sb,
+                                           unsigned efirst) {
     for (int rep = 0; rep < h.reps; rep += PAIR_UNROLL) {
         unsigned e[PAIR_UNROLL];
 #pragma unroll
-        for (int u = 0; u < PAIR_UNROLL; ++u) e[u] = (rep + u < h.reps) ? (unsigned)tp[(rep + u) * nthr] : 0u;
+        for (int u = 0; u < PAIR_UNROLL; ++u)
+            e[u] = (rep + u == 0) ? efirst : ((rep + u < h.reps) ? (unsigned)tp[(rep + u) * nthr] : 0u);
         double2 a[PAIR_UNROLL], b[PAIR_UNROLL];
 #if FH_OPLOOP_VARIANT >= 2
         if (e[0] == 0xffffffffu) buf[0] = make_double2(0.0, 0.0);          // keep the table loads alive
@@ -337,29 +344,63 @@ __device__ __forceinline__ void pair_block(double2 *buf, const OpHdr &h, const u
     }
 }
 
+// The same for ops whose table has no invalid entry and a multiple of four entries per thread (every Givens of a 2^11
+// tile on a 128-thread CTA): no predicates, so the four pairs of a thread form one straight-line block -- four table
+// entries, eight shared-memory loads in flight, then the arithmetic of four independent pairs, then eight stores.
+template <int TYPE>
+__device__ __forceinline__ void pair_block_full4(double2 *buf, const OpHdr &h, const unsigned short *tp, int nthr, unsigned sb,
+                                                 unsigned efirst) {
+    for (int rep = 0; rep < h.reps; rep += 4) {
+        const unsigned e0 = rep == 0 ? efirst : (unsigned)tp[rep * nthr], e1 = tp[(rep + 1) * nthr], e2 = tp[(rep + 2) * nthr], e3 = tp[(rep + 3) * nthr];
+        const unsigned s0 = e0 & 0x1fffu, s1 = e1 & 0x1fffu, s2 = e2 & 0x1fffu, s3 = e3 & 0x1fffu;
+        double2 a0 = buf[s0], b0 = buf[s0 ^ h.xs], a1 = buf[s1], b1 = buf[s1 ^ h.xs];
+        double2 a2 = buf[s2], b2 = buf[s2 ^ h.xs], a3 = buf[s3], b3 = buf[s3 ^ h.xs];
+        pair_math<TYPE>(h, (((e0 >> 13) ^ sb) & 1u) << 31, a0, b0);
+        pair_math<TYPE>(h, (((e1 >> 13) ^ sb) & 1u) << 31, a1, b1);
+        pair_math<TYPE>(h, (((e2 >> 13) ^ sb) & 1u) << 31, a2, b2);
+        pair_math<TYPE>(h, (((e3 >> 13) ^ sb) & 1u) << 31, a3, b3);
+        buf[s0] = a0;
+        buf[s0 ^ h.xs] = b0;
+        buf[s1] = a1;
+        buf[s1 ^ h.xs] = b1;
+        buf[s2] = a2;
+        buf[s2 ^ h.xs] = b2;
+        buf[s3] = a3;
+        buf[s3 ^ h.xs] = b3;
+    }
+}
+
 // diagonal op on one tile: exp(-i sum_m angle_m sgn_m(index)).  Terms whose in-tile z bits sit entirely in local bits
-// 0..5 (or entirely in 6..) are folded into two phase tables built once per (op, tile) as PRODUCTS of the terms' unit
-// phases (cos, sin precomputed on the host: no sincos here); the terms straddling both halves come first in the op's
-// term list (rec->reps of them, sorted by the host) and are evaluated per amplitude from the tile-local z-mask.
+// 0..5 (or entirely in 6..) are folded into two phase tables built once per (op, tile): 2^min(T,6) + 2^(T-6) entries, each
+// the sincos of a signed angle sum; the terms straddling both halves come first in the op's term list (rec->reps of them,
+// sorted by the host) and are evaluated per amplitude from the tile-local z-mask.
 template <bool SWZ>
 __device__ __forceinline__ void apply_diag(double2 *buf, double2 *ph, const TileRec *rec, const TileTerm *tterm,
                                            const TileLaunch &tl, int T, unsigned base, unsigned lomask_g, unsigned himask_g) {
     const TileTerm *dt = tterm + rec->term_off;
     const int cnt = rec->nterms, nstr = rec->reps;
     const unsigned L = 1u << T;
-    for (unsigned v = threadIdx.x; v < 192u; v += blockDim.x) {
-        const bool lo = v < 64u;
-        const unsigned gl = base | (lo ? tile_scatter(tl, T, v, 0, 6) : tile_scatter(tl, T, v - 64u, 6, TILE_BITS_CAP));
-        double2 f = make_double2(1.0, 0.0);
-        for (int m = nstr; m < cnt; ++m) {
-            const unsigned z = (unsigned)dt[m].z;
-            const bool in_lo = (z & himask_g) == 0u;          // no bit in the high half (includes terms with no in-tile bit)
-            if (lo == in_lo) {
-                const double sn = (__popc(gl & z) & 1) ? dt[m].s : -dt[m].s;
-                f = cmul(f, make_double2(dt[m].c, sn));
-            }
+    const unsigned nlo = T < 6 ? L : 64u, nhi = T > 6 ? (L >> 6) : 1u;      // entries of the two phase tables
+    for (unsigned v = threadIdx.x; v < nlo + nhi; v += blockDim.x) {
+        const bool lo = v < nlo;
+        const unsigned gl = base | (lo ? tile_scatter(tl, T, v, 0, 6) : tile_scatter(tl, T, v - nlo, 6, TILE_BITS_CAP));
+        // two partial sums of the signed angles (independent add chains), one sincos per entry
+        double t0 = 0.0, t1 = 0.0;
+        int m = nstr;
+        for (; m + 1 < cnt; m += 2) {
+            const unsigned z0 = (unsigned)dt[m].z, z1 = (unsigned)dt[m + 1].z;
+            const double a0 = (__popc(gl & z0) & 1) ? -dt[m].angle : dt[m].angle;
+            const double a1 = (__popc(gl & z1) & 1) ? -dt[m + 1].angle : dt[m + 1].angle;
+            if (lo == ((z0 & himask_g) == 0u)) t0 += a0;
+            if (lo == ((z1 & himask_g) == 0u)) t1 += a1;
         }
-        ph[v] = f;
+        if (m < cnt) {
+            const unsigned z0 = (unsigned)dt[m].z;
+            if (lo == ((z0 & himask_g) == 0u)) t0 += (__popc(gl & z0) & 1) ? -dt[m].angle : dt[m].angle;
+        }
+        double sn, cs;
+        sincos(t0 + t1, &sn, &cs);
+        ph[lo ? v : 64u + (v - nlo)] = make_double2(cs, -sn);
     }
     __syncthreads();
     for (unsigned l = threadIdx.x; l < L; l += blockDim.x) {
@@ -452,6 +493,8 @@ __device__ __forceinline__ void tile_ops(double2 *buf, double2 *ph, const TileRe
     OpHdr h;
     load_hdr(&rec[0], h);
     const int nthr = (int)blockDim.x;
+    // first table entry of this thread for the current op: fetched together with the header, i.e. before the barrier
+    unsigned efirst = (h.type != 2 && h.reps > 0) ? (unsigned)ptab[h.off + threadIdx.x] : 0u;
     int sidx = 0, mark = 0;
     while (sidx < nsub) {
         if (mark < 40) TMA_TLMARK(4 + mark);
@@ -459,15 +502,21 @@ __device__ __forceinline__ void tile_ops(double2 *buf, double2 *ph, const TileRe
         int step = 1;
         if (h.type != 2) {
 #if FH_OPLOOP_VARIANT < 3
+#ifdef FH_TILE_RUNS
             if (h.run_len >= 2) {
                 fused_run<SWZ>(buf, &rec[sidx], h.run_len, h.run_bits, T, base);
                 step = h.run_len;
-            } else if ((base & h.fixmask_out) == h.fixval_out) {
+            } else
+#endif
+            if ((base & h.fixmask_out) == h.fixval_out) {
                 const unsigned sb = (unsigned)__popc(base & h.zeta);
                 const unsigned short *tp = ptab + h.off + threadIdx.x;
-                if (h.type == 3) pair_block<3>(buf, h, tp, nthr, sb);
-                else if (h.type == 6) pair_block<6>(buf, h, tp, nthr, sb);
-                else pair_block<1>(buf, h, tp, nthr, sb);
+                if (h.full4) {
+                    if (h.type == 3) pair_block_full4<3>(buf, h, tp, nthr, sb, efirst);
+                    else pair_block_full4<6>(buf, h, tp, nthr, sb, efirst);
+                } else if (h.type == 3) pair_block<3>(buf, h, tp, nthr, sb, efirst);
+                else if (h.type == 6) pair_block<6>(buf, h, tp, nthr, sb, efirst);
+                else pair_block<1>(buf, h, tp, nthr, sb, efirst);
             }
 #endif
         } else {
@@ -477,6 +526,7 @@ __device__ __forceinline__ void tile_ops(double2 *buf, double2 *ph, const TileRe
         if (sidx < nsub) {
 #if FH_OPLOOP_VARIANT < 4
             load_hdr(&rec[sidx], h);
+            efirst = (h.type != 2 && h.reps > 0) ? (unsigned)ptab[h.off + threadIdx.x] : 0u;
 #endif
             __syncthreads();
         }

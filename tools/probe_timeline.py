@@ -19,14 +19,16 @@ R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(R, "quantum-simulation-of-fermi-hubbard-model_b200")
 CSRC = os.path.join(PKG, "csrc")
 VARIANT = os.environ.get("FH_OPLOOP_VARIANT", "0")         # see tile_tma.cu: strips the op loop piece by piece
-OUT = os.path.join(CSRC, "build_timeline", f"libfhsim_timeline_v{VARIANT}.so")
+EXTRA = os.environ.get("FH_PROBE_DEFS", "").split()      # extra -D flags, e.g. FH_PROBE_DEFS="-DPAIR_UNROLL=2"
+TAG = "".join(c if c.isalnum() else "_" for c in "".join(EXTRA))
+OUT = os.path.join(CSRC, "build_timeline", f"libfhsim_timeline_v{VARIANT}{TAG}.so")
 
 
 def build():
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     srcs = ["kernels.cu", "tile_tma.cu", "api.cu", "program.cu", "lanczos.cu", "comm.cu", "dress.cu"]
     cmd = ["nvcc", "-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
-           "-DFH_TILE_TIMELINE", f"-DFH_OPLOOP_VARIANT={VARIANT}", "-shared", "-cudart", "static", "-o", OUT] + [os.path.join(CSRC, f) for f in srcs]
+           "-DFH_TILE_TIMELINE", f"-DFH_OPLOOP_VARIANT={VARIANT}", *EXTRA, "-shared", "-cudart", "static", "-o", OUT] + [os.path.join(CSRC, f) for f in srcs]
     subprocess.check_call(cmd)
 
 
