@@ -152,6 +152,17 @@ int fh_program_evaluate(fh_program *prog, uint64_t basis_index, const double *th
                         int n_overlaps, fh_state *const *targets, double *overlaps,
                         fh_state *state_out);
 
+/* Which path the most recent fh_program_evaluate call took.  Energy / screening evaluations (grads == NULL, one table, no
+ * overlaps, no state_out) of circuits that conserve N_up and N_dn (every ADAPT / HVA circuit: models/adapt_vqe.py:325-361,
+ * hva.py:273-303) run on the SECTOR-COMPRESSED state (3x3: 15 876 amplitudes instead of 2^18) resident in the distributed
+ * shared memory of one thread-block cluster: one cluster kernel (ansatz, W, H, W^dagger) + one pool kernel instead of ~19
+ * launches.  Chosen automatically when every op, the observable and the pool map the sector of |basis_index> to itself and
+ * psi + lambda fit one cluster; FHSIM_NO_SECTOR=1 forces the full-space path.  active: 1 if the last call took it;
+ * cluster_size: CTAs of the cluster; sector_dim: amplitudes; n_ops: steps of the cluster kernel (ops, transposes,
+ * checkpoint, H, store); n_transposes / n_remote_ops: layout changes / ops that exchange amplitudes between CTAs. */
+int fh_program_sector_info(const fh_program *prog, int *active, int *cluster_size, uint64_t *sector_dim, int *n_ops,
+                           int *n_transposes, int *n_remote_ops);
+
 /* measurement: bytes one fh_program_evaluate call copies host->device (the theta-dependent op payload, one pinned
  * arena) and at most device->host (scalars + gradient segments + pool outputs) */
 int fh_program_payload_bytes(const fh_program *prog, size_t *h2d_bytes, size_t *d2h_bytes);

@@ -8,6 +8,7 @@
 #include <new>
 
 #include "common.cuh"
+#include "sector_eval.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -556,6 +557,7 @@ extern "C" int fh_table_upload(fh_ctx *ctx, int n_qubits, int n_terms, const uin
         }
         tab->groups.push_back(grp);
         tab->terms.insert(tab->terms.end(), bt.begin(), bt.end());
+        if (gx == 0) tab->diag_terms = bt;
     }
     tab->n_groups = (int)tab->groups.size();
     FH_CUDA(cudaSetDevice(ctx->device));
@@ -600,6 +602,7 @@ extern "C" int fh_table_free(fh_table *tab) {
     cudaFree(tab->d_classes);
     cudaFree(tab->d_vals);
     cudaFree(tab->d_diag);
+    fh_sector_forget_table(tab->uid);
     delete tab;
     return FH_OK;
 }
@@ -852,6 +855,7 @@ extern "C" int fh_pool_free(fh_pool *pool) {
     cudaFree(pool->d_partials);
     cudaFree(pool->d_out);
     cudaFreeHost(pool->h_out);
+    fh_sector_forget_pool(pool->uid);
     delete pool;
     return FH_OK;
 }

@@ -250,6 +250,7 @@ struct fh_table {
     std::vector<TabClass> classes;
     std::vector<double2> vals;
     std::vector<TabTerm> terms;     // host copy in table order (grouped by x-mask)
+    std::vector<TabTerm> diag_terms;      // the x = 0 terms (the diagonal of the observable), for the sector path
 };
 
 struct fh_pool {

@@ -7,6 +7,7 @@
 #include <new>
 
 #include "common.cuh"
+#include "sector_eval.cuh"
 
 int fh_fill_pair(PairOp *op, int n, u64 x, u64 fixmask, u64 fixval, u64 zeta, const double m[8]);
 int fh_enqueue_apply_table(const fh_table *tab, const double2 *in, double2 *out, int result_slot);
@@ -44,6 +45,7 @@ struct EvalKey {
     const void *pool;
     int pool_pos, pool_first, pool_count;
     const void *state_out;
+    int sector, pad_sector;      // 1: the sector-resident path (sector_eval.cu) was planned for this evaluation
     // unique ids of the same handles: a freed handle whose address is reused by a new one gets a new id, so the graph
     // (which bakes in the device pointers behind the handles) is re-captured instead of replayed on freed memory
     u64 table_uid[FH_MAX_RESULT_TABLES], target_uid[FH_MAX_OVERLAPS], pool_uid, state_out_uid;
@@ -106,6 +108,11 @@ struct fh_program {
     std::vector<int> seg_param;       // per processed segment: parameter index
     std::vector<double> seg_scale;    // per processed segment: 2*gscale
     int n_segments = 0;
+    // sector-resident evaluation (sector_eval.cu): ops in execution order, first flat op of every item, the plan
+    std::vector<SecFlatOp> flat;
+    std::vector<int> item_flat_first;
+    fh_sector_plan *sec = nullptr;
+    bool last_sector = false;
     // measurement
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0.0;
@@ -144,6 +151,8 @@ extern "C" int fh_program_destroy(fh_program *p) {
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
     drop_graph(p);
+    fh_sector_plan_free(p->sec);
+    p->sec = nullptr;
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     cudaFree(p->d_tl_fwd);
@@ -587,6 +596,17 @@ extern "C" int fh_program_finalize(fh_program *p) {
     p->d_gseg = p->d_res + 64;
     p->h_gseg = p->h_res + 64;
     FH_CUDA(cudaStreamSynchronize(ctx->stream));
+    // ops in execution order (tiles expanded) for the sector-resident path
+    for (const Item &it : p->items) {
+        p->item_flat_first.push_back((int)p->flat.size());
+        if (it.type == 3) {
+            const TileOp &t = p->tiles[it.index];
+            for (int s = t.first_sub; s < t.first_sub + t.nsub; ++s) p->flat.push_back({p->subs[s].type, p->subs[s].index});
+        } else {
+            p->flat.push_back({it.type, it.index});
+        }
+    }
+    p->item_flat_first.push_back((int)p->flat.size());
     p->finalized = true;
     return FH_OK;
 }
@@ -871,6 +891,17 @@ static int enqueue_evaluation(fh_program *p, const EvalKey &k, fh_table *const *
     const bool want_grads = k.want_grads != 0;
     const bool want_pool = pool != nullptr;
     const bool need_adjoint = want_grads || want_pool;
+    if (k.sector) {
+        // the whole evaluation on the sector-compressed state inside one cluster (sector_eval.cu): two launches
+        double *d_pool_out_s = p->d_res + 64 + p->res_segs;
+        FH_TRY(enqueue_payload_upload(p, false));
+        FH_TRY(fh_sector_enqueue(p->sec, ctx, k.basis, p->d_pairs, p->d_dterms, p->d_res, pool, k.pool_first, k.pool_count,
+                                 d_pool_out_s));
+        const size_t n_res_s = want_pool ? 64 + (size_t)p->res_segs + (size_t)(k.pool_first + k.pool_count) : 4;
+        FH_CUDA(cudaMemcpyAsync(p->h_res, p->d_res, sizeof(double) * n_res_s, cudaMemcpyDeviceToHost, ctx->stream));
+        p->n_segments = 0;
+        return FH_OK;
+    }
     int first_param = n_items, last_param = -1;
     for (int i = 0; i < n_items; ++i)
         if (item_has_param(p, p->items[i])) {
@@ -1008,6 +1039,17 @@ extern "C" int fh_program_evaluate(fh_program *p, uint64_t basis_index, const do
     key.pool_first = pool ? pool_first : 0;
     key.pool_count = pool ? pool_count : 0;
     key.state_out = state_out;
+    // sector-resident path: energy / screening evaluations of number-conserving circuits whose sector fits one cluster
+    p->last_sector = false;
+    // (measured faster than the full-space path up to ~2 000 amplitudes, see sector_eval.cu; FHSIM_SECTOR=1 lifts the limit)
+    if (!grads && n_overlaps == 0 && !state_out && n_tables == 1 && !(p->n & 1) && !getenv("FHSIM_NO_SECTOR")) {
+        const int pool_flat = pool ? p->item_flat_first[pool_pos] : -1;
+        const u64 max_dim = getenv("FHSIM_SECTOR") ? 0ull : 2048ull;
+        FH_TRY(fh_sector_prepare(&p->sec, ctx, p->n, basis_index, p->pairs, p->diagops, p->dterms, p->flat, pool_flat, tables[0],
+                                 pool, max_dim));
+        key.sector = fh_sector_plan_eligible(p->sec) ? 1 : 0;
+        p->last_sector = key.sector != 0;
+    }
 
     static const bool no_graph = getenv("FHSIM_NO_GRAPH") != nullptr;
     if (!p->ev0) {
@@ -1072,6 +1114,16 @@ extern "C" int fh_program_payload_bytes(const fh_program *p, size_t *h2d_bytes, 
     FH_REQUIRE(p && p->finalized, "fh_program_payload_bytes: program missing or not finalized");
     if (h2d_bytes) *h2d_bytes = p->arena_bytes;
     if (d2h_bytes) *d2h_bytes = sizeof(double) * (64 + (size_t)p->res_segs + (size_t)p->res_pool_cap);
+    return FH_OK;
+}
+
+extern "C" int fh_program_sector_info(const fh_program *p, int *active, int *cluster_size, uint64_t *sector_dim, int *n_ops,
+                                      int *n_transposes, int *n_remote_ops) {
+    FH_REQUIRE(p, "fh_program_sector_info: program is NULL");
+    if (active) *active = p->last_sector ? 1 : 0;
+    u64 dim = 0;
+    fh_sector_plan_describe(p->last_sector ? p->sec : nullptr, cluster_size, &dim, n_ops, n_transposes, n_remote_ops, nullptr);
+    if (sector_dim) *sector_dim = dim;
     return FH_OK;
 }
 

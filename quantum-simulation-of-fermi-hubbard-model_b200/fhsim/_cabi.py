@@ -64,6 +64,8 @@ SIGNATURES = {
                             C.c_int, _f64p, C.c_int, _vpp, _f64p, _vp],
     "fh_program_payload_bytes": [_vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)],
     "fh_program_last_stats": [_vp, _f64p, C.POINTER(C.c_int)],
+    "fh_program_sector_info": [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_int),
+                               C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "fh_program_time_items": [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _f64p],
     "fh_lanczos": [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint64, _f64p, _vpp, C.POINTER(C.c_int)],
     "fh_ptable_upload": [_vp, C.c_int, C.c_int, _u64p, _u64p, _f64p, _f64p, _vpp],

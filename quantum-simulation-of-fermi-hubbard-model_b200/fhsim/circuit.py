@@ -540,6 +540,17 @@ class DeviceProgram:
         _cabi.check(_cabi.lib().fh_program_last_stats(self._h, _cabi.C.byref(ms), _cabi.C.byref(nl)))
         return ms.value, nl.value
 
+    def sector_info(self):
+        """Path of the most recent ``evaluate``: dict(active, cluster, dim, ops, transposes, remote_ops); ``active`` is True when
+        the call ran on the sector-compressed state resident in one thread-block cluster (csrc/sector_eval.cu)."""
+        C = _cabi.C
+        act, cl, nops, ntr, nrem = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        dim = C.c_uint64()
+        _cabi.check(_cabi.lib().fh_program_sector_info(self._h, C.byref(act), C.byref(cl), C.byref(dim), C.byref(nops),
+                                                       C.byref(ntr), C.byref(nrem)))
+        return dict(active=bool(act.value), cluster=cl.value, dim=int(dim.value), ops=nops.value, transposes=ntr.value,
+                    remote_ops=nrem.value)
+
     def payload_bytes(self):
         """(host->device, device->host) bytes of one ``evaluate`` call."""
         a, b = _cabi.C.c_size_t(), _cabi.C.c_size_t()

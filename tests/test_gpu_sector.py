@@ -1,0 +1,190 @@
+"""Sector-resident evaluation (csrc/sector_eval.cu: the whole screening on the (N_up, N_dn)-compressed state inside one
+thread-block cluster) against the oracle and against the full-space path of the same program, through the C-ABI.
+Reference semantics: ADAPT.circuit + select_operator, models/adapt_vqe.py:297-361."""
+import numpy as np
+import pytest
+
+from fhsim.backend import Context, DevicePool, DeviceTable
+from fhsim.circuit import Circuit, DiagOpSpec
+from fhsim.symbolic import fermi_hubbard, givens_decomposition_square, jordan_wigner
+from fhsim.tables import GeneratorPlan, PauliTable
+from operators.fourier import fourier_transform_matrix
+from operators.pool import hubbard_interaction_pool_simplified
+from oracle import pauli, statevector as sv
+
+pytestmark = pytest.mark.gpu
+
+E_TOL, G_TOL = 1e-10, 1e-9
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return Context(0)
+
+
+def lattice(nx, ny, u):
+    n = 2 * nx * ny
+    h_tab = PauliTable.from_operator(fermi_hubbard(nx, ny, 1.0, u), n)
+    pool_ops = [jordan_wigner(g) for g in hubbard_interaction_pool_simplified(nx, ny)]
+    dec, diag = givens_decomposition_square(fourier_transform_matrix(nx, ny))
+    o_h = pauli.compress(pauli.jw_table(pauli.hubbard_fermion_terms(nx, ny, 1.0, u), n))
+    o_pool = [pauli.jw_table(op, n) for op in pauli.pool_fermion_terms(nx, ny)]
+    return n, h_tab, pool_ops, dec, diag, o_h, o_pool
+
+
+@pytest.mark.parametrize("lat,u,up,dn", [((2, 2), 4.0, 2, 2), ((2, 3), 4.0, 3, 3), ((2, 3), 4.0, 4, 2), ((3, 3), 6.0, 5, 4)])
+def test_sector_screening_vs_oracle(ctx, lat, u, up, dn, monkeypatch):
+    """Energy and all pool gradients of an ADAPT ansatz state: oracle (closed form, float64) vs the cluster kernel.  W is the
+    separable network (same unitary as the reference's, tests/test_circuit_host.py): the reference's own Givens network
+    rotates between the up and down orbital of a site, so its intermediate states leave the (N_up, N_dn) sector (next test)."""
+    monkeypatch.setenv("FHSIM_SECTOR", "1")
+    n, h_tab, pool_ops, dec, diag, o_h, o_pool = lattice(*lat, u)
+    rng = np.random.default_rng(7)
+    occ_up, occ_dn, _ = pauli.k_space_occupation(*lat, 1.0, up, dn)
+    picks = list(rng.choice(len(pool_ops), size=6, replace=False))
+    th = rng.uniform(-0.4, 0.4, len(picks))
+    plans = [GeneratorPlan(g, n) for g in pool_ops]
+    circ = Circuit(n, len(picks))
+    for p, k in enumerate(picks):
+        circ.generator(plans[k], param=p)
+    circ.marker("ansatz_end")
+    circ.basis_change_separable(*lat)
+    prog = circ.compile(ctx)
+    dtab = DeviceTable(ctx, h_tab)
+    dpool = DevicePool(ctx, plans, n)
+    basis = sum(1 << (n - 1 - q) for q in occ_up + occ_dn)
+    m = prog.markers["ansatz_end"]
+    res = prog.evaluate(basis, th, [dtab], pool=dpool, pool_pos=m)
+    info = prog.sector_info()
+    assert info["active"] and info["cluster"] >= 2
+    assert prog.last_stats()[1] == 2                  # one cluster kernel + one pool kernel
+    gens = [o_pool[k] for k in picks]
+    psi_k = sv.adapt_state(n, occ_up + occ_dn, gens, th)
+    pg_want, e_want, _ = sv.pool_gradients(psi_k, o_h, o_pool, diag, dec, n)
+    assert abs(res["expvals"][0] - e_want) < E_TOL
+    assert np.abs(res["pool"] - pg_want).max() < G_TOL
+    # energy only, pool at the very start / very end, a sub-range of the pool; graph replay with new parameters
+    e_only = prog.evaluate(basis, th, [dtab])
+    assert prog.sector_info()["active"] and abs(e_only["expvals"][0] - e_want) < E_TOL
+    monkeypatch.setenv("FHSIM_NO_SECTOR", "1")
+    full0 = prog.evaluate(basis, th, [dtab], pool=dpool, pool_pos=0)
+    full_end = prog.evaluate(basis, th, [dtab], pool=dpool, pool_pos=prog.n_items)
+    assert not prog.sector_info()["active"]
+    monkeypatch.delenv("FHSIM_NO_SECTOR")
+    sec0 = prog.evaluate(basis, th, [dtab], pool=dpool, pool_pos=0)
+    sec_end = prog.evaluate(basis, th, [dtab], pool=dpool, pool_pos=prog.n_items)
+    assert prog.sector_info()["active"]
+    assert np.abs(sec0["pool"] - full0["pool"]).max() < 1e-12 and np.abs(sec_end["pool"] - full_end["pool"]).max() < 1e-12
+    lo, cnt = 3, max(1, dpool.n_out // 3)
+    sub = prog.evaluate(basis, th, [dtab], pool=dpool, pool_pos=m, pool_range=(lo, cnt))
+    assert np.abs(sub["pool"] - pg_want[lo:lo + cnt]).max() < G_TOL
+    th2 = th + 0.05
+    res2 = prog.evaluate(basis, th2, [dtab], pool=dpool, pool_pos=m)
+    pg2, e2, _ = sv.pool_gradients(sv.adapt_state(n, occ_up + occ_dn, gens, th2), o_h, o_pool, diag, dec, n)
+    assert abs(res2["expvals"][0] - e2) < E_TOL and np.abs(res2["pool"] - pg2).max() < G_TOL
+    assert np.array_equal(prog.evaluate(basis, th2, [dtab], pool=dpool, pool_pos=m)["pool"], res2["pool"])   # bit-reproducible
+
+
+@pytest.mark.parametrize("seed,up,dn", [(1, 3, 2), (2, 2, 4), (3, 1, 1), (4, 5, 3)])
+def test_sector_random_number_conserving_circuits(ctx, seed, up, dn, monkeypatch):
+    """Random circuits of same-spin Givens rotations (with and without a Jordan-Wigner string), pool generators and diagonal
+    layers with Z, same-species ZZ and up-down ZZ terms, the pool evaluated in the middle: cluster kernel vs full space."""
+    nx, ny = 2, 3
+    n, h_tab, pool_ops, dec, diag, o_h, o_pool = lattice(nx, ny, 3.0)
+    rng = np.random.default_rng(seed)
+    plans = [GeneratorPlan(g, n) for g in pool_ops]
+    n_par = 10
+    circ = Circuit(n, n_par)
+
+    def random_ops(count):
+        for _ in range(count):
+            kind = int(rng.integers(0, 4))
+            par = int(rng.integers(0, n_par))
+            if kind == 0:
+                s = int(rng.integers(0, 2))
+                a, b = (int(v) for v in rng.choice(n // 2, size=2, replace=False))
+                circ.fermionic_single_excitation(float(rng.uniform(-2, 2)), 2 * a + s, 2 * b + s)
+            elif kind == 1:
+                s = int(rng.integers(0, 2))
+                a, b = (int(v) for v in rng.choice(n // 2, size=2, replace=False))
+                circ.single_excitation(float(rng.uniform(-2, 2)), 2 * a + s, 2 * b + s)
+            elif kind == 2:
+                circ.generator(plans[int(rng.integers(0, len(plans)))], param=par)
+            else:
+                zs = [int((1 << int(a)) | (1 << int(b))) for a, b in (rng.choice(n, size=2, replace=False) for _ in range(8))]
+                zs += [1 << int(q) for q in rng.choice(n, size=4, replace=False)]
+                circ.ops.append(DiagOpSpec(zs, [float(v) for v in rng.uniform(-1, 1, len(zs))], par, [(0, z) for z in zs]))
+
+    random_ops(14)
+    circ.marker("mid")
+    random_ops(14)
+    prog = circ.compile(ctx)
+    dtab = DeviceTable(ctx, h_tab)
+    dpool = DevicePool(ctx, plans, n)
+    occ = [2 * int(s) for s in rng.choice(n // 2, size=up, replace=False)] + \
+          [2 * int(s) + 1 for s in rng.choice(n // 2, size=dn, replace=False)]
+    basis = sum(1 << (n - 1 - q) for q in occ)
+    th = rng.uniform(-1, 1, n_par)
+    m = prog.markers["mid"]
+    monkeypatch.setenv("FHSIM_NO_SECTOR", "1")
+    full = prog.evaluate(basis, th, [dtab], pool=dpool, pool_pos=m)
+    assert not prog.sector_info()["active"]
+    monkeypatch.delenv("FHSIM_NO_SECTOR")
+    sec = prog.evaluate(basis, th, [dtab], pool=dpool, pool_pos=m)          # 12 qubits: the default takes the sector path
+    info = prog.sector_info()
+    assert info["active"], info
+    assert abs(sec["expvals"][0] - full["expvals"][0]) < 1e-12
+    assert np.abs(sec["pool"] - full["pool"]).max() < 1e-12
+    assert np.abs(full["pool"]).max() > 1e-3
+
+
+def test_sector_path_is_not_taken_when_it_does_not_apply(ctx, monkeypatch):
+    """Circuits that leave the sector (RX), gradient / state / overlap requests and FHSIM_NO_SECTOR use the full-space path;
+    without FHSIM_SECTOR=1 so does a sector above the size limit (3x3: 15 876 amplitudes)."""
+    n, h_tab, pool_ops, dec, diag, o_h, o_pool = lattice(2, 2, 4.0)
+    plans = [GeneratorPlan(g, n) for g in pool_ops]
+    dtab = DeviceTable(ctx, h_tab)
+    basis = sum(1 << (n - 1 - q) for q in (0, 2, 1, 3))
+    c1 = Circuit(n, 1)
+    c1.generator(plans[0], param=0)
+    c1.rx(0.3, 1)
+    p1 = c1.compile(ctx)
+    p1.evaluate(basis, [0.2], [dtab])
+    assert not p1.sector_info()["active"]
+    c2 = Circuit(n, 1)
+    c2.generator(plans[0], param=0)
+    p2 = c2.compile(ctx)
+    a = p2.evaluate(basis, [0.2], [dtab])
+    assert p2.sector_info()["active"]
+    b = p2.evaluate(basis, [0.2], [dtab], grads=True)
+    assert not p2.sector_info()["active"] and abs(a["expvals"][0] - b["expvals"][0]) < 1e-13
+    monkeypatch.setenv("FHSIM_NO_SECTOR", "1")
+    p2.evaluate(basis, [0.2], [dtab])
+    assert not p2.sector_info()["active"]
+    monkeypatch.delenv("FHSIM_NO_SECTOR")
+    # the reference's W network (adjacent-wire Givens rotations: up <-> down of one site) conserves only N_up + N_dn
+    c4 = Circuit(n, 1)
+    c4.generator(plans[0], param=0)
+    c4.basis_change(diag, list(reversed(dec)))
+    p4 = c4.compile(ctx)
+    e4 = p4.evaluate(basis, [0.2], [dtab])["expvals"][0]
+    assert not p4.sector_info()["active"]
+    c5 = Circuit(n, 1)
+    c5.generator(plans[0], param=0)
+    c5.basis_change_separable(2, 2)
+    p5 = c5.compile(ctx)
+    e5 = p5.evaluate(basis, [0.2], [dtab])["expvals"][0]
+    assert p5.sector_info()["active"] and abs(e4 - e5) < 1e-12
+    n3, h3, pool3, *_ = lattice(3, 3, 6.0)
+    c3 = Circuit(n3, 1)
+    c3.generator(GeneratorPlan(pool3[5], n3), param=0)
+    p3 = c3.compile(ctx)
+    occ_up, occ_dn, _ = pauli.k_space_occupation(3, 3, 1.0, 5, 4)
+    b3 = sum(1 << (n3 - 1 - q) for q in occ_up + occ_dn)
+    d3 = DeviceTable(ctx, h3)
+    e_full = p3.evaluate(b3, [0.1], [d3])["expvals"][0]
+    assert not p3.sector_info()["active"]
+    monkeypatch.setenv("FHSIM_SECTOR", "1")
+    e_sec = p3.evaluate(b3, [0.1], [d3])["expvals"][0]
+    assert p3.sector_info()["active"] and p3.sector_info()["dim"] == 15876
+    assert abs(e_sec - e_full) < 1e-12
