@@ -97,6 +97,11 @@ int fh_table_upload(fh_ctx *ctx, int n_qubits, int n_terms, const uint64_t *x, c
                     const double *coeff_re, const double *coeff_im, fh_table **out);
 int fh_table_free(fh_table *tab);
 int fh_table_info(const fh_table *tab, int *n_terms, int *n_groups);
+/* Number of shared-memory tile passes fh_apply_table uses for this table (0: the gather kernel).  From 22 qubits on, a table
+ * whose x-mask groups are covered by at most 3 sets of 12 index bits (the Hubbard Hamiltonian: the up-orbital bits and the
+ * down-orbital bits) is applied pass by pass from tiles staged in shared memory: 80 B of HBM traffic per amplitude for two
+ * passes instead of one gathered partner per (amplitude, term group).  FHSIM_K2_GATHER=1 forces the gather kernel. */
+int fh_table_tile_passes(const fh_table *tab, int *n_passes);
 /* out <- H in (out may be NULL: expectation only); *e = <in|H|in>.  in and out must differ. */
 int fh_apply_table(const fh_table *tab, const fh_state *in, fh_state *out, double *e_re, double *e_im);
 /* out <- out + H in  (sum of partial Hamiltonians, e.g. one table per qubit layout of a sharded state); *e = <in|H|in> */

@@ -589,6 +589,7 @@ extern "C" int fh_table_upload(fh_ctx *ctx, int n_qubits, int n_terms, const uin
             FH_CUDA(cudaMemcpyAsync(tab->d_vals, tab->vals.data(), sizeof(double2) * tab->vals.size(),
                                     cudaMemcpyHostToDevice, ctx->stream));
         FH_CUDA(cudaStreamSynchronize(ctx->stream));
+        FH_TRY(fh_table_plan_tiles(tab));
     }
     *out = tab;
     return FH_OK;
@@ -602,6 +603,7 @@ extern "C" int fh_table_free(fh_table *tab) {
     cudaFree(tab->d_classes);
     cudaFree(tab->d_vals);
     cudaFree(tab->d_diag);
+    fh_table_tiles_free(tab->tiles);
     fh_sector_forget_table(tab->uid);
     delete tab;
     return FH_OK;

@@ -236,8 +236,10 @@ struct fh_state {
     u64 uid = fh_next_uid();
 };
 
+struct fh_table_tiles;      // table_tile.cu: cover of the x-mask groups by shared-memory tile passes (n >= 22), or NULL
 struct fh_table {
     u64 uid = fh_next_uid();
+    fh_table_tiles *tiles = nullptr;
     fh_ctx *ctx;
     int n;
     int n_terms, n_groups;
@@ -308,6 +310,10 @@ void launch_tile_adjoint(cudaStream_t s, double2 *psi, double2 *lam, const TileL
 // mode 0: expectation only; 1: out = H in; 2: out += H in.   Result (re, im of <in|H|in>) -> d_result[0..1]
 void launch_apply_table(cudaStream_t s, int sm, const fh_table *tab, const double2 *in, double2 *out, int mode,
                         double *d_partials, double *d_result);
+int fh_table_plan_tiles(fh_table *tab);                 // called once at upload (host plan + device descriptors)
+void fh_table_tiles_free(fh_table_tiles *t);
+bool launch_apply_table_tiles(cudaStream_t s, int sm, const fh_table *tab, const double2 *in, double2 *out, int mode,
+                              double *d_partials, double *d_result);
 void launch_pool(cudaStream_t s, const PoolEntry *entries, int first_entry, int n_entries, int chunks, int n,
                  const double2 *psi, const double2 *lam, double *d_partials, const int *entry_ids = nullptr,
                  int e0 = 0, int e1 = 0x7fffffff, int row = 0, int narrow = 0);   // narrow: every pattern pins <= 4 bits

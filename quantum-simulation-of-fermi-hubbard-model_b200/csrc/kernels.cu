@@ -1499,6 +1499,8 @@ void launch_apply_table(cudaStream_t s, int sm, const fh_table *tab, const doubl
     const int use_smem = need <= 40 * 1024;
     const size_t smem = use_smem ? need : 0;
     if (!out) mode = 0;
+    // n >= 22 and a table whose x-mask groups are covered by <= 3 sets of 12 index bits: shared-memory tile passes
+    if (tab->tiles && launch_apply_table_tiles(s, sm, tab, in, out, mode, d_partials, d_result)) return;
     int grid;
     if (tab->n >= 11 && use_smem) {
         const int rl = tab->n >= 22 ? 3 : 2;          // 8 outputs per thread once there is parallelism to spare

@@ -156,6 +156,12 @@ class DeviceTable:
         _cabi.check(_cabi.lib().fh_table_info(self._h, C.byref(nt), C.byref(ng)))
         return {"n_terms": nt.value, "n_groups": ng.value}
 
+    def tile_passes(self) -> int:
+        """Shared-memory tile passes K2 uses for this table (0: the gather kernel); csrc/table_tile.cu."""
+        k = C.c_int()
+        _cabi.check(_cabi.lib().fh_table_tile_passes(self._h, C.byref(k)))
+        return k.value
+
     def apply(self, state: State, out: State | None = None) -> complex:
         """out <- H state (optional); returns <state|H|state>."""
         re, im = C.c_double(), C.c_double()

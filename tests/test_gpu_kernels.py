@@ -759,3 +759,77 @@ def test_apply_table_window_traversal_order_is_a_pure_reordering(ctx, monkeypatc
     assert abs(e0 - e1) < 1e-11
     want = sv.apply_table(psi, h22.as_dict(), n)
     assert np.abs(out1.numpy() - want).max() < AMP_TOL
+
+
+def _coverable_random_table(n, rng, n_sets, complex_coeffs):
+    """A random table whose x-masks lie inside `n_sets` sets of 12 index bits (so K2 takes the tile passes), with several
+    z-masks per x-mask (multi-class groups), z bits inside and outside the sets, and diagonal terms of every chunk shape."""
+    table = {}
+    sets = {1: [sorted(int(b) for b in rng.choice(n, size=12, replace=False))],
+            2: [list(range(1, n, 2)), list(range(0, n, 2))],                    # the two spin species of a Hubbard model
+            3: [list(range(0, 7)), list(range(7, 14)), list(range(14, 21))]}[n_sets]
+    for bits in sets:
+        for _ in range(7):
+            k = int(rng.integers(1, 5))
+            x = sum(1 << b for b in rng.choice(bits, size=k, replace=False))
+            for _ in range(int(rng.integers(1, 4))):
+                z = int(rng.integers(0, 1 << n))
+                table[(int(x), z)] = complex(rng.normal(), rng.normal() if complex_coeffs else 0.0)
+    for z in (0, 1 << 3, (1 << 11) | (1 << 12), (1 << 23) | (1 << 24) if n > 24 else (1 << 5) | (1 << 20), (1 << 2) | (1 << 13) | (1 << (n - 1))):
+        table[(0, int(z))] = complex(rng.normal(), 0.0)
+    if not complex_coeffs:
+        # a real-coefficient table is "all real" for the kernel only if every i^k is real: keep strings with an even number of Y
+        table = {(x, z): v for (x, z), v in table.items() if bin(x & z).count("1") % 2 == 0}
+    return table
+
+
+@pytest.mark.parametrize("n_sets,complex_coeffs,seed", [(1, False, 1), (2, True, 2), (3, True, 3), (2, False, 4)])
+def test_apply_table_tile_passes_vs_oracle_and_gather_kernel(ctx, n_sets, complex_coeffs, seed, monkeypatch):
+    """K2 in shared-memory tile passes (n >= 22, csrc/table_tile.cu): out = H psi, <psi|H|psi> alone, and out += H psi against
+    the oracle and against the gather kernel on the same table."""
+    from fhsim import _cabi
+    monkeypatch.setenv("FHSIM_K2_TILE", "2")            # general tables too (the default takes only uniform real passes)
+    n = 22
+    rng = np.random.default_rng(seed)
+    table = _coverable_random_table(n, rng, n_sets, complex_coeffs)
+    keys = list(table)
+    dt = DeviceTable(ctx, PauliTable(n, [k[0] for k in keys], [k[1] for k in keys], [table[k] for k in keys]))
+    assert 1 <= dt.tile_passes() <= 3
+    psi = rand_state(n, 100 + seed)
+    st, out = State.from_numpy(ctx, psi), State(ctx, n)
+    want = sv.apply_table(psi, table, n)
+    e = dt.apply(st, out)
+    got = out.numpy()
+    assert np.abs(got - want).max() < 1e-12
+    assert abs(e - np.vdot(psi, want)) < E_TOL
+    assert abs(dt.apply(st) - np.vdot(psi, want)) < E_TOL                   # expectation only
+    re, im = _cabi.C.c_double(), _cabi.C.c_double()
+    _cabi.check(_cabi.lib().fh_apply_table_accumulate(dt._h, st._h, out._h, _cabi.C.byref(re), _cabi.C.byref(im)))
+    assert np.abs(out.numpy() - 2 * want).max() < 1e-12                      # out += H psi
+    assert abs(complex(re.value, im.value) - np.vdot(psi, want)) < E_TOL
+    monkeypatch.setenv("FHSIM_K2_GATHER", "1")
+    e_g = dt.apply(st, out)
+    assert np.abs(out.numpy() - got).max() < 1e-12 and abs(e_g - e) < 1e-11
+    assert dt.apply(st, out) == e_g                                           # bit-reproducible
+    monkeypatch.delenv("FHSIM_K2_GATHER")
+    assert dt.apply(st, out) == e and np.array_equal(out.numpy(), got)
+
+
+def test_apply_table_tile_passes_hubbard_3x4(ctx):
+    """The 3x4 Hubbard Hamiltonian (24 qubits) is two passes (up-orbital bits, down-orbital bits); properties that do not need
+    the oracle at this size: Hermiticity <a|H b> = conj(<b|H a>), energy = <psi|out>, HF energy of a basis state."""
+    n = 24
+    dt = DeviceTable(ctx, PauliTable.from_operator(fermi_hubbard(3, 4, 1.0, 4.0), n))
+    assert dt.tile_passes() == 2
+    a, b = rand_state(n, 1), rand_state(n, 2)
+    sa, sb, out = State.from_numpy(ctx, a), State.from_numpy(ctx, b), State(ctx, n)
+    ea = dt.apply(sa, out)
+    ha = out.numpy()
+    assert abs(ea - np.vdot(a, ha)) < 1e-10 and abs(ea.imag) < 1e-12
+    dt.apply(sb, out)
+    hb = out.numpy()
+    assert abs(np.vdot(a, hb) - np.conj(np.vdot(b, ha))) < 1e-10
+    basis = np.zeros(1 << n, complex)
+    idx = sum(1 << (n - 1 - q) for q in (0, 1, 4, 7, 10, 13))      # sites 0 (doubly occupied), 2 up, 3 dn, 5 up, 6 dn
+    basis[idx] = 1.0
+    assert abs(dt.apply(State.from_numpy(ctx, basis)) - 4.0) < 1e-12     # U n_up n_dn on one doubly occupied site
