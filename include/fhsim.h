@@ -162,7 +162,11 @@ int fh_program_evaluate(fh_program *prog, uint64_t basis_index, const double *th
  * hva.py:273-303) run on the SECTOR-COMPRESSED state (3x3: 15 876 amplitudes instead of 2^18) resident in the distributed
  * shared memory of one thread-block cluster: one cluster kernel (ansatz, W, H, W^dagger) + one pool kernel instead of ~19
  * launches.  Chosen automatically when every op, the observable and the pool map the sector of |basis_index> to itself and
- * psi + lambda fit one cluster; FHSIM_NO_SECTOR=1 forces the full-space path.  active: 1 if the last call took it;
+ * psi + lambda fit one cluster and the sector has <= 2 048 amplitudes (FHSIM_SECTOR=1: any size that fits; FHSIM_NO_SECTOR=1:
+ * never).  Otherwise, when the circuit, the observable and the pool conserve (N_up, N_dn), the full-space path still screens
+ * the pool (K3) on sector-compressed copies of psi_s / lambda_s (3x3: 1 225 instead of 2^15 pairs per operator; 3x4: the
+ * compressed vectors are L2-resident); FHSIM_NO_SECTOR_POOL=1 keeps K3 in the full space.
+ * active: 1 if the last call ran in the cluster, 2 if only its pool screening ran in the sector, 0 otherwise;
  * cluster_size: CTAs of the cluster; sector_dim: amplitudes; n_ops: steps of the cluster kernel (ops, transposes,
  * checkpoint, H, store); n_transposes / n_remote_ops: layout changes / ops that exchange amplitudes between CTAs. */
 int fh_program_sector_info(const fh_program *prog, int *active, int *cluster_size, uint64_t *sector_dim, int *n_ops,

@@ -45,7 +45,7 @@ struct EvalKey {
     const void *pool;
     int pool_pos, pool_first, pool_count;
     const void *state_out;
-    int sector, pad_sector;      // 1: the sector-resident path (sector_eval.cu) was planned for this evaluation
+    int sector, sector_pool;     // 1: the sector-resident path (sector_eval.cu) / K3 on sector-compressed copies was planned
     // unique ids of the same handles: a freed handle whose address is reused by a new one gets a new id, so the graph
     // (which bakes in the device pointers behind the handles) is re-captured instead of replayed on freed memory
     u64 table_uid[FH_MAX_RESULT_TABLES], target_uid[FH_MAX_OVERLAPS], pool_uid, state_out_uid;
@@ -112,7 +112,8 @@ struct fh_program {
     std::vector<SecFlatOp> flat;
     std::vector<int> item_flat_first;
     fh_sector_plan *sec = nullptr;
-    bool last_sector = false;
+    fh_sector_pool_plan *sec_pool = nullptr;
+    bool last_sector = false, last_sector_pool = false;
     // measurement
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0.0;
@@ -153,6 +154,8 @@ extern "C" int fh_program_destroy(fh_program *p) {
     drop_graph(p);
     fh_sector_plan_free(p->sec);
     p->sec = nullptr;
+    fh_sector_pool_plan_free(p->sec_pool);
+    p->sec_pool = nullptr;
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     cudaFree(p->d_tl_fwd);
@@ -949,12 +952,15 @@ static int enqueue_evaluation(fh_program *p, const EvalKey &k, fh_table *const *
         if (chk_pos < n_items) psi = p->d_chk;
         int stop = want_grads ? first_param : n_items;      // lowest item the sweep must undo
         if (want_pool && k.pool_pos < stop) stop = k.pool_pos;
-        if (want_pool && k.pool_pos == chk_pos)
-            FH_TRY(fh_enqueue_pool(pool, psi, lam, k.pool_first, k.pool_count, d_pool_out));
+        // K3: on sector-compressed copies of psi_s / lambda_s when the whole evaluation conserves (N_up, N_dn)
+        auto enqueue_pool = [&](const double2 *ps, const double2 *lm) -> int {
+            if (k.sector_pool) return fh_sector_pool_enqueue(p->sec_pool, ctx, ps, lm, pool, k.pool_first, k.pool_count, d_pool_out);
+            return fh_enqueue_pool(pool, ps, lm, k.pool_first, k.pool_count, d_pool_out);
+        };
+        if (want_pool && k.pool_pos == chk_pos) FH_TRY(enqueue_pool(psi, lam));
         for (int i = chk_pos - 1; i >= stop; --i) {
             adjoint_item(p, p->items[i], psi, lam, want_grads);
-            if (want_pool && k.pool_pos == i)
-                FH_TRY(fh_enqueue_pool(pool, psi, lam, k.pool_first, k.pool_count, d_pool_out));
+            if (want_pool && k.pool_pos == i) FH_TRY(enqueue_pool(psi, lam));
         }
         if (p->n_segments > 0) launch_sum_strided(ctx->stream, p->d_gpart, FH_GRAD_BLOCKS, p->n_segments, p->d_gseg);
         // scalars, gradient segments and pool outputs in one copy
@@ -1050,6 +1056,12 @@ extern "C" int fh_program_evaluate(fh_program *p, uint64_t basis_index, const do
         key.sector = fh_sector_plan_eligible(p->sec) ? 1 : 0;
         p->last_sector = key.sector != 0;
     }
+    p->last_sector_pool = false;
+    if (pool && !key.sector && n_tables >= 1 && !(p->n & 1) && p->n <= 31 && !getenv("FHSIM_NO_SECTOR_POOL")) {
+        FH_TRY(fh_sector_pool_prepare(&p->sec_pool, ctx, p->n, basis_index, p->pairs, p->flat, tables[0], pool));
+        key.sector_pool = fh_sector_pool_plan_eligible(p->sec_pool) ? 1 : 0;
+        p->last_sector_pool = key.sector_pool != 0;
+    }
 
     static const bool no_graph = getenv("FHSIM_NO_GRAPH") != nullptr;
     if (!p->ev0) {
@@ -1120,7 +1132,7 @@ extern "C" int fh_program_payload_bytes(const fh_program *p, size_t *h2d_bytes, 
 extern "C" int fh_program_sector_info(const fh_program *p, int *active, int *cluster_size, uint64_t *sector_dim, int *n_ops,
                                       int *n_transposes, int *n_remote_ops) {
     FH_REQUIRE(p, "fh_program_sector_info: program is NULL");
-    if (active) *active = p->last_sector ? 1 : 0;
+    if (active) *active = p->last_sector ? 1 : (p->last_sector_pool ? 2 : 0);
     u64 dim = 0;
     fh_sector_plan_describe(p->last_sector ? p->sec : nullptr, cluster_size, &dim, n_ops, n_transposes, n_remote_ops, nullptr);
     if (sector_dim) *sector_dim = dim;

@@ -669,6 +669,26 @@ struct SecTableCache {
     }
 };
 
+// every x != 0 group tabulated (<= 4 x bits) and every live pattern keeps (N_up, N_dn)?
+static bool sec_table_conserves(const fh_table *tab, u64 upmask, u64 dnmask) {
+    for (const TabGroup &g : tab->groups) {
+        if (g.x == 0) continue;
+        if (g.kbits == 0) return false;
+        for (int pat = 0; pat < (1 << g.kbits); ++pat) {
+            if (!((g.live >> pat) & 1u)) continue;
+            int dup = 0, ddn = 0;
+            for (int b = 0; b < g.kbits; ++b) {
+                const u64 bit = 1ull << g.pos[b];
+                const int was = (pat >> b) & 1;
+                if (bit & upmask) dup += 1 - 2 * was;
+                if (bit & dnmask) ddn += 1 - 2 * was;
+            }
+            if (dup != 0 || ddn != 0) return false;
+        }
+    }
+    return true;
+}
+
 static int sec_build_table(const fh_table *tab, const SecGeomHost &G, u64 upmask, u64 dnmask, SecTableCache &T, bool *ok) {
     *ok = false;
     std::vector<SecGroup> groups;
@@ -1241,5 +1261,135 @@ int fh_sector_enqueue(fh_sector_plan *P, fh_ctx *ctx, u64 basis, const PairOp *d
             fprintf(stderr, "\n");
         }
     }
+    return FH_OK;
+}
+
+
+// ----------------------------------------------------------------------------------------------
+// K3 on compressed copies of FULL-SPACE states (the 19-launch path keeps its tile kernels for the circuit, but screens the
+// pool in the sector): psi_s and lambda_s are gathered into rank order (k_sector_compress2), then k_sector_pool.
+// 3x3: 324 x 1 225 pairs instead of 324 x 2^15; 3x4: the two compressed vectors are 13.7 MB each and stay in L2, while the
+// full-space kernel streams 4 * 2^24 B per gradient from HBM.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sector_compress2(const unsigned *__restrict__ index, unsigned dim, const double2 *__restrict__ a,
+                                                          const double2 *__restrict__ b, double2 *__restrict__ ac,
+                                                          double2 *__restrict__ bc) {
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < dim; r += stride) {
+        const unsigned i = __ldg(index + r);
+        ac[r] = a[i];
+        bc[r] = b[i];
+    }
+}
+
+struct fh_sector_pool_plan {
+    bool eligible = false;
+    int n_up = -1, n_dn = -1;
+    u64 table_uid = 0, pool_uid = 0;
+    unsigned d_up = 0, d_dn = 0;
+    unsigned *d_index = nullptr;          // full index of every sector state, rank order
+    double2 *d_psi = nullptr, *d_lam = nullptr;
+    void release() {
+        cudaFree(d_index); cudaFree(d_psi); cudaFree(d_lam);
+        d_index = nullptr; d_psi = d_lam = nullptr;
+    }
+};
+
+void fh_sector_pool_plan_free(fh_sector_pool_plan *plan) {
+    if (!plan) return;
+    plan->release();
+    delete plan;
+}
+bool fh_sector_pool_plan_eligible(const fh_sector_pool_plan *plan) { return plan && plan->eligible; }
+
+int fh_sector_pool_prepare(fh_sector_pool_plan **slot, fh_ctx *ctx, int n, u64 basis, const std::vector<PairOp> &pairs,
+                           const std::vector<SecFlatOp> &flat, const fh_table *tab, const fh_pool *pool) {
+    if (!*slot) *slot = new fh_sector_pool_plan();
+    fh_sector_pool_plan *P = *slot;
+    const int half = n / 2;
+    u64 upmask = 0, dnmask = 0;
+    for (int b = 0; b < half; ++b) {
+        upmask |= 1ull << (2 * b + 1);
+        dnmask |= 1ull << (2 * b);
+    }
+    const int n_up = __builtin_popcountll(basis & upmask), n_dn = __builtin_popcountll(basis & dnmask);
+    if (P->n_up == n_up && P->n_dn == n_dn && P->table_uid == tab->uid && P->pool_uid == pool->uid) return FH_OK;
+    P->release();
+    P->eligible = false;
+    P->n_up = n_up;
+    P->n_dn = n_dn;
+    P->table_uid = tab->uid;
+    P->pool_uid = pool->uid;
+    if ((n & 1) || half < 1 || half > 15 || n > 31) return FH_OK;
+    // psi_s and lambda_s stay in the sector when every op, the observable and the pool map it to itself
+    for (const SecFlatOp &f : flat)
+        if (f.type == 1) {
+            const PairOp &op = pairs[f.index];
+            if (!sec_pattern_conserves(op.x, op.fixmask, op.fixval, upmask, dnmask)) return FH_OK;
+        }
+    if (!sec_table_conserves(tab, upmask, dnmask)) return FH_OK;
+    SecGeomHost G;
+    G.n = n;
+    G.half = half;
+    G.n_up = n_up;
+    G.n_dn = n_dn;
+    sec_patterns(half, n_up, G.cfgU, G.rankU);
+    sec_patterns(half, n_dn, G.cfgD, G.rankD);
+    if (G.d_up() > SEC_MAX_D || G.d_dn() > SEC_MAX_D) return FH_OK;
+    SecPoolCache &Pc = g_sec_pools[pool->uid];
+    if (Pc.pool_uid != pool->uid || Pc.n_up != n_up || Pc.n_dn != n_dn) {
+        bool ok = false;
+        FH_TRY(sec_build_pool(pool, G, upmask, dnmask, Pc, &ok));
+        if (!ok) {
+            fh_sector_forget_pool(pool->uid);
+            return FH_OK;
+        }
+    }
+    const u64 dim = (u64)G.d_up() * G.d_dn();
+    std::vector<unsigned> index((size_t)dim);
+    std::vector<unsigned> depU(G.d_up()), depD(G.d_dn());
+    for (unsigned r = 0; r < G.d_up(); ++r) {
+        unsigned dep = 0;
+        for (int b = 0; b < half; ++b)
+            if (G.cfgU[r] >> b & 1u) dep |= 1u << (2 * b + 1);
+        depU[r] = dep;
+    }
+    for (unsigned r = 0; r < G.d_dn(); ++r) {
+        unsigned dep = 0;
+        for (int b = 0; b < half; ++b)
+            if (G.cfgD[r] >> b & 1u) dep |= 1u << (2 * b);
+        depD[r] = dep;
+    }
+    for (unsigned ru = 0; ru < G.d_up(); ++ru)
+        for (unsigned rd = 0; rd < G.d_dn(); ++rd) index[(size_t)ru * G.d_dn() + rd] = depU[ru] | depD[rd];
+    FH_TRY(sec_upload(&P->d_index, index));
+    FH_CUDA(cudaMalloc(&P->d_psi, sizeof(double2) * dim));
+    FH_CUDA(cudaMalloc(&P->d_lam, sizeof(double2) * dim));
+    P->d_up = G.d_up();
+    P->d_dn = G.d_dn();
+    P->eligible = true;
+    (void)ctx;
+    return FH_OK;
+}
+
+// pool outputs o in [first, first+count) of full-space states psi / lam -> d_pool_out[o]
+int fh_sector_pool_enqueue(fh_sector_pool_plan *P, fh_ctx *ctx, const double2 *psi, const double2 *lam, const fh_pool *pool,
+                           int pool_first, int pool_count, double *d_pool_out) {
+    if (pool_count <= 0) return FH_OK;
+    const SecPoolCache &Pc = g_sec_pools[pool->uid];
+    const unsigned dim = P->d_up * P->d_dn;
+    int cgrid = (int)((dim + 255u) / 256u);
+    if (cgrid > ctx->sm_count * 8) cgrid = ctx->sm_count * 8;
+    ++g_fh_launch_count;
+    k_sector_compress2<<<cgrid, 256, 0, ctx->stream>>>(P->d_index, dim, psi, lam, P->d_psi, P->d_lam);
+    const int e0 = pool->out_first[pool_first], e1 = pool->out_first[pool_first + pool_count];
+    int grid = e1 - e0;
+    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+    if (grid < 1) grid = 1;
+    ++g_fh_launch_count;
+    k_sector_pool<<<grid, 256, sizeof(unsigned) * std::max(1u, Pc.max_words), ctx->stream>>>(
+        Pc.d_entries, Pc.d_lists, e0, e1, P->d_dn, P->d_psi, P->d_lam, Pc.d_partial, pool->d_out_first, pool_first, pool_count,
+        d_pool_out, Pc.d_counter);
+    FH_CUDA(cudaGetLastError());
     return FH_OK;
 }

@@ -188,3 +188,52 @@ def test_sector_path_is_not_taken_when_it_does_not_apply(ctx, monkeypatch):
     e_sec = p3.evaluate(b3, [0.1], [d3])["expvals"][0]
     assert p3.sector_info()["active"] and p3.sector_info()["dim"] == 15876
     assert abs(e_sec - e_full) < 1e-12
+
+
+@pytest.mark.parametrize("lat,u,up,dn", [((2, 3), 4.0, 3, 3), ((3, 3), 6.0, 5, 4)])
+def test_pool_screening_on_sector_compressed_copies(ctx, lat, u, up, dn, monkeypatch):
+    """Full-space circuit kernels + K3 on sector-compressed psi_s / lambda_s (the default at 3x3) against K3 in the full
+    space, for a screening call, a training call that also screens (grads=True) and a sub-range of the pool."""
+    monkeypatch.setenv("FHSIM_NO_SECTOR", "1")           # keep the cluster path out of the way at 2x3
+    n, h_tab, pool_ops, dec, diag, o_h, o_pool = lattice(*lat, u)
+    rng = np.random.default_rng(11)
+    occ_up, occ_dn, _ = pauli.k_space_occupation(*lat, 1.0, up, dn)
+    picks = list(rng.choice(len(pool_ops), size=5, replace=False))
+    th = rng.uniform(-0.4, 0.4, len(picks))
+    plans = [GeneratorPlan(g, n) for g in pool_ops]
+    circ = Circuit(n, len(picks))
+    for p, k in enumerate(picks):
+        circ.generator(plans[k], param=p)
+    circ.marker("ansatz_end")
+    circ.basis_change_separable(*lat)
+    prog = circ.compile(ctx)
+    dtab = DeviceTable(ctx, h_tab)
+    dpool = DevicePool(ctx, plans, n)
+    basis = sum(1 << (n - 1 - q) for q in occ_up + occ_dn)
+    m = prog.markers["ansatz_end"]
+    a = prog.evaluate(basis, th, [dtab], pool=dpool, pool_pos=m)
+    info = prog.sector_info()
+    assert info["pool_in_sector"] and not info["active"]
+    ag = prog.evaluate(basis, th, [dtab], grads=True, pool=dpool, pool_pos=m)
+    assert prog.sector_info()["pool_in_sector"]
+    asub = prog.evaluate(basis, th, [dtab], pool=dpool, pool_pos=m, pool_range=(2, 7))
+    monkeypatch.setenv("FHSIM_NO_SECTOR_POOL", "1")
+    b = prog.evaluate(basis, th, [dtab], pool=dpool, pool_pos=m)
+    assert not prog.sector_info()["pool_in_sector"]
+    bg = prog.evaluate(basis, th, [dtab], grads=True, pool=dpool, pool_pos=m)
+    assert np.abs(a["pool"] - b["pool"]).max() < 1e-12 and np.abs(b["pool"]).max() > 1e-3
+    assert np.abs(ag["pool"] - bg["pool"]).max() < 1e-12 and np.abs(ag["grads"] - bg["grads"]).max() < 1e-13
+    assert np.abs(asub["pool"] - b["pool"][2:9]).max() < 1e-12
+    pg_want, e_want, _ = sv.pool_gradients(sv.adapt_state(n, occ_up + occ_dn, [o_pool[k] for k in picks], th), o_h, o_pool, diag, dec, n)
+    assert np.abs(a["pool"] - pg_want).max() < G_TOL and abs(a["expvals"][0] - e_want) < E_TOL
+    # the reference W network leaves the sector op by op: K3 stays in the full space
+    c2 = Circuit(n, len(picks))
+    for p, k in enumerate(picks):
+        c2.generator(plans[k], param=p)
+    c2.marker("ansatz_end")
+    c2.basis_change(diag, list(reversed(dec)))
+    monkeypatch.delenv("FHSIM_NO_SECTOR_POOL")
+    p2 = c2.compile(ctx)
+    r2 = p2.evaluate(basis, th, [dtab], pool=dpool, pool_pos=p2.markers["ansatz_end"])
+    assert not p2.sector_info()["pool_in_sector"]
+    assert np.abs(r2["pool"] - pg_want).max() < G_TOL
