@@ -119,6 +119,15 @@ int fh_pool_free(fh_pool *pool);
 /* gradients of outputs [first, first+count) -> out[count]   (pool sharding across GPUs uses first/count) */
 int fh_pool_gradients(const fh_pool *pool, const fh_state *psi, const fh_state *lambda, int first, int count, double *out);
 
+/* The same gradients for states that live in the (n_up, n_dn) sector (every amplitude outside it is zero: any ADAPT / HVA
+ * state, models/adapt_vqe.py:325-361), evaluated on sector-compressed copies: psi and lambda are gathered into rank order
+ * (rank = rank_up * D_dn + rank_dn, even wires = up) and the connected pairs of every entry are enumerated as the product
+ * of two short lists (up patterns x down patterns matching the entry) -- 3x3: 1 225 pairs per operator instead of 2^15; 3x4:
+ * both compressed vectors (13.7 MB) stay in L2.  FH_EINVAL if an entry does not conserve both particle numbers.
+ * out == NULL: enqueue only.  fh_program_evaluate screens this way by itself when the whole evaluation conserves them. */
+int fh_pool_gradients_sector(const fh_pool *pool, const fh_state *psi, const fh_state *lambda, int n_up, int n_dn, int first,
+                             int count, double *out);
+
 /* ---- compiled circuits ----------------------------------------------------------------------
  * replaces the QNode tape built by ADAPT.circuit / HVA.circuit / IQCC.get_circuit / VQE.circuit
  * (models/adapt_vqe.py:325-361, hva.py:273-303, iqcc_hubbard.py:59-80, vqe_hea.py:43-57).

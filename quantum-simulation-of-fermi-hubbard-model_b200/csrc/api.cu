@@ -858,6 +858,7 @@ extern "C" int fh_pool_free(fh_pool *pool) {
     cudaFree(pool->d_out);
     cudaFreeHost(pool->h_out);
     fh_sector_forget_pool(pool->uid);
+    fh_sector_forget_pool_plan(pool->uid);
     delete pool;
     return FH_OK;
 }

@@ -1393,3 +1393,49 @@ int fh_sector_pool_enqueue(fh_sector_pool_plan *P, fh_ctx *ctx, const double2 *p
     FH_CUDA(cudaGetLastError());
     return FH_OK;
 }
+
+
+// ---- the same screening as a stand-alone call on caller-owned full-space states --------------------------------
+static std::map<u64, fh_sector_pool_plan *> g_sec_pool_plans;      // per pool handle (freed with the pool)
+void fh_sector_forget_pool_plan(u64 uid) {
+    auto it = g_sec_pool_plans.find(uid);
+    if (it != g_sec_pool_plans.end()) {
+        fh_sector_pool_plan_free(it->second);
+        g_sec_pool_plans.erase(it);
+    }
+}
+
+extern "C" int fh_pool_gradients_sector(const fh_pool *pool, const fh_state *psi, const fh_state *lambda, int n_up, int n_dn,
+                                        int first, int count, double *out) {
+    FH_REQUIRE(pool && psi && lambda, "fh_pool_gradients_sector: NULL argument");
+    FH_REQUIRE(psi->n == pool->n && lambda->n == pool->n, "fh_pool_gradients_sector: qubit count mismatch");
+    FH_REQUIRE(first >= 0 && count >= 0 && first + count <= pool->n_out, "fh_pool_gradients_sector: range [%d, %d) outside pool of %d",
+               first, first + count, pool->n_out);
+    const int n = pool->n, half = n / 2;
+    FH_REQUIRE(!(n & 1) && half >= 1 && half <= 15, "fh_pool_gradients_sector: needs an even qubit count <= 30");
+    FH_REQUIRE(n_up >= 0 && n_up <= half && n_dn >= 0 && n_dn <= half, "fh_pool_gradients_sector: bad particle numbers");
+    if (count == 0) return FH_OK;
+    fh_ctx *ctx = pool->ctx;
+    FH_CUDA(cudaSetDevice(ctx->device));
+    fh_sector_pool_plan *&P = g_sec_pool_plans[pool->uid];
+    if (!P) P = new fh_sector_pool_plan();
+    if (!(P->eligible && P->n_up == n_up && P->n_dn == n_dn)) {
+        // a basis state of the sector stands in for the one a program would start from; no ops, no observable to check
+        u64 basis = 0;
+        for (int b = 0; b < n_up; ++b) basis |= 1ull << (2 * b + 1);
+        for (int b = 0; b < n_dn; ++b) basis |= 1ull << (2 * b);
+        fh_table dummy;
+        dummy.uid = ~0ull;
+        dummy.n = n;
+        P->n_up = -1;
+        FH_TRY(fh_sector_pool_prepare(&P, ctx, n, basis, std::vector<PairOp>(), std::vector<SecFlatOp>(), &dummy, pool));
+        FH_REQUIRE(P->eligible, "fh_pool_gradients_sector: the pool does not conserve (N_up, N_dn) = (%d, %d) or the sector is too large",
+                   n_up, n_dn);
+    }
+    FH_TRY(fh_sector_pool_enqueue(P, ctx, psi->d, lambda->d, pool, first, count, pool->d_out));
+    if (!out) return FH_OK;          // enqueue only (timing)
+    FH_CUDA(cudaMemcpyAsync(pool->h_out, pool->d_out + first, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    FH_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(out, pool->h_out, sizeof(double) * count);
+    return FH_OK;
+}

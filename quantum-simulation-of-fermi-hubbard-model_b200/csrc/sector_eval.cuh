@@ -35,3 +35,4 @@ bool fh_sector_pool_plan_eligible(const fh_sector_pool_plan *plan);
 int fh_sector_pool_enqueue(fh_sector_pool_plan *plan, fh_ctx *ctx, const double2 *psi, const double2 *lam, const fh_pool *pool,
                            int pool_first, int pool_count, double *d_pool_out);
 void fh_sector_pool_plan_free(fh_sector_pool_plan *plan);
+void fh_sector_forget_pool_plan(u64 uid);

@@ -51,6 +51,7 @@ SIGNATURES = {
     "fh_pool_upload": [_vp, C.c_int, C.c_int, _u64p, _u64p, _u64p, _u64p, _f64p, _f64p, _i32p, C.c_int, _vpp],
     "fh_pool_free": [_vp],
     "fh_pool_gradients": [_vp, _vp, _vp, C.c_int, C.c_int, _f64p],
+    "fh_pool_gradients_sector": [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _f64p],
     "fh_program_create": [_vp, C.c_int, C.c_int, _vpp],
     "fh_program_destroy": [_vp],
     "fh_program_add_pair": [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_double,

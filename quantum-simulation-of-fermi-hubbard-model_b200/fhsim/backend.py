@@ -231,6 +231,15 @@ class DevicePool:
             count = self.n_out - first
         _cabi.check(_cabi.lib().fh_pool_gradients(self._h, psi._h, lam._h, int(first), int(count), None))
 
+    def gradients_sector(self, psi: State, lam: State, n_up: int, n_dn: int, first=0, count=None, enqueue_only=False):
+        """K3 on sector-compressed copies of psi / lambda (states confined to the (n_up, n_dn) sector); csrc/sector_eval.cu."""
+        if count is None:
+            count = self.n_out - first
+        out = np.zeros(max(count, 1))
+        _cabi.check(_cabi.lib().fh_pool_gradients_sector(self._h, psi._h, lam._h, int(n_up), int(n_dn), int(first), int(count),
+                                                         None if enqueue_only else out.ctypes.data_as(_cabi._f64p)))
+        return None if enqueue_only else out[:count]
+
     def gradients(self, psi: State, lam: State, first=0, count=None) -> np.ndarray:
         if count is None:
             count = self.n_out - first

@@ -117,11 +117,28 @@ def measure_lattice(ctx, lat, pk, pool_cap=400, verbose=True):
         dpool.enqueue(psi, lam)
         ts.append(ctx.timer_stop())
     rec("screening", min(ts) * 1e-3, 4.0 * dim * len(plans), {"ops": len(plans), "per_gradient_us": min(ts) * 1e3 / len(plans)})
+    # K3 on sector-compressed copies (what fh_program_evaluate does for number-conserving evaluations): same pool, the
+    # half-filled sector; 4 * 2^n B per gradient is the FULL-SPACE algorithmic figure, so this row is an effective rate
+    try:
+        ns = nx * ny
+        n_up = (ns + 1) // 2
+        n_dn = ns - n_up
+        dpool.gradients_sector(psi, lam, n_up, n_dn, enqueue_only=True)
+        ts = []
+        for _ in range(3):
+            ctx.timer_start()
+            dpool.gradients_sector(psi, lam, n_up, n_dn, enqueue_only=True)
+            ts.append(ctx.timer_stop())
+        from math import comb
+        rec("screening_sector", min(ts) * 1e-3, 4.0 * dim * len(plans),
+            {"ops": len(plans), "per_gradient_us": min(ts) * 1e3 / len(plans), "sector_dim": comb(ns, n_up) * comb(ns, n_dn)})
+    except Exception as exc:                    # sector too large for the 12-bit list fields (more than 4096 patterns per spin)
+        res["screening_sector"] = {"us": float("nan"), "GBps": float("nan"), "frac": float("nan"), "error": repr(exc)}
     for o in (dpool, dtab, psi, lam):
         o.close()
     if verbose:
         print(f"--- {lat}  n={n}  state={res['state_MiB']:.0f} MiB  pool={res['pool']}  H terms/groups={res['h_terms']}/{res['h_groups']}")
-        for k in ("pair_fermi4", "pair_dense", "givens", "diag_coulomb", "tile_W", "h_apply", "screening"):
+        for k in ("pair_fermi4", "pair_dense", "givens", "diag_coulomb", "tile_W", "h_apply", "screening", "screening_sector"):
             v = res[k]
             print(f"    {k:13s} {v['us']:12.1f} us  {v['GBps']:9.1f} GB/s  {100 * v['frac']:6.1f} % of {pk:.0f}")
         sys.stdout.flush()
