@@ -127,6 +127,13 @@ int fh_pool_gradients(const fh_pool *pool, const fh_state *psi, const fh_state *
  * out == NULL: enqueue only.  fh_program_evaluate screens this way by itself when the whole evaluation conserves them. */
 int fh_pool_gradients_sector(const fh_pool *pool, const fh_state *psi, const fh_state *lambda, int n_up, int n_dn, int first,
                              int count, double *out);
+/* The same with an arbitrary assignment of index bits to species: up_mask / dn_mask = the index bits of the up / down orbitals
+ * (disjoint, together all n bits, at most 16 per species; sectors of up to 16 384 patterns per spin).  This is the form a SLAB of
+ * a sharded state needs: after global<->local qubit swaps the local bits are a permutation of the orbitals, and the slab of
+ * rank r holds the sector (N_up - ups among the rank bits, N_dn - downs among them) of its local orbitals.  4x4 over 8 GPUs:
+ * 22 M compressed amplitudes per slab instead of 2^29. */
+int fh_pool_gradients_sector_masks(const fh_pool *pool, const fh_state *psi, const fh_state *lambda, uint64_t up_mask,
+                                   uint64_t dn_mask, int n_up, int n_dn, int first, int count, double *out);
 
 /* ---- compiled circuits ----------------------------------------------------------------------
  * replaces the QNode tape built by ADAPT.circuit / HVA.circuit / IQCC.get_circuit / VQE.circuit

@@ -1058,7 +1058,10 @@ extern "C" int fh_program_evaluate(fh_program *p, uint64_t basis_index, const do
     }
     p->last_sector_pool = false;
     if (pool && !key.sector && n_tables >= 1 && !(p->n & 1) && p->n <= 31 && !getenv("FHSIM_NO_SECTOR_POOL")) {
-        FH_TRY(fh_sector_pool_prepare(&p->sec_pool, ctx, p->n, basis_index, p->pairs, p->flat, tables[0], pool));
+        u64 upm = 0, dnm = 0;
+        for (int b = 0; b < p->n; ++b) ((b & 1) ? upm : dnm) |= 1ull << b;          // even wires = up = odd index bits
+        FH_TRY(fh_sector_pool_prepare(&p->sec_pool, ctx, p->n, upm, dnm, __builtin_popcountll(basis_index & upm),
+                                      __builtin_popcountll(basis_index & dnm), p->pairs, p->flat, tables[0], pool));
         key.sector_pool = fh_sector_pool_plan_eligible(p->sec_pool) ? 1 : 0;
         p->last_sector_pool = key.sector_pool != 0;
     }

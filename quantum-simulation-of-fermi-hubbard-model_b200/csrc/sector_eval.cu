@@ -40,7 +40,9 @@ extern long long g_fh_launch_count;
 
 #define SEC_MAX_C 16
 #define SEC_THREADS 256
-#define SEC_MAX_D 4096      // patterns per spin (12-bit list fields)
+#define SEC_FB 14            // bits of the rank fields of a list entry: rank | partner << SEC_FB | sign << 31
+#define SEC_FM 0x3fffu
+#define SEC_MAX_D 16384     // patterns per spin
 
 enum { SV_PAIR = 1, SV_DIAG = 2, SV_TRANSPOSE = 3, SV_CHECKPOINT = 4, SV_HAPPLY = 5, SV_STORE = 6 };
 enum { SF_DAGGER = 1, SF_COL = 2, SF_CLUSTER_AFTER = 4, SF_WANT_LAMBDA = 8, SF_LOCAL = 16 };
@@ -194,7 +196,7 @@ __device__ __forceinline__ void sec_pair_decode(const unsigned *LA, const unsign
                                                 unsigned cmask, unsigned &offi, unsigned &offj, unsigned &ctaj, unsigned &sbit) {
     const unsigned ai = p / nB, bi = p - ai * nB;
     const unsigned ea = LA[ai], eb = LB[bi];
-    const unsigned a = ea & 0xfffu, ap = (ea >> 12) & 0xfffu, b = eb & 0xfffu, bp = (eb >> 12) & 0xfffu;
+    const unsigned a = ea & SEC_FM, ap = (ea >> SEC_FB) & SEC_FM, b = eb & SEC_FM, bp = (eb >> SEC_FB) & SEC_FM;
     sbit = (ea ^ eb) & 0x80000000u;
     offi = ((a >> logC) * dB + b) * 16u;
     offj = ((ap >> logC) * dB + bp) * 16u;
@@ -554,7 +556,7 @@ __global__ void __launch_bounds__(256) k_sector_pool(const SecPoolEntry *__restr
         for (unsigned p = threadIdx.x; p < P; p += blockDim.x) {
             const unsigned ai = p / E.nD, bi = p - ai * E.nD;
             const unsigned ea = sl[ai], eb = sl[E.nU + bi];
-            const unsigned i = (ea & 0xfffu) * d_dn + (eb & 0xfffu), j = ((ea >> 12) & 0xfffu) * d_dn + ((eb >> 12) & 0xfffu);
+            const unsigned i = (ea & SEC_FM) * d_dn + (eb & SEC_FM), j = ((ea >> SEC_FB) & SEC_FM) * d_dn + ((eb >> SEC_FB) & SEC_FM);
             const double2 pi = psi[i], pj = psi[j], li = lam[i], lj = lam[j];
             // Im( conj(li) B pj + conj(lj) conj(B) pi ), sign applied afterwards
             const double2 bpj = make_double2(E.br * pj.x - E.bi * pj.y, E.br * pj.y + E.bi * pj.x);
@@ -586,6 +588,29 @@ __global__ void __launch_bounds__(256) k_sector_pool(const SecPoolEntry *__restr
 // ----------------------------------------------------------------------------------------------
 struct SecGeomHost {
     int n = 0, half = 0, n_up = 0, n_dn = 0;
+    // index bits of the up / down orbitals, ascending; orbital k of a species is bit k (up) / 16 + k (down) of a compact mask.
+    // Standard layout (even wires = up): up = odd index bits, down = even index bits; a slab of a sharded state has its own.
+    std::vector<int> upbits, dnbits;
+    void standard(int nq) {
+        n = nq;
+        half = nq / 2;
+        upbits.clear();
+        dnbits.clear();
+        for (int b = 0; b < half; ++b) {
+            upbits.push_back(2 * b + 1);
+            dnbits.push_back(2 * b);
+        }
+    }
+    void from_masks(int nq, u64 upmask, u64 dnmask) {
+        n = nq;
+        upbits.clear();
+        dnbits.clear();
+        for (int b = 0; b < nq; ++b) {
+            if (upmask >> b & 1ull) upbits.push_back(b);
+            else if (dnmask >> b & 1ull) dnbits.push_back(b);
+        }
+        half = (int)std::max(upbits.size(), dnbits.size());
+    }
     std::vector<unsigned short> cfgU, cfgD, rankU, rankD;
     unsigned short *d_cfgU = nullptr, *d_cfgD = nullptr, *d_rankU = nullptr, *d_rankD = nullptr;
     unsigned d_up() const { return (unsigned)cfgU.size(); }
@@ -596,10 +621,10 @@ struct SecGeomHost {
     }
 };
 
-static void sec_patterns(int half, int count, std::vector<unsigned short> &cfg, std::vector<unsigned short> &rank) {
-    rank.assign((size_t)1 << half, 0xffffu);
+static void sec_patterns(int nbits, int count, std::vector<unsigned short> &cfg, std::vector<unsigned short> &rank) {
+    rank.assign((size_t)1 << nbits, 0xffffu);
     cfg.clear();
-    for (unsigned pat = 0; pat < (1u << half); ++pat)
+    for (unsigned pat = 0; pat < (1u << nbits); ++pat)
         if (__builtin_popcount(pat) == count) {
             rank[pat] = (unsigned short)cfg.size();
             cfg.push_back((unsigned short)pat);
@@ -607,15 +632,21 @@ static void sec_patterns(int half, int count, std::vector<unsigned short> &cfg, 
 }
 
 // full-index mask -> compact packed mask (up orbital b = index bit 2b+1 -> bit b; down orbital b = index bit 2b -> bit 16+b)
-static unsigned sec_compact(u64 m, int half) {
+static unsigned sec_compact(u64 m, const SecGeomHost &G) {
     unsigned out = 0;
-    for (int b = 0; b < half; ++b) {
-        if (m >> (2 * b + 1) & 1ull) out |= 1u << b;
-        if (m >> (2 * b) & 1ull) out |= 1u << (16 + b);
-    }
+    for (size_t k = 0; k < G.upbits.size(); ++k)
+        if (m >> G.upbits[k] & 1ull) out |= 1u << k;
+    for (size_t k = 0; k < G.dnbits.size(); ++k)
+        if (m >> G.dnbits[k] & 1ull) out |= 1u << (16 + k);
     return out;
 }
-static int sec_compact_pos(int p) { return (p & 1) ? (p - 1) / 2 : 16 + p / 2; }
+static int sec_compact_pos(int p, const SecGeomHost &G) {
+    for (size_t k = 0; k < G.upbits.size(); ++k)
+        if (G.upbits[k] == p) return (int)k;
+    for (size_t k = 0; k < G.dnbits.size(); ++k)
+        if (G.dnbits[k] == p) return 16 + (int)k;
+    return 31;
+}
 
 template <typename T>
 static int sec_upload(T **d, const std::vector<T> &v) {
@@ -634,7 +665,7 @@ static bool sec_pattern_conserves(u64 x, u64 fixmask, u64 fixval, u64 upmask, u6
     return 2 * up1 == up && 2 * dn1 == dn;
 }
 
-// the two lists of a pattern-pinned pair (x, fixmask, fixval, zeta) in compact coordinates; entry = rank | partner << 12 | sign << 31
+// the two lists of a pattern-pinned pair (x, fixmask, fixval, zeta) in compact coordinates; entry = rank | partner << SEC_FB | sign << 31
 static void sec_build_lists(const SecGeomHost &G, unsigned xc, unsigned fmc, unsigned fvc, unsigned ztc, std::vector<unsigned> &LU,
                             std::vector<unsigned> &LD) {
     LU.clear();
@@ -645,13 +676,13 @@ static void sec_build_lists(const SecGeomHost &G, unsigned xc, unsigned fmc, uns
         const unsigned u = G.cfgU[r];
         if ((u & fmu) != fvu) continue;
         const unsigned pr = G.rankU[u ^ xu];
-        LU.push_back(r | (pr << 12) | ((unsigned)(__builtin_popcount(u & zu) & 1) << 31));
+        LU.push_back(r | (pr << SEC_FB) | ((unsigned)(__builtin_popcount(u & zu) & 1) << 31));
     }
     for (unsigned r = 0; r < G.d_dn(); ++r) {
         const unsigned d = G.cfgD[r];
         if ((d & fmd) != fvd) continue;
         const unsigned pr = G.rankD[d ^ xd];
-        LD.push_back(r | (pr << 12) | ((unsigned)(__builtin_popcount(d & zd) & 1) << 31));
+        LD.push_back(r | (pr << SEC_FB) | ((unsigned)(__builtin_popcount(d & zd) & 1) << 31));
     }
 }
 
@@ -711,22 +742,22 @@ static int sec_build_table(const fh_table *tab, const SecGeomHost &G, u64 upmask
         }
         SecGroup s;
         memset(&s, 0, sizeof(s));
-        s.x = sec_compact(g.x, G.half);
+        s.x = sec_compact(g.x, G);
         s.first_class = (int)classes.size();
         s.n_class = g.n_class;
         s.live = g.live;
         s.kbits = g.kbits;
-        for (int b = 0; b < 4; ++b) s.pos[b] = b < g.kbits ? (unsigned char)sec_compact_pos(g.pos[b]) : 31;
+        for (int b = 0; b < 4; ++b) s.pos[b] = b < g.kbits ? (unsigned char)sec_compact_pos(g.pos[b], G) : 31;
         for (int c = g.first_class; c < g.first_class + g.n_class; ++c) {
             SecClass sc;
-            sc.zeta = sec_compact(tab->classes[c].zeta, G.half);
+            sc.zeta = sec_compact(tab->classes[c].zeta, G);
             sc.vofs = tab->classes[c].vofs;
             classes.push_back(sc);
         }
         groups.push_back(s);
     }
     for (const TabTerm &t : tab->diag_terms) {
-        const unsigned zc = sec_compact(t.z, G.half);
+        const unsigned zc = sec_compact(t.z, G);
         for (unsigned ru = 0; ru < G.d_up(); ++ru)
             for (unsigned rd = 0; rd < G.d_dn(); ++rd) {
                 const unsigned cfg = (unsigned)G.cfgU[ru] | ((unsigned)G.cfgD[rd] << 16);
@@ -757,7 +788,7 @@ static int sec_build_table(const fh_table *tab, const SecGeomHost &G, u64 upmask
 
 // ---- per-pool cache ----
 struct SecPoolCache {
-    u64 pool_uid = 0;
+    u64 pool_uid = 0, upmask = 0, dnmask = 0;
     int n_up = -1, n_dn = -1;
     SecPoolEntry *d_entries = nullptr;
     unsigned *d_lists = nullptr, *d_counter = nullptr;
@@ -776,8 +807,7 @@ static int sec_build_pool(const fh_pool *pool, const SecGeomHost &G, u64 upmask,
     unsigned max_words = 0;
     for (const PoolEntry &e : pool->entries) {
         if (!sec_pattern_conserves(e.x, e.fixmask, e.fixval, upmask, dnmask)) return FH_OK;
-        sec_build_lists(G, sec_compact(e.x, G.half), sec_compact(e.fixmask, G.half), sec_compact(e.fixval, G.half),
-                        sec_compact(e.zeta, G.half), LU, LD);
+        sec_build_lists(G, sec_compact(e.x, G), sec_compact(e.fixmask, G), sec_compact(e.fixval, G), sec_compact(e.zeta, G), LU, LD);
         SecPoolEntry s;
         s.listU = (unsigned)lists.size();
         s.nU = (unsigned)LU.size();
@@ -926,8 +956,7 @@ int fh_sector_prepare(fh_sector_plan **slot, fh_ctx *ctx, int n, u64 basis, cons
     if ((n & 1) || half < 1 || half > 15) return FH_OK;
 
     SecGeomHost &G = P->G;
-    G.n = n;
-    G.half = half;
+    G.standard(n);
     G.n_up = n_up;
     G.n_dn = n_dn;
     sec_patterns(half, n_up, G.cfgU, G.rankU);
@@ -954,7 +983,7 @@ int fh_sector_prepare(fh_sector_plan **slot, fh_ctx *ctx, int n, u64 basis, cons
             L.kind = SV_PAIR;
             L.index = f.index;
             L.nterms = 0;
-            L.xc = sec_compact(pairs[f.index].x, half);
+            L.xc = sec_compact(pairs[f.index].x, P->G);
         } else {
             L.kind = SV_DIAG;
             L.index = diagops[f.index].first;
@@ -1047,8 +1076,8 @@ int fh_sector_prepare(fh_sector_plan **slot, fh_ctx *ctx, int n, u64 basis, cons
             const PairOp &op = pairs[L.index];
             auto it = list_of_pair.find(L.index);
             if (it == list_of_pair.end()) {
-                sec_build_lists(G, sec_compact(op.x, half), sec_compact(op.fixmask, half), sec_compact(op.fixval, half),
-                                sec_compact(op.zeta, half), LU, LD);
+                sec_build_lists(G, sec_compact(op.x, G), sec_compact(op.fixmask, G), sec_compact(op.fixval, G), sec_compact(op.zeta, G),
+                                LU, LD);
                 // group by owner (rank % C), stable
                 std::vector<unsigned short> offs(2 * (SEC_MAX_C + 1), 0);
                 auto grouped = [&](const std::vector<unsigned> &Lx, unsigned short *off) {
@@ -1056,7 +1085,7 @@ int fh_sector_prepare(fh_sector_plan **slot, fh_ctx *ctx, int n, u64 basis, cons
                     for (int c = 0; c < C; ++c) {
                         off[c] = (unsigned short)out.size();
                         for (unsigned e : Lx)
-                            if ((int)((e & 0xfffu) & (unsigned)(C - 1)) == c) out.push_back(e);
+                            if ((int)((e & SEC_FM) & (unsigned)(C - 1)) == c) out.push_back(e);
                     }
                     for (int c = C; c <= SEC_MAX_C; ++c) off[c] = (unsigned short)out.size();
                     return out;
@@ -1123,7 +1152,7 @@ int fh_sector_prepare(fh_sector_plan **slot, fh_ctx *ctx, int n, u64 basis, cons
     if (smem > 200 * 1024) return FH_OK;
 
     std::vector<unsigned> zc(std::max<size_t>(1, dterms.size()), 0u);
-    for (size_t m = 0; m < dterms.size(); ++m) zc[m] = sec_compact(dterms[m].z, half);
+    for (size_t m = 0; m < dterms.size(); ++m) zc[m] = sec_compact(dterms[m].z, G);
     if (lists.empty()) lists.push_back(0u);
     FH_TRY(sec_upload(&G.d_cfgU, G.cfgU));
     FH_TRY(sec_upload(&G.d_cfgD, G.cfgD));
@@ -1271,12 +1300,14 @@ int fh_sector_enqueue(fh_sector_plan *P, fh_ctx *ctx, u64 basis, const PairOp *d
 // 3x3: 324 x 1 225 pairs instead of 324 x 2^15; 3x4: the two compressed vectors are 13.7 MB each and stay in L2, while the
 // full-space kernel streams 4 * 2^24 B per gradient from HBM.
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_sector_compress2(const unsigned *__restrict__ index, unsigned dim, const double2 *__restrict__ a,
+__global__ void __launch_bounds__(256) k_sector_compress2(const unsigned *__restrict__ depU, const unsigned *__restrict__ depD,
+                                                          unsigned d_dn, unsigned dim, const double2 *__restrict__ a,
                                                           const double2 *__restrict__ b, double2 *__restrict__ ac,
                                                           double2 *__restrict__ bc) {
     const unsigned stride = gridDim.x * blockDim.x;
     for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < dim; r += stride) {
-        const unsigned i = __ldg(index + r);
+        const unsigned ru = r / d_dn, rd = r - ru * d_dn;
+        const unsigned i = __ldg(depU + ru) | __ldg(depD + rd);          // full index of sector state r
         ac[r] = a[i];
         bc[r] = b[i];
     }
@@ -1285,13 +1316,13 @@ __global__ void __launch_bounds__(256) k_sector_compress2(const unsigned *__rest
 struct fh_sector_pool_plan {
     bool eligible = false;
     int n_up = -1, n_dn = -1;
-    u64 table_uid = 0, pool_uid = 0;
+    u64 table_uid = 0, pool_uid = 0, upmask = 0, dnmask = 0;
     unsigned d_up = 0, d_dn = 0;
-    unsigned *d_index = nullptr;          // full index of every sector state, rank order
+    unsigned *d_depU = nullptr, *d_depD = nullptr;      // index bits of every up / down pattern, rank order
     double2 *d_psi = nullptr, *d_lam = nullptr;
     void release() {
-        cudaFree(d_index); cudaFree(d_psi); cudaFree(d_lam);
-        d_index = nullptr; d_psi = d_lam = nullptr;
+        cudaFree(d_depU); cudaFree(d_depD); cudaFree(d_psi); cudaFree(d_lam);
+        d_depU = d_depD = nullptr; d_psi = d_lam = nullptr;
     }
 };
 
@@ -1302,25 +1333,31 @@ void fh_sector_pool_plan_free(fh_sector_pool_plan *plan) {
 }
 bool fh_sector_pool_plan_eligible(const fh_sector_pool_plan *plan) { return plan && plan->eligible; }
 
-int fh_sector_pool_prepare(fh_sector_pool_plan **slot, fh_ctx *ctx, int n, u64 basis, const std::vector<PairOp> &pairs,
-                           const std::vector<SecFlatOp> &flat, const fh_table *tab, const fh_pool *pool) {
+// upmask / dnmask: the index bits of the up / down orbitals (together all n bits); 0, 0 = the standard layout
+int fh_sector_pool_prepare(fh_sector_pool_plan **slot, fh_ctx *ctx, int n, u64 upmask, u64 dnmask, int n_up, int n_dn,
+                           const std::vector<PairOp> &pairs, const std::vector<SecFlatOp> &flat, const fh_table *tab,
+                           const fh_pool *pool) {
     if (!*slot) *slot = new fh_sector_pool_plan();
     fh_sector_pool_plan *P = *slot;
-    const int half = n / 2;
-    u64 upmask = 0, dnmask = 0;
-    for (int b = 0; b < half; ++b) {
-        upmask |= 1ull << (2 * b + 1);
-        dnmask |= 1ull << (2 * b);
-    }
-    const int n_up = __builtin_popcountll(basis & upmask), n_dn = __builtin_popcountll(basis & dnmask);
-    if (P->n_up == n_up && P->n_dn == n_dn && P->table_uid == tab->uid && P->pool_uid == pool->uid) return FH_OK;
+    if (upmask == 0 && dnmask == 0)
+        for (int b = 0; b < n; ++b) ((b & 1) ? upmask : dnmask) |= 1ull << b;
+    if (P->n_up == n_up && P->n_dn == n_dn && P->table_uid == tab->uid && P->pool_uid == pool->uid && P->upmask == upmask &&
+        P->dnmask == dnmask)
+        return FH_OK;
     P->release();
     P->eligible = false;
     P->n_up = n_up;
     P->n_dn = n_dn;
     P->table_uid = tab->uid;
     P->pool_uid = pool->uid;
-    if ((n & 1) || half < 1 || half > 15 || n > 31) return FH_OK;
+    P->upmask = upmask;
+    P->dnmask = dnmask;
+    const u64 full = n >= 64 ? ~0ull : ((1ull << n) - 1ull);
+    if (n < 2 || n > 31 || (upmask & dnmask) || (upmask | dnmask) != full) return FH_OK;
+    SecGeomHost G;
+    G.from_masks(n, upmask, dnmask);
+    const int nbu = (int)G.upbits.size(), nbd = (int)G.dnbits.size();
+    if (nbu < 1 || nbd < 1 || nbu > 16 || nbd > 16 || n_up < 0 || n_up > nbu || n_dn < 0 || n_dn > nbd) return FH_OK;
     // psi_s and lambda_s stay in the sector when every op, the observable and the pool map it to itself
     for (const SecFlatOp &f : flat)
         if (f.type == 1) {
@@ -1328,41 +1365,38 @@ int fh_sector_pool_prepare(fh_sector_pool_plan **slot, fh_ctx *ctx, int n, u64 b
             if (!sec_pattern_conserves(op.x, op.fixmask, op.fixval, upmask, dnmask)) return FH_OK;
         }
     if (!sec_table_conserves(tab, upmask, dnmask)) return FH_OK;
-    SecGeomHost G;
-    G.n = n;
-    G.half = half;
     G.n_up = n_up;
     G.n_dn = n_dn;
-    sec_patterns(half, n_up, G.cfgU, G.rankU);
-    sec_patterns(half, n_dn, G.cfgD, G.rankD);
-    if (G.d_up() > SEC_MAX_D || G.d_dn() > SEC_MAX_D) return FH_OK;
+    sec_patterns(nbu, n_up, G.cfgU, G.rankU);
+    sec_patterns(nbd, n_dn, G.cfgD, G.rankD);
+    if (G.d_up() > SEC_MAX_D || G.d_dn() > SEC_MAX_D || (u64)G.d_up() * G.d_dn() >= (1ull << 32)) return FH_OK;
     SecPoolCache &Pc = g_sec_pools[pool->uid];
-    if (Pc.pool_uid != pool->uid || Pc.n_up != n_up || Pc.n_dn != n_dn) {
+    if (Pc.pool_uid != pool->uid || Pc.n_up != n_up || Pc.n_dn != n_dn || Pc.upmask != upmask || Pc.dnmask != dnmask) {
         bool ok = false;
         FH_TRY(sec_build_pool(pool, G, upmask, dnmask, Pc, &ok));
         if (!ok) {
             fh_sector_forget_pool(pool->uid);
             return FH_OK;
         }
+        Pc.upmask = upmask;
+        Pc.dnmask = dnmask;
     }
     const u64 dim = (u64)G.d_up() * G.d_dn();
-    std::vector<unsigned> index((size_t)dim);
     std::vector<unsigned> depU(G.d_up()), depD(G.d_dn());
     for (unsigned r = 0; r < G.d_up(); ++r) {
         unsigned dep = 0;
-        for (int b = 0; b < half; ++b)
-            if (G.cfgU[r] >> b & 1u) dep |= 1u << (2 * b + 1);
+        for (int b = 0; b < nbu; ++b)
+            if (G.cfgU[r] >> b & 1u) dep |= 1u << G.upbits[b];
         depU[r] = dep;
     }
     for (unsigned r = 0; r < G.d_dn(); ++r) {
         unsigned dep = 0;
-        for (int b = 0; b < half; ++b)
-            if (G.cfgD[r] >> b & 1u) dep |= 1u << (2 * b);
+        for (int b = 0; b < nbd; ++b)
+            if (G.cfgD[r] >> b & 1u) dep |= 1u << G.dnbits[b];
         depD[r] = dep;
     }
-    for (unsigned ru = 0; ru < G.d_up(); ++ru)
-        for (unsigned rd = 0; rd < G.d_dn(); ++rd) index[(size_t)ru * G.d_dn() + rd] = depU[ru] | depD[rd];
-    FH_TRY(sec_upload(&P->d_index, index));
+    FH_TRY(sec_upload(&P->d_depU, depU));
+    FH_TRY(sec_upload(&P->d_depD, depD));
     FH_CUDA(cudaMalloc(&P->d_psi, sizeof(double2) * dim));
     FH_CUDA(cudaMalloc(&P->d_lam, sizeof(double2) * dim));
     P->d_up = G.d_up();
@@ -1372,28 +1406,37 @@ int fh_sector_pool_prepare(fh_sector_pool_plan **slot, fh_ctx *ctx, int n, u64 b
     return FH_OK;
 }
 
+static bool g_sec_pool_attr[64];
 // pool outputs o in [first, first+count) of full-space states psi / lam -> d_pool_out[o]
 int fh_sector_pool_enqueue(fh_sector_pool_plan *P, fh_ctx *ctx, const double2 *psi, const double2 *lam, const fh_pool *pool,
                            int pool_first, int pool_count, double *d_pool_out) {
     if (pool_count <= 0) return FH_OK;
     const SecPoolCache &Pc = g_sec_pools[pool->uid];
     const unsigned dim = P->d_up * P->d_dn;
-    int cgrid = (int)((dim + 255u) / 256u);
-    if (cgrid > ctx->sm_count * 8) cgrid = ctx->sm_count * 8;
+    unsigned cgrid = (dim + 255u) / 256u;
+    if (cgrid > (unsigned)ctx->sm_count * 8u) cgrid = (unsigned)ctx->sm_count * 8u;
     ++g_fh_launch_count;
-    k_sector_compress2<<<cgrid, 256, 0, ctx->stream>>>(P->d_index, dim, psi, lam, P->d_psi, P->d_lam);
+    k_sector_compress2<<<cgrid, 256, 0, ctx->stream>>>(P->d_depU, P->d_depD, P->d_dn, dim, psi, lam, P->d_psi, P->d_lam);
     const int e0 = pool->out_first[pool_first], e1 = pool->out_first[pool_first + pool_count];
     int grid = e1 - e0;
     if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
     if (grid < 1) grid = 1;
+    const size_t smem = sizeof(unsigned) * std::max(1u, Pc.max_words);
+    if (smem > 48 * 1024) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev &= 63;
+        if (!g_sec_pool_attr[dev]) {
+            FH_CUDA(cudaFuncSetAttribute(k_sector_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            g_sec_pool_attr[dev] = true;
+        }
+    }
     ++g_fh_launch_count;
-    k_sector_pool<<<grid, 256, sizeof(unsigned) * std::max(1u, Pc.max_words), ctx->stream>>>(
-        Pc.d_entries, Pc.d_lists, e0, e1, P->d_dn, P->d_psi, P->d_lam, Pc.d_partial, pool->d_out_first, pool_first, pool_count,
-        d_pool_out, Pc.d_counter);
+    k_sector_pool<<<grid, 256, smem, ctx->stream>>>(Pc.d_entries, Pc.d_lists, e0, e1, P->d_dn, P->d_psi, P->d_lam, Pc.d_partial,
+                                                    pool->d_out_first, pool_first, pool_count, d_pool_out, Pc.d_counter);
     FH_CUDA(cudaGetLastError());
     return FH_OK;
 }
-
 
 // ---- the same screening as a stand-alone call on caller-owned full-space states --------------------------------
 static std::map<u64, fh_sector_pool_plan *> g_sec_pool_plans;      // per pool handle (freed with the pool)
@@ -1405,37 +1448,39 @@ void fh_sector_forget_pool_plan(u64 uid) {
     }
 }
 
-extern "C" int fh_pool_gradients_sector(const fh_pool *pool, const fh_state *psi, const fh_state *lambda, int n_up, int n_dn,
-                                        int first, int count, double *out) {
-    FH_REQUIRE(pool && psi && lambda, "fh_pool_gradients_sector: NULL argument");
-    FH_REQUIRE(psi->n == pool->n && lambda->n == pool->n, "fh_pool_gradients_sector: qubit count mismatch");
-    FH_REQUIRE(first >= 0 && count >= 0 && first + count <= pool->n_out, "fh_pool_gradients_sector: range [%d, %d) outside pool of %d",
-               first, first + count, pool->n_out);
-    const int n = pool->n, half = n / 2;
-    FH_REQUIRE(!(n & 1) && half >= 1 && half <= 15, "fh_pool_gradients_sector: needs an even qubit count <= 30");
-    FH_REQUIRE(n_up >= 0 && n_up <= half && n_dn >= 0 && n_dn <= half, "fh_pool_gradients_sector: bad particle numbers");
+static int pool_gradients_sector_impl(const char *who, const fh_pool *pool, const fh_state *psi, const fh_state *lambda, u64 upmask,
+                                      u64 dnmask, int n_up, int n_dn, int first, int count, double *out) {
+    FH_REQUIRE(pool && psi && lambda, "%s: NULL argument", who);
+    FH_REQUIRE(psi->n == pool->n && lambda->n == pool->n, "%s: qubit count mismatch", who);
+    FH_REQUIRE(first >= 0 && count >= 0 && first + count <= pool->n_out, "%s: range [%d, %d) outside pool of %d", who, first,
+               first + count, pool->n_out);
     if (count == 0) return FH_OK;
     fh_ctx *ctx = pool->ctx;
     FH_CUDA(cudaSetDevice(ctx->device));
     fh_sector_pool_plan *&P = g_sec_pool_plans[pool->uid];
-    if (!P) P = new fh_sector_pool_plan();
-    if (!(P->eligible && P->n_up == n_up && P->n_dn == n_dn)) {
-        // a basis state of the sector stands in for the one a program would start from; no ops, no observable to check
-        u64 basis = 0;
-        for (int b = 0; b < n_up; ++b) basis |= 1ull << (2 * b + 1);
-        for (int b = 0; b < n_dn; ++b) basis |= 1ull << (2 * b);
-        fh_table dummy;
-        dummy.uid = ~0ull;
-        dummy.n = n;
-        P->n_up = -1;
-        FH_TRY(fh_sector_pool_prepare(&P, ctx, n, basis, std::vector<PairOp>(), std::vector<SecFlatOp>(), &dummy, pool));
-        FH_REQUIRE(P->eligible, "fh_pool_gradients_sector: the pool does not conserve (N_up, N_dn) = (%d, %d) or the sector is too large",
-                   n_up, n_dn);
-    }
+    fh_table dummy;          // no ops, no observable to check: the caller vouches for the states
+    dummy.uid = ~0ull;
+    dummy.n = pool->n;
+    FH_TRY(fh_sector_pool_prepare(&P, ctx, pool->n, upmask, dnmask, n_up, n_dn, std::vector<PairOp>(), std::vector<SecFlatOp>(),
+                                  &dummy, pool));
+    FH_REQUIRE(P->eligible, "%s: masks / particle numbers invalid, an entry does not conserve (N_up, N_dn) = (%d, %d), or the sector "
+               "is too large (> 16 384 patterns per spin)", who, n_up, n_dn);
     FH_TRY(fh_sector_pool_enqueue(P, ctx, psi->d, lambda->d, pool, first, count, pool->d_out));
     if (!out) return FH_OK;          // enqueue only (timing)
     FH_CUDA(cudaMemcpyAsync(pool->h_out, pool->d_out + first, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->stream));
     FH_CUDA(cudaStreamSynchronize(ctx->stream));
     memcpy(out, pool->h_out, sizeof(double) * count);
     return FH_OK;
+}
+
+extern "C" int fh_pool_gradients_sector(const fh_pool *pool, const fh_state *psi, const fh_state *lambda, int n_up, int n_dn,
+                                        int first, int count, double *out) {
+    return pool_gradients_sector_impl("fh_pool_gradients_sector", pool, psi, lambda, 0, 0, n_up, n_dn, first, count, out);
+}
+
+extern "C" int fh_pool_gradients_sector_masks(const fh_pool *pool, const fh_state *psi, const fh_state *lambda, uint64_t up_mask,
+                                              uint64_t dn_mask, int n_up, int n_dn, int first, int count, double *out) {
+    FH_REQUIRE(up_mask != 0 || dn_mask != 0, "fh_pool_gradients_sector_masks: both masks empty");
+    return pool_gradients_sector_impl("fh_pool_gradients_sector_masks", pool, psi, lambda, up_mask, dn_mask, n_up, n_dn, first, count,
+                                      out);
 }

@@ -29,8 +29,9 @@ void fh_sector_forget_pool(u64 uid);
 
 // K3 in the sector for the full-space path: compress psi_s / lambda_s (full 2^n states) into rank order, then the pool kernel
 struct fh_sector_pool_plan;
-int fh_sector_pool_prepare(fh_sector_pool_plan **slot, fh_ctx *ctx, int n, u64 basis, const std::vector<PairOp> &pairs,
-                           const std::vector<SecFlatOp> &flat, const fh_table *tab, const fh_pool *pool);
+int fh_sector_pool_prepare(fh_sector_pool_plan **slot, fh_ctx *ctx, int n, u64 upmask, u64 dnmask, int n_up, int n_dn,
+                           const std::vector<PairOp> &pairs, const std::vector<SecFlatOp> &flat, const fh_table *tab,
+                           const fh_pool *pool);
 bool fh_sector_pool_plan_eligible(const fh_sector_pool_plan *plan);
 int fh_sector_pool_enqueue(fh_sector_pool_plan *plan, fh_ctx *ctx, const double2 *psi, const double2 *lam, const fh_pool *pool,
                            int pool_first, int pool_count, double *d_pool_out);

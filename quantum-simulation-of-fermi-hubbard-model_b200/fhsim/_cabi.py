@@ -52,6 +52,7 @@ SIGNATURES = {
     "fh_pool_free": [_vp],
     "fh_pool_gradients": [_vp, _vp, _vp, C.c_int, C.c_int, _f64p],
     "fh_pool_gradients_sector": [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _f64p],
+    "fh_pool_gradients_sector_masks": [_vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, _f64p],
     "fh_program_create": [_vp, C.c_int, C.c_int, _vpp],
     "fh_program_destroy": [_vp],
     "fh_program_add_pair": [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_double,

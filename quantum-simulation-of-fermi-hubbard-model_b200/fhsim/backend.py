@@ -231,13 +231,21 @@ class DevicePool:
             count = self.n_out - first
         _cabi.check(_cabi.lib().fh_pool_gradients(self._h, psi._h, lam._h, int(first), int(count), None))
 
-    def gradients_sector(self, psi: State, lam: State, n_up: int, n_dn: int, first=0, count=None, enqueue_only=False):
-        """K3 on sector-compressed copies of psi / lambda (states confined to the (n_up, n_dn) sector); csrc/sector_eval.cu."""
+    def gradients_sector(self, psi: State, lam: State, n_up: int, n_dn: int, first=0, count=None, enqueue_only=False,
+                         up_mask=None, dn_mask=None):
+        """K3 on sector-compressed copies of psi / lambda (states confined to the (n_up, n_dn) sector); csrc/sector_eval.cu.
+        up_mask / dn_mask: index bits of the up / down orbitals when they are not the standard odd / even bits (a slab of
+        a sharded state)."""
         if count is None:
             count = self.n_out - first
         out = np.zeros(max(count, 1))
-        _cabi.check(_cabi.lib().fh_pool_gradients_sector(self._h, psi._h, lam._h, int(n_up), int(n_dn), int(first), int(count),
-                                                         None if enqueue_only else out.ctypes.data_as(_cabi._f64p)))
+        optr = None if enqueue_only else out.ctypes.data_as(_cabi._f64p)
+        if up_mask is None:
+            _cabi.check(_cabi.lib().fh_pool_gradients_sector(self._h, psi._h, lam._h, int(n_up), int(n_dn), int(first), int(count),
+                                                             optr))
+        else:
+            _cabi.check(_cabi.lib().fh_pool_gradients_sector_masks(self._h, psi._h, lam._h, int(up_mask), int(dn_mask), int(n_up),
+                                                                   int(n_dn), int(first), int(count), optr))
         return None if enqueue_only else out[:count]
 
     def gradients(self, psi: State, lam: State, first=0, count=None) -> np.ndarray:

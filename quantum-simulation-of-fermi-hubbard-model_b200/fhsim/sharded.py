@@ -29,6 +29,8 @@ tests on CPU.  There is no CPU fallback in the product: ``CudaEngine`` needs the
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from .circuit import DiagOpSpec, Marker, PairOpSpec
@@ -208,6 +210,51 @@ def lower_pool_entries(entries, layout: QubitLayout, rank: int, todo):
     return local, done
 
 
+def _is_up_bit(logical_bit: int, n: int) -> bool:
+    """wire = n - 1 - bit; even wires are the up orbitals (linalg/exact_diagonalization.py:34-51)."""
+    return (n - 1 - logical_bit) % 2 == 0
+
+
+def conserves_species(ops, n: int) -> bool:
+    """True when every pair op pins all its x bits and moves as many electrons in as out of each spin species, i.e. the
+    circuit maps every (N_up, N_dn) sector to itself op by op (diagonal ops always do)."""
+    up = sum(1 << b for b in range(n) if _is_up_bit(b, n))
+    for op in ops:
+        if isinstance(op, DiagOpSpec):
+            continue
+        x, fm, fv = int(op.x), int(op.fixmask), int(op.fixval)
+        if x & ~fm:
+            return False
+        for mask in (up, ~up & ((1 << n) - 1)):
+            if 2 * bin(fv & x & mask).count("1") != bin(x & mask).count("1"):
+                return False
+    return True
+
+
+def local_sector(layout: QubitLayout, rank: int, n_up: int, n_dn: int):
+    """(up_mask, dn_mask, n_up_local, n_dn_local) of the slab of ``rank``: which local physical bits are up / down orbitals and
+    how many electrons of each species they hold once the occupations of the rank bits are taken out; None when this slab
+    holds no amplitude of the sector."""
+    n, nl = layout.n, layout.nl
+    up_mask = dn_mask = 0
+    for b in range(n):
+        p = layout.perm[b]
+        isup = _is_up_bit(b, n)
+        if p < nl:
+            if isup:
+                up_mask |= 1 << p
+            else:
+                dn_mask |= 1 << p
+        elif (rank >> (p - nl)) & 1:
+            if isup:
+                n_up -= 1
+            else:
+                n_dn -= 1
+    if n_up < 0 or n_dn < 0 or n_up > bin(up_mask).count("1") or n_dn > bin(dn_mask).count("1"):
+        return None
+    return up_mask, dn_mask, n_up, n_dn
+
+
 def pool_entries_of(plans):
     entries = []
     for k, plan in enumerate(plans):
@@ -352,6 +399,8 @@ class ShardedSimulator:
         self.profile = {}
         self._keepalive = {}           # op lists whose ids key the engine's compiled-program cache
         self._dagger_cache = {}
+        self._conserve_cache = {}
+        self.sector_pool_used = False
         self.swap_count = 0            # all-to-alls issued (per state)
         self.pass_count = {"table": 0, "pool": 0}
 
@@ -491,9 +540,10 @@ class ShardedSimulator:
         return complex(red[0], red[1])
 
     # -- K3 --------------------------------------------------------------------------------------
-    def pool_gradients(self, plans, psi: ShardedState, lam: ShardedState) -> np.ndarray:
+    def pool_gradients(self, plans, psi: ShardedState, lam: ShardedState, sector=None) -> np.ndarray:
         """g_k = 2 Im <lam|G_k|psi> for every generator plan; psi and lam must share a layout (they are re-laid
-        out together between passes)."""
+        out together between passes).  sector = (N_up, N_dn): psi and lam are confined to that sector, so every slab is
+        screened on its sector-compressed copy (``fh_pool_gradients_sector_masks``) instead of in its full 2^n_local space."""
         if not (psi.layout == lam.layout):
             self.to_layout(lam, psi.layout)
         entries = pool_entries_of(plans)
@@ -505,7 +555,13 @@ class ShardedSimulator:
             local, done = lower_pool_entries(entries, psi.layout, rank, todo)
             if done:
                 self.pass_count["pool"] += 1
-                acc += self.engine.pool_partial(local, psi.h, lam.h, n_out)
+                loc = local_sector(psi.layout, rank, *sector) if sector is not None else False
+                if loc is None:
+                    pass                                   # this slab holds no amplitude of the sector
+                elif loc:
+                    acc += self.engine.pool_partial(local, psi.h, lam.h, n_out, sector=loc)
+                else:
+                    acc += self.engine.pool_partial(local, psi.h, lam.h, n_out)
                 done_set = set(done)
                 todo = [e for e in todo if e not in done_set]
             if not todo:
@@ -537,7 +593,7 @@ class ShardedSimulator:
 
     # -- the cfg-5 evaluation ---------------------------------------------------------------------
     def adapt_screening(self, basis_index, ansatz_ops, basis_change_ops, h_table: PauliTable, plans, thetas=(),
-                        n_params=0, want_gradients=True):
+                        n_params=0, want_gradients=True, sector_pool=True):
         """psi_k = ansatz|basis>, phi = W psi_k, E = <phi|H|phi>, lam = W^dagger H phi, g = pool gradients
         (reference ADAPT.select_operator, models/adapt_vqe.py:297-323, on a sharded state)."""
         import time
@@ -571,7 +627,20 @@ class ShardedSimulator:
             t = lap("W_dagger", t)
             self.to_layout(lam, psi.layout)
             t = lap("align_layouts", t)
-            grads = self.pool_gradients(plans, psi, lam)
+            # every op conserves N_up and N_dn (and the Hubbard Hamiltonian does): psi_s and lambda_s live in the sector of
+            # the basis state, so the pool is screened on sector-compressed slabs
+            sector = None
+            if sector_pool and os.environ.get("FHSIM_NO_SECTOR_POOL") is None:
+                key = (id(ansatz_ops), id(basis_change_ops))
+                ok = self._conserve_cache.get(key)
+                if ok is None:
+                    ok = self._conserve_cache[key] = (conserves_species(list(ansatz_ops) + list(basis_change_ops), self.n)
+                                                      and h_table.conserves_species())
+                if ok:
+                    up = sum(1 << b for b in range(self.n) if _is_up_bit(b, self.n))
+                    sector = (bin(int(basis_index) & up).count("1"), bin(int(basis_index) & ~up).count("1"))
+            self.sector_pool_used = sector is not None
+            grads = self.pool_gradients(plans, psi, lam, sector)
             t = lap("pool_scan", t)
             lam.close()
         else:
@@ -777,7 +846,7 @@ class CudaEngine:
                             C.byref(re), C.byref(im)))
         return complex(re.value, im.value)
 
-    def pool_partial(self, local_entries, h_psi, h_lam, n_out):
+    def pool_partial(self, local_entries, h_psi, h_lam, n_out, sector=None):
         from .backend import DevicePool
         if not local_entries:
             return np.zeros(n_out)
@@ -788,6 +857,9 @@ class CudaEngine:
             if len(self._pools) >= 8:
                 self._pools.pop(next(iter(self._pools))).close()
             pool = self._pools[key] = DevicePool.from_entries(self.ctx, self.n_local, local_entries, n_out)
+        if sector is not None and max(bin(sector[0]).count("1"), bin(sector[1]).count("1")) <= 16:
+            up_mask, dn_mask, n_up, n_dn = sector
+            return pool.gradients_sector(h_psi[0].st, h_lam[0].st, n_up, n_dn, up_mask=up_mask, dn_mask=dn_mask).copy()
         return pool.gradients(h_psi[0].st, h_lam[0].st).copy()
 
     def inner(self, ha, hb):

@@ -97,6 +97,38 @@ class PauliTable:
     def as_dict(self):
         return {(int(a), int(b)): complex(c) for a, b, c in zip(self.x, self.z, self.coeff)}
 
+    def conserves_species(self) -> bool:
+        """Does the operator commute with N_up and N_dn (even wires = up orbitals)?  Per x-mask group: the weight of the
+        partner with x-bit pattern ``pat`` is sum_m d_m (-1)^popcount(z_m & pat-bits) class by class (a class = the z bits
+        outside x); every pattern with a non-zero weight must move as many electrons into as out of each species.
+        Groups with more than four x bits are not analysed (-> False).  Same rule as the device planner (csrc/sector_eval.cu)."""
+        n = self.n_qubits
+        up = sum(1 << b for b in range(n) if (n - 1 - b) % 2 == 0)
+        i_pow = (1, 1j, -1, -1j)
+        groups = {}
+        for x, z, c, k in zip(self.x, self.z, self.coeff, self.k):
+            groups.setdefault(int(x), []).append((int(z), complex(c) * i_pow[int(k)]))
+        for x, terms in groups.items():
+            if x == 0:
+                continue
+            pos = [b for b in range(n) if x >> b & 1]
+            if len(pos) > 4:
+                return False
+            classes = {}
+            for z, d in terms:
+                classes.setdefault(z & ~x, []).append((z, d))
+            for pat in range(1 << len(pos)):
+                dep = sum(1 << pos[b] for b in range(len(pos)) if pat >> b & 1)
+                live = any(abs(sum(d * (-1) ** bin(dep & z).count("1") for z, d in cl)) > 0 for cl in classes.values())
+                if not live:
+                    continue
+                # the partner j carries `pat` on the x bits, the output i = j ^ x the complement
+                dup = sum((1 - 2 * (pat >> b & 1)) for b in range(len(pos)) if up >> pos[b] & 1)
+                ddn = sum((1 - 2 * (pat >> b & 1)) for b in range(len(pos)) if not up >> pos[b] & 1)
+                if dup != 0 or ddn != 0:
+                    return False
+        return True
+
     # -- iQCC dressing on packed masks (reference models/iqcc_hubbard.py:184-189) -----------------------------
     def dressed(self, xp: int, zp: int, tau: float, tol: float = 1e-12) -> "PauliTable":
         """exp(i tau P / 2) H exp(-i tau P / 2) for the Pauli string P = (xp, zp), i.e. the reference's

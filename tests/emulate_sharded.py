@@ -97,7 +97,7 @@ class NumpyEngine:
             h_out[0] = (h_out[0] + acc) if accumulate else acc
         return complex(np.vdot(psi, acc))
 
-    def pool_partial(self, entries, h_psi, h_lam, n_out):
+    def pool_partial(self, entries, h_psi, h_lam, n_out, sector=None):
         self.calls["pool_partial"] += 1
         n = self.n_local
         psi, lam = h_psi[0], h_lam[0]

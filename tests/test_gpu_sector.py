@@ -237,3 +237,41 @@ def test_pool_screening_on_sector_compressed_copies(ctx, lat, u, up, dn, monkeyp
     r2 = p2.evaluate(basis, th, [dtab], pool=dpool, pool_pos=p2.markers["ansatz_end"])
     assert not p2.sector_info()["pool_in_sector"]
     assert np.abs(r2["pool"] - pg_want).max() < G_TOL
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_sector_screening_with_permuted_species_bits(ctx, seed):
+    """fh_pool_gradients_sector_masks: the form a slab of a sharded state needs.  The index bits of a 2x3 ADAPT state are
+    permuted at random (so up / down orbitals are no longer the odd / even bits), the pool is lowered to that layout, and
+    the sector-compressed screening with the permuted species masks must equal the full-space kernel and the oracle."""
+    from fhsim.backend import State
+    from fhsim.sharded import QubitLayout, local_sector, lower_pool_entries, pool_entries_of
+    lat, u, up, dn = (2, 3), 4.0, 3, 3
+    n, h_tab, pool_ops, dec, diag, o_h, o_pool = lattice(*lat, u)
+    rng = np.random.default_rng(seed)
+    occ_up, occ_dn, _ = pauli.k_space_occupation(*lat, 1.0, up, dn)
+    picks = list(rng.choice(len(pool_ops), size=5, replace=False))
+    th = rng.uniform(-0.4, 0.4, len(picks))
+    psi = sv.adapt_state(n, occ_up + occ_dn, [o_pool[k] for k in picks], th)
+    g_want, _, lam = sv.pool_gradients(psi, o_h, o_pool, diag, dec, n)
+    layout = QubitLayout(n, 0, [int(v) for v in rng.permutation(n)])
+    idx = np.arange(1 << n)
+    pidx = np.zeros_like(idx)
+    for b in range(n):
+        pidx |= ((idx >> b) & 1) << layout.perm[b]
+    psi_p, lam_p = np.zeros_like(psi), np.zeros_like(lam)
+    psi_p[pidx], lam_p[pidx] = psi, lam
+    plans = [GeneratorPlan(g, n) for g in pool_ops]
+    entries = pool_entries_of(plans)
+    local, done = lower_pool_entries(entries, layout, 0, list(range(len(entries))))
+    assert len(done) == len(entries)
+    dpool = DevicePool.from_entries(ctx, n, local, len(plans))
+    sp, sl = State.from_numpy(ctx, psi_p), State.from_numpy(ctx, lam_p)
+    up_mask, dn_mask, nu, nd = local_sector(layout, 0, up, dn)
+    assert (nu, nd) == (up, dn) and up_mask | dn_mask == (1 << n) - 1
+    g_full = dpool.gradients(sp, sl)
+    g_sec = dpool.gradients_sector(sp, sl, nu, nd, up_mask=up_mask, dn_mask=dn_mask)
+    assert np.abs(g_full - g_want).max() < G_TOL
+    assert np.abs(g_sec - g_full).max() < 1e-12
+    with pytest.raises(ValueError):
+        dpool.gradients_sector(sp, sl, nu, nd, up_mask=up_mask, dn_mask=dn_mask | 1 | up_mask)      # overlapping masks

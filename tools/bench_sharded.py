@@ -159,8 +159,12 @@ def run_sharded(lattice="4x4", u=4.0, n_ops=16, steps=2, dist=None, local_rank=0
             "gradients_per_s": n_pool / best["screening_s"],
             "screening_effective_GBps_all_gpus": alg_bytes / best["screening_s"] / 1e9,
             "check_vs_single_gpu": check,
+            "pool_scan": ("every slab screened on its sector-compressed copy (fh_pool_gradients_sector_masks)"
+                          if getattr(sim, "sector_pool_used", False) else "full local space (k_pool32 / k_pool_tile)"),
+            "grad_l2_reference_full_space_scan": 9.543770434819237 if (lattice == "4x4" and len(picks) == 16) else None,
         }
         if peak_gbs and phases and phases.get("pool_scan"):
+            # 4 * 2^n B per gradient is the full-space figure: with the sector scan this is an effective rate (can exceed 1)
             out["pool_scan_hbm_frac_per_gpu"] = alg_bytes / world / phases["pool_scan"] / 1e9 / peak_gbs
     engine.close()                       # slabs, cached tables / pools / programs, communicator
     torch.cuda.empty_cache()
