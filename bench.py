@@ -534,6 +534,9 @@ def run_gpu_arm(args, rank, world, local_rank):
                            ("diag_coulomb", "k_diag: Coulomb layer, 32*2^n B"),
                            ("tile_W", "k_tile: one fused launch of W, 32*2^n B"),
                            ("h_apply", "k_table_pass x2 (K2 in shared-memory tile passes): H psi + <H>, 32*2^n B"),
+                           ("h_apply_sector", "k_sector_compress1 + k_sector_happly + memset + k_sector_scatter1: the same H psi + <H> on "
+                                              "the sector-compressed state (what fh_program_evaluate runs for number-conserving "
+                                              "evaluations); effective rate on 32*2^n B"),
                            ("screening_sector", "k_sector_compress2 + k_sector_pool: the same 400 gradients on sector-compressed "
                                                 "psi / lambda (853 776 amplitudes, L2-resident); effective rate on 4*2^n B each")):
             if key not in row:

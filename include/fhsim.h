@@ -104,6 +104,11 @@ int fh_table_info(const fh_table *tab, int *n_terms, int *n_groups);
 int fh_table_tile_passes(const fh_table *tab, int *n_passes);
 /* out <- H in (out may be NULL: expectation only); *e = <in|H|in>.  in and out must differ. */
 int fh_apply_table(const fh_table *tab, const fh_state *in, fh_state *out, double *e_re, double *e_im);
+/* The same for a state confined to the (n_up, n_dn) sector (even wires = up) and a table that conserves both numbers: `in` is
+ * gathered into rank order, H is applied to the compressed vector (partners through two rank tables; 3x4: 13.7 MB, L2-resident)
+ * and H in is scattered back into `out` (zeroed first; may be NULL: expectation only).  FH_EINVAL when the table does not
+ * qualify.  e_re == e_im == NULL: enqueue only.  fh_program_evaluate takes this route by itself (fh_program_sector_info). */
+int fh_apply_table_sector(const fh_table *tab, const fh_state *in, fh_state *out, int n_up, int n_dn, double *e_re, double *e_im);
 /* out <- out + H in  (sum of partial Hamiltonians, e.g. one table per qubit layout of a sharded state); *e = <in|H|in> */
 int fh_apply_table_accumulate(const fh_table *tab, const fh_state *in, fh_state *out, double *e_re, double *e_im);
 
@@ -182,7 +187,9 @@ int fh_program_evaluate(fh_program *prog, uint64_t basis_index, const double *th
  * never).  Otherwise, when the circuit, the observable and the pool conserve (N_up, N_dn), the full-space path still screens
  * the pool (K3) on sector-compressed copies of psi_s / lambda_s (3x3: 1 225 instead of 2^15 pairs per operator; 3x4: the
  * compressed vectors are L2-resident); FHSIM_NO_SECTOR_POOL=1 keeps K3 in the full space.
- * active: 1 if the last call ran in the cluster, 2 if only its pool screening ran in the sector, 0 otherwise;
+ * K2 of tables[0] takes the same shortcut (compress, gather over the term groups on the compressed vector, scatter of H psi back
+ * when the adjoint part needs it: from 20 qubits on; FHSIM_NO_SECTOR_K2=1 disables it).
+ * active: 1 if the last call ran in the cluster; otherwise a bit set: 2 = K3 in the sector, 4 = K2 in the sector; 0 = full space;
  * cluster_size: CTAs of the cluster; sector_dim: amplitudes; n_ops: steps of the cluster kernel (ops, transposes,
  * checkpoint, H, store); n_transposes / n_remote_ops: layout changes / ops that exchange amplitudes between CTAs. */
 int fh_program_sector_info(const fh_program *prog, int *active, int *cluster_size, uint64_t *sector_dim, int *n_ops,

@@ -605,6 +605,7 @@ extern "C" int fh_table_free(fh_table *tab) {
     cudaFree(tab->d_diag);
     fh_table_tiles_free(tab->tiles);
     fh_sector_forget_table(tab->uid);
+    fh_sector_forget_table_plan(tab->uid);
     delete tab;
     return FH_OK;
 }

@@ -46,6 +46,7 @@ struct EvalKey {
     int pool_pos, pool_first, pool_count;
     const void *state_out;
     int sector, sector_pool;     // 1: the sector-resident path (sector_eval.cu) / K3 on sector-compressed copies was planned
+    int sector_k2, pad_k2;       // 1: K2 of tables[0] on the sector-compressed state
     // unique ids of the same handles: a freed handle whose address is reused by a new one gets a new id, so the graph
     // (which bakes in the device pointers behind the handles) is re-captured instead of replayed on freed memory
     u64 table_uid[FH_MAX_RESULT_TABLES], target_uid[FH_MAX_OVERLAPS], pool_uid, state_out_uid;
@@ -113,7 +114,7 @@ struct fh_program {
     std::vector<int> item_flat_first;
     fh_sector_plan *sec = nullptr;
     fh_sector_pool_plan *sec_pool = nullptr;
-    bool last_sector = false, last_sector_pool = false;
+    bool last_sector = false, last_sector_pool = false, last_sector_k2 = false;
     // measurement
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0.0;
@@ -930,7 +931,11 @@ static int enqueue_evaluation(fh_program *p, const EvalKey &k, fh_table *const *
     for (int t = 0; t < k.n_tables; ++t) {
         const fh_table *tab = tables[t];
         double2 *h_out = (t == 0 && need_adjoint) ? p->d_lam : nullptr;
-        launch_apply_table(ctx->stream, ctx->sm_count, tab, psi, h_out, h_out ? 1 : 0, ctx->d_partials, p->d_res + 2 * t);
+        // K2 in the sector: always when only <H> is wanted; with lambda (memset + scatter of the full vector) from 20 qubits on
+        if (t == 0 && k.sector_k2 && (h_out == nullptr || p->n >= 20))
+            FH_TRY(fh_sector_table_enqueue(p->sec_pool, ctx, tab, psi, h_out, p->d_res + 2 * t));
+        else
+            launch_apply_table(ctx->stream, ctx->sm_count, tab, psi, h_out, h_out ? 1 : 0, ctx->d_partials, p->d_res + 2 * t);
     }
     for (int v = 0; v < k.n_overlaps; ++v)
         launch_inner(ctx->stream, ctx->sm_count, targets[v]->d, psi, 1ull << p->n, ctx->d_partials,
@@ -1057,13 +1062,16 @@ extern "C" int fh_program_evaluate(fh_program *p, uint64_t basis_index, const do
         p->last_sector = key.sector != 0;
     }
     p->last_sector_pool = false;
-    if (pool && !key.sector && n_tables >= 1 && !(p->n & 1) && p->n <= 31 && !getenv("FHSIM_NO_SECTOR_POOL")) {
+    p->last_sector_k2 = false;
+    if (!key.sector && n_tables >= 1 && !(p->n & 1) && p->n <= 31 && !getenv("FHSIM_NO_SECTOR_POOL")) {
         u64 upm = 0, dnm = 0;
         for (int b = 0; b < p->n; ++b) ((b & 1) ? upm : dnm) |= 1ull << b;          // even wires = up = odd index bits
         FH_TRY(fh_sector_pool_prepare(&p->sec_pool, ctx, p->n, upm, dnm, __builtin_popcountll(basis_index & upm),
                                       __builtin_popcountll(basis_index & dnm), p->pairs, p->flat, tables[0], pool));
-        key.sector_pool = fh_sector_pool_plan_eligible(p->sec_pool) ? 1 : 0;
+        key.sector_pool = (pool && fh_sector_pool_plan_eligible(p->sec_pool)) ? 1 : 0;
+        key.sector_k2 = fh_sector_pool_plan_table_ok(p->sec_pool) ? 1 : 0;
         p->last_sector_pool = key.sector_pool != 0;
+        p->last_sector_k2 = key.sector_k2 != 0;
     }
 
     static const bool no_graph = getenv("FHSIM_NO_GRAPH") != nullptr;
@@ -1135,7 +1143,7 @@ extern "C" int fh_program_payload_bytes(const fh_program *p, size_t *h2d_bytes, 
 extern "C" int fh_program_sector_info(const fh_program *p, int *active, int *cluster_size, uint64_t *sector_dim, int *n_ops,
                                       int *n_transposes, int *n_remote_ops) {
     FH_REQUIRE(p, "fh_program_sector_info: program is NULL");
-    if (active) *active = p->last_sector ? 1 : (p->last_sector_pool ? 2 : 0);
+    if (active) *active = p->last_sector ? 1 : ((p->last_sector_pool ? 2 : 0) | (p->last_sector_k2 ? 4 : 0));
     u64 dim = 0;
     fh_sector_plan_describe(p->last_sector ? p->sec : nullptr, cluster_size, &dim, n_ops, n_transposes, n_remote_ops, nullptr);
     if (sector_dim) *sector_dim = dim;

@@ -1314,15 +1314,22 @@ __global__ void __launch_bounds__(256) k_sector_compress2(const unsigned *__rest
 }
 
 struct fh_sector_pool_plan {
-    bool eligible = false;
-    int n_up = -1, n_dn = -1;
+    bool eligible = false;           // K3 in the sector
+    bool table_ok = false;           // K2 in the sector as well (standard species layout, observable in compact form)
+    int n_up = -1, n_dn = -1, n = 0, half = 0;
     u64 table_uid = 0, pool_uid = 0, upmask = 0, dnmask = 0;
     unsigned d_up = 0, d_dn = 0;
     unsigned *d_depU = nullptr, *d_depD = nullptr;      // index bits of every up / down pattern, rank order
-    double2 *d_psi = nullptr, *d_lam = nullptr;
+    double2 *d_psi = nullptr, *d_lam = nullptr;         // K3: compressed psi_s, lambda_s
+    double2 *d_in = nullptr, *d_out = nullptr;          // K2: compressed psi, H psi
+    unsigned short *d_cfgU = nullptr, *d_cfgD = nullptr, *d_rankU = nullptr, *d_rankD = nullptr;
+    double *d_k2_partials = nullptr;
+    unsigned *d_k2_counter = nullptr;
     void release() {
-        cudaFree(d_depU); cudaFree(d_depD); cudaFree(d_psi); cudaFree(d_lam);
-        d_depU = d_depD = nullptr; d_psi = d_lam = nullptr;
+        cudaFree(d_depU); cudaFree(d_depD); cudaFree(d_psi); cudaFree(d_lam); cudaFree(d_in); cudaFree(d_out);
+        cudaFree(d_cfgU); cudaFree(d_cfgD); cudaFree(d_rankU); cudaFree(d_rankD); cudaFree(d_k2_partials); cudaFree(d_k2_counter);
+        d_depU = d_depD = nullptr; d_psi = d_lam = d_in = d_out = nullptr;
+        d_cfgU = d_cfgD = d_rankU = d_rankD = nullptr; d_k2_partials = nullptr; d_k2_counter = nullptr;
     }
 };
 
@@ -1332,6 +1339,7 @@ void fh_sector_pool_plan_free(fh_sector_pool_plan *plan) {
     delete plan;
 }
 bool fh_sector_pool_plan_eligible(const fh_sector_pool_plan *plan) { return plan && plan->eligible; }
+bool fh_sector_pool_plan_table_ok(const fh_sector_pool_plan *plan) { return plan && plan->table_ok; }
 
 // upmask / dnmask: the index bits of the up / down orbitals (together all n bits); 0, 0 = the standard layout
 int fh_sector_pool_prepare(fh_sector_pool_plan **slot, fh_ctx *ctx, int n, u64 upmask, u64 dnmask, int n_up, int n_dn,
@@ -1341,15 +1349,19 @@ int fh_sector_pool_prepare(fh_sector_pool_plan **slot, fh_ctx *ctx, int n, u64 u
     fh_sector_pool_plan *P = *slot;
     if (upmask == 0 && dnmask == 0)
         for (int b = 0; b < n; ++b) ((b & 1) ? upmask : dnmask) |= 1ull << b;
-    if (P->n_up == n_up && P->n_dn == n_dn && P->table_uid == tab->uid && P->pool_uid == pool->uid && P->upmask == upmask &&
-        P->dnmask == dnmask)
+    const u64 pool_uid = pool ? pool->uid : 0;
+    // a plan built with a pool also serves the calls without one (drivers alternate screening and training evaluations)
+    if (P->n_up == n_up && P->n_dn == n_dn && P->table_uid == tab->uid && (P->pool_uid == pool_uid || !pool) && P->upmask == upmask &&
+        P->dnmask == dnmask && P->n == n)
         return FH_OK;
     P->release();
     P->eligible = false;
+    P->table_ok = false;
+    P->n = n;
     P->n_up = n_up;
     P->n_dn = n_dn;
     P->table_uid = tab->uid;
-    P->pool_uid = pool->uid;
+    P->pool_uid = pool_uid;
     P->upmask = upmask;
     P->dnmask = dnmask;
     const u64 full = n >= 64 ? ~0ull : ((1ull << n) - 1ull);
@@ -1370,17 +1382,32 @@ int fh_sector_pool_prepare(fh_sector_pool_plan **slot, fh_ctx *ctx, int n, u64 u
     sec_patterns(nbu, n_up, G.cfgU, G.rankU);
     sec_patterns(nbd, n_dn, G.cfgD, G.rankD);
     if (G.d_up() > SEC_MAX_D || G.d_dn() > SEC_MAX_D || (u64)G.d_up() * G.d_dn() >= (1ull << 32)) return FH_OK;
-    SecPoolCache &Pc = g_sec_pools[pool->uid];
-    if (Pc.pool_uid != pool->uid || Pc.n_up != n_up || Pc.n_dn != n_dn || Pc.upmask != upmask || Pc.dnmask != dnmask) {
-        bool ok = false;
-        FH_TRY(sec_build_pool(pool, G, upmask, dnmask, Pc, &ok));
-        if (!ok) {
-            fh_sector_forget_pool(pool->uid);
-            return FH_OK;
+    bool pool_ok = false;
+    if (pool) {
+        SecPoolCache &Pc = g_sec_pools[pool->uid];
+        pool_ok = true;
+        if (Pc.pool_uid != pool->uid || Pc.n_up != n_up || Pc.n_dn != n_dn || Pc.upmask != upmask || Pc.dnmask != dnmask) {
+            FH_TRY(sec_build_pool(pool, G, upmask, dnmask, Pc, &pool_ok));
+            if (!pool_ok) fh_sector_forget_pool(pool->uid);
+            Pc.upmask = upmask;
+            Pc.dnmask = dnmask;
         }
-        Pc.upmask = upmask;
-        Pc.dnmask = dnmask;
     }
+    // K2 in the sector: the observable in compact coordinates (standard species layout, real table handle only)
+    bool standard = !(n & 1) && n / 2 <= 15;
+    for (int b = 0; b < n && standard; ++b) standard = ((upmask >> b) & 1ull) == (u64)(b & 1);
+    bool table_ok = false;
+    if (standard && tab->uid != ~0ull && !getenv("FHSIM_NO_SECTOR_K2")) {
+        SecTableCache &T = g_sec_tables[tab->uid];
+        table_ok = true;
+        if (T.table_uid != tab->uid || T.n_up != n_up || T.n_dn != n_dn) {
+            SecGeomHost Gs = G;
+            Gs.standard(n);
+            FH_TRY(sec_build_table(tab, Gs, upmask, dnmask, T, &table_ok));
+            if (!table_ok) fh_sector_forget_table(tab->uid);
+        }
+    }
+    if (!pool_ok && !table_ok) return FH_OK;
     const u64 dim = (u64)G.d_up() * G.d_dn();
     std::vector<unsigned> depU(G.d_up()), depD(G.d_dn());
     for (unsigned r = 0; r < G.d_up(); ++r) {
@@ -1397,12 +1424,157 @@ int fh_sector_pool_prepare(fh_sector_pool_plan **slot, fh_ctx *ctx, int n, u64 u
     }
     FH_TRY(sec_upload(&P->d_depU, depU));
     FH_TRY(sec_upload(&P->d_depD, depD));
-    FH_CUDA(cudaMalloc(&P->d_psi, sizeof(double2) * dim));
-    FH_CUDA(cudaMalloc(&P->d_lam, sizeof(double2) * dim));
+    if (pool_ok) {
+        FH_CUDA(cudaMalloc(&P->d_psi, sizeof(double2) * dim));
+        FH_CUDA(cudaMalloc(&P->d_lam, sizeof(double2) * dim));
+    }
+    if (table_ok) {
+        FH_CUDA(cudaMalloc(&P->d_in, sizeof(double2) * dim));
+        FH_CUDA(cudaMalloc(&P->d_out, sizeof(double2) * dim));
+        FH_TRY(sec_upload(&P->d_cfgU, G.cfgU));
+        FH_TRY(sec_upload(&P->d_cfgD, G.cfgD));
+        FH_TRY(sec_upload(&P->d_rankU, G.rankU));
+        FH_TRY(sec_upload(&P->d_rankD, G.rankD));
+        FH_CUDA(cudaMalloc(&P->d_k2_partials, sizeof(double) * 2 * 4096));
+        FH_CUDA(cudaMalloc(&P->d_k2_counter, sizeof(unsigned)));
+        FH_CUDA(cudaMemset(P->d_k2_counter, 0, sizeof(unsigned)));
+    }
+    P->half = G.half;
     P->d_up = G.d_up();
     P->d_dn = G.d_dn();
-    P->eligible = true;
+    P->eligible = pool_ok;
+    P->table_ok = table_ok;
     (void)ctx;
+    return FH_OK;
+}
+
+// ---- K2 on the compressed state: lam_c = H psi_c, E = <psi|H|psi>; optionally scattered back into a full-space vector ----
+__global__ void __launch_bounds__(256) k_sector_compress1(const unsigned *__restrict__ depU, const unsigned *__restrict__ depD,
+                                                          unsigned d_dn, unsigned dim, const double2 *__restrict__ a,
+                                                          double2 *__restrict__ ac) {
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < dim; r += stride) {
+        const unsigned ru = r / d_dn, rd = r - ru * d_dn;
+        ac[r] = a[__ldg(depU + ru) | __ldg(depD + rd)];
+    }
+}
+__global__ void __launch_bounds__(256) k_sector_scatter1(const unsigned *__restrict__ depU, const unsigned *__restrict__ depD,
+                                                         unsigned d_dn, unsigned dim, const double2 *__restrict__ ac,
+                                                         double2 *__restrict__ a) {
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < dim; r += stride) {
+        const unsigned ru = r / d_dn, rd = r - ru * d_dn;
+        a[__ldg(depU + ru) | __ldg(depD + rd)] = ac[r];
+    }
+}
+
+// gather over the x-mask groups in compact coordinates (as the H step of k_sector_eval, on global compressed vectors).  Four
+// lanes share an amplitude and split its groups (g = lane, lane + 4, ...): four times the parallelism and a quarter of the
+// dependent L2 round trips per thread; the four partial sums are folded by shuffles in a fixed order.  Per-CTA energy
+// partials, folded by the last CTA in slot order.
+#define SEC_HSPLIT 4
+__global__ void __launch_bounds__(256) k_sector_happly(const SecGroup *__restrict__ groups, int ngroups, const SecClass *__restrict__ classes,
+                                                       const double2 *__restrict__ vals, const double2 *__restrict__ hdiag,
+                                                       const unsigned short *__restrict__ cfgU, const unsigned short *__restrict__ cfgD,
+                                                       const unsigned short *__restrict__ rankU, const unsigned short *__restrict__ rankD,
+                                                       unsigned d_dn, unsigned dim, const double2 *__restrict__ in,
+                                                       double2 *__restrict__ out, double *__restrict__ partials,
+                                                       unsigned *__restrict__ counter, double *__restrict__ result) {
+    __shared__ double red[16];
+    __shared__ unsigned is_last;
+    double e_re = 0.0, e_im = 0.0;
+    const unsigned sub = threadIdx.x & (SEC_HSPLIT - 1);
+    const unsigned per_cta = 256 / SEC_HSPLIT;
+    const unsigned stride = gridDim.x * per_cta;
+    const unsigned rounds = (dim + stride - 1) / stride;          // uniform trip count: the shuffles need whole warps
+    for (unsigned it = 0; it < rounds; ++it) {
+        const unsigned r = it * stride + blockIdx.x * per_cta + (threadIdx.x / SEC_HSPLIT);
+        const bool ok = r < dim;
+        const unsigned rr = ok ? r : 0u;
+        const unsigned ru = rr / d_dn, rd = rr - ru * d_dn;
+        const unsigned cfg = (unsigned)__ldg(cfgU + ru) | ((unsigned)__ldg(cfgD + rd) << 16);
+        double ar = 0.0, ai = 0.0;
+        for (int g = (int)sub; g < ngroups; g += SEC_HSPLIT) {
+            const uint4 g0 = __ldg(reinterpret_cast<const uint4 *>(groups + g));          // x, first_class, n_class, live
+            const unsigned gp = __ldg(reinterpret_cast<const unsigned *>(groups + g) + 4);   // pos[4]
+            const unsigned j = cfg ^ g0.x;
+            const unsigned pat = ((j >> (gp & 0xffu)) & 1u) | (((j >> ((gp >> 8) & 0xffu)) & 1u) << 1) |
+                                 (((j >> ((gp >> 16) & 0xffu)) & 1u) << 2) | (((j >> (gp >> 24)) & 1u) << 3);
+            if (!((g0.w >> pat) & 1u)) continue;
+            double wr = 0.0, wi = 0.0;
+            for (int c = (int)g0.y; c < (int)(g0.y + g0.z); ++c) {
+                const uint2 cl = __ldg(reinterpret_cast<const uint2 *>(classes + c));      // zeta, vofs
+                const double2 w = __ldg(vals + cl.y + pat);
+                const bool neg = (__popc(j & cl.x) & 1) != 0;
+                wr += neg ? -w.x : w.x;
+                wi += neg ? -w.y : w.y;
+            }
+            const unsigned qu = __ldg(rankU + (j & 0xffffu)), qd = __ldg(rankD + (j >> 16));
+            const double2 pv = in[qu * d_dn + qd];
+            ar += wr * pv.x - wi * pv.y;
+            ai += wr * pv.y + wi * pv.x;
+        }
+#pragma unroll
+        for (int o = 1; o < SEC_HSPLIT; o <<= 1) {
+            ar += __shfl_xor_sync(0xffffffffu, ar, o);
+            ai += __shfl_xor_sync(0xffffffffu, ai, o);
+        }
+        if (ok && sub == 0) {
+            const double2 self = in[r];
+            const double2 hd = __ldg(hdiag + r);
+            ar += hd.x * self.x - hd.y * self.y;
+            ai += hd.x * self.y + hd.y * self.x;
+            out[r] = make_double2(ar, ai);
+            e_re += self.x * ar + self.y * ai;
+            e_im += self.x * ai - self.y * ar;
+        }
+    }
+    sec_block_sum2(e_re, e_im, red);
+    if (threadIdx.x == 0) {
+        partials[2 * blockIdx.x] = e_re;
+        partials[2 * blockIdx.x + 1] = e_im;
+        __threadfence();
+        is_last = (atomicAdd(counter, 1u) == gridDim.x - 1u) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double r = 0.0, im = 0.0;
+        for (unsigned t = threadIdx.x; t < gridDim.x; t += blockDim.x) {
+            r += __ldcg(partials + 2 * t);
+            im += __ldcg(partials + 2 * t + 1);
+        }
+        sec_block_sum2(r, im, red);
+        if (threadIdx.x == 0) {
+            result[0] = r;
+            result[1] = im;
+            *counter = 0u;
+        }
+    }
+}
+
+// out (full space, may be NULL) <- H in; E -> d_result[0..1].  `in` must be confined to the plan's sector.
+int fh_sector_table_enqueue(fh_sector_pool_plan *P, fh_ctx *ctx, const fh_table *tab, const double2 *in, double2 *out,
+                            double *d_result) {
+    const SecTableCache &T = g_sec_tables[tab->uid];
+    const unsigned dim = P->d_up * P->d_dn;
+    unsigned cgrid = (dim + 255u) / 256u;
+    if (cgrid > (unsigned)ctx->sm_count * 8u) cgrid = (unsigned)ctx->sm_count * 8u;
+    ++g_fh_launch_count;
+    k_sector_compress1<<<cgrid, 256, 0, ctx->stream>>>(P->d_depU, P->d_depD, P->d_dn, dim, in, P->d_in);
+    unsigned hgrid = (dim + (256u / SEC_HSPLIT) - 1u) / (256u / SEC_HSPLIT);
+    if (hgrid > 4096u) hgrid = 4096u;                 // the energy partial array
+    if (hgrid < 1) hgrid = 1;
+    ++g_fh_launch_count;
+    k_sector_happly<<<hgrid, 256, 0, ctx->stream>>>(T.d_groups, T.ngroups, T.d_classes, T.d_vals, T.d_hdiag, P->d_cfgU, P->d_cfgD,
+                                                    P->d_rankU, P->d_rankD, P->d_dn, dim, P->d_in, P->d_out, P->d_k2_partials,
+                                                    P->d_k2_counter, d_result);
+    if (out) {
+        FH_CUDA(cudaMemsetAsync(out, 0, sizeof(double2) << P->n, ctx->stream));
+        ++g_fh_launch_count;
+        k_sector_scatter1<<<cgrid, 256, 0, ctx->stream>>>(P->d_depU, P->d_depD, P->d_dn, dim, P->d_out, out);
+    }
+    FH_CUDA(cudaGetLastError());
     return FH_OK;
 }
 
@@ -1483,4 +1655,34 @@ extern "C" int fh_pool_gradients_sector_masks(const fh_pool *pool, const fh_stat
     FH_REQUIRE(up_mask != 0 || dn_mask != 0, "fh_pool_gradients_sector_masks: both masks empty");
     return pool_gradients_sector_impl("fh_pool_gradients_sector_masks", pool, psi, lambda, up_mask, dn_mask, n_up, n_dn, first, count,
                                       out);
+}
+
+// ---- K2 in the sector as a stand-alone call --------------------------------------------------------------------
+static std::map<u64, fh_sector_pool_plan *> g_sec_table_plans;      // per table handle (freed with the table)
+void fh_sector_forget_table_plan(u64 uid) {
+    auto it = g_sec_table_plans.find(uid);
+    if (it != g_sec_table_plans.end()) {
+        fh_sector_pool_plan_free(it->second);
+        g_sec_table_plans.erase(it);
+    }
+}
+
+extern "C" int fh_apply_table_sector(const fh_table *tab, const fh_state *in, fh_state *out, int n_up, int n_dn, double *e_re,
+                                     double *e_im) {
+    FH_REQUIRE(tab && in, "fh_apply_table_sector: NULL argument");
+    FH_REQUIRE(in->n == tab->n && (!out || out->n == tab->n), "fh_apply_table_sector: qubit count mismatch");
+    FH_REQUIRE(!out || out->d != in->d, "fh_apply_table_sector: in and out must differ");
+    fh_ctx *ctx = tab->ctx;
+    FH_CUDA(cudaSetDevice(ctx->device));
+    fh_sector_pool_plan *&P = g_sec_table_plans[tab->uid];
+    FH_TRY(fh_sector_pool_prepare(&P, ctx, tab->n, 0, 0, n_up, n_dn, std::vector<PairOp>(), std::vector<SecFlatOp>(), tab, nullptr));
+    FH_REQUIRE(P->table_ok, "fh_apply_table_sector: the table does not conserve (N_up, N_dn) = (%d, %d), has a term group with more "
+               "than four X/Y factors, or the qubit count is odd / above 30", n_up, n_dn);
+    FH_TRY(fh_sector_table_enqueue(P, ctx, tab, in->d, out ? out->d : nullptr, ctx->d_result));
+    if (!e_re && !e_im) return FH_OK;        // enqueue only (timing)
+    FH_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FH_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (e_re) *e_re = ctx->h_result[0];
+    if (e_im) *e_im = ctx->h_result[1];
+    return FH_OK;
 }

@@ -37,3 +37,8 @@ int fh_sector_pool_enqueue(fh_sector_pool_plan *plan, fh_ctx *ctx, const double2
                            int pool_first, int pool_count, double *d_pool_out);
 void fh_sector_pool_plan_free(fh_sector_pool_plan *plan);
 void fh_sector_forget_pool_plan(u64 uid);
+bool fh_sector_pool_plan_table_ok(const fh_sector_pool_plan *plan);
+// K2 of a sector-confined full-space state on its compressed copy: out (may be NULL) <- H in, E -> d_result[0..1]
+int fh_sector_table_enqueue(fh_sector_pool_plan *plan, fh_ctx *ctx, const fh_table *tab, const double2 *in, double2 *out,
+                            double *d_result);
+void fh_sector_forget_table_plan(u64 uid);

@@ -45,6 +45,7 @@ SIGNATURES = {
     "fh_table_upload": [_vp, C.c_int, C.c_int, _u64p, _u64p, _f64p, _f64p, _vpp],
     "fh_table_free": [_vp],
     "fh_table_tile_passes": [_vp, C.POINTER(C.c_int)],
+    "fh_apply_table_sector": [_vp, _vp, _vp, C.c_int, C.c_int, _f64p, _f64p],
     "fh_table_info": [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "fh_apply_table": [_vp, _vp, _vp, _f64p, _f64p],
     "fh_apply_table_accumulate": [_vp, _vp, _vp, _f64p, _f64p],

@@ -172,6 +172,13 @@ class DeviceTable:
     def expval(self, state: State) -> float:
         return self.apply(state).real
 
+    def apply_sector(self, state: State, out: State | None, n_up: int, n_dn: int, enqueue_only=False):
+        """K2 on the sector-compressed copy of a state confined to the (n_up, n_dn) sector (csrc/sector_eval.cu)."""
+        re, im = C.c_double(), C.c_double()
+        _cabi.check(_cabi.lib().fh_apply_table_sector(self._h, state._h, out._h if out is not None else None, int(n_up), int(n_dn),
+                                                      None if enqueue_only else C.byref(re), None if enqueue_only else C.byref(im)))
+        return None if enqueue_only else complex(re.value, im.value)
+
     def close(self):
         if self._h:
             _cabi.lib().fh_table_free(self._h)

@@ -543,13 +543,15 @@ class DeviceProgram:
     def sector_info(self):
         """Path of the most recent ``evaluate``: dict(active, pool_in_sector, cluster, dim, ops, transposes, remote_ops).
         ``active``: the call ran on the sector-compressed state resident in one thread-block cluster (csrc/sector_eval.cu);
-        ``pool_in_sector``: full-space circuit kernels, but K3 screened the pool on sector-compressed copies of psi / lambda."""
+        ``pool_in_sector`` / ``k2_in_sector``: full-space circuit kernels, but K3 screened the pool / K2 applied the first
+        observable on sector-compressed copies of the state (K2 with lambda output only from 20 qubits on)."""
         C = _cabi.C
         act, cl, nops, ntr, nrem = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
         dim = C.c_uint64()
         _cabi.check(_cabi.lib().fh_program_sector_info(self._h, C.byref(act), C.byref(cl), C.byref(dim), C.byref(nops),
                                                        C.byref(ntr), C.byref(nrem)))
-        return dict(active=act.value == 1, pool_in_sector=act.value == 2, cluster=cl.value, dim=int(dim.value), ops=nops.value, transposes=ntr.value,
+        return dict(active=act.value == 1, pool_in_sector=bool(act.value & 2) and act.value != 1,
+                    k2_in_sector=bool(act.value & 4) and act.value != 1, cluster=cl.value, dim=int(dim.value), ops=nops.value, transposes=ntr.value,
                     remote_ops=nrem.value)
 
     def payload_bytes(self):

@@ -275,3 +275,62 @@ def test_sector_screening_with_permuted_species_bits(ctx, seed):
     assert np.abs(g_sec - g_full).max() < 1e-12
     with pytest.raises(ValueError):
         dpool.gradients_sector(sp, sl, nu, nd, up_mask=up_mask, dn_mask=dn_mask | 1 | up_mask)      # overlapping masks
+
+
+@pytest.mark.parametrize("lat,u,up,dn", [((2, 3), 4.0, 3, 3), ((2, 3), 4.0, 2, 4), ((3, 3), 6.0, 5, 4)])
+def test_apply_table_on_the_sector_compressed_state(ctx, lat, u, up, dn):
+    """fh_apply_table_sector: compress, gather over the term groups in compact coordinates, scatter back -- vs the oracle."""
+    from fhsim.backend import State
+    n, h_tab, pool_ops, dec, diag, o_h, o_pool = lattice(*lat, u)
+    rng = np.random.default_rng(3)
+    occ_up, occ_dn, _ = pauli.k_space_occupation(*lat, 1.0, up, dn)
+    picks = list(rng.choice(len(pool_ops), size=6, replace=False))
+    psi = sv.adapt_state(n, occ_up + occ_dn, [o_pool[k] for k in picks], rng.uniform(-0.5, 0.5, len(picks)))
+    phi = sv.basis_change(psi, diag, dec, n)                 # a dense vector of the sector (W conserves both numbers)
+    want = sv.apply_table(phi, o_h, n)
+    dt = DeviceTable(ctx, h_tab)
+    st, out = State.from_numpy(ctx, phi), State.from_numpy(ctx, np.ones(1 << n, complex))      # out must be overwritten
+    e = dt.apply_sector(st, out, up, dn)
+    assert np.abs(out.numpy() - want).max() < 1e-12
+    assert abs(e - np.vdot(phi, want)) < E_TOL
+    assert abs(dt.apply_sector(st, None, up, dn) - e) < 1e-13
+    assert abs(dt.apply(st) - e) < 1e-11                      # the full-space kernel agrees
+    xx = DeviceTable(ctx, PauliTable(n, [0b11], [0], [1.0]))  # X X alone moves an electron pair in: not number conserving
+    with pytest.raises(ValueError):
+        xx.apply_sector(st, out, up, dn)
+
+
+def test_evaluate_takes_k2_and_k3_in_the_sector_at_20_qubits(ctx, monkeypatch):
+    """2x5 (20 qubits): from here on fh_program_evaluate applies H on the compressed state even when lambda is needed
+    (memset + scatter), and screens in the sector; both against the full-space kernels of the same program."""
+    lat, u, up, dn = (2, 5), 4.0, 5, 5
+    n = 20
+    h_tab = PauliTable.from_operator(fermi_hubbard(*lat, 1.0, u), n)
+    pool_ops = [jordan_wigner(g) for g in hubbard_interaction_pool_simplified(*lat)]
+    rng = np.random.default_rng(5)
+    occ_up, occ_dn, _ = pauli.k_space_occupation(*lat, 1.0, up, dn)
+    picks = list(rng.choice(len(pool_ops), size=4, replace=False))
+    th = rng.uniform(-0.4, 0.4, len(picks))
+    plans = [GeneratorPlan(g, n) for g in pool_ops]
+    circ = Circuit(n, len(picks))
+    for p, k in enumerate(picks):
+        circ.generator(plans[k], param=p)
+    circ.marker("ansatz_end")
+    circ.basis_change_separable(*lat)
+    prog = circ.compile(ctx)
+    dtab = DeviceTable(ctx, h_tab)
+    dpool = DevicePool(ctx, plans[:150], n)
+    basis = sum(1 << (n - 1 - q) for q in occ_up + occ_dn)
+    m = prog.markers["ansatz_end"]
+    a = prog.evaluate(basis, th, [dtab], pool=dpool, pool_pos=m)
+    info = prog.sector_info()
+    assert info["pool_in_sector"] and info["k2_in_sector"] and not info["active"]
+    ag = prog.evaluate(basis, th, [dtab], grads=True)
+    assert prog.sector_info()["k2_in_sector"]
+    monkeypatch.setenv("FHSIM_NO_SECTOR_POOL", "1")
+    b = prog.evaluate(basis, th, [dtab], pool=dpool, pool_pos=m)
+    bg = prog.evaluate(basis, th, [dtab], grads=True)
+    assert not prog.sector_info()["k2_in_sector"]
+    assert abs(a["expvals"][0] - b["expvals"][0]) < 1e-11 and np.abs(a["pool"] - b["pool"]).max() < 1e-11
+    assert np.abs(b["pool"]).max() > 1e-3
+    assert abs(ag["expvals"][0] - bg["expvals"][0]) < 1e-11 and np.abs(ag["grads"] - bg["grads"]).max() < 1e-11

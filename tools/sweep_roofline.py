@@ -117,6 +117,19 @@ def measure_lattice(ctx, lat, pk, pool_cap=400, verbose=True):
         dpool.enqueue(psi, lam)
         ts.append(ctx.timer_stop())
     rec("screening", min(ts) * 1e-3, 4.0 * dim * len(plans), {"ops": len(plans), "per_gradient_us": min(ts) * 1e3 / len(plans)})
+    # K2 on the sector-compressed copy (compress + gather on the compressed vector + memset / scatter of H psi)
+    try:
+        ns_ = nx * ny
+        nu_, nd_ = (ns_ + 1) // 2, ns_ - (ns_ + 1) // 2
+        dtab.apply_sector(psi, lam, nu_, nd_, enqueue_only=True)
+        ts = []
+        for _ in range(max(3, reps // 2)):
+            ctx.timer_start()
+            dtab.apply_sector(psi, lam, nu_, nd_, enqueue_only=True)
+            ts.append(ctx.timer_stop())
+        rec("h_apply_sector", min(ts) * 1e-3, 32.0 * dim)
+    except Exception as exc:
+        res["h_apply_sector"] = {"us": float("nan"), "GBps": float("nan"), "frac": float("nan"), "error": repr(exc)}
     # K3 on sector-compressed copies (what fh_program_evaluate does for number-conserving evaluations): same pool, the
     # half-filled sector; 4 * 2^n B per gradient is the FULL-SPACE algorithmic figure, so this row is an effective rate
     try:
@@ -138,7 +151,7 @@ def measure_lattice(ctx, lat, pk, pool_cap=400, verbose=True):
         o.close()
     if verbose:
         print(f"--- {lat}  n={n}  state={res['state_MiB']:.0f} MiB  pool={res['pool']}  H terms/groups={res['h_terms']}/{res['h_groups']}")
-        for k in ("pair_fermi4", "pair_dense", "givens", "diag_coulomb", "tile_W", "h_apply", "screening", "screening_sector"):
+        for k in ("pair_fermi4", "pair_dense", "givens", "diag_coulomb", "tile_W", "h_apply", "h_apply_sector", "screening", "screening_sector"):
             v = res[k]
             print(f"    {k:13s} {v['us']:12.1f} us  {v['GBps']:9.1f} GB/s  {100 * v['frac']:6.1f} % of {pk:.0f}")
         sys.stdout.flush()
