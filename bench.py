@@ -617,6 +617,8 @@ def run_gpu_arm(args, rank, world, local_rank):
                    "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
                    "launch_items": prog.n_items, "tile_kernels": prog.n_tiles,
                    "path": ("sector-resident cluster kernel" if step_info["active"] else
+                            "full-space tile kernels for the ansatz, then W (two dense sector blocks), H, W^dagger and K3 on "
+                            "sector-compressed vectors" if step_info.get("dense_tail") else
                             "full-space tile kernels + K2, K3 on sector-compressed psi_s / lambda_s" if step_info["pool_in_sector"]
                             else "full-space tile kernels + K2 + K3")},
         "e2e": {"value": e2e_value, "unit": "gradients/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -189,7 +189,11 @@ int fh_program_evaluate(fh_program *prog, uint64_t basis_index, const double *th
  * compressed vectors are L2-resident); FHSIM_NO_SECTOR_POOL=1 keeps K3 in the full space.
  * K2 of tables[0] takes the same shortcut (compress, gather over the term groups on the compressed vector, scatter of H psi back
  * when the adjoint part needs it: from 20 qubits on; FHSIM_NO_SECTOR_K2=1 disables it).
- * active: 1 if the last call ran in the cluster; otherwise a bit set: 2 = K3 in the sector, 4 = K2 in the sector; 0 = full space;
+ * Screening / energy-only calls whose trailing ops are a FIXED network of single-species ops (the basis change W of the drivers,
+ * models/adapt_vqe.py:344-356) run that whole tail on compressed vectors: W = S (U_up (x) U_dn) S with two dense sector blocks
+ * built once per program, then H, W^dagger and K3 (sectors of <= 512 patterns per spin; FHSIM_NO_SECTOR_DENSE=1 disables it).
+ * active: 1 if the last call ran in the cluster; otherwise a bit set: 2 = K3 in the sector, 4 = K2 in the sector, 8 = dense
+ * tail; 0 = full space;
  * cluster_size: CTAs of the cluster; sector_dim: amplitudes; n_ops: steps of the cluster kernel (ops, transposes,
  * checkpoint, H, store); n_transposes / n_remote_ops: layout changes / ops that exchange amplitudes between CTAs. */
 int fh_program_sector_info(const fh_program *prog, int *active, int *cluster_size, uint64_t *sector_dim, int *n_ops,

@@ -46,7 +46,7 @@ struct EvalKey {
     int pool_pos, pool_first, pool_count;
     const void *state_out;
     int sector, sector_pool;     // 1: the sector-resident path (sector_eval.cu) / K3 on sector-compressed copies was planned
-    int sector_k2, pad_k2;       // 1: K2 of tables[0] on the sector-compressed state
+    int sector_k2, sector_dense; // 1: K2 of tables[0] on the sector-compressed state / the whole tail (W, H, W^dagger, K3) there
     // unique ids of the same handles: a freed handle whose address is reused by a new one gets a new id, so the graph
     // (which bakes in the device pointers behind the handles) is re-captured instead of replayed on freed memory
     u64 table_uid[FH_MAX_RESULT_TABLES], target_uid[FH_MAX_OVERLAPS], pool_uid, state_out_uid;
@@ -114,7 +114,8 @@ struct fh_program {
     std::vector<int> item_flat_first;
     fh_sector_plan *sec = nullptr;
     fh_sector_pool_plan *sec_pool = nullptr;
-    bool last_sector = false, last_sector_pool = false, last_sector_k2 = false;
+    fh_sector_dense *sec_dense = nullptr;
+    bool last_sector = false, last_sector_pool = false, last_sector_k2 = false, last_sector_dense = false;
     // measurement
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0.0;
@@ -157,6 +158,8 @@ extern "C" int fh_program_destroy(fh_program *p) {
     p->sec = nullptr;
     fh_sector_pool_plan_free(p->sec_pool);
     p->sec_pool = nullptr;
+    fh_sector_dense_free(p->sec_dense);
+    p->sec_dense = nullptr;
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     cudaFree(p->d_tl_fwd);
@@ -906,6 +909,20 @@ static int enqueue_evaluation(fh_program *p, const EvalKey &k, fh_table *const *
         p->n_segments = 0;
         return FH_OK;
     }
+    if (k.sector_dense) {
+        // full-space tile kernels for the items before the fixed tail, then W, H, W^dagger and K3 on compressed vectors
+        double *d_pool_out_s = p->d_res + 64 + p->res_segs;
+        FH_TRY(enqueue_payload_upload(p, capturing));
+        p->chain_region = capturing ? 0 : 1;
+        p->chain_used_runs[p->chain_region] = p->chain_used_maps[p->chain_region] = 0;
+        FH_TRY(apply_range(p, 0, fh_sector_dense_tail_item(p->sec_dense), p->d_psi, 0, nullptr, -1, (long long)k.basis));
+        FH_TRY(fh_sector_dense_enqueue(p->sec_dense, p->sec_pool, ctx, tables[0], p->d_psi, p->d_res, pool, k.pool_first, k.pool_count,
+                                       d_pool_out_s));
+        const size_t n_res_s = want_pool ? 64 + (size_t)p->res_segs + (size_t)(k.pool_first + k.pool_count) : 4;
+        FH_CUDA(cudaMemcpyAsync(p->h_res, p->d_res, sizeof(double) * n_res_s, cudaMemcpyDeviceToHost, ctx->stream));
+        p->n_segments = 0;
+        return FH_OK;
+    }
     int first_param = n_items, last_param = -1;
     for (int i = 0; i < n_items; ++i)
         if (item_has_param(p, p->items[i])) {
@@ -1063,6 +1080,7 @@ extern "C" int fh_program_evaluate(fh_program *p, uint64_t basis_index, const do
     }
     p->last_sector_pool = false;
     p->last_sector_k2 = false;
+    p->last_sector_dense = false;
     if (!key.sector && n_tables >= 1 && !(p->n & 1) && p->n <= 31 && !getenv("FHSIM_NO_SECTOR_POOL")) {
         u64 upm = 0, dnm = 0;
         for (int b = 0; b < p->n; ++b) ((b & 1) ? upm : dnm) |= 1ull << b;          // even wires = up = odd index bits
@@ -1070,8 +1088,15 @@ extern "C" int fh_program_evaluate(fh_program *p, uint64_t basis_index, const do
                                       __builtin_popcountll(basis_index & dnm), p->pairs, p->flat, tables[0], pool));
         key.sector_pool = (pool && fh_sector_pool_plan_eligible(p->sec_pool)) ? 1 : 0;
         key.sector_k2 = fh_sector_pool_plan_table_ok(p->sec_pool) ? 1 : 0;
+        // screening / energy-only calls whose trailing ops are a fixed single-species network (W): the whole tail in the sector
+        if (key.sector_k2 && !grads && n_overlaps == 0 && !state_out && n_tables == 1 && (!pool || key.sector_pool)) {
+            FH_TRY(fh_sector_dense_prepare(&p->sec_dense, p->sec_pool, p->n, p->pairs, p->diagops, p->dterms, p->flat, p->item_flat_first,
+                                           pool ? pool_pos : 0, pool != nullptr));
+            key.sector_dense = fh_sector_dense_ok(p->sec_dense) ? 1 : 0;
+        }
         p->last_sector_pool = key.sector_pool != 0;
         p->last_sector_k2 = key.sector_k2 != 0;
+        p->last_sector_dense = key.sector_dense != 0;
     }
 
     static const bool no_graph = getenv("FHSIM_NO_GRAPH") != nullptr;
@@ -1143,7 +1168,7 @@ extern "C" int fh_program_payload_bytes(const fh_program *p, size_t *h2d_bytes, 
 extern "C" int fh_program_sector_info(const fh_program *p, int *active, int *cluster_size, uint64_t *sector_dim, int *n_ops,
                                       int *n_transposes, int *n_remote_ops) {
     FH_REQUIRE(p, "fh_program_sector_info: program is NULL");
-    if (active) *active = p->last_sector ? 1 : ((p->last_sector_pool ? 2 : 0) | (p->last_sector_k2 ? 4 : 0));
+    if (active) *active = p->last_sector ? 1 : ((p->last_sector_pool ? 2 : 0) | (p->last_sector_k2 ? 4 : 0) | (p->last_sector_dense ? 8 : 0));
     u64 dim = 0;
     fh_sector_plan_describe(p->last_sector ? p->sec : nullptr, cluster_size, &dim, n_ops, n_transposes, n_remote_ops, nullptr);
     if (sector_dim) *sector_dim = dim;

@@ -1686,3 +1686,314 @@ extern "C" int fh_apply_table_sector(const fh_table *tab, const fh_state *in, fh
     if (e_im) *e_im = ctx->h_result[1];
     return FH_OK;
 }
+
+// ----------------------------------------------------------------------------------------------
+// Dense tail: a trailing run of FIXED single-species ops (the basis change W of the ADAPT / HVA drivers) as two dense
+// sector transforms.  In the blocked orbital order (all up, then all down) an up-only op is U (x) 1; the interleaved
+// Jordan-Wigner order differs from it by the diagonal sign S(u, d) = (-1)^#{(i, j): up orbital i and down orbital j occupied,
+// j <= i}, so on the sector matrix Psi[ru][rd]
+//        W Psi = S o ( U_up (S o Psi) U_dn^T ),        W^dagger Psi = S o ( U_up^dagger (S o Psi) conj(U_dn) ).
+// U_up / U_dn (D_up x D_up, D_dn x D_dn) are accumulated on the host once per program from the ops' up / down lists; every op
+// is checked for the sign structure the factorisation needs (its other-species zeta bits must be exactly the crossing mask).
+// Then the whole tail of a screening -- W, H, W^dagger, K3 -- runs on compressed vectors: 2 + 1 + 2 + 1 small launches.
+// ----------------------------------------------------------------------------------------------
+struct SecDense {
+    bool ok = false;
+    int first_flat = 0;                       // the tail = flat ops [first_flat, end)
+    double2 *d_Uup = nullptr, *d_UdnT = nullptr;        // W:        A = U_up,        B = U_dn^T
+    double2 *d_UupH = nullptr, *d_UdnC = nullptr;       // W^dagger: A = U_up^dagger, B = conj(U_dn)
+    unsigned short *d_pp = nullptr;           // per down pattern: prefix parities (sign S = parity(cfgU & pp))
+    double2 *d_t0 = nullptr, *d_t1 = nullptr; // compressed work vectors
+    void release() {
+        cudaFree(d_Uup); cudaFree(d_UdnT); cudaFree(d_UupH); cudaFree(d_UdnC); cudaFree(d_pp); cudaFree(d_t0); cudaFree(d_t1);
+        d_Uup = d_UdnT = d_UupH = d_UdnC = d_t0 = d_t1 = nullptr; d_pp = nullptr;
+        ok = false;
+    }
+};
+
+// C[M x N] = A[M x K] * B'[K x N];  SIGN_B: B'[k][n] = S(k, n) B[k][n] (rows of B are up ranks);  SIGN_C: C is multiplied by
+// S(m, n) on store (rows of C are up ranks).  16 x 16 output tile per CTA; K in chunks of 64 whose 2 x 1024 elements are all
+// requested before the first is used (one memory latency per chunk: the matrices are a few hundred KB and this runs right
+// after other kernels, so the loop is latency-, not flop-bound).
+#define SEC_GK 64
+#define SEC_GCH 2            // K chunks whose loads are all issued before the first use (K <= 128: one memory latency per GEMM)
+// GATHER: B is a FULL-SPACE state read through the sector index (depU[k] | depD[n]) -- the compress step fused into the first
+// GEMM of the tail; the row-block-0 CTAs also write the compressed copy Bc (K3 needs psi_s).
+template <bool SIGN_B, bool SIGN_C, bool GATHER>
+__global__ void __launch_bounds__(256) k_sector_gemm(const double2 *__restrict__ A, const double2 *__restrict__ B, double2 *__restrict__ C,
+                                                     int M, int N, int K, const unsigned short *__restrict__ cfgU,
+                                                     const unsigned short *__restrict__ pp, const unsigned *__restrict__ depU,
+                                                     const unsigned *__restrict__ depD, double2 *__restrict__ Bc) {
+    __shared__ double2 sa[16][SEC_GK + 1], sb[SEC_GK][17];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m0 = blockIdx.y * 16, n0 = blockIdx.x * 16;
+    const int m = m0 + ty, n = n0 + tx;
+    const unsigned ppn = (n < N && SIGN_C) ? (unsigned)__ldg(pp + n) : 0u;
+    double cr = 0.0, ci = 0.0;
+    for (int kbase = 0; kbase < K; kbase += SEC_GK * SEC_GCH) {
+        double2 ra[SEC_GCH][4], rb[SEC_GCH][4];
+#pragma unroll
+        for (int ch = 0; ch < SEC_GCH; ++ch) {
+            const int k0 = kbase + ch * SEC_GK;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {          // A tile: 16 rows x 64 k, element e = q * 256 + tid -> (row e / 64, k e % 64)
+                const int e = q * 256 + (int)threadIdx.x, row = e >> 6, kk = e & 63;
+                ra[ch][q] = (m0 + row < M && k0 + kk < K) ? A[(size_t)(m0 + row) * K + k0 + kk] : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {          // B tile: 64 k x 16 columns, element e -> (k e / 16, column e % 16)
+                const int e = q * 256 + (int)threadIdx.x, kk = e >> 4, col = e & 15;
+                const bool ok = k0 + kk < K && n0 + col < N;
+                double2 v = make_double2(0.0, 0.0);
+                if (ok) {
+                    if (GATHER) {
+                        v = B[__ldg(depU + k0 + kk) | __ldg(depD + n0 + col)];
+                        if (blockIdx.y == 0) Bc[(size_t)(k0 + kk) * N + n0 + col] = v;
+                    } else {
+                        v = B[(size_t)(k0 + kk) * N + n0 + col];
+                    }
+                    if (SIGN_B && (__popc((unsigned)__ldg(cfgU + k0 + kk) & (unsigned)__ldg(pp + n0 + col)) & 1)) v = make_double2(-v.x, -v.y);
+                }
+                rb[ch][q] = v;
+            }
+        }
+#pragma unroll
+        for (int ch = 0; ch < SEC_GCH; ++ch) {
+            if (kbase + ch * SEC_GK >= K) break;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int e = q * 256 + (int)threadIdx.x;
+                sa[e >> 6][e & 63] = ra[ch][q];
+                sb[e >> 4][e & 15] = rb[ch][q];
+            }
+            __syncthreads();
+#pragma unroll 16
+            for (int k = 0; k < SEC_GK; ++k) {
+                const double2 a = sa[ty][k], bb = sb[k][tx];
+                cr += a.x * bb.x - a.y * bb.y;
+                ci += a.x * bb.y + a.y * bb.x;
+            }
+            __syncthreads();
+        }
+    }
+    if (m < M && n < N) {
+        if (SIGN_C && (__popc((unsigned)__ldg(cfgU + m) & ppn) & 1)) {
+            cr = -cr;
+            ci = -ci;
+        }
+        C[(size_t)m * N + n] = make_double2(cr, ci);
+    }
+}
+
+// out = W in (dagger: W^dagger in) on compressed vectors; tmp is a third vector
+static void sec_dense_apply(const fh_sector_pool_plan *P, const SecDense &D, cudaStream_t s, const double2 *in, double2 *tmp, double2 *out,
+                            bool dagger, double2 *gather_copy);
+
+struct fh_sector_dense {
+    SecDense D;
+    int tail_item = -1, n_up = -1, n_dn = -1;
+    u64 pool_plan_key = 0;
+    bool built = false;
+};
+void fh_sector_dense_free(fh_sector_dense *d) {
+    if (!d) return;
+    d->D.release();
+    delete d;
+}
+bool fh_sector_dense_ok(const fh_sector_dense *d) { return d && d->D.ok; }
+int fh_sector_dense_tail_item(const fh_sector_dense *d) { return d ? d->tail_item : -1; }
+
+typedef std::vector<double2> SecMatH;          // row-major square matrix
+static void sec_mat_rows_pair(SecMatH &U, unsigned d, const std::vector<unsigned> &L, const double m[8]) {
+    // rows r (pattern side) and r' of U <- the 2x2 block, with the op's own-species sign
+    for (unsigned e : L) {
+        const unsigned r = e & SEC_FM, rp = (e >> SEC_FB) & SEC_FM;
+        const double sg = (e >> 31) ? -1.0 : 1.0;
+        const double2 m00 = make_double2(m[0], m[1]), m01 = make_double2(sg * m[2], sg * m[3]), m10 = make_double2(sg * m[4], sg * m[5]),
+                      m11 = make_double2(m[6], m[7]);
+        double2 *a = &U[(size_t)r * d], *b = &U[(size_t)rp * d];
+        for (unsigned c = 0; c < d; ++c) {
+            const double2 x = a[c], y = b[c];
+            a[c] = make_double2(m00.x * x.x - m00.y * x.y + m01.x * y.x - m01.y * y.y, m00.x * x.y + m00.y * x.x + m01.x * y.y + m01.y * y.x);
+            b[c] = make_double2(m10.x * x.x - m10.y * x.y + m11.x * y.x - m11.y * y.y, m10.x * x.y + m10.y * x.x + m11.x * y.y + m11.y * y.x);
+        }
+    }
+}
+
+// Build (or reuse) the dense tail of a program.  min_item: the tail may not begin before this item; exact: it must begin
+// exactly there (screening: the pool position).  Leaves D.ok = false when the program has no such tail.
+int fh_sector_dense_prepare(fh_sector_dense **slot, const fh_sector_pool_plan *P, int n, const std::vector<PairOp> &pairs,
+                            const std::vector<DiagOp> &diagops, const std::vector<DiagTerm> &dterms, const std::vector<SecFlatOp> &flat,
+                            const std::vector<int> &item_flat_first, int min_item, bool exact) {
+    if (!*slot) *slot = new fh_sector_dense();
+    fh_sector_dense *X = *slot;
+    const int n_items = (int)item_flat_first.size() - 1;
+    if (!P || !P->table_ok || getenv("FHSIM_NO_SECTOR_DENSE")) {
+        X->D.release();
+        X->built = false;
+        return FH_OK;
+    }
+    SecGeomHost G;
+    G.standard(n);
+    const int half = G.half;
+    const unsigned upc = (1u << half) - 1u;
+    // per flat op: 1 up-only, 2 down-only, 0 not eligible
+    auto classify = [&](const SecFlatOp &f) -> int {
+        if (f.type == 1) {
+            const PairOp &op = pairs[f.index];
+            if (op.kind != 0) return 0;
+            const unsigned xc = sec_compact(op.x, G), zc = sec_compact(op.zeta, G), fmc = sec_compact(op.fixmask, G);
+            const unsigned xu = xc & 0xffffu, xd = xc >> 16;
+            if ((xu != 0u) == (xd != 0u)) return 0;
+            if (xu ? (fmc >> 16) != 0u : (fmc & 0xffffu) != 0u) return 0;       // pattern conditioned on the other species
+            if (xu) {          // other-species zeta = down orbitals j with an odd number of flipped up orbitals i >= j
+                unsigned need = 0;
+                for (int j = 0; j < half; ++j)
+                    if (__builtin_popcount(xu & (upc & ~((1u << j) - 1u))) & 1) need |= 1u << j;
+                return (zc >> 16) == need ? 1 : 0;
+            }
+            unsigned need = 0;  // up orbitals i with an odd number of flipped down orbitals j <= i
+            for (int i = 0; i < half; ++i)
+                if (__builtin_popcount(xd & ((2u << i) - 1u)) & 1) need |= 1u << i;
+            return (zc & 0xffffu) == need ? 2 : 0;
+        }
+        const DiagOp &dop = diagops[f.index];
+        if (dop.param >= 0) return 0;
+        for (int m = dop.first; m < dop.first + dop.count; ++m) {
+            const unsigned zc = sec_compact(dterms[m].z, G);
+            if ((zc & 0xffffu) && (zc >> 16)) return 0;
+        }
+        return 3;               // diagonal, every term inside one species
+    };
+    int i_min = n_items;
+    while (i_min > 0) {
+        bool ok = true;
+        for (int k = item_flat_first[i_min - 1]; k < item_flat_first[i_min] && ok; ++k) ok = classify(flat[k]) != 0;
+        if (!ok) break;
+        --i_min;
+    }
+    int tail_item = i_min < min_item ? min_item : i_min;
+    if (exact && tail_item != min_item) tail_item = -1;
+    const u64 key = ((u64)P->table_uid << 20) ^ ((u64)(unsigned)P->n_up << 8) ^ (u64)(unsigned)P->n_dn;
+    if (X->built && X->tail_item == tail_item && X->pool_plan_key == key) return FH_OK;
+    X->D.release();
+    X->built = true;
+    X->tail_item = tail_item;
+    X->pool_plan_key = key;
+    if (tail_item < 0) return FH_OK;
+    const unsigned d_up = P->d_up, d_dn = P->d_dn;
+    if (d_up > 512 || d_dn > 512) return FH_OK;           // dense blocks only while they are small (3x3: 126 x 126)
+    G.n_up = P->n_up;
+    G.n_dn = P->n_dn;
+    sec_patterns(half, P->n_up, G.cfgU, G.rankU);
+    sec_patterns(half, P->n_dn, G.cfgD, G.rankD);
+    SecMatH Uu((size_t)d_up * d_up, make_double2(0.0, 0.0)), Ud((size_t)d_dn * d_dn, make_double2(0.0, 0.0));
+    for (unsigned r = 0; r < d_up; ++r) Uu[(size_t)r * d_up + r].x = 1.0;
+    for (unsigned r = 0; r < d_dn; ++r) Ud[(size_t)r * d_dn + r].x = 1.0;
+    std::vector<unsigned> LU, LD;
+    for (int k = item_flat_first[tail_item]; k < item_flat_first[n_items]; ++k) {
+        const SecFlatOp &f = flat[k];
+        const int cls = classify(f);
+        if (cls == 1 || cls == 2) {
+            const PairOp &op = pairs[f.index];
+            sec_build_lists(G, sec_compact(op.x, G), sec_compact(op.fixmask, G), sec_compact(op.fixval, G), sec_compact(op.zeta, G), LU, LD);
+            if (cls == 1) sec_mat_rows_pair(Uu, d_up, LU, op.m);
+            else sec_mat_rows_pair(Ud, d_dn, LD, op.m);
+        } else {
+            const DiagOp &dop = diagops[f.index];
+            for (int m = dop.first; m < dop.first + dop.count; ++m) {
+                const unsigned zc = sec_compact(dterms[m].z, G);
+                const bool up = (zc >> 16) == 0u;             // z = 0 (a plain phase) goes to the up block
+                const unsigned zs = up ? (zc & 0xffffu) : (zc >> 16);
+                SecMatH &U = up ? Uu : Ud;
+                const unsigned d = up ? d_up : d_dn;
+                const double c = cos(dterms[m].angle), sn = sin(dterms[m].angle);
+                for (unsigned r = 0; r < d; ++r) {
+                    const unsigned cfg = up ? G.cfgU[r] : G.cfgD[r];
+                    const double2 ph = make_double2(c, (__builtin_popcount(cfg & zs) & 1) ? sn : -sn);      // exp(-i a sigma)
+                    double2 *row = &U[(size_t)r * d];
+                    for (unsigned q = 0; q < d; ++q) row[q] = make_double2(row[q].x * ph.x - row[q].y * ph.y, row[q].x * ph.y + row[q].y * ph.x);
+                }
+            }
+        }
+    }
+    // device forms: W: A = U_up, B = U_dn^T;  W^dagger: A = U_up^dagger, B = conj(U_dn)
+    SecMatH UuH((size_t)d_up * d_up), UdT((size_t)d_dn * d_dn), UdC((size_t)d_dn * d_dn);
+    for (unsigned a = 0; a < d_up; ++a)
+        for (unsigned b = 0; b < d_up; ++b) UuH[(size_t)a * d_up + b] = make_double2(Uu[(size_t)b * d_up + a].x, -Uu[(size_t)b * d_up + a].y);
+    for (unsigned a = 0; a < d_dn; ++a)
+        for (unsigned b = 0; b < d_dn; ++b) {
+            UdT[(size_t)a * d_dn + b] = Ud[(size_t)b * d_dn + a];
+            UdC[(size_t)a * d_dn + b] = make_double2(Ud[(size_t)a * d_dn + b].x, -Ud[(size_t)a * d_dn + b].y);
+        }
+    std::vector<unsigned short> pp(d_dn);
+    for (unsigned r = 0; r < d_dn; ++r) {
+        unsigned v = 0;
+        for (int i = 0; i < half; ++i)
+            if (__builtin_popcount((unsigned)G.cfgD[r] & ((2u << i) - 1u)) & 1) v |= 1u << i;
+        pp[r] = (unsigned short)v;
+    }
+    SecDense &D = X->D;
+    FH_TRY(sec_upload(&D.d_Uup, Uu));
+    FH_TRY(sec_upload(&D.d_UdnT, UdT));
+    FH_TRY(sec_upload(&D.d_UupH, UuH));
+    FH_TRY(sec_upload(&D.d_UdnC, UdC));
+    FH_TRY(sec_upload(&D.d_pp, pp));
+    const size_t dim = (size_t)d_up * d_dn;
+    FH_CUDA(cudaMalloc(&D.d_t0, sizeof(double2) * dim));
+    FH_CUDA(cudaMalloc(&D.d_t1, sizeof(double2) * dim));
+    D.first_flat = item_flat_first[tail_item];
+    D.ok = true;
+    return FH_OK;
+}
+
+static void sec_dense_apply(const fh_sector_pool_plan *P, const SecDense &D, cudaStream_t s, const double2 *in, double2 *tmp, double2 *out,
+                            bool dagger, double2 *gather_copy) {
+    const int du = (int)P->d_up, dd = (int)P->d_dn;
+    const dim3 grid((dd + 15) / 16, (du + 15) / 16);
+    g_fh_launch_count += 2;
+    // tmp = A (S o in);  out = S o (tmp B).  gather_copy != NULL: `in` is a full-space state, its compressed copy is written there
+    if (gather_copy)
+        k_sector_gemm<true, false, true><<<grid, 256, 0, s>>>(dagger ? D.d_UupH : D.d_Uup, in, tmp, du, dd, du, P->d_cfgU, D.d_pp, P->d_depU,
+                                                              P->d_depD, gather_copy);
+    else
+        k_sector_gemm<true, false, false><<<grid, 256, 0, s>>>(dagger ? D.d_UupH : D.d_Uup, in, tmp, du, dd, du, P->d_cfgU, D.d_pp, nullptr,
+                                                               nullptr, nullptr);
+    k_sector_gemm<false, true, false><<<grid, 256, 0, s>>>(tmp, dagger ? D.d_UdnC : D.d_UdnT, out, du, dd, dd, P->d_cfgU, D.d_pp, nullptr,
+                                                           nullptr, nullptr);
+}
+
+// The tail of an evaluation on compressed vectors: psi_full = the state after the items before the tail.
+// E -> d_result[0..1]; with a pool: outputs o in [first, first + count) -> d_pool_out[o].
+int fh_sector_dense_enqueue(fh_sector_dense *X, fh_sector_pool_plan *P, fh_ctx *ctx, const fh_table *tab, const double2 *psi_full,
+                            double *d_result, const fh_pool *pool, int pool_first, int pool_count, double *d_pool_out) {
+    const SecDense &D = X->D;
+    const SecTableCache &T = g_sec_tables[tab->uid];
+    const unsigned dim = P->d_up * P->d_dn;
+    unsigned cgrid = (dim + 255u) / 256u;
+    if (cgrid > (unsigned)ctx->sm_count * 8u) cgrid = (unsigned)ctx->sm_count * 8u;
+    // psi_s (compressed) lives in the K3 buffer when a pool is screened, else in the K2 input buffer
+    double2 *psi_s = (pool && P->d_psi) ? P->d_psi : P->d_in;
+    (void)cgrid;
+    sec_dense_apply(P, D, ctx->stream, psi_full, D.d_t0, D.d_t1, false, psi_s);       // phi = W psi_s (t1); psi_s compressed on the way
+    unsigned hgrid = (dim + (256u / SEC_HSPLIT) - 1u) / (256u / SEC_HSPLIT);
+    if (hgrid > 4096u) hgrid = 4096u;
+    ++g_fh_launch_count;
+    k_sector_happly<<<hgrid, 256, 0, ctx->stream>>>(T.d_groups, T.ngroups, T.d_classes, T.d_vals, T.d_hdiag, P->d_cfgU, P->d_cfgD,
+                                                    P->d_rankU, P->d_rankD, P->d_dn, dim, D.d_t1, P->d_out, P->d_k2_partials,
+                                                    P->d_k2_counter, d_result);       // H phi               (d_out)
+    if (pool && pool_count > 0) {
+        sec_dense_apply(P, D, ctx->stream, P->d_out, D.d_t0, P->d_lam, true, nullptr); // lambda_s = W^dagger H phi
+        const SecPoolCache &Pc = g_sec_pools[pool->uid];
+        const int e0 = pool->out_first[pool_first], e1 = pool->out_first[pool_first + pool_count];
+        int grid = e1 - e0;
+        if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+        if (grid < 1) grid = 1;
+        ++g_fh_launch_count;
+        k_sector_pool<<<grid, 256, sizeof(unsigned) * std::max(1u, Pc.max_words), ctx->stream>>>(
+            Pc.d_entries, Pc.d_lists, e0, e1, P->d_dn, P->d_psi, P->d_lam, Pc.d_partial, pool->d_out_first, pool_first, pool_count,
+            d_pool_out, Pc.d_counter);
+    }
+    FH_CUDA(cudaGetLastError());
+    return FH_OK;
+}

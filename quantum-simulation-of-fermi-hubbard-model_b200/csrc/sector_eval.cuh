@@ -42,3 +42,15 @@ bool fh_sector_pool_plan_table_ok(const fh_sector_pool_plan *plan);
 int fh_sector_table_enqueue(fh_sector_pool_plan *plan, fh_ctx *ctx, const fh_table *tab, const double2 *in, double2 *out,
                             double *d_result);
 void fh_sector_forget_table_plan(u64 uid);
+
+// Dense tail (sector_eval.cu): a trailing run of fixed single-species ops as two dense sector transforms, so W, H, W^dagger
+// and K3 of a screening all run on compressed vectors
+struct fh_sector_dense;
+int fh_sector_dense_prepare(fh_sector_dense **slot, const fh_sector_pool_plan *plan, int n, const std::vector<PairOp> &pairs,
+                            const std::vector<DiagOp> &diagops, const std::vector<DiagTerm> &dterms, const std::vector<SecFlatOp> &flat,
+                            const std::vector<int> &item_flat_first, int min_item, bool exact);
+bool fh_sector_dense_ok(const fh_sector_dense *d);
+int fh_sector_dense_tail_item(const fh_sector_dense *d);
+int fh_sector_dense_enqueue(fh_sector_dense *d, fh_sector_pool_plan *plan, fh_ctx *ctx, const fh_table *tab, const double2 *psi_full,
+                            double *d_result, const fh_pool *pool, int pool_first, int pool_count, double *d_pool_out);
+void fh_sector_dense_free(fh_sector_dense *d);

@@ -544,14 +544,16 @@ class DeviceProgram:
         """Path of the most recent ``evaluate``: dict(active, pool_in_sector, cluster, dim, ops, transposes, remote_ops).
         ``active``: the call ran on the sector-compressed state resident in one thread-block cluster (csrc/sector_eval.cu);
         ``pool_in_sector`` / ``k2_in_sector``: full-space circuit kernels, but K3 screened the pool / K2 applied the first
-        observable on sector-compressed copies of the state (K2 with lambda output only from 20 qubits on)."""
+        observable on sector-compressed copies of the state (K2 with lambda output only from 20 qubits on); ``dense_tail``:
+        the trailing fixed single-species network (W), H, W^dagger and K3 all ran on compressed vectors (two dense blocks per W)."""
         C = _cabi.C
         act, cl, nops, ntr, nrem = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
         dim = C.c_uint64()
         _cabi.check(_cabi.lib().fh_program_sector_info(self._h, C.byref(act), C.byref(cl), C.byref(dim), C.byref(nops),
                                                        C.byref(ntr), C.byref(nrem)))
         return dict(active=act.value == 1, pool_in_sector=bool(act.value & 2) and act.value != 1,
-                    k2_in_sector=bool(act.value & 4) and act.value != 1, cluster=cl.value, dim=int(dim.value), ops=nops.value, transposes=ntr.value,
+                    k2_in_sector=bool(act.value & 4) and act.value != 1,
+                    dense_tail=bool(act.value & 8) and act.value != 1, cluster=cl.value, dim=int(dim.value), ops=nops.value, transposes=ntr.value,
                     remote_ops=nrem.value)
 
     def payload_bytes(self):

@@ -334,3 +334,57 @@ def test_evaluate_takes_k2_and_k3_in_the_sector_at_20_qubits(ctx, monkeypatch):
     assert abs(a["expvals"][0] - b["expvals"][0]) < 1e-11 and np.abs(a["pool"] - b["pool"]).max() < 1e-11
     assert np.abs(b["pool"]).max() > 1e-3
     assert abs(ag["expvals"][0] - bg["expvals"][0]) < 1e-11 and np.abs(ag["grads"] - bg["grads"]).max() < 1e-11
+
+
+@pytest.mark.parametrize("lat,u,up,dn", [((2, 2), 4.0, 2, 2), ((2, 3), 4.0, 3, 3), ((2, 3), 4.0, 4, 1), ((3, 3), 6.0, 5, 4)])
+def test_dense_tail_screening_vs_oracle_and_full_space(ctx, lat, u, up, dn, monkeypatch):
+    """W as two dense sector blocks (W = S (U_up x U_dn) S), then H, W^dagger and K3 on compressed vectors: against the
+    oracle and against the op-by-op full-space kernels of the same program; energy-only calls; graph replay."""
+    monkeypatch.setenv("FHSIM_NO_SECTOR", "1")           # not the cluster kernel
+    n, h_tab, pool_ops, dec, diag, o_h, o_pool = lattice(*lat, u)
+    rng = np.random.default_rng(21)
+    occ_up, occ_dn, _ = pauli.k_space_occupation(*lat, 1.0, up, dn)
+    picks = list(rng.choice(len(pool_ops), size=5, replace=False))
+    th = rng.uniform(-0.4, 0.4, len(picks))
+    plans = [GeneratorPlan(g, n) for g in pool_ops]
+    circ = Circuit(n, len(picks))
+    for p, k in enumerate(picks):
+        circ.generator(plans[k], param=p)
+    circ.marker("ansatz_end")
+    circ.basis_change_separable(*lat)
+    prog = circ.compile(ctx)
+    dtab = DeviceTable(ctx, h_tab)
+    dpool = DevicePool(ctx, plans, n)
+    basis = sum(1 << (n - 1 - q) for q in occ_up + occ_dn)
+    m = prog.markers["ansatz_end"]
+    a = prog.evaluate(basis, th, [dtab], pool=dpool, pool_pos=m)
+    assert prog.sector_info()["dense_tail"]
+    e_only = prog.evaluate(basis, th, [dtab])
+    assert prog.sector_info()["dense_tail"]
+    sub = prog.evaluate(basis, th, [dtab], pool=dpool, pool_pos=m, pool_range=(1, 5))
+    monkeypatch.setenv("FHSIM_NO_SECTOR_DENSE", "1")
+    b = prog.evaluate(basis, th, [dtab], pool=dpool, pool_pos=m)
+    assert not prog.sector_info()["dense_tail"]
+    monkeypatch.delenv("FHSIM_NO_SECTOR_DENSE")
+    gens = [o_pool[k] for k in picks]
+    pg_want, e_want, _ = sv.pool_gradients(sv.adapt_state(n, occ_up + occ_dn, gens, th), o_h, o_pool, diag, dec, n)
+    assert abs(a["expvals"][0] - e_want) < E_TOL and np.abs(a["pool"] - pg_want).max() < G_TOL
+    assert abs(a["expvals"][0] - b["expvals"][0]) < 1e-12 and np.abs(a["pool"] - b["pool"]).max() < 1e-12
+    assert abs(e_only["expvals"][0] - e_want) < E_TOL
+    assert np.abs(sub["pool"] - pg_want[1:6]).max() < G_TOL
+    th2 = th - 0.07
+    a2 = prog.evaluate(basis, th2, [dtab], pool=dpool, pool_pos=m)
+    pg2, e2, _ = sv.pool_gradients(sv.adapt_state(n, occ_up + occ_dn, gens, th2), o_h, o_pool, diag, dec, n)
+    assert abs(a2["expvals"][0] - e2) < E_TOL and np.abs(a2["pool"] - pg2).max() < G_TOL
+    # first-epoch screening (no ansatz at all) and a pool position that is not the start of the fixed tail
+    c0 = Circuit(n, 0)
+    c0.marker("ansatz_end")
+    c0.basis_change_separable(*lat)
+    p0 = c0.compile(ctx)
+    g0 = p0.evaluate(basis, [], [dtab], pool=dpool, pool_pos=0)
+    assert p0.sector_info()["dense_tail"]
+    pg0, e0, _ = sv.pool_gradients(sv.basis_state(n, occ_up + occ_dn), o_h, o_pool, diag, dec, n)
+    assert abs(g0["expvals"][0] - e0) < E_TOL and np.abs(g0["pool"] - pg0).max() < G_TOL
+    mid = prog.evaluate(basis, th, [dtab], pool=dpool, pool_pos=max(m - 1, 0))
+    if m > 0:
+        assert not prog.sector_info()["dense_tail"]          # parametrised ops after the pool position: op-by-op path
