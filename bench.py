@@ -41,9 +41,9 @@ L2_FLUSH_BYTES = 256 << 20
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_pool launch of this workload (ncu --set full,
 # profiles/r01_s2_ncu_full_18q.md rows "k_pool"): psi and lambda (8 MiB) are read from HBM once, everything else hits L2
 K3_DRAM_BYTES_PER_LAUNCH = 8431360
-# the same for one k_tile launch of this workload (profiles/r01_s6_ncu_full_18q.md, dram_rd 6.59 MB + dram_wr ~0: ncu
+# the same for one k_tile_tma launch of this workload (profiles/r02_final_ncu_full_18q.md, dram_rd 4.245 MB + dram_wr ~0: ncu
 # replays every kernel with a cold cache; inside the step the 4 MiB state comes from L2)
-K_TILE_DRAM_BYTES_PER_LAUNCH = 6590000
+K_TILE_DRAM_BYTES_PER_LAUNCH = 4245000
 
 
 def measured_peak_gbs():
@@ -500,11 +500,17 @@ def run_gpu_arm(args, rank, world, local_rank):
     tile = None
     try:
         if prog.n_tiles == prog.n_items:
-            n_dag = prog.n_items - marker
-            t_fwd = statistics.median(prog.time_items(phi, 0, prog.n_items, False, 20) for _ in range(5))
-            t_dag = statistics.median(prog.time_items(lam, marker, n_dag, True, 20) for _ in range(5))
-            n_tile_launches = prog.n_items + n_dag
-            tile_s = (t_fwd + t_dag) * 1e-3
+            if step_info.get("dense_tail"):
+                # the step launches only the tile runs before the fixed tail (the ansatz); W / W^dagger run as dense sector blocks
+                t_fwd = statistics.median(prog.time_items(phi, 0, marker, False, 20) for _ in range(5))
+                n_tile_launches = marker
+                tile_s = t_fwd * 1e-3
+            else:
+                n_dag = prog.n_items - marker
+                t_fwd = statistics.median(prog.time_items(phi, 0, prog.n_items, False, 20) for _ in range(5))
+                t_dag = statistics.median(prog.time_items(lam, marker, n_dag, True, 20) for _ in range(5))
+                n_tile_launches = prog.n_items + n_dag
+                tile_s = (t_fwd + t_dag) * 1e-3
             tile_alg = 32.0 * (1 << n) * n_tile_launches          # one read + one write of the state per launch
             tile = {"bound": "hbm", "kernel": "k_tile_tma (fused runs of rotations on TMA-staged shared-memory tiles)",
                     "achieved": tile_alg / tile_s / 1e9, "peak": peak, "unit": "GB/s",
@@ -512,9 +518,10 @@ def run_gpu_arm(args, rank, world, local_rank):
                     "peak_source": peak_src, "kernel_ms": 1e3 * tile_s / n_tile_launches,
                     "launches_per_step": n_tile_launches, "share_of_step": 1e3 * tile_s / (total_ms / args.steps),
                     "note": "18-qubit state (4 MiB) is L2-resident and the launches are latency-bound (128 CTAs, one "
-                            "dependent chain per fused op): effective GB/s vs HBM peak; algorithmic bytes = 32*2^n per "
-                            "launch; traffic = ncu dram bytes of one launch under cold-cache replay; the HBM-bound "
-                            "figure for this kernel is hbm_regime.tile_W"}
+                            "dependent chain per fused op, 6.3 us launch-to-launch floor): effective GB/s vs HBM peak; "
+                            "algorithmic bytes = 32*2^n per launch; traffic = ncu dram bytes of one launch under cold-cache "
+                            "replay; the HBM-bound figure for this kernel is hbm_regime.tile_W; the rest of the step (W, H, "
+                            "W^dagger, K3 on sector-compressed vectors) is roofline_k3 / profiles/r02_final_ncu_full_18q.md"}
     except Exception as exc:                                       # never lose the bench line over a side measurement
         print(f"k_tile roofline measurement failed: {exc}", file=sys.stderr)
         tile = None

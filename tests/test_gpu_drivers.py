@@ -421,9 +421,14 @@ def test_cfg3_bench_workload_pool_and_ansatz_gradients_float64():
     e2, g_ans = sv.adjoint_gradient(n, occ, [pool[k] for k in picks], thetas, h, diag, layers)
     assert abs(e2 - e_or) < 1e-12
     assert np.abs(res['grads'] - g_ans).max() < 1e-9
-    # the screening-only call the benchmark times returns the same 324 numbers bit for bit
+    # the screening-only call the benchmark times (W as two dense sector blocks, H, W^dagger and K3 on compressed vectors)
+    # returns the same 324 numbers to rounding -- and bit for bit when repeated
     res2 = prog.evaluate(wl['basis'], thetas, [dtab], pool=dpool, pool_pos=prog.markers['ansatz_end'])
-    assert np.array_equal(res2['pool'], res['pool'])
+    assert prog.sector_info()['dense_tail']
+    assert np.abs(res2['pool'] - res['pool']).max() < 1e-12 and np.abs(res2['pool'] - g_pool).max() < 1e-9
+    assert abs(res2['expvals'][0] - e_or) < 1e-10
+    res3 = prog.evaluate(wl['basis'], thetas, [dtab], pool=dpool, pool_pos=prog.markers['ansatz_end'])
+    assert np.array_equal(res3['pool'], res2['pool']) and res3['expvals'][0] == res2['expvals'][0]
     # selected operators of a pool operator and its ansatz gradient agree: d/d e_k at e=0 of an operator already in the
     # ansatz at the LAST position equals its ansatz gradient
     assert abs(res['pool'][picks[-1]] - res['grads'][-1]) < 1e-9

@@ -44,11 +44,21 @@ once(lambda cc: cc.generator(coulomb, angle=0.2))                     # k_diag_b
 once(lambda cc: cc.basis_change_separable(nx, ny), fuse=True, reps=1) # k_tile
 tab = DeviceTable(ctx, PauliTable.from_operator(h, n))
 for _ in range(2):
-    tab.apply(psi, lam)                                               # k_apply_table4
+    tab.apply(psi, lam)                                               # k_table_pass x 2 (K2 in tile passes)
+ns = nx * ny
+n_up, n_dn = (ns + 1) // 2, ns - (ns + 1) // 2
+os.environ["FHSIM_K2_GATHER"] = "1"
+tab.apply(psi, lam)                                                   # k_apply_table4 (gather kernel)
+del os.environ["FHSIM_K2_GATHER"]
+for _ in range(2):
+    tab.apply_sector(psi, lam, n_up, n_dn)                            # k_sector_compress1 + k_sector_happly + k_sector_scatter1
 for tb in ("0", "12"):
     os.environ["FHSIM_POOL_TILE_BITS"] = tb
     pool = DevicePool(ctx, plans, n)
     for _ in range(2):
         pool.gradients(psi, lam)                                      # k_pool32 / k_pool_tile
+    if tb == "0":
+        for _ in range(2):
+            pool.gradients_sector(psi, lam, n_up, n_dn)               # k_sector_compress2 + k_sector_pool
     pool.close()
 print("done", lat, n)
