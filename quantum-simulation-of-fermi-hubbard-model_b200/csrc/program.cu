@@ -47,6 +47,7 @@ struct EvalKey {
     const void *state_out;
     int sector, sector_pool;     // 1: the sector-resident path (sector_eval.cu) / K3 on sector-compressed copies was planned
     int sector_k2, sector_dense; // 1: K2 of tables[0] on the sector-compressed state / the whole tail (W, H, W^dagger, K3) there
+    int sector_prefix, pad_prefix;      // 1: the ops before the dense tail run in the cluster kernel (no full-space state at all)
     // unique ids of the same handles: a freed handle whose address is reused by a new one gets a new id, so the graph
     // (which bakes in the device pointers behind the handles) is re-captured instead of replayed on freed memory
     u64 table_uid[FH_MAX_RESULT_TABLES], target_uid[FH_MAX_OVERLAPS], pool_uid, state_out_uid;
@@ -115,7 +116,8 @@ struct fh_program {
     fh_sector_plan *sec = nullptr;
     fh_sector_pool_plan *sec_pool = nullptr;
     fh_sector_dense *sec_dense = nullptr;
-    bool last_sector = false, last_sector_pool = false, last_sector_k2 = false, last_sector_dense = false;
+    fh_sector_plan *sec_prefix = nullptr;
+    bool last_sector = false, last_sector_pool = false, last_sector_k2 = false, last_sector_dense = false, last_sector_prefix = false;
     // measurement
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0.0;
@@ -160,6 +162,8 @@ extern "C" int fh_program_destroy(fh_program *p) {
     p->sec_pool = nullptr;
     fh_sector_dense_free(p->sec_dense);
     p->sec_dense = nullptr;
+    fh_sector_plan_free(p->sec_prefix);
+    p->sec_prefix = nullptr;
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     cudaFree(p->d_tl_fwd);
@@ -912,12 +916,21 @@ static int enqueue_evaluation(fh_program *p, const EvalKey &k, fh_table *const *
     if (k.sector_dense) {
         // full-space tile kernels for the items before the fixed tail, then W, H, W^dagger and K3 on compressed vectors
         double *d_pool_out_s = p->d_res + 64 + p->res_segs;
-        FH_TRY(enqueue_payload_upload(p, capturing));
-        p->chain_region = capturing ? 0 : 1;
-        p->chain_used_runs[p->chain_region] = p->chain_used_maps[p->chain_region] = 0;
-        FH_TRY(apply_range(p, 0, fh_sector_dense_tail_item(p->sec_dense), p->d_psi, 0, nullptr, -1, (long long)k.basis));
-        FH_TRY(fh_sector_dense_enqueue(p->sec_dense, p->sec_pool, ctx, tables[0], p->d_psi, p->d_res, pool, k.pool_first, k.pool_count,
-                                       d_pool_out_s));
+        if (k.sector_prefix) {
+            // the ops before the tail in ONE cluster kernel on the compressed state (DSMEM), which leaves psi_s in rank order
+            FH_TRY(enqueue_payload_upload(p, false));
+            FH_TRY(fh_sector_enqueue(p->sec_prefix, ctx, k.basis, p->d_pairs, p->d_dterms, p->d_res, nullptr, 0, 0, nullptr,
+                                     fh_sector_dense_psi_buffer(p->sec_pool, pool)));
+            FH_TRY(fh_sector_dense_enqueue(p->sec_dense, p->sec_pool, ctx, tables[0], nullptr, p->d_res, pool, k.pool_first, k.pool_count,
+                                           d_pool_out_s));
+        } else {
+            FH_TRY(enqueue_payload_upload(p, capturing));
+            p->chain_region = capturing ? 0 : 1;
+            p->chain_used_runs[p->chain_region] = p->chain_used_maps[p->chain_region] = 0;
+            FH_TRY(apply_range(p, 0, fh_sector_dense_tail_item(p->sec_dense), p->d_psi, 0, nullptr, -1, (long long)k.basis));
+            FH_TRY(fh_sector_dense_enqueue(p->sec_dense, p->sec_pool, ctx, tables[0], p->d_psi, p->d_res, pool, k.pool_first, k.pool_count,
+                                           d_pool_out_s));
+        }
         const size_t n_res_s = want_pool ? 64 + (size_t)p->res_segs + (size_t)(k.pool_first + k.pool_count) : 4;
         FH_CUDA(cudaMemcpyAsync(p->h_res, p->d_res, sizeof(double) * n_res_s, cudaMemcpyDeviceToHost, ctx->stream));
         p->n_segments = 0;
@@ -1081,6 +1094,7 @@ extern "C" int fh_program_evaluate(fh_program *p, uint64_t basis_index, const do
     p->last_sector_pool = false;
     p->last_sector_k2 = false;
     p->last_sector_dense = false;
+    p->last_sector_prefix = false;
     if (!key.sector && n_tables >= 1 && !(p->n & 1) && p->n <= 31 && !getenv("FHSIM_NO_SECTOR_POOL")) {
         u64 upm = 0, dnm = 0;
         for (int b = 0; b < p->n; ++b) ((b & 1) ? upm : dnm) |= 1ull << b;          // even wires = up = odd index bits
@@ -1093,10 +1107,18 @@ extern "C" int fh_program_evaluate(fh_program *p, uint64_t basis_index, const do
             FH_TRY(fh_sector_dense_prepare(&p->sec_dense, p->sec_pool, p->n, p->pairs, p->diagops, p->dterms, p->flat, p->item_flat_first,
                                            pool ? pool_pos : 0, pool != nullptr));
             key.sector_dense = fh_sector_dense_ok(p->sec_dense) ? 1 : 0;
+            // ... and the ops before it (the ansatz) in the cluster kernel: opt-in (FHSIM_SECTOR_PREFIX=1), see sector_eval.cu
+            const int pf = key.sector_dense ? fh_sector_dense_first_flat(p->sec_dense) : 0;
+            if (pf > 0 && getenv("FHSIM_SECTOR_PREFIX")) {
+                FH_TRY(fh_sector_prepare(&p->sec_prefix, ctx, p->n, basis_index, p->pairs, p->diagops, p->dterms, p->flat, -1, tables[0],
+                                         nullptr, 0, pf));
+                key.sector_prefix = fh_sector_plan_eligible(p->sec_prefix) ? 1 : 0;
+            }
         }
         p->last_sector_pool = key.sector_pool != 0;
         p->last_sector_k2 = key.sector_k2 != 0;
         p->last_sector_dense = key.sector_dense != 0;
+        p->last_sector_prefix = key.sector_prefix != 0;
     }
 
     static const bool no_graph = getenv("FHSIM_NO_GRAPH") != nullptr;
@@ -1168,7 +1190,7 @@ extern "C" int fh_program_payload_bytes(const fh_program *p, size_t *h2d_bytes, 
 extern "C" int fh_program_sector_info(const fh_program *p, int *active, int *cluster_size, uint64_t *sector_dim, int *n_ops,
                                       int *n_transposes, int *n_remote_ops) {
     FH_REQUIRE(p, "fh_program_sector_info: program is NULL");
-    if (active) *active = p->last_sector ? 1 : ((p->last_sector_pool ? 2 : 0) | (p->last_sector_k2 ? 4 : 0) | (p->last_sector_dense ? 8 : 0));
+    if (active) *active = p->last_sector ? 1 : ((p->last_sector_pool ? 2 : 0) | (p->last_sector_k2 ? 4 : 0) | (p->last_sector_dense ? 8 : 0) | (p->last_sector_prefix ? 16 : 0));
     u64 dim = 0;
     fh_sector_plan_describe(p->last_sector ? p->sec : nullptr, cluster_size, &dim, n_ops, n_transposes, n_remote_ops, nullptr);
     if (sector_dim) *sector_dim = dim;

@@ -859,6 +859,7 @@ struct fh_sector_plan {
     // key
     int n_up = -1, n_dn = -1, pool_flat = -1, has_pool = 0, C = 0;
     u64 table_uid = 0, pool_uid = 0, max_dim = 0;
+    int prefix_flat = -1;
     SecGeomHost G;
     SecVOp *d_vops = nullptr;
     int *d_term_first = nullptr;
@@ -931,7 +932,9 @@ struct SecLogical {
 // Build (or reuse) the plan.  Returns FH_OK with plan->eligible telling whether the sector path applies.
 int fh_sector_prepare(fh_sector_plan **slot, fh_ctx *ctx, int n, u64 basis, const std::vector<PairOp> &pairs,
                       const std::vector<DiagOp> &diagops, const std::vector<DiagTerm> &dterms, const std::vector<SecFlatOp> &flat,
-                      int pool_flat, const fh_table *tab, const fh_pool *pool, u64 max_dim) {
+                      int pool_flat, const fh_table *tab, const fh_pool *pool, u64 max_dim, int prefix_flat) {
+    // prefix_flat >= 0: only the flat ops [0, prefix_flat) and a checkpoint of the compressed state (no observable, no pool):
+    // the ansatz part of a screening whose tail runs as dense sector blocks
     if (!*slot) *slot = new fh_sector_plan();
     fh_sector_plan *P = *slot;
     const int half = n / 2;
@@ -942,7 +945,8 @@ int fh_sector_prepare(fh_sector_plan **slot, fh_ctx *ctx, int n, u64 basis, cons
     }
     const int n_up = __builtin_popcountll(basis & upmask), n_dn = __builtin_popcountll(basis & dnmask);
     const bool same = P->n_up == n_up && P->n_dn == n_dn && P->pool_flat == pool_flat && P->has_pool == (pool ? 1 : 0) &&
-                      P->table_uid == tab->uid && P->pool_uid == (pool ? pool->uid : 0) && P->max_dim == max_dim;
+                      P->table_uid == tab->uid && P->pool_uid == (pool ? pool->uid : 0) && P->max_dim == max_dim &&
+                      P->prefix_flat == prefix_flat;
     if (same) return FH_OK;
     P->release();
     P->eligible = false;
@@ -953,6 +957,7 @@ int fh_sector_prepare(fh_sector_plan **slot, fh_ctx *ctx, int n, u64 basis, cons
     P->table_uid = tab->uid;
     P->pool_uid = pool ? pool->uid : 0;
     P->max_dim = max_dim;
+    P->prefix_flat = prefix_flat;
     if ((n & 1) || half < 1 || half > 15) return FH_OK;
 
     SecGeomHost &G = P->G;
@@ -993,15 +998,21 @@ int fh_sector_prepare(fh_sector_plan **slot, fh_ctx *ctx, int n, u64 basis, cons
         seq.push_back(L);
     };
     const int nflat = (int)flat.size();
-    for (int k = 0; k < nflat; ++k) {
-        if (pool && k == pool_flat) seq.push_back({SV_CHECKPOINT, 0, 0, 0, 0});
-        push_op(flat[k], 0);
-    }
-    if (pool && pool_flat == nflat) seq.push_back({SV_CHECKPOINT, 0, 0, 0, 0});
-    seq.push_back({SV_HAPPLY, 0, 0, 0, 0});
-    if (pool) {
-        for (int k = nflat - 1; k >= pool_flat; --k) push_op(flat[k], 1);
-        seq.push_back({SV_STORE, 0, 0, 0, 0});
+    const bool prefix = prefix_flat >= 0;
+    if (prefix) {
+        for (int k = 0; k < prefix_flat && k < nflat; ++k) push_op(flat[k], 0);
+        seq.push_back({SV_CHECKPOINT, 0, 0, 0, 0});
+    } else {
+        for (int k = 0; k < nflat; ++k) {
+            if (pool && k == pool_flat) seq.push_back({SV_CHECKPOINT, 0, 0, 0, 0});
+            push_op(flat[k], 0);
+        }
+        if (pool && pool_flat == nflat) seq.push_back({SV_CHECKPOINT, 0, 0, 0, 0});
+        seq.push_back({SV_HAPPLY, 0, 0, 0, 0});
+        if (pool) {
+            for (int k = nflat - 1; k >= pool_flat; --k) push_op(flat[k], 1);
+            seq.push_back({SV_STORE, 0, 0, 0, 0});
+        }
     }
 
     // usable cluster size decides the distribution
@@ -1125,8 +1136,9 @@ int fh_sector_prepare(fh_sector_plan **slot, fh_ctx *ctx, int n, u64 basis, cons
     // shared memory
     const unsigned dmax = std::max(d_up, d_dn), rmax = (dmax + C - 1) >> logC;
     const unsigned S = std::max(((d_up + C - 1) >> logC) * d_dn, ((d_dn + C - 1) >> logC) * d_up);
-    SecTableCache &T = g_sec_tables[tab->uid];
-    if (T.table_uid != tab->uid || T.n_up != n_up || T.n_dn != n_dn) {
+    SecTableCache Tnone;                     // prefix plans read no observable
+    SecTableCache &T = prefix ? Tnone : g_sec_tables[tab->uid];
+    if (!prefix && (T.table_uid != tab->uid || T.n_up != n_up || T.n_dn != n_dn)) {
         bool ok = false;
         FH_TRY(sec_build_table(tab, G, upmask, dnmask, T, &ok));
         if (!ok) {
@@ -1134,7 +1146,7 @@ int fh_sector_prepare(fh_sector_plan **slot, fh_ctx *ctx, int n, u64 basis, cons
             return FH_OK;
         }
     }
-    if (pool) {
+    if (pool && !prefix) {
         SecPoolCache &Pc = g_sec_pools[pool->uid];
         if (Pc.pool_uid != pool->uid || Pc.n_up != n_up || Pc.n_dn != n_dn) {
             bool ok = false;
@@ -1190,9 +1202,10 @@ void fh_sector_plan_describe(const fh_sector_plan *plan, int *cluster, u64 *dim,
 
 // Enqueue the evaluation: E -> d_res[0..1]; pool outputs -> d_pool_out[first .. first+count)
 int fh_sector_enqueue(fh_sector_plan *P, fh_ctx *ctx, u64 basis, const PairOp *d_pairs, const DiagTerm *d_dterms, double *d_res,
-                      const fh_pool *pool, int pool_first, int pool_count, double *d_pool_out) {
+                      const fh_pool *pool, int pool_first, int pool_count, double *d_pool_out, double2 *chk_override) {
     const SecGeomHost &G = P->G;
-    const SecTableCache &T = g_sec_tables[P->table_uid];
+    const SecTableCache Tnone;
+    const SecTableCache &T = P->prefix_flat >= 0 ? Tnone : g_sec_tables[P->table_uid];
     SecArgs A;
     memset(&A, 0, sizeof(A));
     A.half = G.half;
@@ -1221,7 +1234,7 @@ int fh_sector_enqueue(fh_sector_plan *P, fh_ctx *ctx, u64 basis, const PairOp *d
     A.ngroups = T.ngroups;
     A.nclasses = T.nclasses;
     A.nvals = T.nvals;
-    A.chk = P->d_chk;
+    A.chk = chk_override ? chk_override : P->d_chk;
     A.lam_out = P->d_lam;
     A.res = d_res;
     u64 upc = 0, dnc = 0;
@@ -1254,7 +1267,7 @@ int fh_sector_enqueue(fh_sector_plan *P, fh_ctx *ctx, u64 basis, const PairOp *d
     cfg.numAttrs = 1;
     ++g_fh_launch_count;
     FH_CUDA(cudaLaunchKernelEx(&cfg, k_sector_eval, A));
-    if (pool && pool_count > 0) {
+    if (pool && pool_count > 0 && P->prefix_flat < 0) {
         const SecPoolCache &Pc = g_sec_pools[pool->uid];
         const int e0 = pool->out_first[pool_first], e1 = pool->out_first[pool_first + pool_count];
         int grid = e1 - e0;
@@ -1802,6 +1815,7 @@ void fh_sector_dense_free(fh_sector_dense *d) {
 }
 bool fh_sector_dense_ok(const fh_sector_dense *d) { return d && d->D.ok; }
 int fh_sector_dense_tail_item(const fh_sector_dense *d) { return d ? d->tail_item : -1; }
+int fh_sector_dense_first_flat(const fh_sector_dense *d) { return d ? d->D.first_flat : -1; }
 
 typedef std::vector<double2> SecMatH;          // row-major square matrix
 static void sec_mat_rows_pair(SecMatH &U, unsigned d, const std::vector<unsigned> &L, const double m[8]) {
@@ -1965,6 +1979,9 @@ static void sec_dense_apply(const fh_sector_pool_plan *P, const SecDense &D, cud
 
 // The tail of an evaluation on compressed vectors: psi_full = the state after the items before the tail.
 // E -> d_result[0..1]; with a pool: outputs o in [first, first + count) -> d_pool_out[o].
+double2 *fh_sector_dense_psi_buffer(fh_sector_pool_plan *P, const fh_pool *pool) { return (pool && P->d_psi) ? P->d_psi : P->d_in; }
+
+// psi_full == NULL: the compressed psi_s is already in fh_sector_dense_psi_buffer() (written by the cluster kernel)
 int fh_sector_dense_enqueue(fh_sector_dense *X, fh_sector_pool_plan *P, fh_ctx *ctx, const fh_table *tab, const double2 *psi_full,
                             double *d_result, const fh_pool *pool, int pool_first, int pool_count, double *d_pool_out) {
     const SecDense &D = X->D;
@@ -1975,7 +1992,8 @@ int fh_sector_dense_enqueue(fh_sector_dense *X, fh_sector_pool_plan *P, fh_ctx *
     // psi_s (compressed) lives in the K3 buffer when a pool is screened, else in the K2 input buffer
     double2 *psi_s = (pool && P->d_psi) ? P->d_psi : P->d_in;
     (void)cgrid;
-    sec_dense_apply(P, D, ctx->stream, psi_full, D.d_t0, D.d_t1, false, psi_s);       // phi = W psi_s (t1); psi_s compressed on the way
+    if (psi_full) sec_dense_apply(P, D, ctx->stream, psi_full, D.d_t0, D.d_t1, false, psi_s);   // phi = W psi_s (t1); psi_s compressed on the way
+    else sec_dense_apply(P, D, ctx->stream, psi_s, D.d_t0, D.d_t1, false, nullptr);
     unsigned hgrid = (dim + (256u / SEC_HSPLIT) - 1u) / (256u / SEC_HSPLIT);
     if (hgrid > 4096u) hgrid = 4096u;
     ++g_fh_launch_count;

@@ -15,14 +15,14 @@ struct SecFlatOp {
 // Not stream-ordered (allocates and uploads): call outside stream capture.
 int fh_sector_prepare(fh_sector_plan **slot, fh_ctx *ctx, int n, u64 basis, const std::vector<PairOp> &pairs,
                       const std::vector<DiagOp> &diagops, const std::vector<DiagTerm> &dterms, const std::vector<SecFlatOp> &flat,
-                      int pool_flat, const fh_table *tab, const fh_pool *pool, u64 max_dim);
+                      int pool_flat, const fh_table *tab, const fh_pool *pool, u64 max_dim, int prefix_flat = -1);
 // max_dim: sectors with more amplitudes are not planned (0: no limit)
 bool fh_sector_plan_eligible(const fh_sector_plan *plan);
 void fh_sector_plan_describe(const fh_sector_plan *plan, int *cluster, u64 *dim, int *nvops, int *transposes, int *remote_ops,
                              size_t *smem);
 // Enqueue (capturable): E -> d_res[0..1]; pool outputs o in [first, first+count) -> d_pool_out[o]
 int fh_sector_enqueue(fh_sector_plan *plan, fh_ctx *ctx, u64 basis, const PairOp *d_pairs, const DiagTerm *d_dterms, double *d_res,
-                      const fh_pool *pool, int pool_first, int pool_count, double *d_pool_out);
+                      const fh_pool *pool, int pool_first, int pool_count, double *d_pool_out, double2 *chk_override = nullptr);
 void fh_sector_plan_free(fh_sector_plan *plan);
 void fh_sector_forget_table(u64 uid);
 void fh_sector_forget_pool(u64 uid);
@@ -54,3 +54,5 @@ int fh_sector_dense_tail_item(const fh_sector_dense *d);
 int fh_sector_dense_enqueue(fh_sector_dense *d, fh_sector_pool_plan *plan, fh_ctx *ctx, const fh_table *tab, const double2 *psi_full,
                             double *d_result, const fh_pool *pool, int pool_first, int pool_count, double *d_pool_out);
 void fh_sector_dense_free(fh_sector_dense *d);
+double2 *fh_sector_dense_psi_buffer(fh_sector_pool_plan *plan, const fh_pool *pool);
+int fh_sector_dense_first_flat(const fh_sector_dense *d);

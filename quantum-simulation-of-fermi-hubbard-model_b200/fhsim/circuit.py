@@ -553,7 +553,8 @@ class DeviceProgram:
                                                        C.byref(ntr), C.byref(nrem)))
         return dict(active=act.value == 1, pool_in_sector=bool(act.value & 2) and act.value != 1,
                     k2_in_sector=bool(act.value & 4) and act.value != 1,
-                    dense_tail=bool(act.value & 8) and act.value != 1, cluster=cl.value, dim=int(dim.value), ops=nops.value, transposes=ntr.value,
+                    dense_tail=bool(act.value & 8) and act.value != 1,
+                    cluster_prefix=bool(act.value & 16) and act.value != 1, cluster=cl.value, dim=int(dim.value), ops=nops.value, transposes=ntr.value,
                     remote_ops=nrem.value)
 
     def payload_bytes(self):

@@ -362,6 +362,13 @@ def test_dense_tail_screening_vs_oracle_and_full_space(ctx, lat, u, up, dn, monk
     e_only = prog.evaluate(basis, th, [dtab])
     assert prog.sector_info()["dense_tail"]
     sub = prog.evaluate(basis, th, [dtab], pool=dpool, pool_pos=m, pool_range=(1, 5))
+    # opt-in: the ansatz in the cluster kernel as well -- the screening never touches a full-space state (7 launches)
+    monkeypatch.setenv("FHSIM_SECTOR_PREFIX", "1")
+    ap = prog.evaluate(basis, th, [dtab], pool=dpool, pool_pos=m)
+    info_p = prog.sector_info()
+    assert info_p["cluster_prefix"] and info_p["dense_tail"] and prog.last_stats()[1] <= 7
+    assert abs(ap["expvals"][0] - a["expvals"][0]) < 1e-12 and np.abs(ap["pool"] - a["pool"]).max() < 1e-12
+    monkeypatch.delenv("FHSIM_SECTOR_PREFIX")
     monkeypatch.setenv("FHSIM_NO_SECTOR_DENSE", "1")
     b = prog.evaluate(basis, th, [dtab], pool=dpool, pool_pos=m)
     assert not prog.sector_info()["dense_tail"]
