@@ -418,7 +418,10 @@ def run_gpu_arm(args, rank, world, local_rank):
                             "speedup": times["single_gpu"] / times["pool_sharded"], "ops_per_rank": -(-n24 // world),
                             "max_abs_diff_vs_single_gpu": parity,
                             "collective": "all_gather of <= %d doubles per rank (NCCL); psi / lambda recomputed per rank" % -(-n24 // world),
-                            "at_18_qubits": "withdrawn: replicas only (K3 is ~17 % of the step; see DESIGN 6)"}
+                            "at_18_qubits": "withdrawn: replicas only (K3 is ~10 % of the step; see DESIGN 6)",
+                            "note": "K3 runs on sector-compressed vectors inside fh_program_evaluate (400 gradients at 24 qubits: 0.21 ms "
+                                    "instead of 4.09 ms), so it no longer dominates this screening and splitting the pool does not pay; "
+                                    "kept as a measured negative result"}
             for o in (wl24["prog"], wl24["dpool"], wl24["dtab"]):
                 o.close()
         except Exception as exc:

@@ -31,6 +31,7 @@
 
 #include <algorithm>
 #include <map>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -835,10 +836,14 @@ static int sec_build_pool(const fh_pool *pool, const SecGeomHost &G, u64 upmask,
     return FH_OK;
 }
 
-// caches live as long as the process (tables and pools are few and long-lived in the drivers); keyed by handle uid
+// caches live as long as their table / pool handle; keyed by handle uid.  Handles are not thread-safe, but these maps are
+// shared by all of them: every function that touches one holds g_sec_mutex (recursive: prepare calls build / forget)
+static std::recursive_mutex g_sec_mutex;
+#define SEC_LOCK std::lock_guard<std::recursive_mutex> sec_lock_guard_(g_sec_mutex)
 static std::map<u64, SecTableCache> g_sec_tables;
 static std::map<u64, SecPoolCache> g_sec_pools;
 void fh_sector_forget_table(u64 uid) {
+    SEC_LOCK;
     auto it = g_sec_tables.find(uid);
     if (it != g_sec_tables.end()) {
         it->second.release();
@@ -846,6 +851,7 @@ void fh_sector_forget_table(u64 uid) {
     }
 }
 void fh_sector_forget_pool(u64 uid) {
+    SEC_LOCK;
     auto it = g_sec_pools.find(uid);
     if (it != g_sec_pools.end()) {
         it->second.release();
@@ -933,6 +939,7 @@ struct SecLogical {
 int fh_sector_prepare(fh_sector_plan **slot, fh_ctx *ctx, int n, u64 basis, const std::vector<PairOp> &pairs,
                       const std::vector<DiagOp> &diagops, const std::vector<DiagTerm> &dterms, const std::vector<SecFlatOp> &flat,
                       int pool_flat, const fh_table *tab, const fh_pool *pool, u64 max_dim, int prefix_flat) {
+    SEC_LOCK;
     // prefix_flat >= 0: only the flat ops [0, prefix_flat) and a checkpoint of the compressed state (no observable, no pool):
     // the ansatz part of a screening whose tail runs as dense sector blocks
     if (!*slot) *slot = new fh_sector_plan();
@@ -1203,6 +1210,7 @@ void fh_sector_plan_describe(const fh_sector_plan *plan, int *cluster, u64 *dim,
 // Enqueue the evaluation: E -> d_res[0..1]; pool outputs -> d_pool_out[first .. first+count)
 int fh_sector_enqueue(fh_sector_plan *P, fh_ctx *ctx, u64 basis, const PairOp *d_pairs, const DiagTerm *d_dterms, double *d_res,
                       const fh_pool *pool, int pool_first, int pool_count, double *d_pool_out, double2 *chk_override) {
+    SEC_LOCK;
     const SecGeomHost &G = P->G;
     const SecTableCache Tnone;
     const SecTableCache &T = P->prefix_flat >= 0 ? Tnone : g_sec_tables[P->table_uid];
@@ -1358,6 +1366,7 @@ bool fh_sector_pool_plan_table_ok(const fh_sector_pool_plan *plan) { return plan
 int fh_sector_pool_prepare(fh_sector_pool_plan **slot, fh_ctx *ctx, int n, u64 upmask, u64 dnmask, int n_up, int n_dn,
                            const std::vector<PairOp> &pairs, const std::vector<SecFlatOp> &flat, const fh_table *tab,
                            const fh_pool *pool) {
+    SEC_LOCK;
     if (!*slot) *slot = new fh_sector_pool_plan();
     fh_sector_pool_plan *P = *slot;
     if (upmask == 0 && dnmask == 0)
@@ -1569,6 +1578,7 @@ __global__ void __launch_bounds__(256) k_sector_happly(const SecGroup *__restric
 // out (full space, may be NULL) <- H in; E -> d_result[0..1].  `in` must be confined to the plan's sector.
 int fh_sector_table_enqueue(fh_sector_pool_plan *P, fh_ctx *ctx, const fh_table *tab, const double2 *in, double2 *out,
                             double *d_result) {
+    SEC_LOCK;
     const SecTableCache &T = g_sec_tables[tab->uid];
     const unsigned dim = P->d_up * P->d_dn;
     unsigned cgrid = (dim + 255u) / 256u;
@@ -1595,6 +1605,7 @@ static bool g_sec_pool_attr[64];
 // pool outputs o in [first, first+count) of full-space states psi / lam -> d_pool_out[o]
 int fh_sector_pool_enqueue(fh_sector_pool_plan *P, fh_ctx *ctx, const double2 *psi, const double2 *lam, const fh_pool *pool,
                            int pool_first, int pool_count, double *d_pool_out) {
+    SEC_LOCK;
     if (pool_count <= 0) return FH_OK;
     const SecPoolCache &Pc = g_sec_pools[pool->uid];
     const unsigned dim = P->d_up * P->d_dn;
@@ -1626,6 +1637,7 @@ int fh_sector_pool_enqueue(fh_sector_pool_plan *P, fh_ctx *ctx, const double2 *p
 // ---- the same screening as a stand-alone call on caller-owned full-space states --------------------------------
 static std::map<u64, fh_sector_pool_plan *> g_sec_pool_plans;      // per pool handle (freed with the pool)
 void fh_sector_forget_pool_plan(u64 uid) {
+    SEC_LOCK;
     auto it = g_sec_pool_plans.find(uid);
     if (it != g_sec_pool_plans.end()) {
         fh_sector_pool_plan_free(it->second);
@@ -1635,6 +1647,7 @@ void fh_sector_forget_pool_plan(u64 uid) {
 
 static int pool_gradients_sector_impl(const char *who, const fh_pool *pool, const fh_state *psi, const fh_state *lambda, u64 upmask,
                                       u64 dnmask, int n_up, int n_dn, int first, int count, double *out) {
+    SEC_LOCK;
     FH_REQUIRE(pool && psi && lambda, "%s: NULL argument", who);
     FH_REQUIRE(psi->n == pool->n && lambda->n == pool->n, "%s: qubit count mismatch", who);
     FH_REQUIRE(first >= 0 && count >= 0 && first + count <= pool->n_out, "%s: range [%d, %d) outside pool of %d", who, first,
@@ -1673,6 +1686,7 @@ extern "C" int fh_pool_gradients_sector_masks(const fh_pool *pool, const fh_stat
 // ---- K2 in the sector as a stand-alone call --------------------------------------------------------------------
 static std::map<u64, fh_sector_pool_plan *> g_sec_table_plans;      // per table handle (freed with the table)
 void fh_sector_forget_table_plan(u64 uid) {
+    SEC_LOCK;
     auto it = g_sec_table_plans.find(uid);
     if (it != g_sec_table_plans.end()) {
         fh_sector_pool_plan_free(it->second);
@@ -1682,6 +1696,7 @@ void fh_sector_forget_table_plan(u64 uid) {
 
 extern "C" int fh_apply_table_sector(const fh_table *tab, const fh_state *in, fh_state *out, int n_up, int n_dn, double *e_re,
                                      double *e_im) {
+    SEC_LOCK;
     FH_REQUIRE(tab && in, "fh_apply_table_sector: NULL argument");
     FH_REQUIRE(in->n == tab->n && (!out || out->n == tab->n), "fh_apply_table_sector: qubit count mismatch");
     FH_REQUIRE(!out || out->d != in->d, "fh_apply_table_sector: in and out must differ");
@@ -1984,6 +1999,7 @@ double2 *fh_sector_dense_psi_buffer(fh_sector_pool_plan *P, const fh_pool *pool)
 // psi_full == NULL: the compressed psi_s is already in fh_sector_dense_psi_buffer() (written by the cluster kernel)
 int fh_sector_dense_enqueue(fh_sector_dense *X, fh_sector_pool_plan *P, fh_ctx *ctx, const fh_table *tab, const double2 *psi_full,
                             double *d_result, const fh_pool *pool, int pool_first, int pool_count, double *d_pool_out) {
+    SEC_LOCK;
     const SecDense &D = X->D;
     const SecTableCache &T = g_sec_tables[tab->uid];
     const unsigned dim = P->d_up * P->d_dn;
