@@ -65,7 +65,8 @@ struct __align__(16) SecGroup {    // 32 bytes: TabGroup in compact coordinates 
     unsigned live;
     unsigned char pos[4];          // compact bit positions of the x bits; unused = 31 (always 0: half <= 15)
     int kbits;
-    int pad[2];
+    unsigned zeta1;                // single-class groups (every hopping group): the class's zeta and value offset inline, so the
+    int vofs1;                     // gather needs no class record
 };
 struct __align__(8) SecClass {
     unsigned zeta;
@@ -749,6 +750,11 @@ static int sec_build_table(const fh_table *tab, const SecGeomHost &G, u64 upmask
         s.live = g.live;
         s.kbits = g.kbits;
         for (int b = 0; b < 4; ++b) s.pos[b] = b < g.kbits ? (unsigned char)sec_compact_pos(g.pos[b], G) : 31;
+        s.zeta1 = sec_compact(tab->classes[g.first_class].zeta, G);
+        s.vofs1 = tab->classes[g.first_class].vofs;
+        // bits 8..9 of kbits: 1 = x touches up orbitals only, 2 = down orbitals only (the partner keeps the other rank)
+        if ((s.x >> 16) == 0u) s.kbits |= 1 << 8;
+        else if ((s.x & 0xffffu) == 0u) s.kbits |= 2 << 8;
         for (int c = g.first_class; c < g.first_class + g.n_class; ++c) {
             SecClass sc;
             sc.zeta = sec_compact(tab->classes[c].zeta, G);
@@ -1494,7 +1500,9 @@ __global__ void __launch_bounds__(256) k_sector_scatter1(const unsigned *__restr
 // lanes share an amplitude and split its groups (g = lane, lane + 4, ...): four times the parallelism and a quarter of the
 // dependent L2 round trips per thread; the four partial sums are folded by shuffles in a fixed order.  Per-CTA energy
 // partials, folded by the last CTA in slot order.
-#define SEC_HSPLIT 4
+// SPLIT lanes share an amplitude: 4 for small sectors (parallelism, shorter dependent chains), 1 for large ones (a warp is then
+// 32 consecutive ranks applying the same group: the partner loads of an up-hop are one contiguous 512-byte run)
+template <bool REAL, int SPLIT>
 __global__ void __launch_bounds__(256) k_sector_happly(const SecGroup *__restrict__ groups, int ngroups, const SecClass *__restrict__ classes,
                                                        const double2 *__restrict__ vals, const double2 *__restrict__ hdiag,
                                                        const unsigned short *__restrict__ cfgU, const unsigned short *__restrict__ cfgD,
@@ -1505,39 +1513,55 @@ __global__ void __launch_bounds__(256) k_sector_happly(const SecGroup *__restric
     __shared__ double red[16];
     __shared__ unsigned is_last;
     double e_re = 0.0, e_im = 0.0;
-    const unsigned sub = threadIdx.x & (SEC_HSPLIT - 1);
-    const unsigned per_cta = 256 / SEC_HSPLIT;
+    const unsigned sub = threadIdx.x & (SPLIT - 1);
+    const unsigned per_cta = 256 / SPLIT;
     const unsigned stride = gridDim.x * per_cta;
     const unsigned rounds = (dim + stride - 1) / stride;          // uniform trip count: the shuffles need whole warps
     for (unsigned it = 0; it < rounds; ++it) {
-        const unsigned r = it * stride + blockIdx.x * per_cta + (threadIdx.x / SEC_HSPLIT);
+        const unsigned r = it * stride + blockIdx.x * per_cta + (threadIdx.x / SPLIT);
         const bool ok = r < dim;
         const unsigned rr = ok ? r : 0u;
         const unsigned ru = rr / d_dn, rd = rr - ru * d_dn;
         const unsigned cfg = (unsigned)__ldg(cfgU + ru) | ((unsigned)__ldg(cfgD + rd) << 16);
         double ar = 0.0, ai = 0.0;
-        for (int g = (int)sub; g < ngroups; g += SEC_HSPLIT) {
+        for (int g = (int)sub; g < ngroups; g += SPLIT) {
             const uint4 g0 = __ldg(reinterpret_cast<const uint4 *>(groups + g));          // x, first_class, n_class, live
-            const unsigned gp = __ldg(reinterpret_cast<const unsigned *>(groups + g) + 4);   // pos[4]
+            const uint4 g1 = __ldg(reinterpret_cast<const uint4 *>(groups + g) + 1);      // pos[4], kbits, zeta1, vofs1
+            const unsigned gp = g1.x;
             const unsigned j = cfg ^ g0.x;
             const unsigned pat = ((j >> (gp & 0xffu)) & 1u) | (((j >> ((gp >> 8) & 0xffu)) & 1u) << 1) |
                                  (((j >> ((gp >> 16) & 0xffu)) & 1u) << 2) | (((j >> (gp >> 24)) & 1u) << 3);
             if (!((g0.w >> pat) & 1u)) continue;
             double wr = 0.0, wi = 0.0;
-            for (int c = (int)g0.y; c < (int)(g0.y + g0.z); ++c) {
-                const uint2 cl = __ldg(reinterpret_cast<const uint2 *>(classes + c));      // zeta, vofs
-                const double2 w = __ldg(vals + cl.y + pat);
-                const bool neg = (__popc(j & cl.x) & 1) != 0;
-                wr += neg ? -w.x : w.x;
-                wi += neg ? -w.y : w.y;
+            if (g0.z == 1u) {               // one class: zeta and the table offset sit in the group record
+                const double2 w = __ldg(vals + g1.w + pat);
+                const bool neg = (__popc(j & g1.z) & 1) != 0;
+                wr = neg ? -w.x : w.x;
+                if (!REAL) wi = neg ? -w.y : w.y;
+            } else {
+                for (int c = (int)g0.y; c < (int)(g0.y + g0.z); ++c) {
+                    const uint2 cl = __ldg(reinterpret_cast<const uint2 *>(classes + c));      // zeta, vofs
+                    const double2 w = __ldg(vals + cl.y + pat);
+                    const bool neg = (__popc(j & cl.x) & 1) != 0;
+                    wr += neg ? -w.x : w.x;
+                    if (!REAL) wi += neg ? -w.y : w.y;
+                }
             }
-            const unsigned qu = __ldg(rankU + (j & 0xffffu)), qd = __ldg(rankD + (j >> 16));
+            // partner rank: a single-species x-mask keeps the other species' rank (one table lookup instead of two)
+            const unsigned sp = (g1.y >> 8) & 3u;
+            const unsigned qu = sp == 2u ? ru : (unsigned)__ldg(rankU + (j & 0xffffu));
+            const unsigned qd = sp == 1u ? rd : (unsigned)__ldg(rankD + (j >> 16));
             const double2 pv = in[qu * d_dn + qd];
-            ar += wr * pv.x - wi * pv.y;
-            ai += wr * pv.y + wi * pv.x;
+            if (REAL) {
+                ar += wr * pv.x;
+                ai += wr * pv.y;
+            } else {
+                ar += wr * pv.x - wi * pv.y;
+                ai += wr * pv.y + wi * pv.x;
+            }
         }
 #pragma unroll
-        for (int o = 1; o < SEC_HSPLIT; o <<= 1) {
+        for (int o = 1; o < SPLIT; o <<= 1) {
             ar += __shfl_xor_sync(0xffffffffu, ar, o);
             ai += __shfl_xor_sync(0xffffffffu, ai, o);
         }
@@ -1575,6 +1599,22 @@ __global__ void __launch_bounds__(256) k_sector_happly(const SecGroup *__restric
     }
 }
 
+template <bool REAL>
+static void sec_launch_happly(cudaStream_t st, const SecTableCache &T, const fh_sector_pool_plan *P, unsigned dim, const double2 *in,
+                              double2 *out, double *d_result) {
+    const bool split = dim < (1u << 17);
+    const unsigned per_cta = split ? 64u : 256u;
+    unsigned hgrid = (dim + per_cta - 1u) / per_cta;
+    if (hgrid > 4096u) hgrid = 4096u;                 // the energy partial array
+    if (hgrid < 1u) hgrid = 1u;
+    if (split)
+        k_sector_happly<REAL, 4><<<hgrid, 256, 0, st>>>(T.d_groups, T.ngroups, T.d_classes, T.d_vals, T.d_hdiag, P->d_cfgU, P->d_cfgD, P->d_rankU,
+                                                        P->d_rankD, P->d_dn, dim, in, out, P->d_k2_partials, P->d_k2_counter, d_result);
+    else
+        k_sector_happly<REAL, 1><<<hgrid, 256, 0, st>>>(T.d_groups, T.ngroups, T.d_classes, T.d_vals, T.d_hdiag, P->d_cfgU, P->d_cfgD, P->d_rankU,
+                                                        P->d_rankD, P->d_dn, dim, in, out, P->d_k2_partials, P->d_k2_counter, d_result);
+}
+
 // out (full space, may be NULL) <- H in; E -> d_result[0..1].  `in` must be confined to the plan's sector.
 int fh_sector_table_enqueue(fh_sector_pool_plan *P, fh_ctx *ctx, const fh_table *tab, const double2 *in, double2 *out,
                             double *d_result) {
@@ -1585,13 +1625,9 @@ int fh_sector_table_enqueue(fh_sector_pool_plan *P, fh_ctx *ctx, const fh_table 
     if (cgrid > (unsigned)ctx->sm_count * 8u) cgrid = (unsigned)ctx->sm_count * 8u;
     ++g_fh_launch_count;
     k_sector_compress1<<<cgrid, 256, 0, ctx->stream>>>(P->d_depU, P->d_depD, P->d_dn, dim, in, P->d_in);
-    unsigned hgrid = (dim + (256u / SEC_HSPLIT) - 1u) / (256u / SEC_HSPLIT);
-    if (hgrid > 4096u) hgrid = 4096u;                 // the energy partial array
-    if (hgrid < 1) hgrid = 1;
     ++g_fh_launch_count;
-    k_sector_happly<<<hgrid, 256, 0, ctx->stream>>>(T.d_groups, T.ngroups, T.d_classes, T.d_vals, T.d_hdiag, P->d_cfgU, P->d_cfgD,
-                                                    P->d_rankU, P->d_rankD, P->d_dn, dim, P->d_in, P->d_out, P->d_k2_partials,
-                                                    P->d_k2_counter, d_result);
+    if (tab->all_real) sec_launch_happly<true>(ctx->stream, T, P, dim, P->d_in, P->d_out, d_result);
+    else sec_launch_happly<false>(ctx->stream, T, P, dim, P->d_in, P->d_out, d_result);
     if (out) {
         FH_CUDA(cudaMemsetAsync(out, 0, sizeof(double2) << P->n, ctx->stream));
         ++g_fh_launch_count;
@@ -2010,12 +2046,9 @@ int fh_sector_dense_enqueue(fh_sector_dense *X, fh_sector_pool_plan *P, fh_ctx *
     (void)cgrid;
     if (psi_full) sec_dense_apply(P, D, ctx->stream, psi_full, D.d_t0, D.d_t1, false, psi_s);   // phi = W psi_s (t1); psi_s compressed on the way
     else sec_dense_apply(P, D, ctx->stream, psi_s, D.d_t0, D.d_t1, false, nullptr);
-    unsigned hgrid = (dim + (256u / SEC_HSPLIT) - 1u) / (256u / SEC_HSPLIT);
-    if (hgrid > 4096u) hgrid = 4096u;
     ++g_fh_launch_count;
-    k_sector_happly<<<hgrid, 256, 0, ctx->stream>>>(T.d_groups, T.ngroups, T.d_classes, T.d_vals, T.d_hdiag, P->d_cfgU, P->d_cfgD,
-                                                    P->d_rankU, P->d_rankD, P->d_dn, dim, D.d_t1, P->d_out, P->d_k2_partials,
-                                                    P->d_k2_counter, d_result);       // H phi               (d_out)
+    if (tab->all_real) sec_launch_happly<true>(ctx->stream, T, P, dim, D.d_t1, P->d_out, d_result);          // H phi (d_out)
+    else sec_launch_happly<false>(ctx->stream, T, P, dim, D.d_t1, P->d_out, d_result);
     if (pool && pool_count > 0) {
         sec_dense_apply(P, D, ctx->stream, P->d_out, D.d_t0, P->d_lam, true, nullptr); // lambda_s = W^dagger H phi
         const SecPoolCache &Pc = g_sec_pools[pool->uid];
