@@ -97,11 +97,12 @@ class PauliTable:
     def as_dict(self):
         return {(int(a), int(b)): complex(c) for a, b, c in zip(self.x, self.z, self.coeff)}
 
-    def conserves_species(self) -> bool:
+    def conserves_species(self, tol: float = 0.0) -> bool:
         """Does the operator commute with N_up and N_dn (even wires = up orbitals)?  Per x-mask group: the weight of the
         partner with x-bit pattern ``pat`` is sum_m d_m (-1)^popcount(z_m & pat-bits) class by class (a class = the z bits
         outside x); every pattern with a non-zero weight must move as many electrons into as out of each species.
-        Groups with more than four x bits are not analysed (-> False).  Same rule as the device planner (csrc/sector_eval.cu)."""
+        Groups with more than four x bits are not analysed (-> False).  Same rule as the device planner (csrc/sector_eval.cu),
+        which uses tol = 0 (exact cancellation, true for every table the drivers build)."""
         n = self.n_qubits
         up = sum(1 << b for b in range(n) if (n - 1 - b) % 2 == 0)
         i_pow = (1, 1j, -1, -1j)
@@ -119,7 +120,7 @@ class PauliTable:
                 classes.setdefault(z & ~x, []).append((z, d))
             for pat in range(1 << len(pos)):
                 dep = sum(1 << pos[b] for b in range(len(pos)) if pat >> b & 1)
-                live = any(abs(sum(d * (-1) ** bin(dep & z).count("1") for z, d in cl)) > 0 for cl in classes.values())
+                live = any(abs(sum(d * (-1) ** bin(dep & z).count("1") for z, d in cl)) > tol for cl in classes.values())
                 if not live:
                     continue
                 # the partner j carries `pat` on the x bits, the output i = j ^ x the complement
