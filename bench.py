@@ -453,6 +453,23 @@ def run_gpu_arm(args, rank, world, local_rank):
     h_launches = prog.last_stats()[1]
     step()   # restore the screening graph
 
+    # ---- one optimiser step of the same circuit: E + the 52 ansatz gradients by the adjoint sweep (information) ----
+    train = None
+    try:
+        for _ in range(3):
+            prog.evaluate(basis, thetas, [dtab], grads=True)
+        t_ms = []
+        for _ in range(min(args.steps, 200)):
+            ctx.flush_l2(L2_FLUSH_BYTES)
+            ctx.sync()
+            prog.evaluate(basis, thetas, [dtab], grads=True)
+            t_ms.append(prog.last_stats()[0])
+        train = {"ms": statistics.median(t_ms), "launches": prog.last_stats()[1],
+                 "what": "fh_program_evaluate(grads=True): energy + 52 ansatz gradients (adjoint sweep), device time"}
+    except Exception as exc:
+        print(f"train-step measurement failed: {exc!r}", file=sys.stderr)
+    step()   # restore the screening graph
+
     # ---- dominant kernel (K3 pool screening) timed alone for the roofline ----
     n = N_QUBITS
     psi_k, lam = State(ctx, n), State(ctx, n)
@@ -637,6 +654,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         "launches_per_step": launches,
         "h_evals_per_s": world * len(h_ms) / (sum(h_ms) * 1e-3),
         "h_eval_ms": statistics.median(h_ms), "h_eval_launches": h_launches,
+        "train_step": train,
         "roofline": tile if tile is not None else roofline_k3,
         "roofline_k3": roofline_k3,
         "roofline_k3_full_space": roofline_k3_full,

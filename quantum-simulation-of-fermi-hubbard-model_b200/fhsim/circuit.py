@@ -608,8 +608,14 @@ class DeviceProgram:
             raise ValueError(f"program expects {self.n_params} parameters, got {n_th}")
         if n_th:
             th[:n_th] = thetas
-        tab_arr = (C.c_void_p * nt)(*[t._h for t in tables])
-        tgt_arr = (C.c_void_p * max(nv, 1))(*[t._h for t in targets])
+        # handle arrays: rebuilt only when the handles change (the objects are kept alive by the key's references)
+        hk = self.__dict__.get("_eval_handles")
+        if hk is None or len(hk[0]) != nt or len(hk[1]) != nv or any(a is not b for a, b in zip(hk[0], tables)) or \
+                any(a is not b for a, b in zip(hk[1], targets)) or any(t._h.value != v for t, v in zip(tables, hk[4])):
+            hk = (list(tables), list(targets), (C.c_void_p * nt)(*[t._h for t in tables]),
+                  (C.c_void_p * max(nv, 1))(*[t._h for t in targets]), [t._h.value for t in tables])
+            self._eval_handles = hk
+        tab_arr, tgt_arr = hk[2], hk[3]
         _cabi.check(_cabi.lib().fh_program_evaluate(
             self._h, int(basis_index), th_p, n_th, nt, tab_arr, ex_p,
             g_p if grads else None,
