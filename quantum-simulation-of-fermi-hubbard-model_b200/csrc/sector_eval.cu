@@ -32,12 +32,42 @@
 #include <algorithm>
 #include <map>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
 #include "sector_eval.cuh"
 
 extern long long g_fh_launch_count;
+extern thread_local int g_fh_tile_pdl_scope;      // > 0 inside fh_program_evaluate: consecutive kernels of the graph use PDL
+
+// Programmatic dependent launch for the small kernels of the sector tail: the next kernel's CTAs become resident while this one
+// drains, and wait for its memory right here.  Without the launch attribute both instructions are no-ops.
+#define SEC_PDL_PROLOGUE()                                      \
+    do {                                                        \
+        asm volatile("griddepcontrol.launch_dependents;");      \
+        asm volatile("griddepcontrol.wait;" ::: "memory");      \
+    } while (0)
+
+template <typename... KArgs, typename... Args>
+static void sec_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    // measured on the 18-qubit screening: PDL between these small kernels makes the step SLOWER (0.132 vs 0.124 ms: the early
+    // CTAs of the dependent kernel take slots while the producer still runs), so it is opt-in (FHSIM_SECTOR_PDL=1)
+    static const bool pdl_off = getenv("FHSIM_NO_PDL") != nullptr || getenv("FHSIM_SECTOR_PDL") == nullptr;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (!pdl_off && g_fh_tile_pdl_scope > 0) ? 1 : 0;
+    ++g_fh_launch_count;
+    cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 #define SEC_MAX_C 16
 #define SEC_THREADS 256
@@ -544,6 +574,7 @@ __global__ void __launch_bounds__(256) k_sector_pool(const SecPoolEntry *__restr
                                                      const double2 *__restrict__ lam, double *__restrict__ partial,
                                                      const int *__restrict__ out_first, int first_out, int count,
                                                      double *__restrict__ d_out, unsigned *__restrict__ counter) {
+    SEC_PDL_PROLOGUE();
     extern __shared__ unsigned sl[];
     __shared__ double red[16];
     __shared__ unsigned is_last;
@@ -1331,6 +1362,7 @@ __global__ void __launch_bounds__(256) k_sector_compress2(const unsigned *__rest
                                                           unsigned d_dn, unsigned dim, const double2 *__restrict__ a,
                                                           const double2 *__restrict__ b, double2 *__restrict__ ac,
                                                           double2 *__restrict__ bc) {
+    SEC_PDL_PROLOGUE();
     const unsigned stride = gridDim.x * blockDim.x;
     for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < dim; r += stride) {
         const unsigned ru = r / d_dn, rd = r - ru * d_dn;
@@ -1480,6 +1512,7 @@ int fh_sector_pool_prepare(fh_sector_pool_plan **slot, fh_ctx *ctx, int n, u64 u
 __global__ void __launch_bounds__(256) k_sector_compress1(const unsigned *__restrict__ depU, const unsigned *__restrict__ depD,
                                                           unsigned d_dn, unsigned dim, const double2 *__restrict__ a,
                                                           double2 *__restrict__ ac) {
+    SEC_PDL_PROLOGUE();
     const unsigned stride = gridDim.x * blockDim.x;
     for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < dim; r += stride) {
         const unsigned ru = r / d_dn, rd = r - ru * d_dn;
@@ -1489,6 +1522,7 @@ __global__ void __launch_bounds__(256) k_sector_compress1(const unsigned *__rest
 __global__ void __launch_bounds__(256) k_sector_scatter1(const unsigned *__restrict__ depU, const unsigned *__restrict__ depD,
                                                          unsigned d_dn, unsigned dim, const double2 *__restrict__ ac,
                                                          double2 *__restrict__ a) {
+    SEC_PDL_PROLOGUE();
     const unsigned stride = gridDim.x * blockDim.x;
     for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < dim; r += stride) {
         const unsigned ru = r / d_dn, rd = r - ru * d_dn;
@@ -1510,6 +1544,7 @@ __global__ void __launch_bounds__(256) k_sector_happly(const SecGroup *__restric
                                                        unsigned d_dn, unsigned dim, const double2 *__restrict__ in,
                                                        double2 *__restrict__ out, double *__restrict__ partials,
                                                        unsigned *__restrict__ counter, double *__restrict__ result) {
+    SEC_PDL_PROLOGUE();
     __shared__ double red[16];
     __shared__ unsigned is_last;
     double e_re = 0.0, e_im = 0.0;
@@ -1608,11 +1643,15 @@ static void sec_launch_happly(cudaStream_t st, const SecTableCache &T, const fh_
     if (hgrid > 4096u) hgrid = 4096u;                 // the energy partial array
     if (hgrid < 1u) hgrid = 1u;
     if (split)
-        k_sector_happly<REAL, 4><<<hgrid, 256, 0, st>>>(T.d_groups, T.ngroups, T.d_classes, T.d_vals, T.d_hdiag, P->d_cfgU, P->d_cfgD, P->d_rankU,
-                                                        P->d_rankD, P->d_dn, dim, in, out, P->d_k2_partials, P->d_k2_counter, d_result);
+        sec_launch(k_sector_happly<REAL, 4>, dim3(hgrid), dim3(256), 0, st, (const SecGroup *)T.d_groups, T.ngroups, (const SecClass *)T.d_classes,
+                   (const double2 *)T.d_vals, (const double2 *)T.d_hdiag, (const unsigned short *)P->d_cfgU, (const unsigned short *)P->d_cfgD,
+                   (const unsigned short *)P->d_rankU, (const unsigned short *)P->d_rankD, P->d_dn, dim, in, out, P->d_k2_partials,
+                   P->d_k2_counter, d_result);
     else
-        k_sector_happly<REAL, 1><<<hgrid, 256, 0, st>>>(T.d_groups, T.ngroups, T.d_classes, T.d_vals, T.d_hdiag, P->d_cfgU, P->d_cfgD, P->d_rankU,
-                                                        P->d_rankD, P->d_dn, dim, in, out, P->d_k2_partials, P->d_k2_counter, d_result);
+        sec_launch(k_sector_happly<REAL, 1>, dim3(hgrid), dim3(256), 0, st, (const SecGroup *)T.d_groups, T.ngroups, (const SecClass *)T.d_classes,
+                   (const double2 *)T.d_vals, (const double2 *)T.d_hdiag, (const unsigned short *)P->d_cfgU, (const unsigned short *)P->d_cfgD,
+                   (const unsigned short *)P->d_rankU, (const unsigned short *)P->d_rankD, P->d_dn, dim, in, out, P->d_k2_partials,
+                   P->d_k2_counter, d_result);
 }
 
 // out (full space, may be NULL) <- H in; E -> d_result[0..1].  `in` must be confined to the plan's sector.
@@ -1625,7 +1664,6 @@ int fh_sector_table_enqueue(fh_sector_pool_plan *P, fh_ctx *ctx, const fh_table 
     if (cgrid > (unsigned)ctx->sm_count * 8u) cgrid = (unsigned)ctx->sm_count * 8u;
     ++g_fh_launch_count;
     k_sector_compress1<<<cgrid, 256, 0, ctx->stream>>>(P->d_depU, P->d_depD, P->d_dn, dim, in, P->d_in);
-    ++g_fh_launch_count;
     if (tab->all_real) sec_launch_happly<true>(ctx->stream, T, P, dim, P->d_in, P->d_out, d_result);
     else sec_launch_happly<false>(ctx->stream, T, P, dim, P->d_in, P->d_out, d_result);
     if (out) {
@@ -1788,6 +1826,7 @@ __global__ void __launch_bounds__(256) k_sector_gemm(const double2 *__restrict__
                                                      int M, int N, int K, const unsigned short *__restrict__ cfgU,
                                                      const unsigned short *__restrict__ pp, const unsigned *__restrict__ depU,
                                                      const unsigned *__restrict__ depD, double2 *__restrict__ Bc) {
+    SEC_PDL_PROLOGUE();
     __shared__ double2 sa[16][SEC_GK + 1], sb[SEC_GK][17];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int m0 = blockIdx.y * 16, n0 = blockIdx.x * 16;
@@ -2016,20 +2055,20 @@ static void sec_dense_apply(const fh_sector_pool_plan *P, const SecDense &D, cud
                             bool dagger, double2 *gather_copy) {
     const int du = (int)P->d_up, dd = (int)P->d_dn;
     const dim3 grid((dd + 15) / 16, (du + 15) / 16);
-    g_fh_launch_count += 2;
     // tmp = A (S o in);  out = S o (tmp B).  gather_copy != NULL: `in` is a full-space state, its compressed copy is written there
+    const unsigned *nou = nullptr;
+    double2 *nod = nullptr;
     if (gather_copy)
-        k_sector_gemm<true, false, true><<<grid, 256, 0, s>>>(dagger ? D.d_UupH : D.d_Uup, in, tmp, du, dd, du, P->d_cfgU, D.d_pp, P->d_depU,
-                                                              P->d_depD, gather_copy);
+        sec_launch(k_sector_gemm<true, false, true>, grid, dim3(256), 0, s, (const double2 *)(dagger ? D.d_UupH : D.d_Uup), in, tmp, du, dd, du,
+                   (const unsigned short *)P->d_cfgU, (const unsigned short *)D.d_pp, (const unsigned *)P->d_depU, (const unsigned *)P->d_depD,
+                   gather_copy);
     else
-        k_sector_gemm<true, false, false><<<grid, 256, 0, s>>>(dagger ? D.d_UupH : D.d_Uup, in, tmp, du, dd, du, P->d_cfgU, D.d_pp, nullptr,
-                                                               nullptr, nullptr);
-    k_sector_gemm<false, true, false><<<grid, 256, 0, s>>>(tmp, dagger ? D.d_UdnC : D.d_UdnT, out, du, dd, dd, P->d_cfgU, D.d_pp, nullptr,
-                                                           nullptr, nullptr);
+        sec_launch(k_sector_gemm<true, false, false>, grid, dim3(256), 0, s, (const double2 *)(dagger ? D.d_UupH : D.d_Uup), in, tmp, du, dd, du,
+                   (const unsigned short *)P->d_cfgU, (const unsigned short *)D.d_pp, nou, nou, nod);
+    sec_launch(k_sector_gemm<false, true, false>, grid, dim3(256), 0, s, (const double2 *)tmp, (const double2 *)(dagger ? D.d_UdnC : D.d_UdnT), out,
+               du, dd, dd, (const unsigned short *)P->d_cfgU, (const unsigned short *)D.d_pp, nou, nou, nod);
 }
 
-// The tail of an evaluation on compressed vectors: psi_full = the state after the items before the tail.
-// E -> d_result[0..1]; with a pool: outputs o in [first, first + count) -> d_pool_out[o].
 double2 *fh_sector_dense_psi_buffer(fh_sector_pool_plan *P, const fh_pool *pool) { return (pool && P->d_psi) ? P->d_psi : P->d_in; }
 
 // psi_full == NULL: the compressed psi_s is already in fh_sector_dense_psi_buffer() (written by the cluster kernel)
@@ -2046,7 +2085,6 @@ int fh_sector_dense_enqueue(fh_sector_dense *X, fh_sector_pool_plan *P, fh_ctx *
     (void)cgrid;
     if (psi_full) sec_dense_apply(P, D, ctx->stream, psi_full, D.d_t0, D.d_t1, false, psi_s);   // phi = W psi_s (t1); psi_s compressed on the way
     else sec_dense_apply(P, D, ctx->stream, psi_s, D.d_t0, D.d_t1, false, nullptr);
-    ++g_fh_launch_count;
     if (tab->all_real) sec_launch_happly<true>(ctx->stream, T, P, dim, D.d_t1, P->d_out, d_result);          // H phi (d_out)
     else sec_launch_happly<false>(ctx->stream, T, P, dim, D.d_t1, P->d_out, d_result);
     if (pool && pool_count > 0) {
@@ -2056,10 +2094,9 @@ int fh_sector_dense_enqueue(fh_sector_dense *X, fh_sector_pool_plan *P, fh_ctx *
         int grid = e1 - e0;
         if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
         if (grid < 1) grid = 1;
-        ++g_fh_launch_count;
-        k_sector_pool<<<grid, 256, sizeof(unsigned) * std::max(1u, Pc.max_words), ctx->stream>>>(
-            Pc.d_entries, Pc.d_lists, e0, e1, P->d_dn, P->d_psi, P->d_lam, Pc.d_partial, pool->d_out_first, pool_first, pool_count,
-            d_pool_out, Pc.d_counter);
+        sec_launch(k_sector_pool, dim3(grid), dim3(256), sizeof(unsigned) * std::max(1u, Pc.max_words), ctx->stream,
+                   (const SecPoolEntry *)Pc.d_entries, (const unsigned *)Pc.d_lists, e0, e1, P->d_dn, (const double2 *)P->d_psi,
+                   (const double2 *)P->d_lam, Pc.d_partial, (const int *)pool->d_out_first, pool_first, pool_count, d_pool_out, Pc.d_counter);
     }
     FH_CUDA(cudaGetLastError());
     return FH_OK;
